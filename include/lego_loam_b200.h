@@ -1,0 +1,206 @@
+/*
+ * lego_loam_b200.h -- C ABI of the B200 (sm_100a) implementation of LeGO-LOAM-BOR's
+ * per-scan hot path.  Plain pointers and sizes only; no C++/torch types cross it.
+ *
+ * The reference has no FFI: its boundary is three C++ classes, two payload structs
+ * and the yaml keys.  Each entry point below names the reference
+ * interface it stands behind (paths relative to /root/reference/LeGO-LOAM):
+ *
+ *   ll_image_projection      ImageProjection::cloudHandler          src/imageProjection.cpp:153-174
+ *   ll_feature_association   FeatureAssociation::runFeatureAssociation loop body
+ *                                                                    src/featureAssociation.cpp:1386-1450
+ *   ll_scan_to_map           MapOptimization::scan2MapOptimization  src/mapOptmization.cpp:1315-1332
+ *   LegoLoamParams           config/loam_config.yaml:1-35 (same key names)
+ *   LL_BUF_SEG_* / ll_cloud_info   cloud_msgs/msg/cloud_info.msg:1-13
+ *
+ * A handle owns all device memory for `batch` independent sequences that advance
+ * in lock step (one scan per sequence per call).  One CUDA stream per handle; a handle
+ * is not thread-safe (the reference drives each stage object from exactly one thread).
+ * Every function returns 0 on success or a negative ll_status; nothing throws.
+ * There is no CPU fallback: if no CUDA device is usable, ll_create fails.
+ */
+#ifndef LEGO_LOAM_B200_H
+#define LEGO_LOAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ll_handle ll_handle;
+
+typedef enum ll_status {
+  LL_OK = 0,
+  LL_ERR_INVALID_ARG = -1,
+  LL_ERR_CUDA = -2,
+  LL_ERR_NO_DEVICE = -3,
+  LL_ERR_CAPACITY = -4,
+  LL_ERR_STATE = -5
+} ll_status;
+
+/* Fields are the 21 keys of config/loam_config.yaml, same names and units. */
+typedef struct LegoLoamParams {
+  /* laser: */
+  int32_t num_vertical_scans;
+  int32_t num_horizontal_scans;
+  int32_t ground_scan_index;
+  float vertical_angle_bottom; /* degrees */
+  float vertical_angle_top;    /* degrees */
+  float sensor_mount_angle;    /* degrees */
+  float scan_period;           /* seconds */
+  /* imageProjection: */
+  int32_t segment_valid_point_num;
+  int32_t segment_valid_line_num;
+  float segment_theta; /* degrees */
+  /* featureAssociation: */
+  float edge_threshold;
+  float surf_threshold;
+  float nearest_feature_search_distance;
+  /* mapping: */
+  int32_t enable_loop_closure;
+  int32_t mapping_frequency_divider;
+  float surrounding_keyframe_search_radius;
+  int32_t surrounding_keyframe_search_num;
+  float history_keyframe_search_radius;
+  int32_t history_keyframe_search_num;
+  float history_keyframe_fitness_score;
+  float global_map_visualization_search_radius;
+} LegoLoamParams;
+
+/* Fills *p with the values of the reference's config/loam_config.yaml (VLP-16). */
+void ll_default_params(LegoLoamParams* p);
+
+/* Device-resident arrays that ll_download / ll_upload can address, per sequence.
+ * Element types are given on the right; "pt" = 4 floats (x, y, z, intensity), the
+ * 16-byte form of pcl::PointXYZI (utility.h:46). */
+typedef enum ll_buffer {
+  /* ImageProjection state (imageProjection.h:30-81) */
+  LL_BUF_RANGE_MAT = 0,   /* f32[N]  _range_mat, row-major, FLT_MAX = no return */
+  LL_BUF_FULL_CLOUD = 1,  /* pt[N]   _full_cloud (NaN xyz where empty) */
+  LL_BUF_GROUND_MAT = 2,  /* i8[N]   _ground_mat */
+  LL_BUF_LABEL_MAT = 3,   /* i32[N]  _label_mat */
+  /* ProjectionOut (utility.h:64-70) and cloud_info (cloud_info.msg:1-13) */
+  LL_BUF_SEG_CLOUD = 4,        /* pt[S]  segmented_cloud (after ll_feature_association: axis-swapped + time-tagged) */
+  LL_BUF_SEG_GROUND_FLAG = 5,  /* u8[S]  segmentedCloudGroundFlag */
+  LL_BUF_SEG_COL_IND = 6,      /* u32[S] segmentedCloudColInd */
+  LL_BUF_SEG_RANGE = 7,        /* f32[S] segmentedCloudRange */
+  LL_BUF_START_RING_INDEX = 8, /* i32[V] */
+  LL_BUF_END_RING_INDEX = 9,   /* i32[V] */
+  LL_BUF_ORIENTATION = 10,     /* f32[3] startOrientation, endOrientation, orientationDiff */
+  LL_BUF_OUTLIER_CLOUD = 11,   /* pt[O]  outlier_cloud */
+  /* FeatureAssociation state (featureAssociation.h:66-70) */
+  LL_BUF_CLOUD_CURVATURE = 12,  /* f32[N] */
+  LL_BUF_NEIGHBOR_PICKED = 13,  /* i32[N] */
+  LL_BUF_CLOUD_LABEL = 14,      /* i32[N] */
+  LL_BUF_CORNER_SHARP = 15,     /* pt[..] cornerPointsSharp */
+  LL_BUF_CORNER_LESS_SHARP = 16,
+  LL_BUF_SURF_FLAT = 17,
+  LL_BUF_SURF_LESS_FLAT = 18,
+  LL_BUF_CORNER_SHARP_IND = 19, /* i32[..] index into the segmented cloud of every picked point */
+  LL_BUF_CORNER_LESS_SHARP_IND = 20,
+  LL_BUF_SURF_FLAT_IND = 21,
+  LL_BUF_CORNER_LAST = 22, /* pt[..] laserCloudCornerLast */
+  LL_BUF_SURF_LAST = 23,   /* pt[..] laserCloudSurfLast */
+  LL_BUF_TRANSFORM_CUR = 24, /* f32[6] */
+  LL_BUF_TRANSFORM_SUM = 25, /* f32[6] */
+  LL_BUF_ODOM_ITERS = 26,    /* i32[2] LM iterations actually run (surf, corner) in the last frame */
+  /* MapOptimization scan-to-map slice (mapOptimization.h:120-150,190-210) */
+  LL_BUF_MAP_CORNER = 27,    /* pt[..] laserCloudCornerFromMapDS */
+  LL_BUF_MAP_SURF = 28,      /* pt[..] laserCloudSurfFromMapDS */
+  LL_BUF_SCAN_CORNER_DS = 29,     /* pt[..] laserCloudCornerLastDS */
+  LL_BUF_SCAN_SURF_TOTAL_DS = 30, /* pt[..] laserCloudSurfTotalLastDS */
+  LL_BUF_TRANSFORM_TOBE_MAPPED = 31, /* f32[6] */
+  LL_BUF_MAP_ITERS = 32,             /* i32[2] iterations run, rows in the last iteration */
+  LL_BUF_OUTLIER_LAST = 33,          /* pt[O] outlier cloud after adjustOutlierCloud (featureAssociation.cpp:1273-1283) */
+  LL_BUF_SURF_LESS_FLAT_RAW_COUNT = 34, /* i32[V] less-flat points per ring before the 0.2 m VoxelGrid */
+  LL_BUF_COUNT_
+} ll_buffer;
+
+/* ---- lifetime ---------------------------------------------------------------- */
+
+/* batch: sequences processed per call (>=1).  max_points: capacity of one input
+ * scan (points).  cuda_stream: a cudaStream_t to enqueue on, or NULL to let the
+ * handle create its own.  device: CUDA ordinal. */
+int ll_create(const LegoLoamParams* params, int batch, int max_points, int device,
+              void* cuda_stream, ll_handle** out);
+int ll_destroy(ll_handle* h);
+/* Forget all per-sequence history (first-frame state, transformCur/Sum, last clouds). */
+int ll_reset(ll_handle* h);
+const char* ll_last_error(const ll_handle* h);
+/* Number of kernels this handle has launched since creation (bench "gpu_launches"). */
+int64_t ll_kernel_launches(const ll_handle* h);
+
+/* ---- input (replaces sensor_msgs::PointCloud2 of imageProjection.cpp:153-161) -- */
+
+/* Host scans: xyzi[batch][stride_points][4] floats, n_points[batch] valid points each
+ * (NaN points must already be removed, as pcl::removeNaNFromPointCloud does).
+ * Copies host->device on the handle's stream (async if the memory is pinned). */
+int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, int stride_points);
+/* Same, for scans that already live in device memory (no copy is made; the buffer
+ * must stay valid until the next ll_image_projection has been enqueued). */
+int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_points, int stride_points);
+
+/* ---- the hot path ------------------------------------------------------------- */
+
+/* resetParameters + findStartEndAngle + projectPointCloud + groundRemoval +
+ * cloudSegmentation/labelComponents (imageProjection.cpp:107-150,178-308,352-496). */
+int ll_image_projection(ll_handle* h);
+/* adjustDistortion, calculateSmoothness, markOccludedPoints, extractFeatures, then
+ * (first frame) checkSystemInitialization, (later frames) updateTransformation,
+ * integrateTransformation, publishCloudsLast (featureAssociation.cpp:161-383,
+ * 503-1032,1181-1270,1329-1359). */
+int ll_feature_association(ll_handle* h);
+
+/* Local map of one sequence for scan-to-map, already down-sampled
+ * (laserCloudCornerFromMapDS / laserCloudSurfFromMapDS, mapOptmization.cpp:989-995).
+ * Host pointers; copied to the device. */
+int ll_map_set_local(ll_handle* h, int seq, const float* corner_xyzi, int n_corner,
+                     const float* surf_xyzi, int n_surf);
+/* Down-sampled current scan of one sequence (laserCloudCornerLastDS and
+ * laserCloudSurfTotalLastDS, mapOptmization.cpp:999-1026), host pointers. */
+int ll_map_set_scan(ll_handle* h, int seq, const float* corner_xyzi, int n_corner,
+                    const float* surf_total_xyzi, int n_surf_total);
+/* On-device downsampleCurrentScan (mapOptmization.cpp:999-1026): VoxelGrid 0.2 m of
+ * corner_last, 0.4 m of surf_last and outlier_last, concat, 0.4 m again -- for all
+ * sequences, from the clouds ll_feature_association left on the device. */
+int ll_map_downsample_current_scan(ll_handle* h);
+/* transformTobeMapped initial guess, f32[batch][6] host (result of
+ * transformAssociateToMap, mapOptmization.cpp:264-387, computed by the host class). */
+int ll_map_set_initial_guess(ll_handle* h, const float* transform_tobe_mapped);
+/* kd-tree replacement build + <=10 x (cornerOptimization, surfOptimization,
+ * LMOptimization) (mapOptmization.cpp:1028-1332) for all sequences. */
+int ll_scan_to_map(ll_handle* h);
+
+/* One full frame for every sequence: ll_image_projection + ll_feature_association,
+ * and every mapping_frequency_divider-th odometry frame also
+ * ll_map_downsample_current_scan + ll_scan_to_map when a local map is set. */
+int ll_process_scans(ll_handle* h);
+
+/* ---- results ------------------------------------------------------------------- */
+
+/* Poses of all sequences, f32[batch][6] each, host pointers (any may be NULL).
+ * Synchronises the stream. */
+int ll_get_poses(ll_handle* h, float* transform_sum, float* transform_cur, float* transform_tobe_mapped);
+/* Copy one array of one sequence to host.  *n_elems receives the element count
+ * (points for "pt" buffers).  dst may be NULL to query the count only.
+ * Synchronises the stream. */
+int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, size_t* n_elems);
+/* Overwrite persistent state of one sequence (teacher-forced parity runs):
+ * LL_BUF_TRANSFORM_CUR, LL_BUF_TRANSFORM_SUM, LL_BUF_TRANSFORM_TOBE_MAPPED. */
+int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems);
+int ll_synchronize(ll_handle* h);
+
+/* Per-stage device time of the last ll_process_scans call, in milliseconds:
+ * [0] projection+ground, [1] segmentation, [2] feature extraction,
+ * [3] scan-to-scan LM + glue, [4] scan-to-map (0 if not run).  Needs
+ * ll_enable_stage_timing(h, 1) before the call; synchronises the stream. */
+int ll_enable_stage_timing(ll_handle* h, int enable);
+int ll_get_stage_times_ms(ll_handle* h, float* ms5);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LEGO_LOAM_B200_H */

@@ -1,0 +1,57 @@
+/*
+ * lego_oracle.h -- TEST INFRASTRUCTURE, not product code.
+ *
+ * C interface of the CPU oracle: a from-scratch restatement of the reference's hot path
+ * (ImageProjection, FeatureAssociation, MapOptimization::scan2MapOptimization) used only
+ * by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+ * Nothing under lego_loam_bor_b200/ may include, link or call this.
+ *
+ * It mirrors include/lego_loam_b200.h (same LegoLoamParams, same ll_buffer ids) for ONE
+ * sequence, so a parity test is "run both, download the same buffer id, compare".
+ */
+#ifndef LEGO_ORACLE_H
+#define LEGO_ORACLE_H
+
+#include "../include/lego_loam_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lo_handle lo_handle;
+
+/* Global backend switches (affect objects created afterwards and all math calls). */
+void lo_set_math_backend(int use_libm);      /* 0 = portable (default), 1 = glibc float libm */
+void lo_set_knn_backend(int use_nanoflann);  /* 1 = reference nanoflann (if compiled in), 0 = port kd-tree */
+int lo_has_nanoflann(void);
+
+lo_handle* lo_create(const LegoLoamParams* p);
+void lo_destroy(lo_handle* h);
+void lo_reset(lo_handle* h);
+
+int lo_image_projection(lo_handle* h, const float* xyzi, int n_points);
+/* returns 1 when this frame would be handed to MapOptimization (featureAssociation.cpp:1432), else 0 */
+int lo_feature_association(lo_handle* h);
+int lo_map_set_local(lo_handle* h, const float* corner, int nc, const float* surf, int ns);
+int lo_map_set_scan(lo_handle* h, const float* corner, int nc, const float* surf_total, int ns);
+int lo_map_downsample_current_scan(lo_handle* h);
+int lo_map_set_initial_guess(lo_handle* h, const float* t6);
+int lo_scan_to_map(lo_handle* h);
+int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n_elems);
+int lo_upload(lo_handle* h, int buffer, const void* src, size_t n_elems);
+
+/* pcl::VoxelGrid restatement on its own: out must hold n points; returns output count. */
+int lo_voxel_grid(const float* xyzi, int n, float leaf, float* out_xyzi);
+/* k-NN on its own (for kd-tree pin tests): idx[nq*k], d2[nq*k]. */
+int lo_knn(const float* cloud_xyzi, int n, const float* query_xyzi, int nq, int k, int* idx, float* d2);
+
+/* Wall-clock seconds spent inside each stage since the last lo_reset_timers:
+ * [0] image projection, [1] feature extraction (adjust..extract), [2] scan-to-scan LM + glue,
+ * [3] scan-to-map incl. tree builds, [4] downsampleCurrentScan. */
+void lo_get_timers(lo_handle* h, double* sec5);
+void lo_reset_timers(lo_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
