@@ -1,0 +1,205 @@
+"""ctypes binding of the C ABI in include/lego_loam_b200.h (what tests/ and bench.py call).
+
+There is no CPU fallback: importing works anywhere, but creating a `LegoLoam` needs the CUDA
+shared library built by `lego_loam_bor_b200.build` and a CUDA device."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._paths import LIB_CUDA
+from .params import LegoLoamParams
+
+# name -> (ll_buffer id, numpy dtype, columns); mirrors `enum ll_buffer`
+BUFFERS = {
+    "RANGE_MAT": (0, np.float32, 1), "FULL_CLOUD": (1, np.float32, 4), "GROUND_MAT": (2, np.int8, 1),
+    "LABEL_MAT": (3, np.int32, 1), "SEG_CLOUD": (4, np.float32, 4), "SEG_GROUND_FLAG": (5, np.uint8, 1),
+    "SEG_COL_IND": (6, np.uint32, 1), "SEG_RANGE": (7, np.float32, 1), "START_RING_INDEX": (8, np.int32, 1),
+    "END_RING_INDEX": (9, np.int32, 1), "ORIENTATION": (10, np.float32, 1), "OUTLIER_CLOUD": (11, np.float32, 4),
+    "CLOUD_CURVATURE": (12, np.float32, 1), "NEIGHBOR_PICKED": (13, np.int32, 1), "CLOUD_LABEL": (14, np.int32, 1),
+    "CORNER_SHARP": (15, np.float32, 4), "CORNER_LESS_SHARP": (16, np.float32, 4), "SURF_FLAT": (17, np.float32, 4),
+    "SURF_LESS_FLAT": (18, np.float32, 4), "CORNER_SHARP_IND": (19, np.int32, 1),
+    "CORNER_LESS_SHARP_IND": (20, np.int32, 1), "SURF_FLAT_IND": (21, np.int32, 1),
+    "CORNER_LAST": (22, np.float32, 4), "SURF_LAST": (23, np.float32, 4), "TRANSFORM_CUR": (24, np.float32, 1),
+    "TRANSFORM_SUM": (25, np.float32, 1), "ODOM_ITERS": (26, np.int32, 1), "MAP_CORNER": (27, np.float32, 4),
+    "MAP_SURF": (28, np.float32, 4), "SCAN_CORNER_DS": (29, np.float32, 4), "SCAN_SURF_TOTAL_DS": (30, np.float32, 4),
+    "TRANSFORM_TOBE_MAPPED": (31, np.float32, 1), "MAP_ITERS": (32, np.int32, 1),
+    "OUTLIER_LAST": (33, np.float32, 4), "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
+}
+
+EXPORTS = [
+    "ll_default_params", "ll_create", "ll_destroy", "ll_reset", "ll_last_error", "ll_kernel_launches",
+    "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
+    "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
+    "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_download", "ll_upload", "ll_synchronize",
+    "ll_enable_stage_timing", "ll_get_stage_times_ms",
+]
+
+_lib = None
+
+
+class LegoLoamError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_CUDA
+    if not os.path.exists(path):
+        raise LegoLoamError(f"{path} is missing: run `python -m lego_loam_bor_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, ip, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.ll_default_params.argtypes = [vp]
+    lib.ll_default_params.restype = None
+    lib.ll_create.argtypes = [vp, ip, ip, ip, vp, C.POINTER(vp)]
+    lib.ll_destroy.argtypes = [vp]
+    lib.ll_reset.argtypes = [vp]
+    lib.ll_last_error.argtypes = [vp]
+    lib.ll_last_error.restype = C.c_char_p
+    lib.ll_kernel_launches.argtypes = [vp]
+    lib.ll_kernel_launches.restype = C.c_int64
+    lib.ll_set_scans_host.argtypes = [vp, vp, vp, ip]
+    lib.ll_set_scans_device.argtypes = [vp, vp, vp, ip]
+    for name in ("ll_image_projection", "ll_feature_association", "ll_map_downsample_current_scan",
+                 "ll_scan_to_map", "ll_process_scans", "ll_synchronize"):
+        getattr(lib, name).argtypes = [vp]
+    lib.ll_map_set_local.argtypes = [vp, ip, vp, ip, vp, ip]
+    lib.ll_map_set_scan.argtypes = [vp, ip, vp, ip, vp, ip]
+    lib.ll_map_set_initial_guess.argtypes = [vp, vp]
+    lib.ll_get_poses.argtypes = [vp, vp, vp, vp]
+    lib.ll_download.argtypes = [vp, ip, ip, vp, sz, C.POINTER(sz)]
+    lib.ll_upload.argtypes = [vp, ip, ip, vp, sz]
+    lib.ll_enable_stage_timing.argtypes = [vp, ip]
+    lib.ll_get_stage_times_ms.argtypes = [vp, vp]
+    if path == LIB_CUDA:
+        _lib = lib
+    return lib
+
+
+class LegoLoam:
+    """`batch` independent sequences advancing in lock step on one GPU."""
+
+    def __init__(self, params: LegoLoamParams, batch=1, max_points=None, device=0, stream=None):
+        self.lib = load_library()
+        self.params = params
+        self.batch = batch
+        self.V, self.H = params.num_vertical_scans, params.num_horizontal_scans
+        self.N = self.V * self.H
+        self.max_points = max_points or self.N
+        h = C.c_void_p()
+        rc = self.lib.ll_create(C.addressof(params), batch, self.max_points, device, stream, C.byref(h))
+        if rc != 0:
+            raise LegoLoamError(f"ll_create failed with status {rc} (no CUDA device, or bad parameters)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ll_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise LegoLoamError(f"{what} -> {rc}: {self.lib.ll_last_error(self.h).decode()}")
+        return rc
+
+    def reset(self):
+        self._ck(self.lib.ll_reset(self.h), "ll_reset")
+
+    def set_scans_host(self, scans):
+        """scans: list (len batch) of float32 [n_i, 4] arrays, or (packed [batch, stride, 4], counts)."""
+        if isinstance(scans, tuple):
+            packed, counts = scans
+        else:
+            stride = max(1, max(len(s) for s in scans))
+            packed = np.zeros((self.batch, stride, 4), np.float32)
+            counts = np.zeros(self.batch, np.int32)
+            for i, s in enumerate(scans):
+                packed[i, :len(s)] = s
+                counts[i] = len(s)
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._keep = (packed, counts)
+        self._ck(self.lib.ll_set_scans_host(self.h, packed.ctypes.data, counts.ctypes.data, packed.shape[1]),
+                 "ll_set_scans_host")
+
+    def set_scans_host_ptr(self, ptr, counts, stride):
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._ck(self.lib.ll_set_scans_host(self.h, ptr, counts.ctypes.data, stride), "ll_set_scans_host")
+
+    def set_scans_device(self, dev_ptr, counts, stride):
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._ck(self.lib.ll_set_scans_device(self.h, dev_ptr, counts.ctypes.data, stride), "ll_set_scans_device")
+
+    def image_projection(self):
+        return self._ck(self.lib.ll_image_projection(self.h), "ll_image_projection")
+
+    def feature_association(self):
+        return self._ck(self.lib.ll_feature_association(self.h), "ll_feature_association")
+
+    def process_scans(self):
+        return self._ck(self.lib.ll_process_scans(self.h), "ll_process_scans")
+
+    def map_set_local(self, seq, corner, surf):
+        corner = np.ascontiguousarray(corner, np.float32)
+        surf = np.ascontiguousarray(surf, np.float32)
+        self._ck(self.lib.ll_map_set_local(self.h, seq, corner.ctypes.data, len(corner), surf.ctypes.data, len(surf)),
+                 "ll_map_set_local")
+
+    def map_set_scan(self, seq, corner, surf_total):
+        corner = np.ascontiguousarray(corner, np.float32)
+        surf_total = np.ascontiguousarray(surf_total, np.float32)
+        self._ck(self.lib.ll_map_set_scan(self.h, seq, corner.ctypes.data, len(corner), surf_total.ctypes.data,
+                                          len(surf_total)), "ll_map_set_scan")
+
+    def map_downsample_current_scan(self):
+        self._ck(self.lib.ll_map_downsample_current_scan(self.h), "ll_map_downsample_current_scan")
+
+    def map_set_initial_guess(self, t):
+        t = np.ascontiguousarray(t, np.float32).reshape(self.batch, 6)
+        self._ck(self.lib.ll_map_set_initial_guess(self.h, t.ctypes.data), "ll_map_set_initial_guess")
+
+    def scan_to_map(self):
+        self._ck(self.lib.ll_scan_to_map(self.h), "ll_scan_to_map")
+
+    def synchronize(self):
+        self._ck(self.lib.ll_synchronize(self.h), "ll_synchronize")
+
+    def poses(self):
+        ts = np.zeros((self.batch, 6), np.float32)
+        tc = np.zeros((self.batch, 6), np.float32)
+        tm = np.zeros((self.batch, 6), np.float32)
+        self._ck(self.lib.ll_get_poses(self.h, ts.ctypes.data, tc.ctypes.data, tm.ctypes.data), "ll_get_poses")
+        return ts, tc, tm
+
+    def download(self, name, seq=0):
+        bid, dt, w = BUFFERS[name]
+        n = C.c_size_t(0)
+        self._ck(self.lib.ll_download(self.h, seq, bid, None, 0, C.byref(n)), f"ll_download({name})")
+        out = np.empty((n.value, w) if w > 1 else (n.value,), dt)
+        self._ck(self.lib.ll_download(self.h, seq, bid, out.ctypes.data, max(out.nbytes, 1), C.byref(n)),
+                 f"ll_download({name})")
+        return out
+
+    def upload(self, name, arr, seq=0):
+        bid, dt, w = BUFFERS[name]
+        arr = np.ascontiguousarray(arr, dt)
+        self._ck(self.lib.ll_upload(self.h, seq, bid, arr.ctypes.data, arr.size // w), f"ll_upload({name})")
+
+    def kernel_launches(self):
+        return int(self.lib.ll_kernel_launches(self.h))
+
+    def enable_stage_timing(self, on=True):
+        self._ck(self.lib.ll_enable_stage_timing(self.h, 1 if on else 0), "ll_enable_stage_timing")
+
+    def stage_times_ms(self):
+        ms = np.zeros(5, np.float32)
+        self._ck(self.lib.ll_get_stage_times_ms(self.h, ms.ctypes.data), "ll_get_stage_times_ms")
+        return ms

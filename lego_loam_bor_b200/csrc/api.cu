@@ -1,0 +1,531 @@
+// api.cu -- the C ABI of include/lego_loam_b200.h: handle lifetime, device memory, stage sequencing.
+// No CPU fallback anywhere: without a usable CUDA device ll_create fails with LL_ERR_NO_DEVICE.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ll_device.cuh"
+#include "ll_kernels.h"
+
+struct ll_handle {
+  LegoLoamParams prm;
+  DevState st;
+  LaunchCtx ctx;
+  int device = 0;
+  bool own_stream = false;
+  std::vector<void*> allocs;
+  std::string err;
+  int64_t frames = 0;        // frames seen by ll_feature_association
+  int64_t odom_cycles = 0;   // _cycle_count of featureAssociation.cpp:1429-1433
+  bool map_set = false;
+  bool handed_to_mapping = false;
+  // pinned staging ring for the per-sequence point counts (a slot is reused only after its copy ran)
+  int32_t* h_n_in = nullptr;
+  cudaEvent_t slot_ev[16];
+  bool slot_used[16] = {false};
+  int slot = 0;
+  float4* in_owned = nullptr; // device input buffer used by ll_set_scans_host
+  bool timing = false;
+  cudaEvent_t ev[6];
+  float stage_ms[5];
+  bool ev_valid = false;
+};
+
+namespace {
+
+#define CK(call)                                                                     \
+  do {                                                                               \
+    const cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                        \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+      return LL_ERR_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(ll_handle* h, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  const size_t bytes = (n ? n : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return e;
+  h->allocs.push_back(q);
+  if (zero) e = cudaMemsetAsync(q, 0, bytes, h->ctx.stream);
+  *p = (T*)q;
+  return e;
+}
+
+int next_pow2(int v) {
+  int n = 1;
+  while (n < v) n <<= 1;
+  return n;
+}
+
+int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell) {
+  g->cell = cell;
+  g->inv_cell = 1.0f / cell;
+  g->cap = cap;
+  g->tbl = next_pow2(cap < 1024 ? 2048 : 2 * cap);
+  CK(dev_alloc(h, &g->cell_start, (size_t)B * (g->tbl + 1)));
+  CK(dev_alloc(h, &g->cursor, (size_t)B * g->tbl));
+  CK(dev_alloc(h, &g->sorted, (size_t)B * cap));
+  CK(dev_alloc(h, &g->count, (size_t)B));
+  return LL_OK;
+}
+
+int stage_counts(ll_handle* h, const int32_t* n_points, int stride_points, const char* who) {
+  DevState& st = h->st;
+  const int B = st.p.B;
+  const int slot = h->slot;
+  h->slot = (h->slot + 1) % 16;
+  if (h->slot_used[slot]) CK(cudaEventSynchronize(h->slot_ev[slot]));
+  int32_t* stage = h->h_n_in + (size_t)slot * B;
+  for (int s = 0; s < B; ++s) {
+    if (n_points[s] < 0 || n_points[s] > stride_points) { h->err = std::string(who) + ": n_points out of range"; return LL_ERR_INVALID_ARG; }
+    stage[s] = n_points[s];
+  }
+  CK(cudaMemcpyAsync(st.n_in, stage, sizeof(int32_t) * B, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaEventRecord(h->slot_ev[slot], h->ctx.stream));
+  h->slot_used[slot] = true;
+  return LL_OK;
+}
+
+int check_stream(ll_handle* h, const char* where) {
+  if (h->ctx.first_error != cudaSuccess) {
+    h->err = std::string(where) + ": launch of " + (h->ctx.first_error_kernel ? h->ctx.first_error_kernel : "?") +
+             " failed: " + cudaGetErrorString(h->ctx.first_error);
+    return LL_ERR_CUDA;
+  }
+  return LL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ll_default_params(LegoLoamParams* p) {
+  // LeGO-LOAM/config/loam_config.yaml:5-35
+  p->num_vertical_scans = 16; p->num_horizontal_scans = 1800; p->ground_scan_index = 7;
+  p->vertical_angle_bottom = -15.f; p->vertical_angle_top = 15.f; p->sensor_mount_angle = 0.f; p->scan_period = 0.1f;
+  p->segment_valid_point_num = 5; p->segment_valid_line_num = 3; p->segment_theta = 60.0f;
+  p->edge_threshold = 0.1f; p->surf_threshold = 0.1f; p->nearest_feature_search_distance = 5.f;
+  p->enable_loop_closure = 0; p->mapping_frequency_divider = 5;
+  p->surrounding_keyframe_search_radius = 50.0f; p->surrounding_keyframe_search_num = 50;
+  p->history_keyframe_search_radius = 7.0f; p->history_keyframe_search_num = 25;
+  p->history_keyframe_fitness_score = 0.3f; p->global_map_visualization_search_radius = 500.0f;
+}
+
+int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, void* cuda_stream, ll_handle** out) {
+  if (!prm || !out || batch < 1 || max_points < 1) return LL_ERR_INVALID_ARG;
+  if (prm->num_vertical_scans < 2 || prm->num_vertical_scans > LL_MAX_RINGS || prm->num_horizontal_scans < 16 ||
+      prm->ground_scan_index < 0 || prm->ground_scan_index >= prm->num_vertical_scans)
+    return LL_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LL_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return LL_ERR_NO_DEVICE;
+  ll_handle* h = new ll_handle();
+  h->prm = *prm;
+  h->device = device;
+  if (cuda_stream) {
+    h->ctx.stream = (cudaStream_t)cuda_stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LL_ERR_CUDA; }
+    h->own_stream = true;
+  }
+  memset(&h->st, 0, sizeof(DevState));
+  DevState& st = h->st;
+  DevParams& p = st.p;
+  const int B = batch, V = prm->num_vertical_scans, H = prm->num_horizontal_scans, N = V * H;
+  p.B = B; p.V = V; p.H = H; p.N = N; p.max_pts = max_points;
+  // imageProjection.cpp:64-84 with the promotion rules of SURVEY.md section 10
+  const double DEG_TO_RAD = LL_PI / 180.0;
+  const float bottom = prm->vertical_angle_bottom, top = prm->vertical_angle_top;
+  p.ang_res_x = (float)((LL_PI * 2) / (H));
+  p.ang_res_y = (float)(DEG_TO_RAD * (double)(top - bottom) / (double)(float)(V - 1));
+  p.ang_bottom = (float)(-((double)bottom - 0.1) * DEG_TO_RAD);
+  p.sensor_mount_angle = (float)((double)prm->sensor_mount_angle * DEG_TO_RAD);
+  const float seg_theta = (float)((double)prm->segment_theta * DEG_TO_RAD);
+  p.seg_tan_theta = ll_tanf(seg_theta);              // imageProjection.cpp:414
+  p.sin_ax = ll_sinf(p.ang_res_x); p.cos_ax = ll_cosf(p.ang_res_x);  // :462-463
+  p.sin_ay = ll_sinf(p.ang_res_y); p.cos_ay = ll_cosf(p.ang_res_y);
+  p.gsi = prm->ground_scan_index;
+  p.seg_valid_point_num = prm->segment_valid_point_num;
+  p.seg_valid_line_num = prm->segment_valid_line_num;
+  p.scan_period = prm->scan_period;
+  p.edge_threshold = prm->edge_threshold;
+  p.surf_threshold = prm->surf_threshold;
+  p.nearest_feature_dist_sqr = prm->nearest_feature_search_distance * prm->nearest_feature_search_distance;
+  p.cap_sharp = 12 * V; p.cap_less_sharp = 120 * V; p.cap_flat = 24 * V;
+  st.frame_tag = 0;
+  st.cap_outlier = V * ((H + 4) / 5);
+  st.cap_map_corner = 0; st.cap_map_surf = 0;
+  st.map_max_blocks = 96;
+  const size_t BN = (size_t)B * N;
+  CK(dev_alloc(h, &st.n_in, B));
+  CK(dev_alloc(h, &h->in_owned, (size_t)B * max_points, false));
+  CK(cudaMallocHost((void**)&h->h_n_in, sizeof(int32_t) * B * 16));
+  for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming));
+  CK(dev_alloc(h, &st.winner, BN));
+  CK(dev_alloc(h, &st.range_mat, BN)); CK(dev_alloc(h, &st.full_cloud, BN));
+  CK(dev_alloc(h, &st.ground_mat, BN)); CK(dev_alloc(h, &st.label_mat, BN));
+  CK(dev_alloc(h, &st.parent, BN)); CK(dev_alloc(h, &st.comp_size, BN)); CK(dev_alloc(h, &st.comp_rows, BN));
+  CK(dev_alloc(h, &st.tile_counts, (size_t)B * V * 4));
+  CK(dev_alloc(h, &st.orientation, (size_t)B * 4)); CK(dev_alloc(h, &st.half_idx, B));
+  CK(dev_alloc(h, &st.seg_cloud, BN)); CK(dev_alloc(h, &st.seg_range, BN));
+  CK(dev_alloc(h, &st.seg_col, BN)); CK(dev_alloc(h, &st.seg_ground, BN));
+  CK(dev_alloc(h, &st.start_ring, (size_t)B * V)); CK(dev_alloc(h, &st.end_ring, (size_t)B * V));
+  CK(dev_alloc(h, &st.seg_count, B));
+  CK(dev_alloc(h, &st.outlier_cloud, (size_t)B * st.cap_outlier)); CK(dev_alloc(h, &st.outlier_count, B));
+  CK(dev_alloc(h, &st.curvature, BN)); CK(dev_alloc(h, &st.picked, BN)); CK(dev_alloc(h, &st.cloud_label, BN));
+  CK(dev_alloc(h, &st.smooth_val, BN)); CK(dev_alloc(h, &st.smooth_ind, BN));
+  CK(dev_alloc(h, &st.st_sharp, (size_t)B * V * 12)); CK(dev_alloc(h, &st.st_sharp_ind, (size_t)B * V * 12));
+  CK(dev_alloc(h, &st.st_less_sharp, (size_t)B * V * 120)); CK(dev_alloc(h, &st.st_less_sharp_ind, (size_t)B * V * 120));
+  CK(dev_alloc(h, &st.st_flat, (size_t)B * V * 24)); CK(dev_alloc(h, &st.st_flat_ind, (size_t)B * V * 24));
+  CK(dev_alloc(h, &st.st_less_flat, BN)); CK(dev_alloc(h, &st.ring_counts, (size_t)B * V * 8));
+  CK(dev_alloc(h, &st.corner_sharp, (size_t)B * p.cap_sharp)); CK(dev_alloc(h, &st.corner_sharp_ind, (size_t)B * p.cap_sharp));
+  CK(dev_alloc(h, &st.corner_less_sharp, (size_t)B * p.cap_less_sharp));
+  CK(dev_alloc(h, &st.corner_less_sharp_ind, (size_t)B * p.cap_less_sharp));
+  CK(dev_alloc(h, &st.surf_flat, (size_t)B * p.cap_flat)); CK(dev_alloc(h, &st.surf_flat_ind, (size_t)B * p.cap_flat));
+  CK(dev_alloc(h, &st.surf_less_flat, BN)); CK(dev_alloc(h, &st.feat_counts, (size_t)B * 4));
+  CK(dev_alloc(h, &st.corner_last, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.surf_last, BN));
+  CK(dev_alloc(h, &st.last_counts, (size_t)B * 2));
+  CK(dev_alloc(h, &st.outlier_last, (size_t)B * st.cap_outlier));
+  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f); if (rc) return rc; }
+  CK(dev_alloc(h, &st.transform_cur, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_sum, (size_t)B * 6));
+  CK(dev_alloc(h, &st.odom_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.odom_flags, (size_t)B * 4));
+  CK(dev_alloc(h, &st.odom_matP, (size_t)B * 9));
+  CK(dev_alloc(h, &st.corr_surf, (size_t)B * p.cap_flat * 3)); CK(dev_alloc(h, &st.corr_corner, (size_t)B * p.cap_sharp * 2));
+  CK(dev_alloc(h, &st.map_counts, (size_t)B * 2));
+  CK(dev_alloc(h, &st.scan_corner_ds, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.scan_surf_ds, BN));
+  CK(dev_alloc(h, &st.scan_ds_counts, (size_t)B * 2));
+  CK(dev_alloc(h, &st.transform_tobe_mapped, (size_t)B * 6));
+  CK(dev_alloc(h, &st.map_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.map_flags, (size_t)B * 4));
+  CK(dev_alloc(h, &st.map_matP, (size_t)B * 36));
+  CK(dev_alloc(h, &st.map_partials, (size_t)B * st.map_max_blocks * 28));
+  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->ev[i]));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  *out = h;
+  return LL_OK;
+}
+
+int ll_destroy(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->ctx.stream);
+  for (void* q : h->allocs) cudaFree(q);
+  if (h->h_n_in) cudaFreeHost(h->h_n_in);
+  for (int i = 0; i < 16; ++i) cudaEventDestroy(h->slot_ev[i]);
+  for (int i = 0; i < 6; ++i) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream) cudaStreamDestroy(h->ctx.stream);
+  delete h;
+  return LL_OK;
+}
+
+const char* ll_last_error(const ll_handle* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t ll_kernel_launches(const ll_handle* h) { return h ? h->ctx.launches : 0; }
+
+int ll_reset(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  const DevParams& p = st.p;
+  const size_t BN = (size_t)p.B * p.N;
+  cudaStream_t sm = h->ctx.stream;
+  // featureAssociation.cpp:96-157 initializationValue
+  CK(cudaMemsetAsync(st.curvature, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.picked, 0, BN * 4, sm));
+  CK(cudaMemsetAsync(st.cloud_label, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.smooth_val, 0, BN * 4, sm));
+  CK(cudaMemsetAsync(st.smooth_ind, 0, BN * 4, sm));
+  CK(cudaMemsetAsync(st.transform_cur, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_sum, 0, (size_t)p.B * 24, sm));
+  CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm));
+  CK(cudaMemsetAsync(st.last_counts, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_flags, 0, (size_t)p.B * 16, sm));
+  CK(cudaMemsetAsync(st.odom_iters, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_matP, 0, (size_t)p.B * 36, sm));
+  CK(cudaMemsetAsync(st.map_flags, 0, (size_t)p.B * 16, sm)); CK(cudaMemsetAsync(st.map_matP, 0, (size_t)p.B * 144, sm));
+  CK(cudaMemsetAsync(st.map_iters, 0, (size_t)p.B * 8, sm));
+  CK(cudaMemsetAsync(st.grid_corner_last.cell_start, 0, (size_t)p.B * (st.grid_corner_last.tbl + 1) * 4, sm));
+  CK(cudaMemsetAsync(st.grid_surf_last.cell_start, 0, (size_t)p.B * (st.grid_surf_last.tbl + 1) * 4, sm));
+  h->frames = 0;
+  h->odom_cycles = 0;
+  h->handed_to_mapping = false;
+  return LL_OK;
+}
+
+int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, int stride_points) {
+  if (!h || !xyzi || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  const int B = st.p.B;
+  if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_host: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
+  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_host"); if (rc) return rc; }
+  // one copy per sequence of just the valid points (no batched-memcpy API is used)
+  for (int s = 0; s < B; ++s) {
+    if (n_points[s] == 0) continue;
+    CK(cudaMemcpyAsync(h->in_owned + (size_t)s * st.p.max_pts, xyzi + (size_t)s * stride_points * 4,
+                       (size_t)n_points[s] * 16, cudaMemcpyHostToDevice, h->ctx.stream));
+  }
+  st.in_pts = h->in_owned;
+  st.in_stride = st.p.max_pts;
+  return LL_OK;
+}
+
+int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_points, int stride_points) {
+  if (!h || !xyzi_dev || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_device: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
+  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_device"); if (rc) return rc; }
+  st.in_pts = (const float4*)xyzi_dev;
+  st.in_stride = stride_points;
+  return LL_OK;
+}
+
+int ll_image_projection(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!h->st.in_pts) { h->err = "ll_image_projection: no scans set"; return LL_ERR_STATE; }
+  h->st.frame_tag += 1;
+  if (h->timing) cudaEventRecord(h->ev[0], h->ctx.stream);
+  launch_projection(h->ctx, h->st);
+  if (h->timing) cudaEventRecord(h->ev[1], h->ctx.stream);
+  launch_segmentation(h->ctx, h->st);
+  if (h->timing) cudaEventRecord(h->ev[2], h->ctx.stream);
+  return check_stream(h, "ll_image_projection");
+}
+
+int ll_feature_association(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  const bool first = (h->frames == 0);
+  launch_feature_extraction(h->ctx, h->st);
+  if (h->timing) cudaEventRecord(h->ev[3], h->ctx.stream);
+  launch_odometry(h->ctx, h->st, first);
+  if (h->timing) cudaEventRecord(h->ev[4], h->ctx.stream);
+  h->frames += 1;
+  h->handed_to_mapping = false;
+  if (!first) {
+    // featureAssociation.cpp:1429-1433
+    h->odom_cycles += 1;
+    if (h->odom_cycles == h->prm.mapping_frequency_divider) {
+      h->odom_cycles = 0;
+      h->handed_to_mapping = true;
+    }
+  }
+  const int rc = check_stream(h, "ll_feature_association");
+  if (rc) return rc;
+  return h->handed_to_mapping ? 1 : 0;
+}
+
+static int ensure_map_capacity(ll_handle* h, int nc, int ns) {
+  DevState& st = h->st;
+  const int B = st.p.B;
+  if (nc <= st.cap_map_corner && ns <= st.cap_map_surf) return LL_OK;
+  // (re)allocate with headroom; maps of other sequences are preserved
+  const int ncap = nc > st.cap_map_corner ? (int)(nc * 1.25) + 1024 : st.cap_map_corner;
+  const int scap = ns > st.cap_map_surf ? (int)(ns * 1.25) + 1024 : st.cap_map_surf;
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  float4 *mc = nullptr, *ms = nullptr;
+  CK(dev_alloc(h, &mc, (size_t)B * ncap));
+  CK(dev_alloc(h, &ms, (size_t)B * scap));
+  if (st.map_corner) CK(cudaMemcpy2DAsync(mc, (size_t)ncap * 16, st.map_corner, (size_t)st.cap_map_corner * 16, (size_t)st.cap_map_corner * 16, B, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  if (st.map_surf) CK(cudaMemcpy2DAsync(ms, (size_t)scap * 16, st.map_surf, (size_t)st.cap_map_surf * 16, (size_t)st.cap_map_surf * 16, B, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  st.map_corner = mc; st.map_surf = ms;
+  st.cap_map_corner = ncap; st.cap_map_surf = scap;
+  { const int rc = alloc_grid(h, &st.grid_map_corner, B, ncap, 1.0f); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_map_surf, B, scap, 1.0f); if (rc) return rc; }
+  return LL_OK;
+}
+
+int ll_map_set_local(ll_handle* h, int seq, const float* corner, int nc, const float* surf, int ns) {
+  if (!h || seq < 0 || seq >= h->st.p.B || nc < 0 || ns < 0) return LL_ERR_INVALID_ARG;
+  const int rc = ensure_map_capacity(h, nc, ns);
+  if (rc) return rc;
+  DevState& st = h->st;
+  if (nc) CK(cudaMemcpyAsync(st.map_corner + (size_t)seq * st.cap_map_corner, corner, (size_t)nc * 16, cudaMemcpyHostToDevice, h->ctx.stream));
+  if (ns) CK(cudaMemcpyAsync(st.map_surf + (size_t)seq * st.cap_map_surf, surf, (size_t)ns * 16, cudaMemcpyHostToDevice, h->ctx.stream));
+  const int cnt[2] = {nc, ns};
+  CK(cudaMemcpyAsync(st.map_counts + seq * 2, cnt, 8, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  h->map_set = true;
+  return LL_OK;
+}
+
+int ll_map_set_scan(ll_handle* h, int seq, const float* corner, int nc, const float* surf, int ns) {
+  if (!h || seq < 0 || seq >= h->st.p.B || nc < 0 || ns < 0) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  if (nc > st.p.cap_less_sharp || ns > st.p.N) { h->err = "ll_map_set_scan: cloud larger than capacity"; return LL_ERR_CAPACITY; }
+  if (nc) CK(cudaMemcpyAsync(st.scan_corner_ds + (size_t)seq * st.p.cap_less_sharp, corner, (size_t)nc * 16, cudaMemcpyHostToDevice, h->ctx.stream));
+  if (ns) CK(cudaMemcpyAsync(st.scan_surf_ds + (size_t)seq * st.p.N, surf, (size_t)ns * 16, cudaMemcpyHostToDevice, h->ctx.stream));
+  const int cnt[2] = {nc, ns};
+  CK(cudaMemcpyAsync(st.scan_ds_counts + seq * 2, cnt, 8, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_map_downsample_current_scan(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  launch_downsample_current_scan(h->ctx, h->st);
+  return check_stream(h, "ll_map_downsample_current_scan");
+}
+
+int ll_map_set_initial_guess(ll_handle* h, const float* t) {
+  if (!h || !t) return LL_ERR_INVALID_ARG;
+  CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_scan_to_map(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!h->map_set) { h->err = "ll_scan_to_map: no local map set"; return LL_ERR_STATE; }
+  launch_scan_to_map(h->ctx, h->st);
+  return check_stream(h, "ll_scan_to_map");
+}
+
+int ll_process_scans(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  int rc = ll_image_projection(h);
+  if (rc < 0) return rc;
+  rc = ll_feature_association(h);
+  if (rc < 0) return rc;
+  if (rc == 1 && h->map_set) {
+    rc = ll_map_downsample_current_scan(h);
+    if (rc < 0) return rc;
+    rc = ll_scan_to_map(h);
+    if (rc < 0) return rc;
+    if (h->timing) cudaEventRecord(h->ev[5], h->ctx.stream);
+    h->ev_valid = true;
+    return 1;
+  }
+  if (h->timing) cudaEventRecord(h->ev[5], h->ctx.stream);
+  h->ev_valid = true;
+  return 0;
+}
+
+int ll_synchronize(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_get_poses(ll_handle* h, float* tsum, float* tcur, float* tmap) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  const size_t bytes = (size_t)h->st.p.B * 24;
+  if (tsum) CK(cudaMemcpyAsync(tsum, h->st.transform_sum, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  if (tcur) CK(cudaMemcpyAsync(tcur, h->st.transform_cur, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_enable_stage_timing(ll_handle* h, int enable) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  h->timing = enable != 0;
+  h->ev_valid = false;
+  return LL_OK;
+}
+
+int ll_get_stage_times_ms(ll_handle* h, float* ms5) {
+  if (!h || !ms5) return LL_ERR_INVALID_ARG;
+  if (!h->timing || !h->ev_valid) { h->err = "ll_get_stage_times_ms: timing not enabled or no frame processed"; return LL_ERR_STATE; }
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  for (int i = 0; i < 5; ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    ms5[i] = ms;
+  }
+  return LL_OK;
+}
+
+static int fetch_count(ll_handle* h, const int* dev, int* out) {
+  CK(cudaMemcpyAsync(out, dev, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, size_t* n_elems) {
+  if (!h || seq < 0 || seq >= h->st.p.B) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  const DevParams& p = st.p;
+  const size_t N = p.N;
+  const void* src = nullptr;
+  size_t elem = 0, n = 0;
+  int cnt = 0;
+#define FIXED(ptr, esz, count) do { src = (const char*)(ptr) + (size_t)seq * (count) * (esz); elem = (esz); n = (count); } while (0)
+#define COUNTED(ptr, esz, stride, cntptr) do { const int rc__ = fetch_count(h, (cntptr), &cnt); if (rc__) return rc__; \
+    src = (const char*)(ptr) + (size_t)seq * (stride) * (esz); elem = (esz); n = (size_t)cnt; } while (0)
+  switch (buffer) {
+    case LL_BUF_RANGE_MAT: FIXED(st.range_mat, 4, N); break;
+    case LL_BUF_FULL_CLOUD: FIXED(st.full_cloud, 16, N); break;
+    case LL_BUF_GROUND_MAT: FIXED(st.ground_mat, 1, N); break;
+    case LL_BUF_LABEL_MAT: FIXED(st.label_mat, 4, N); break;
+    case LL_BUF_SEG_CLOUD: COUNTED(st.seg_cloud, 16, N, st.seg_count + seq); break;
+    case LL_BUF_SEG_GROUND_FLAG: COUNTED(st.seg_ground, 1, N, st.seg_count + seq); break;
+    case LL_BUF_SEG_COL_IND: COUNTED(st.seg_col, 4, N, st.seg_count + seq); break;
+    case LL_BUF_SEG_RANGE: COUNTED(st.seg_range, 4, N, st.seg_count + seq); break;
+    case LL_BUF_START_RING_INDEX: FIXED(st.start_ring, 4, (size_t)p.V); break;
+    case LL_BUF_END_RING_INDEX: FIXED(st.end_ring, 4, (size_t)p.V); break;
+    case LL_BUF_ORIENTATION: src = st.orientation + seq * 4; elem = 4; n = 3; break;
+    case LL_BUF_OUTLIER_CLOUD: COUNTED(st.outlier_cloud, 16, (size_t)st.cap_outlier, st.outlier_count + seq); break;
+    case LL_BUF_CLOUD_CURVATURE: FIXED(st.curvature, 4, N); break;
+    case LL_BUF_NEIGHBOR_PICKED: FIXED(st.picked, 4, N); break;
+    case LL_BUF_CLOUD_LABEL: FIXED(st.cloud_label, 4, N); break;
+    case LL_BUF_CORNER_SHARP: COUNTED(st.corner_sharp, 16, (size_t)p.cap_sharp, st.feat_counts + seq * 4 + 0); break;
+    case LL_BUF_CORNER_LESS_SHARP: COUNTED(st.corner_less_sharp, 16, (size_t)p.cap_less_sharp, st.feat_counts + seq * 4 + 1); break;
+    case LL_BUF_SURF_FLAT: COUNTED(st.surf_flat, 16, (size_t)p.cap_flat, st.feat_counts + seq * 4 + 2); break;
+    case LL_BUF_SURF_LESS_FLAT: COUNTED(st.surf_less_flat, 16, N, st.feat_counts + seq * 4 + 3); break;
+    case LL_BUF_CORNER_SHARP_IND: COUNTED(st.corner_sharp_ind, 4, (size_t)p.cap_sharp, st.feat_counts + seq * 4 + 0); break;
+    case LL_BUF_CORNER_LESS_SHARP_IND: COUNTED(st.corner_less_sharp_ind, 4, (size_t)p.cap_less_sharp, st.feat_counts + seq * 4 + 1); break;
+    case LL_BUF_SURF_FLAT_IND: COUNTED(st.surf_flat_ind, 4, (size_t)p.cap_flat, st.feat_counts + seq * 4 + 2); break;
+    case LL_BUF_CORNER_LAST: COUNTED(st.corner_last, 16, (size_t)p.cap_less_sharp, st.last_counts + seq * 2 + 0); break;
+    case LL_BUF_SURF_LAST: COUNTED(st.surf_last, 16, N, st.last_counts + seq * 2 + 1); break;
+    case LL_BUF_TRANSFORM_CUR: src = st.transform_cur + seq * 6; elem = 4; n = 6; break;
+    case LL_BUF_TRANSFORM_SUM: src = st.transform_sum + seq * 6; elem = 4; n = 6; break;
+    case LL_BUF_ODOM_ITERS: src = st.odom_iters + seq * 2; elem = 4; n = 2; break;
+    case LL_BUF_MAP_CORNER: if (!st.map_corner) { n = 0; elem = 16; src = nullptr; break; }
+      COUNTED(st.map_corner, 16, (size_t)st.cap_map_corner, st.map_counts + seq * 2 + 0); break;
+    case LL_BUF_MAP_SURF: if (!st.map_surf) { n = 0; elem = 16; src = nullptr; break; }
+      COUNTED(st.map_surf, 16, (size_t)st.cap_map_surf, st.map_counts + seq * 2 + 1); break;
+    case LL_BUF_SCAN_CORNER_DS: COUNTED(st.scan_corner_ds, 16, (size_t)p.cap_less_sharp, st.scan_ds_counts + seq * 2 + 0); break;
+    case LL_BUF_SCAN_SURF_TOTAL_DS: COUNTED(st.scan_surf_ds, 16, N, st.scan_ds_counts + seq * 2 + 1); break;
+    case LL_BUF_TRANSFORM_TOBE_MAPPED: src = st.transform_tobe_mapped + seq * 6; elem = 4; n = 6; break;
+    case LL_BUF_MAP_ITERS: src = st.map_iters + seq * 2; elem = 4; n = 2; break;
+    case LL_BUF_OUTLIER_LAST: COUNTED(st.outlier_last, 16, (size_t)st.cap_outlier, st.odom_flags + seq * 4 + 3); break;
+    case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: {
+      // gathered from the per-ring counters (stride 8)
+      std::vector<int> rc((size_t)p.V * 8);
+      CK(cudaMemcpyAsync(rc.data(), st.ring_counts + (size_t)seq * p.V * 8, rc.size() * 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaStreamSynchronize(h->ctx.stream));
+      if (n_elems) *n_elems = p.V;
+      if (!dst) return LL_OK;
+      if (dst_bytes < (size_t)p.V * 4) return LL_ERR_CAPACITY;
+      for (int i = 0; i < p.V; ++i) ((int*)dst)[i] = rc[(size_t)i * 8 + 4];
+      return LL_OK;
+    }
+    default: return LL_ERR_INVALID_ARG;
+  }
+#undef FIXED
+#undef COUNTED
+  if (n_elems) *n_elems = n;
+  if (!dst) return LL_OK;
+  if (dst_bytes < n * elem) return LL_ERR_CAPACITY;
+  if (n) {
+    CK(cudaMemcpyAsync(dst, src, n * elem, cudaMemcpyDeviceToHost, h->ctx.stream));
+    CK(cudaStreamSynchronize(h->ctx.stream));
+  }
+  return LL_OK;
+}
+
+int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems) {
+  if (!h || seq < 0 || seq >= h->st.p.B || !src) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  float* dst = nullptr;
+  switch (buffer) {
+    case LL_BUF_TRANSFORM_CUR: dst = st.transform_cur + seq * 6; break;
+    case LL_BUF_TRANSFORM_SUM: dst = st.transform_sum + seq * 6; break;
+    case LL_BUF_TRANSFORM_TOBE_MAPPED: dst = st.transform_tobe_mapped + seq * 6; break;
+    default: return LL_ERR_INVALID_ARG;
+  }
+  if (n_elems != 6) return LL_ERR_INVALID_ARG;
+  CK(cudaMemcpyAsync(dst, src, 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+}  // extern "C"

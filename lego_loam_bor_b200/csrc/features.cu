@@ -1,0 +1,496 @@
+// features.cu -- FeatureAssociation::adjustDistortion / calculateSmoothness / markOccludedPoints /
+// extractFeatures (reference: LeGO-LOAM/src/featureAssociation.cpp:161-383).
+//
+//   k_feature_prep     one thread per segmented point.  adjustDistortion with the sequential
+//       halfPassed flag resolved from the first-trigger index found by k_seg_emit; the 11-tap
+//       curvature stencil over the FLATTENED range array from a shared-memory tile with a 6-point
+//       halo; markOccludedPoints turned into a gather (all its writes are idempotent "= 1").
+//       The persistent arrays (cloudCurvature / cloudNeighborPicked / cloudLabel /
+//       cloudSmoothness) are only rewritten on [5, S-5) like the reference, stale values elsewhere
+//       survive across frames.
+//   k_extract_features one block per (ring, sequence).  Sorts the six sextants of the ring in shared
+//       memory (bitonic, key = (curvature, index)), runs the two greedy pick scans with one warp
+//       (32 sorted candidates tested per step), collects the less-flat points and applies the
+//       per-ring 0.2 m VoxelGrid (sort by voxel index, sequential centroid per voxel).
+//   k_feature_compact  one block per (ring, sequence): concatenates the per-ring results in ring order.
+#include "ll_device.cuh"
+#include "ll_kernels.h"
+
+namespace {
+
+#define FP_THREADS 256
+#define FP_HALO 8
+
+__global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
+  __shared__ float sh_r[FP_THREADS + 2 * FP_HALO];
+  __shared__ int sh_c[FP_THREADS + 2 * FP_HALO];
+  const DevParams& p = st.p;
+  const int s = blockIdx.y;
+  const int S = st.seg_count[s];
+  const int b0 = blockIdx.x * FP_THREADS;
+  if (b0 >= S) return;
+  const size_t base = (size_t)s * p.N;
+  for (int t = threadIdx.x; t < FP_THREADS + 2 * FP_HALO; t += FP_THREADS) {
+    const int idx = b0 - FP_HALO + t;
+    const bool ok = idx >= 0 && idx < S;
+    sh_r[t] = ok ? st.seg_range[base + idx] : 0.f;
+    sh_c[t] = ok ? (int)st.seg_col[base + idx] : 0;
+  }
+  __syncthreads();
+  const int i = b0 + threadIdx.x;
+  if (i >= S) return;
+  // ---- adjustDistortion (featureAssociation.cpp:161-197) ----
+  {
+    const float start_ori = st.orientation[s * 4 + 0];
+    const float end_ori = st.orientation[s * 4 + 1];
+    const float ori_diff = st.orientation[s * 4 + 2];
+    const int half = st.half_idx[s];
+    const float4 sp = st.seg_cloud[base + i];
+    const float px = sp.y, py = sp.z, pz = sp.x;
+    float ori = -ll_atan2f(px, pz);
+    if (i <= half) {
+      if ((double)ori < (double)start_ori - LL_PI / 2)
+        ori = (float)((double)ori + 2 * LL_PI);
+      else if ((double)ori > (double)start_ori + LL_PI * 3 / 2)
+        ori = (float)((double)ori - 2 * LL_PI);
+    } else {
+      ori = (float)((double)ori + 2 * LL_PI);
+      if ((double)ori < (double)end_ori - LL_PI * 3 / 2)
+        ori = (float)((double)ori + 2 * LL_PI);
+      else if ((double)ori > (double)end_ori + LL_PI / 2)
+        ori = (float)((double)ori - 2 * LL_PI);
+    }
+    const float rel = (ori - start_ori) / ori_diff;
+    const float inten = (float)(int)sp.w + p.scan_period * rel;
+    st.seg_cloud[base + i] = make_float4(px, py, pz, inten);
+  }
+  const float* r = sh_r + FP_HALO + threadIdx.x;  // r[k] = range of point i + k
+  const int* c = sh_c + FP_HALO + threadIdx.x;
+  const bool interior = (i >= 5 && i < S - 5);
+  // ---- markOccludedPoints as a gather (featureAssociation.cpp:226-262) ----
+  bool mark = false;
+#pragma unroll
+  for (int d = -6; d <= 5; ++d) {
+    const int k = i + d;  // loop index of the reference that could write picked[i]
+    if (k < 5 || k >= S - 6) continue;
+    const float depth1 = r[d], depth2 = r[d + 1];
+    const int cdiff = abs(c[d + 1] - c[d]);
+    if (cdiff < 10) {
+      const bool far_near = (double)(depth1 - depth2) > 0.3;   // marks k-5 .. k
+      const bool near_far = !far_near && (double)(depth2 - depth1) > 0.3;  // marks k+1 .. k+6
+      if (far_near && d >= 0) mark = true;
+      if (near_far && d <= -1) mark = true;
+    }
+  }
+  if (i >= 5 && i < S - 6) {
+    const float diff1 = fabsf(r[-1] - r[0]);
+    const float diff2 = fabsf(r[1] - r[0]);
+    if ((double)diff1 > 0.02 * (double)r[0] && (double)diff2 > 0.02 * (double)r[0]) mark = true;
+  }
+  if (interior) {
+    // ---- calculateSmoothness (featureAssociation.cpp:200-223), strictly left to right ----
+    const float d = r[-5] + r[-4] + r[-3] + r[-2] + r[-1] - r[0] * 10 + r[1] + r[2] + r[3] + r[4] + r[5];
+    const float curv = d * d;
+    st.curvature[base + i] = curv;
+    st.picked[base + i] = mark ? 1 : 0;
+    st.cloud_label[base + i] = 0;
+    st.smooth_val[base + i] = curv;
+    st.smooth_ind[base + i] = i;
+  } else if (mark) {
+    st.picked[base + i] = 1;  // outside [5, S-5) the array is never reset
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int n /* pow2 */, int total /* multiple of n */) {
+  // sorts every aligned block of n keys ascending (direction-free bitonic network)
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i) {
+          const unsigned long long a = key[i], b = key[l];
+          if (a > b) { key[i] = b; key[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// order-preserving float <-> int map (an involution), for shared-memory atomicMin/Max on floats
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+#define EX_THREADS 256
+
+// dynamic shared memory layout (ints unless noted), L = span length <= H + 16, P = padded sextant size:
+//   curv[L] float | col[L] | picked[L] u8 | ground[L] u8 | label[L] i8 | keys[max(6P, pow2(H))] u64 | list[6][P+1] | lfpos[H]
+__global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, int P, int sort_cap) {
+  extern __shared__ unsigned long long sh_raw[];
+  __shared__ int warp_tot[33];
+  __shared__ int sh_sp[6], sh_ep[6];
+  __shared__ int sh_counts[8];
+  __shared__ int sh_imn[3], sh_imx[3];
+  const DevParams& p = st.p;
+  const int ring = blockIdx.x, s = blockIdx.y;
+  const size_t base = (size_t)s * p.N;
+  const int S = st.seg_count[s];
+  const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
+  const int a = start - 4, b = end + 6;  // this ring's points are [a, b)
+  const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
+  const int L = max(0, span_hi - span_lo);
+  const int Lcap = p.H + 16;
+  // carve shared memory
+  unsigned long long* keys = sh_raw;                          // [sort_cap]
+  float* sm_curv = (float*)(keys + sort_cap);                 // [Lcap]
+  int* sm_col = (int*)(sm_curv + Lcap);                       // [Lcap]
+  int* sm_list = sm_col + Lcap;                               // [6][P+1]
+  int* sm_lfpos = sm_list + 6 * (P + 1);                      // [H]
+  unsigned char* sm_picked = (unsigned char*)(sm_lfpos + p.H);  // [Lcap]
+  unsigned char* sm_ground = sm_picked + Lcap;                  // [Lcap]
+  signed char* sm_label = (signed char*)(sm_ground + Lcap);     // [Lcap]
+
+  float4* o_sharp = st.st_sharp + ((size_t)s * p.V + ring) * 12;
+  int* o_sharp_i = st.st_sharp_ind + ((size_t)s * p.V + ring) * 12;
+  float4* o_lsharp = st.st_less_sharp + ((size_t)s * p.V + ring) * 120;
+  int* o_lsharp_i = st.st_less_sharp_ind + ((size_t)s * p.V + ring) * 120;
+  float4* o_flat = st.st_flat + ((size_t)s * p.V + ring) * 24;
+  int* o_flat_i = st.st_flat_ind + ((size_t)s * p.V + ring) * 24;
+  float4* o_lflat = st.st_less_flat + ((size_t)s * p.V + ring) * p.H;
+  int* o_counts = st.ring_counts + ((size_t)s * p.V + ring) * 8;
+
+  if (threadIdx.x < 8) sh_counts[threadIdx.x] = 0;
+  if (threadIdx.x < 6) {
+    const int j = threadIdx.x;
+    // featureAssociation.cpp:275-281 (integer division as written)
+    sh_sp[j] = (start * (6 - j) + end * j) / 6;
+    sh_ep[j] = (start * (5 - j) + end * (j + 1)) / 6 - 1;
+  }
+  for (int t = threadIdx.x; t < L; t += EX_THREADS) {
+    const int g = span_lo + t;
+    sm_curv[t] = st.curvature[base + g];
+    sm_col[t] = (int)st.seg_col[base + g];
+    sm_picked[t] = (unsigned char)(st.picked[base + g] != 0);
+    sm_ground[t] = st.seg_ground[base + g];
+    sm_label[t] = (signed char)st.cloud_label[base + g];
+  }
+  for (int t = threadIdx.x; t < 6 * P; t += EX_THREADS) keys[t] = ~0ull;
+  __syncthreads();
+  // ---- sort keys: sextant j occupies keys[j*P .. j*P + (ep-sp)) ----
+  for (int j = 0; j < 6; ++j) {
+    const int sp = sh_sp[j], ep = sh_ep[j];
+    if (sp >= ep) continue;
+    for (int t = threadIdx.x; t < ep - sp; t += EX_THREADS) {
+      const float v = st.smooth_val[base + sp + t];
+      const int ind = st.smooth_ind[base + sp + t];
+      keys[j * P + t] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)ind;  // values are >= 0
+    }
+  }
+  __syncthreads();
+  bitonic_sort_u64(keys, P, 6 * P);
+  // write the sorted order back (std::sort is in place, featureAssociation.cpp:285) and build scan lists
+  for (int j = 0; j < 6; ++j) {
+    const int sp = sh_sp[j], ep = sh_ep[j];
+    if (sp >= ep) continue;
+    for (int t = threadIdx.x; t <= ep - sp; t += EX_THREADS) {
+      int ind;
+      if (t < ep - sp) {
+        const unsigned long long k = keys[j * P + t];
+        ind = (int)(unsigned)(k & 0xffffffffull);
+        st.smooth_val[base + sp + t] = __uint_as_float((unsigned)(k >> 32));
+        st.smooth_ind[base + sp + t] = ind;
+      } else {
+        ind = st.smooth_ind[base + ep];  // position ep is scanned but not sorted (sic)
+      }
+      sm_list[j * (P + 1) + t] = ind;
+    }
+  }
+  __syncthreads();
+
+  // ---- greedy picks, one warp, sextants strictly in order ----
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+    const int colsz = p.N;  // segInfo.segmentedCloudColInd.size()
+    auto in_span = [&](int g) { return g >= span_lo && g < span_hi; };
+    auto get_picked = [&](int g) -> int { return in_span(g) ? (int)sm_picked[g - span_lo] : st.picked[base + g]; };
+    auto set_picked = [&](int g) { if (in_span(g)) sm_picked[g - span_lo] = 1; else st.picked[base + g] = 1; };
+    auto get_curv = [&](int g) -> float { return in_span(g) ? sm_curv[g - span_lo] : st.curvature[base + g]; };
+    auto get_ground = [&](int g) -> int { return in_span(g) ? (int)sm_ground[g - span_lo] : (int)st.seg_ground[base + g]; };
+    auto get_col = [&](int g) -> int { return in_span(g) ? sm_col[g - span_lo] : (int)st.seg_col[base + g]; };
+    auto set_label = [&](int g, int v) { if (in_span(g)) sm_label[g - span_lo] = (signed char)v; else st.cloud_label[base + g] = v; };
+    auto mark_neighbors = [&](int ind) {  // featureAssociation.cpp:306-326 (lane 0 only)
+      set_picked(ind);
+      for (int l = 1; l <= 5; l++) {
+        if (ind + l >= colsz) continue;
+        const int cdiff = abs(get_col(ind + l) - get_col(ind + l - 1));
+        if (cdiff > 10) break;
+        set_picked(ind + l);
+      }
+      for (int l = -1; l >= -5; l--) {
+        if (ind + l < 0) continue;
+        const int cdiff = abs(get_col(ind + l) - get_col(ind + l + 1));
+        if (cdiff > 10) break;
+        set_picked(ind + l);
+      }
+    };
+    for (int j = 0; j < 6; ++j) {
+      const int sp = sh_sp[j], ep = sh_ep[j];
+      if (sp >= ep) continue;
+      const int len = ep - sp + 1;
+      const int* list = sm_list + j * (P + 1);
+      // descending scan for edge points (featureAssociation.cpp:288-328)
+      int largest = 0;
+      int top = len - 1;
+      while (top >= 0 && largest < 20) {
+        const int t = top - lane;
+        bool cand = false;
+        int ind = 0;
+        if (t >= 0) {
+          ind = list[t];
+          cand = get_picked(ind) == 0 && get_curv(ind) > p.edge_threshold && get_ground(ind) == 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m == 0) { top -= 32; continue; }
+        const int w = __ffs(m) - 1;
+        const int pick = __shfl_sync(0xffffffffu, ind, w);
+        largest++;
+        if (lane == 0) {
+          const float4 pt = st.seg_cloud[base + pick];
+          if (largest <= 2) {
+            set_label(pick, 2);
+            o_sharp[n_sharp] = pt; o_sharp_i[n_sharp] = pick;
+            o_lsharp[n_lsharp] = pt; o_lsharp_i[n_lsharp] = pick;
+          } else {
+            set_label(pick, 1);
+            o_lsharp[n_lsharp] = pt; o_lsharp_i[n_lsharp] = pick;
+          }
+          mark_neighbors(pick);
+        }
+        if (largest <= 2) n_sharp++;
+        n_lsharp++;
+        __syncwarp();
+        top = top - w - 1;
+      }
+      // ascending scan for flat points (featureAssociation.cpp:330-368)
+      int smallest = 0;
+      int bot = 0;
+      while (bot < len) {
+        const int t = bot + lane;
+        bool cand = false;
+        int ind = 0;
+        if (t < len) {
+          ind = list[t];
+          cand = get_picked(ind) == 0 && get_curv(ind) < p.surf_threshold && get_ground(ind) != 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m == 0) { bot += 32; continue; }
+        const int w = __ffs(m) - 1;
+        const int pick = __shfl_sync(0xffffffffu, ind, w);
+        smallest++;
+        if (lane == 0) {
+          set_label(pick, -1);
+          o_flat[n_flat] = st.seg_cloud[base + pick];
+          o_flat_i[n_flat] = pick;
+          if (smallest < 4) mark_neighbors(pick);  // the 4th pick breaks before the suppression (sic, :339-342)
+        }
+        n_flat++;
+        __syncwarp();
+        if (smallest >= 4) break;
+        bot = bot + w + 1;
+      }
+    }
+    if (lane == 0) { sh_counts[0] = n_sharp; sh_counts[1] = n_lsharp; sh_counts[2] = n_flat; }
+  }
+  __syncthreads();
+  // persist the mutated per-point state of this ring's span (only entries this block may have changed)
+  for (int t = threadIdx.x; t < L; t += EX_THREADS) {
+    const int g = span_lo + t;
+    if (g >= a - 1 && g < b) {
+      if (sm_picked[t]) st.picked[base + g] = 1;
+      st.cloud_label[base + g] = (int)sm_label[t];
+    }
+  }
+  // ---- less-flat collection (featureAssociation.cpp:370-374): by POSITION k over the active sextants ----
+  int n_raw = 0;
+  {
+    const int k_lo = sh_sp[0], k_hi = sh_ep[5];
+    int run = 0;
+    for (int k0 = k_lo; k0 <= k_hi; k0 += EX_THREADS) {
+      const int k = k0 + threadIdx.x;
+      int f = 0;
+      if (k <= k_hi) {
+        bool active = false;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) active = active || (sh_sp[j] < sh_ep[j] && k >= sh_sp[j] && k <= sh_ep[j]);
+        if (active && k >= span_lo && k < span_hi && sm_label[k - span_lo] <= 0) f = 1;
+      }
+      int total;
+      const int ex = block_exclusive_scan(f, warp_tot, &total);
+      if (f) sm_lfpos[run + ex] = k;
+      run += total;
+    }
+    n_raw = run;
+  }
+  __syncthreads();
+  // ---- pcl::VoxelGrid, leaf 0.2 (featureAssociation.cpp:101,377-381; algorithm: SURVEY.md section 8 f1) ----
+  int n_ds = 0;
+  if (n_raw > 0) {
+    const float inv = 1.0f / 0.2f;
+    if (threadIdx.x < 3) { sh_imn[threadIdx.x] = f2ord(FLT_MAX); sh_imx[threadIdx.x] = f2ord(-FLT_MAX); }
+    __syncthreads();
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int t = threadIdx.x; t < n_raw; t += EX_THREADS) {
+      const float4 q = st.seg_cloud[base + sm_lfpos[t]];
+      mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
+      mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
+      mn[2] = fminf(mn[2], q.z); mx[2] = fmaxf(mx[2], q.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+        mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicMin(&sh_imn[d], f2ord(mn[d]));
+        atomicMax(&sh_imx[d], f2ord(mx[d]));
+      }
+    }
+    __syncthreads();
+    float bmn[3], bmx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      bmn[d] = ord2f(sh_imn[d]);
+      bmx[d] = ord2f(sh_imx[d]);
+    }
+    const long long dx = (long long)((bmx[0] - bmn[0]) * inv) + 1;
+    const long long dy = (long long)((bmx[1] - bmn[1]) * inv) + 1;
+    const long long dz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
+    if (dx * dy * dz > 2147483647LL) {
+      // PCL refuses to filter (index overflow) and returns the input unchanged
+      for (int t = threadIdx.x; t < n_raw; t += EX_THREADS) o_lflat[t] = st.seg_cloud[base + sm_lfpos[t]];
+      n_ds = n_raw;
+    } else {
+      const int minb0 = (int)floorf(bmn[0] * inv), minb1 = (int)floorf(bmn[1] * inv), minb2 = (int)floorf(bmn[2] * inv);
+      const int div0 = (int)floorf(bmx[0] * inv) - minb0 + 1, div1 = (int)floorf(bmx[1] * inv) - minb1 + 1;
+      int n2 = 1;
+      while (n2 < n_raw) n2 <<= 1;
+      for (int t = threadIdx.x; t < n2; t += EX_THREADS) {
+        unsigned long long k = ~0ull;
+        if (t < n_raw) {
+          const float4 q = st.seg_cloud[base + sm_lfpos[t]];
+          const int i0 = (int)floorf(q.x * inv) - minb0;
+          const int i1 = (int)floorf(q.y * inv) - minb1;
+          const int i2 = (int)floorf(q.z * inv) - minb2;
+          const int idx = i0 + i1 * div0 + i2 * div0 * div1;
+          k = ((unsigned long long)(unsigned)idx << 32) | (unsigned)t;  // stable: ties keep input order
+        }
+        keys[t] = k;
+      }
+      __syncthreads();
+      bitonic_sort_u64(keys, n2, n2);
+      int run = 0;
+      for (int t0 = 0; t0 < n_raw; t0 += EX_THREADS) {
+        const int t = t0 + threadIdx.x;
+        int head = 0;
+        if (t < n_raw) head = (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
+        int total;
+        const int ex = block_exclusive_scan(head, warp_tot, &total);
+        if (head) {
+          const unsigned vox = (unsigned)(keys[t] >> 32);
+          float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
+          int cnt = 0;
+          for (int u = t; u < n_raw && (unsigned)(keys[u] >> 32) == vox; ++u) {
+            const float4 q = st.seg_cloud[base + sm_lfpos[(int)(keys[u] & 0xffffffffull)]];
+            cx += q.x; cy += q.y; cz += q.z; ci += q.w;
+            ++cnt;
+          }
+          const float fc = (float)cnt;
+          o_lflat[run + ex] = make_float4(cx / fc, cy / fc, cz / fc, ci / fc);
+        }
+        run += total;
+      }
+      n_ds = run;
+    }
+  }
+  if (threadIdx.x == 0) {
+    o_counts[0] = sh_counts[0];
+    o_counts[1] = sh_counts[1];
+    o_counts[2] = sh_counts[2];
+    o_counts[3] = n_ds;
+    o_counts[4] = n_raw;
+  }
+  (void)S;
+}
+
+__global__ void __launch_bounds__(256) k_feature_compact(DevState st) {
+  __shared__ int sh_off[4];
+  const DevParams& p = st.p;
+  const int ring = blockIdx.x, s = blockIdx.y;
+  if (threadIdx.x < 4) sh_off[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x < ring) {
+    const int* rc = st.ring_counts + ((size_t)s * p.V + threadIdx.x) * 8;
+    atomicAdd(&sh_off[0], rc[0]);
+    atomicAdd(&sh_off[1], rc[1]);
+    atomicAdd(&sh_off[2], rc[2]);
+    atomicAdd(&sh_off[3], rc[3]);
+  }
+  __syncthreads();
+  const int* rc = st.ring_counts + ((size_t)s * p.V + ring) * 8;
+  const size_t rs = (size_t)s * p.V + ring;
+  for (int t = threadIdx.x; t < rc[0]; t += blockDim.x) {
+    st.corner_sharp[(size_t)s * p.cap_sharp + sh_off[0] + t] = st.st_sharp[rs * 12 + t];
+    st.corner_sharp_ind[(size_t)s * p.cap_sharp + sh_off[0] + t] = st.st_sharp_ind[rs * 12 + t];
+  }
+  for (int t = threadIdx.x; t < rc[1]; t += blockDim.x) {
+    st.corner_less_sharp[(size_t)s * p.cap_less_sharp + sh_off[1] + t] = st.st_less_sharp[rs * 120 + t];
+    st.corner_less_sharp_ind[(size_t)s * p.cap_less_sharp + sh_off[1] + t] = st.st_less_sharp_ind[rs * 120 + t];
+  }
+  for (int t = threadIdx.x; t < rc[2]; t += blockDim.x) {
+    st.surf_flat[(size_t)s * p.cap_flat + sh_off[2] + t] = st.st_flat[rs * 24 + t];
+    st.surf_flat_ind[(size_t)s * p.cap_flat + sh_off[2] + t] = st.st_flat_ind[rs * 24 + t];
+  }
+  for (int t = threadIdx.x; t < rc[3]; t += blockDim.x)
+    st.surf_less_flat[(size_t)s * p.N + sh_off[3] + t] = st.st_less_flat[rs * p.H + t];
+  if (ring == p.V - 1 && threadIdx.x < 4) st.feat_counts[s * 4 + threadIdx.x] = sh_off[threadIdx.x] + rc[threadIdx.x];
+}
+
+int next_pow2(int v) {
+  int n = 1;
+  while (n < v) n <<= 1;
+  return n;
+}
+
+}  // namespace
+
+void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
+  const DevParams& p = st.p;
+  {
+    dim3 grid((p.N + FP_THREADS - 1) / FP_THREADS, p.B);
+    k_feature_prep<<<grid, FP_THREADS, 0, ctx.stream>>>(st);
+    ctx.count("k_feature_prep");
+  }
+  {
+    const int P = next_pow2(p.H / 6 + 2);
+    const int sort_cap = max(6 * P, next_pow2(p.H));
+    const int Lcap = p.H + 16;
+    const size_t smem = (size_t)sort_cap * 8 + (size_t)Lcap * 4 * 2 + (size_t)6 * (P + 1) * 4 + (size_t)p.H * 4 + (size_t)Lcap * 3 + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaFuncSetAttribute(k_extract_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    dim3 grid(p.V, p.B);
+    k_extract_features<<<grid, EX_THREADS, smem, ctx.stream>>>(st, P, sort_cap);
+    ctx.count("k_extract_features");
+    k_feature_compact<<<grid, 256, 0, ctx.stream>>>(st);
+    ctx.count("k_feature_compact");
+  }
+}

@@ -1,0 +1,173 @@
+// ll_device.cuh -- device-side state shared by all kernels of the hot path.
+//
+// Data layout in HBM (DESIGN.md section "Layout"): everything is batched over B independent
+// sequences; per-sequence arrays are contiguous slabs of N = V*H elements (range image order,
+// row-major: cell = row*H + col) or of a fixed capacity, so one launch covers all sequences
+// with blockIdx.y (or a flattened index) selecting the sequence.  Points are 16-byte float4
+// (x, y, z, intensity) -- the packed form of pcl::PointXYZI (utility.h:46).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "../../include/lego_loam_b200.h"
+#include "../../include/ll_portable_math.h"
+
+#define LL_MAX_RINGS 128
+#define LL_INVALID_LABEL 999999
+
+// hash grid over a point cloud (replaces nanoflann::KdTreeFLANN, nanoflann_pcl.h:54-152)
+struct HashGrid {
+  int* cell_start;   // [B][tbl+1] exclusive prefix of bucket counts
+  int* cursor;       // [B][tbl]   fill cursors
+  float4* sorted;    // [B][cap]   points bucket by bucket; .w carries the original index (int bits)
+  int* count;        // [B]        points indexed
+  float inv_cell;    // 1 / cell size
+  float cell;        // cell size (m)
+  int tbl;           // buckets per sequence (power of two)
+  int cap;           // point capacity per sequence
+};
+
+struct DevParams {
+  int B, V, H, N, max_pts;
+  // ImageProjection derived constants (imageProjection.cpp:64-84), computed on the host with
+  // the same portable math the kernels use
+  float ang_bottom, ang_res_x, ang_res_y, sensor_mount_angle;
+  float seg_tan_theta, sin_ax, cos_ax, sin_ay, cos_ay;
+  int gsi, seg_valid_point_num, seg_valid_line_num;
+  // FeatureAssociation (featureAssociation.cpp:69-81)
+  float scan_period, edge_threshold, surf_threshold, nearest_feature_dist_sqr;
+  // capacities
+  int cap_sharp, cap_less_sharp, cap_flat;  // 12V, 120V, 24V
+};
+
+struct DevState {
+  DevParams p;
+  // ---- input ----
+  const float4* in_pts;  // [B][in_stride]
+  int in_stride;
+  int* n_in;             // [B]
+  uint32_t frame_tag;    // increases every frame; makes `winner` self-clearing
+  // ---- ImageProjection ----
+  unsigned long long* winner;  // [B][N] (frame_tag << 32) | input index of the last writer
+  float* range_mat;            // [B][N]
+  float4* full_cloud;          // [B][N]
+  int8_t* ground_mat;          // [B][N]
+  int* label_mat;              // [B][N]
+  int* parent;                 // [B][N] union-find forest, -1 = not a segmentation candidate
+  int* comp_size;              // [B][N] at roots: pixel count
+  unsigned* comp_rows;         // [B][N] at roots: bit (row - root row) for every non-seed pixel
+  int* tile_counts;            // [B][V][4] per row: feasible roots, kept pixels, outliers
+  float* orientation;          // [B][4] start, end, diff
+  int* half_idx;               // [B] first segmented index whose branch-1 orientation passes pi (adjustDistortion)
+  // ProjectionOut / cloud_info
+  float4* seg_cloud;           // [B][N]
+  float* seg_range;            // [B][N]
+  uint32_t* seg_col;           // [B][N]
+  uint8_t* seg_ground;         // [B][N]
+  int* start_ring;             // [B][V]
+  int* end_ring;               // [B][V]
+  int* seg_count;              // [B]
+  float4* outlier_cloud;       // [B][N/5+V]
+  int* outlier_count;          // [B]
+  int cap_outlier;
+  // ---- FeatureAssociation ----
+  float* curvature;            // [B][N] cloudCurvature (persistent)
+  int* picked;                 // [B][N] cloudNeighborPicked (persistent)
+  int* cloud_label;            // [B][N] cloudLabel (persistent)
+  float* smooth_val;           // [B][N] cloudSmoothness[].value (persistent, sorted in place)
+  int* smooth_ind;             // [B][N] cloudSmoothness[].ind
+  // per-ring staging written by the extraction kernel
+  float4* st_sharp;  int* st_sharp_ind;       // [B][V][12]
+  float4* st_less_sharp; int* st_less_sharp_ind;  // [B][V][120]
+  float4* st_flat; int* st_flat_ind;          // [B][V][24]
+  float4* st_less_flat;                       // [B][V][H]
+  int* ring_counts;                           // [B][V][8]: sharp, lessSharp, flat, lessFlatDS, lessFlatRaw
+  // compacted feature clouds of the current frame
+  float4* corner_sharp; int* corner_sharp_ind;            // [B][12V]
+  float4* corner_less_sharp; int* corner_less_sharp_ind;  // [B][120V]
+  float4* surf_flat; int* surf_flat_ind;                  // [B][24V]
+  float4* surf_less_flat;                                 // [B][N]
+  int* feat_counts;                                       // [B][4]
+  // last-frame clouds (double buffered by pointer swap like featureAssociation.cpp:1344-1350)
+  float4* corner_last;  // [B][120V]
+  float4* surf_last;    // [B][N]
+  int* last_counts;     // [B][2]
+  float4* outlier_last; // [B][cap_outlier]
+  HashGrid grid_corner_last, grid_surf_last;  // index the clouds the "kd-trees" were last built on
+  float4* tree_corner;  // [B][120V] copy of the cloud the corner tree was built on (see odometry.cu)
+  float4* tree_surf;    // [B][N]
+  int* tree_counts;     // [B][2]
+  float* transform_cur;  // [B][6]
+  float* transform_sum;  // [B][6]
+  int* odom_iters;       // [B][2]
+  int* odom_flags;       // [B][4]: 0 isDegenerate, 1 systemInitedLM
+  float* odom_matP;      // [B][9]
+  int* corr_surf;        // [B][24V][3] closest / ring-window indices (pointSearchSurfInd1..3)
+  int* corr_corner;      // [B][12V][2]
+  // ---- MapOptimization scan-to-map ----
+  float4* map_corner; float4* map_surf;   // [B][cap_map_corner], [B][cap_map_surf]
+  int* map_counts;                        // [B][2]
+  int cap_map_corner, cap_map_surf;
+  HashGrid grid_map_corner, grid_map_surf;
+  float4* scan_corner_ds; float4* scan_surf_ds;  // [B][120V], [B][N]
+  int* scan_ds_counts;                           // [B][2]
+  float* transform_tobe_mapped;                  // [B][6]
+  int* map_iters;                                // [B][2]
+  int* map_flags;                                // [B][4]: 0 isDegenerate, 1 converged/done
+  float* map_matP;                               // [B][36]
+  double* map_partials;                          // [B][max_blocks][28]
+  int* map_rows;                                 // [B][max_blocks]
+  int map_max_blocks;
+};
+
+// ---- small device helpers --------------------------------------------------------------
+
+__device__ __forceinline__ float4 ld_pt(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ float warp_min_f(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// `warp_tot` is a 33-int shared scratch.  Returns the exclusive prefix; *total gets the block sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? warp_tot[lane] : 0;
+    int winc = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < nw) warp_tot[lane] = winc - w;
+    if (lane == 31) warp_tot[32] = winc;
+  }
+  __syncthreads();
+  const int res = warp_tot[wid] + inc - v;
+  *total = warp_tot[32];
+  __syncthreads();
+  return res;
+}
+
+__device__ __forceinline__ uint32_t grid_hash(int ix, int iy, int iz, int tbl) {
+  const uint32_t h = (uint32_t)ix * 73856093u ^ (uint32_t)iy * 19349663u ^ (uint32_t)iz * 83492791u;
+  return (h ^ (h >> 15)) & (uint32_t)(tbl - 1);
+}

@@ -1,0 +1,259 @@
+// mapping.cu -- MapOptimization::scan2MapOptimization (reference: LeGO-LOAM/src/mapOptmization.cpp:
+// 397-426 pointAssociateToMap, 1028-1134 cornerOptimization, 1136-1197 surfOptimization,
+// 1199-1312 LMOptimization, 1315-1332 scan2MapOptimization) and downsampleCurrentScan (:999-1026).
+//
+//   grid build (hashgrid.cu)  replaces the two kd-tree builds of every mapping cycle (:1317-1318);
+//       cell = 1 m = the acceptance radius of :1036,1144, so a 27-cell lookup is exact.
+//   k_map_iter   one thread per down-sampled scan point: pointAssociateToMap, exact 5-NN, line fit
+//       (3x3 symmetric eigen-solve) or plane fit (5x3 column-pivoted QR), residual + 6-column
+//       Jacobian row, J^T J / J^T r partial sums (exact double products) per block.
+//   k_map_solve  one block per sequence: fixed-order sum of the partials, 6x6 solve, degeneracy
+//       projection, pose update and convergence flag.  Ten (iter, solve) pairs are enqueued; a
+//       converged sequence makes its remaining pairs no-ops, so there is no host round trip.
+//   k_voxel_*    pcl::VoxelGrid on whole clouds for downsampleCurrentScan (one block per sequence
+//       and cloud: stable LSD radix sort by voxel index in shared/global memory, sequential centroids).
+#include "../../include/ll_smallmat.h"
+#include "hashgrid.cuh"
+#include "ll_kernels.h"
+
+namespace {
+
+#define MAP_BLOCKS 96
+#define MAP_THREADS 128
+#define MAP_NACC 28  // 21 upper-triangle J^T J + 6 J^T r + row count
+
+__device__ __forceinline__ bool map_guard(const DevState& st, int s) {
+  return st.map_counts[s * 2 + 0] > 10 && st.map_counts[s * 2 + 1] > 100;  // mapOptmization.cpp:1316
+}
+
+struct MapPose {
+  float cRoll, sRoll, cPitch, sPitch, cYaw, sYaw, tX, tY, tZ;
+};
+
+__device__ __forceinline__ MapPose make_map_pose(const float* T) {  // mapOptmization.cpp:397-410
+  MapPose m;
+  ll_sincosf(T[0], &m.sRoll, &m.cRoll);
+  ll_sincosf(T[1], &m.sPitch, &m.cPitch);
+  ll_sincosf(T[2], &m.sYaw, &m.cYaw);
+  m.tX = T[3]; m.tY = T[4]; m.tZ = T[5];
+  return m;
+}
+
+__device__ __forceinline__ float4 point_associate_to_map(const MapPose& m, const float4 pi) {  // :412-426
+  const float x1 = m.cYaw * pi.x - m.sYaw * pi.y;
+  const float y1 = m.sYaw * pi.x + m.cYaw * pi.y;
+  const float z1 = pi.z;
+  const float x2 = x1;
+  const float y2 = m.cRoll * y1 - m.sRoll * z1;
+  const float z2 = m.sRoll * y1 + m.cRoll * z1;
+  return make_float4(m.cPitch * x2 + m.sPitch * z2 + m.tX, y2 + m.tY, -m.sPitch * x2 + m.cPitch * z2 + m.tZ, pi.w);
+}
+
+// cornerOptimization body for one point; returns false if rejected
+__device__ __forceinline__ bool corner_fit(const DevState& st, int s, const float4 sel, float4* coeff) {
+  float d2[5];
+  int idx[5];
+  const int n = thread_knn5(st.grid_map_corner, s, sel.x, sel.y, sel.z, 1.0f, d2, idx);
+  if (n < 5) return false;  // pointSearchSqDis[4] < 1.0
+  const float4* mp = st.map_corner + (size_t)s * st.cap_map_corner;
+  float4 q[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) q[j] = mp[idx[j]];
+  float cx = 0, cy = 0, cz = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) { cx += q[j].x; cy += q[j].y; cz += q[j].z; }
+  cx /= 5; cy /= 5; cz /= 5;
+  float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const float ax = q[j].x - cx, ay = q[j].y - cy, az = q[j].z - cz;
+    a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+    a22 += ay * ay; a23 += ay * az; a33 += az * az;
+  }
+  a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+  const float matA1[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+  float matD1[3], matV1[9];
+  llm::self_adjoint_eigen<3>(matA1, matD1, matV1);
+  if (!(matD1[2] > 3 * matD1[1])) return false;
+  const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+  // row 0 of the eigenvector matrix (sic), mapOptmization.cpp:1086-1091; 0.1 * v in double
+  const float x1 = (float)((double)cx + 0.1 * (double)matV1[0]);
+  const float y1 = (float)((double)cy + 0.1 * (double)matV1[1]);
+  const float z1 = (float)((double)cz + 0.1 * (double)matV1[2]);
+  const float x2 = (float)((double)cx - 0.1 * (double)matV1[0]);
+  const float y2 = (float)((double)cy - 0.1 * (double)matV1[1]);
+  const float z2 = (float)((double)cz - 0.1 * (double)matV1[2]);
+  const float a012 = sqrtf(((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) +
+                           ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) +
+                           ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)));
+  const float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+  const float la = ((y1 - y2) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) +
+                    (z1 - z2) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1))) / a012 / l12;
+  const float lb = -((x1 - x2) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) -
+                     (z1 - z2) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1))) / a012 / l12;
+  const float lc = -((x1 - x2) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) +
+                     (y1 - y2) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1))) / a012 / l12;
+  const float ld2 = a012 / l12;
+  const float w = (float)(1 - 0.9 * (double)fabsf(ld2));
+  *coeff = make_float4(w * la, w * lb, w * lc, w * ld2);
+  return (double)w > 0.1;
+}
+
+// surfOptimization body for one point
+__device__ __forceinline__ bool surf_fit(const DevState& st, int s, const float4 sel, float4* coeff) {
+  float d2[5];
+  int idx[5];
+  const int n = thread_knn5(st.grid_map_surf, s, sel.x, sel.y, sel.z, 1.0f, d2, idx);
+  if (n < 5) return false;
+  const float4* mp = st.map_surf + (size_t)s * st.cap_map_surf;
+  float4 q[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) q[j] = mp[idx[j]];
+  float matA0[15], matX0[3];
+  const float matB0[5] = {-1, -1, -1, -1, -1};
+#pragma unroll
+  for (int j = 0; j < 5; j++) { matA0[j * 3 + 0] = q[j].x; matA0[j * 3 + 1] = q[j].y; matA0[j * 3 + 2] = q[j].z; }
+  llm::colpiv_qr_solve<5, 3>(matA0, matB0, matX0);
+  float pa = matX0[0], pb = matX0[1], pc = matX0[2], pd = 1;
+  const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+  bool planeValid = true;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    if ((double)fabsf(pa * q[j].x + pb * q[j].y + pc * q[j].z + pd) > 0.2) { planeValid = false; break; }
+  }
+  if (!planeValid) return false;
+  const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+  const float w = (float)(1 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
+  *coeff = make_float4(w * pa, w * pb, w * pc, w * pd2);
+  return (double)w > 0.1;
+}
+
+__global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st) {
+  __shared__ double sh_part[MAP_THREADS / 32][MAP_NACC];
+  const DevParams& p = st.p;
+  const int s = blockIdx.y;
+  double* out = st.map_partials + ((size_t)s * MAP_BLOCKS + blockIdx.x) * MAP_NACC;
+  if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
+  float T[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) T[k] = st.transform_tobe_mapped[s * 6 + k];
+  const MapPose mp = make_map_pose(T);
+  const float srx = mp.sRoll, crx = mp.cRoll, sry = mp.sPitch, cry = mp.cPitch, srz = mp.sYaw, crz = mp.cYaw;
+  const int nc = st.scan_ds_counts[s * 2 + 0], ns = st.scan_ds_counts[s * 2 + 1];
+  double acc[MAP_NACC];
+#pragma unroll
+  for (int k = 0; k < MAP_NACC; ++k) acc[k] = 0.0;
+  for (int q = blockIdx.x * MAP_THREADS + threadIdx.x; q < nc + ns; q += MAP_BLOCKS * MAP_THREADS) {
+    const bool corner = q < nc;
+    const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
+    const float4 sel = point_associate_to_map(mp, ori);
+    float4 cf;
+    const bool ok = corner ? corner_fit(st, s, sel, &cf) : surf_fit(st, s, sel, &cf);
+    if (!ok) continue;
+    // mapOptmization.cpp:1223-1255
+    const float arx = (crx * sry * srz * ori.x + crx * crz * sry * ori.y - srx * sry * ori.z) * cf.x +
+                      (-srx * srz * ori.x - crz * srx * ori.y - crx * ori.z) * cf.y +
+                      (crx * cry * srz * ori.x + crx * cry * crz * ori.y - cry * srx * ori.z) * cf.z;
+    const float ary = ((cry * srx * srz - crz * sry) * ori.x + (sry * srz + cry * crz * srx) * ori.y + crx * cry * ori.z) * cf.x +
+                      ((-cry * crz - srx * sry * srz) * ori.x + (cry * srz - crz * srx * sry) * ori.y - crx * sry * ori.z) * cf.z;
+    const float arz = ((crz * srx * sry - cry * srz) * ori.x + (-cry * crz - srx * sry * srz) * ori.y) * cf.x +
+                      (crx * crz * ori.x - crx * srz * ori.y) * cf.y +
+                      ((sry * srz + cry * crz * srx) * ori.x + (crz * sry - cry * srx * srz) * ori.y) * cf.z;
+    const double a[6] = {arx, ary, arz, cf.x, cf.y, cf.z};
+    const double b = (double)(-cf.w);
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) acc[k++] += a[r] * a[c];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) acc[21 + r] += a[r] * b;
+    acc[27] += 1.0;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < MAP_NACC; ++k) {
+    const double v = warp_sum_d(acc[k]);
+    if (lane == 0) sh_part[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < MAP_NACC) {
+    double v = 0.0;
+    for (int w = 0; w < MAP_THREADS / 32; ++w) v += sh_part[w][threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
+  __shared__ double tot[MAP_NACC];
+  const int s = blockIdx.x;
+  if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
+  if (threadIdx.x < MAP_NACC) {
+    const double* part = st.map_partials + (size_t)s * MAP_BLOCKS * MAP_NACC;
+    double v = 0.0;
+    for (int b = 0; b < MAP_BLOCKS; ++b) v += part[b * MAP_NACC + threadIdx.x];
+    tot[threadIdx.x] = v;
+  }
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  float* T = st.transform_tobe_mapped + s * 6;
+  const int rows = (int)tot[27];
+  st.map_iters[s * 2 + 0] = iter + 1;
+  st.map_iters[s * 2 + 1] = rows;
+  if (rows < 50) return;  // LMOptimization returns false: keep iterating (mapOptmization.cpp:1208-1210)
+  float AtA[36], AtB[6], A2[36], X[6];
+  int k = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) { AtA[r * 6 + c] = AtA[c * 6 + r] = (float)tot[k]; ++k; }
+  for (int r = 0; r < 6; ++r) AtB[r] = (float)tot[21 + r];
+  for (int i = 0; i < 36; ++i) A2[i] = AtA[i];
+  llm::colpiv_qr_solve<6, 6>(A2, AtB, X);
+  float* matP = st.map_matP + s * 36;
+  if (iter == 0) st.map_flags[s * 4 + 0] = llm::degeneracy_projector<6>(AtA, 100.f, matP) ? 1 : 0;
+  if (st.map_flags[s * 4 + 0]) {
+    float X2[6];
+    for (int i = 0; i < 6; ++i) X2[i] = X[i];
+    for (int r = 0; r < 6; ++r) {
+      float v = 0.f;
+      for (int c = 0; c < 6; ++c) v += matP[r * 6 + c] * X2[c];
+      X[r] = v;
+    }
+  }
+  for (int i = 0; i < 6; ++i) T[i] += X[i];
+  const float r2d = 57.29578f;  // pcl::rad2deg(float)
+  const double r0 = (double)(X[0] * r2d), r1 = (double)(X[1] * r2d), r2 = (double)(X[2] * r2d);
+  const double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
+  const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
+  const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+  if ((double)deltaR < 0.05 && (double)deltaT < 0.05) st.map_flags[s * 4 + 1] = 1;
+}
+
+__global__ void k_map_begin(DevState st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= st.p.B) return;
+  st.map_flags[s * 4 + 1] = 0;
+  st.map_iters[s * 2 + 0] = 0;
+  st.map_iters[s * 2 + 1] = 0;
+}
+
+}  // namespace
+
+void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
+  const DevParams& p = st.p;
+  // kd-tree builds of every mapping cycle (mapOptmization.cpp:1317-1318)
+  launch_grid_build(ctx, st.grid_map_corner, p.B, st.map_corner, st.cap_map_corner, st.map_counts, 2, 0, nullptr, 0);
+  launch_grid_build(ctx, st.grid_map_surf, p.B, st.map_surf, st.cap_map_surf, st.map_counts, 2, 1, nullptr, 0);
+  k_map_begin<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st);
+  ctx.count("k_map_begin");
+  for (int iter = 0; iter < 10; ++iter) {
+    k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st);
+    ctx.count("k_map_iter");
+    k_map_solve<<<p.B, 32, 0, ctx.stream>>>(st, iter);
+    ctx.count("k_map_solve");
+  }
+}
+
+void launch_downsample_current_scan(LaunchCtx& ctx, DevState& st) {
+  (void)ctx; (void)st;  // implemented in voxelgrid.cu
+}

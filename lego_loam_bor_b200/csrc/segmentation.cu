@@ -1,0 +1,318 @@
+// segmentation.cu -- ImageProjection::cloudSegmentation / labelComponents
+// (reference: LeGO-LOAM/src/imageProjection.cpp:352-496).
+//
+// The reference flood-fills with a BFS per seed.  Its edge predicate (imageProjection.cpp:457-465)
+// is symmetric in the two ranges, so a BFS component is a connected component of an undirected
+// graph on the label==0 cells (4-neighbourhood, columns wrap, rows do not) and union-find gives the
+// identical partition.  Roots are forced to be the smallest row-major index of a component, which
+// is exactly the BFS seed (imageProjection.cpp:354-356), so
+//   * "rows touched by non-seed pixels" (lineCountFlag, imageProjection.cpp:469) is the set of rows
+//     of all component pixels except the root pixel, and
+//   * the reference's label numbering (valid components only, in seed order, :489-490) is an
+//     exclusive prefix count of feasible roots in row-major order.
+//
+// Kernels (all HBM/L2-bound integer work):
+//   k_ccl_rows      one block per (sequence, row): horizontal runs by a block-wide max-scan
+//   k_ccl_merge     one thread per cell: vertical edges + the column wrap edge, lock-free union (atomicMin)
+//   k_ccl_flatten   one thread per cell: final root, component size / row mask (warp-aggregated atomics)
+//   k_seg_count     one block per (sequence, row): feasible roots, kept cells, outlier cells
+//   k_seg_emit      one block per (sequence, row): ordered compaction into segmented cloud + cloud_info
+//   k_label_final   one thread per cell: numeric labels of non-root cells / 999999 (imageProjection.cpp:489-495)
+#include "ll_device.cuh"
+#include "ll_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ bool seg_edge(float ra, float rb, float sin_a, float cos_a, float thr) {
+  const float d1 = fmaxf(ra, rb);
+  const float d2 = fminf(ra, rb);
+  const float tang = (d2 * sin_a / (d1 - d2 * cos_a));
+  return tang > thr;
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+  int p = __ldcg(parent + x);
+  while (p != x) {
+    const int gp = __ldcg(parent + p);
+    if (gp != p) parent[x] = gp;  // path halving; any ancestor is a valid parent
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(parent + b, a);  // link the larger root under the smaller
+    if (old == b) return;
+    b = old;
+  }
+}
+
+// block-wide exclusive max-scan, one value per thread; scratch: 33 ints
+__device__ __forceinline__ int block_exclusive_max_scan(int v, int* warp_tot) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, t);
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const int w = lane < nw ? warp_tot[lane] : -1;
+    int winc = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc = max(winc, t);
+    }
+    int wex = __shfl_up_sync(0xffffffffu, winc, 1);
+    if (lane == 0) wex = -1;
+    if (lane < nw) warp_tot[lane] = wex;
+  }
+  __syncthreads();
+  int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = -1;
+  const int res = max(ex, warp_tot[wid]);
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(256) k_ccl_rows(DevState st) {
+  extern __shared__ int sh_head[];  // [H] inclusive max of run starts within a thread's chunk
+  __shared__ int warp_tot[33];
+  const DevParams& p = st.p;
+  const int row = blockIdx.x, s = blockIdx.y;
+  const size_t base = (size_t)s * p.N + (size_t)row * p.H;
+  const int ipt = (p.H + blockDim.x - 1) / blockDim.x;
+  const int c0 = threadIdx.x * ipt, c1 = min(p.H, c0 + ipt);
+  int running = -1;
+  bool left_valid = false;
+  float left_r = 0.f;
+  if (c0 >= 1 && c0 < p.H) {
+    left_valid = st.parent[base + c0 - 1] >= 0;
+    left_r = st.range_mat[base + c0 - 1];
+  }
+  for (int c = c0; c < c1; ++c) {
+    const bool valid = st.parent[base + c] >= 0;
+    const float r = st.range_mat[base + c];
+    if (valid) {
+      const bool joined = left_valid && seg_edge(left_r, r, p.sin_ax, p.cos_ax, p.seg_tan_theta);
+      if (!joined) running = c;
+    }
+    sh_head[c] = running;
+    left_valid = valid;
+    left_r = r;
+  }
+  const int carry = block_exclusive_max_scan(running, warp_tot);
+  for (int c = c0; c < c1; ++c) {
+    if (st.parent[base + c] >= 0) st.parent[base + c] = row * p.H + max(sh_head[c], carry);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_merge(DevState st) {
+  const DevParams& p = st.p;
+  const int s = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= p.N) return;
+  int* parent = st.parent + (size_t)s * p.N;
+  const float* range = st.range_mat + (size_t)s * p.N;
+  if (__ldcg(parent + cell) < 0) return;
+  const int row = cell / p.H, col = cell - row * p.H;
+  const float r = range[cell];
+  if (row + 1 < p.V) {
+    const int up = cell + p.H;
+    if (__ldcg(parent + up) >= 0 && seg_edge(r, range[up], p.sin_ay, p.cos_ay, p.seg_tan_theta)) uf_union(parent, cell, up);
+  }
+  if (col == p.H - 1 && p.H > 1) {
+    const int w = cell - col;  // column 0 of the same row (imageProjection.cpp:446-451)
+    if (__ldcg(parent + w) >= 0 && seg_edge(r, range[w], p.sin_ax, p.cos_ax, p.seg_tan_theta)) uf_union(parent, cell, w);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(DevState st) {
+  const DevParams& p = st.p;
+  const int s = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  int* parent = st.parent + (size_t)s * p.N;
+  int root = -1;
+  if (cell < p.N && parent[cell] >= 0) {
+    int x = cell;
+    int q = parent[x];
+    while (q != x) { x = q; q = __ldcg(parent + x); }
+    root = x;
+    parent[cell] = root;
+  }
+  // warp-aggregated statistics per root
+  const unsigned grp = __match_any_sync(0xffffffffu, root);
+  unsigned bit = 0u;
+  if (root >= 0 && cell != root) {
+    const int d = cell / p.H - root / p.H;
+    bit = 1u << min(d, 31);
+  }
+  const unsigned bits = __reduce_or_sync(grp, bit);
+  if (root >= 0 && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
+    atomicAdd(st.comp_size + (size_t)s * p.N + root, __popc(grp));
+    if (bits) atomicOr(st.comp_rows + (size_t)s * p.N + root, bits);
+  }
+}
+
+__device__ __forceinline__ bool feasible_root(const DevState& st, size_t base, int root) {
+  const int size = st.comp_size[base + root];
+  if (size >= 30) return true;
+  if (size >= st.p.seg_valid_point_num) return __popc(st.comp_rows[base + root]) >= st.p.seg_valid_line_num;
+  return false;
+}
+
+// classification of one cell for the ordered compaction of imageProjection.cpp:360-396
+// bit0: feasible root, bit1: kept in the segmented cloud, bit2: outlier cloud
+__device__ __forceinline__ int classify_cell(const DevState& st, size_t base, int row, int col) {
+  const DevParams& p = st.p;
+  const int cell = row * p.H + col;
+  const int par = st.parent[base + cell];
+  const bool ground = st.ground_mat[base + cell] == 1;
+  int f = 0;
+  const bool lab_pos = par >= 0;
+  if (lab_pos || ground) {
+    const bool feas = lab_pos && feasible_root(st, base, par);
+    if (lab_pos && par == cell && feas) f |= 1;
+    if (lab_pos && !feas) {  // label 999999
+      if (row > p.gsi && col % 5 == 0) f |= 4;
+      return f;
+    }
+    if (ground) {
+      if (col % 5 != 0 && col > 5 && col < p.H - 5) return f;
+    }
+    f |= 2;
+  }
+  return f;
+}
+
+__global__ void __launch_bounds__(256) k_seg_count(DevState st) {
+  __shared__ int sh_cnt[3];
+  const DevParams& p = st.p;
+  const int row = blockIdx.x, s = blockIdx.y;
+  const size_t base = (size_t)s * p.N;
+  if (threadIdx.x < 3) sh_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int c_root = 0, c_keep = 0, c_out = 0;
+  for (int col = threadIdx.x; col < p.H; col += blockDim.x) {
+    const int f = classify_cell(st, base, row, col);
+    c_root += f & 1;
+    c_keep += (f >> 1) & 1;
+    c_out += (f >> 2) & 1;
+  }
+  c_root = warp_sum_i(c_root);
+  c_keep = warp_sum_i(c_keep);
+  c_out = warp_sum_i(c_out);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sh_cnt[0], c_root);
+    atomicAdd(&sh_cnt[1], c_keep);
+    atomicAdd(&sh_cnt[2], c_out);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) st.tile_counts[((size_t)s * p.V + row) * 4 + threadIdx.x] = sh_cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
+  __shared__ int sh_pre[3];
+  __shared__ int warp_tot[33];
+  const DevParams& p = st.p;
+  const int row = blockIdx.x, s = blockIdx.y;
+  const size_t base = (size_t)s * p.N;
+  if (threadIdx.x < 3) sh_pre[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x < row) {
+    const int* tc = st.tile_counts + ((size_t)s * p.V + threadIdx.x) * 4;
+    atomicAdd(&sh_pre[0], tc[0]);
+    atomicAdd(&sh_pre[1], tc[1]);
+    atomicAdd(&sh_pre[2], tc[2]);
+  }
+  __syncthreads();
+  int run_root = sh_pre[0], run_keep = sh_pre[1], run_out = sh_pre[2];
+  const int keep_before_row = run_keep;
+  const float start_ori = st.orientation[s * 4 + 0];
+  for (int c0 = 0; c0 < p.H; c0 += blockDim.x) {
+    const int col = c0 + threadIdx.x;
+    const int f = col < p.H ? classify_cell(st, base, row, col) : 0;
+    // one packed scan for the three flags (each partial sum <= 256 < 2^10)
+    const int packed = (f & 1) | (((f >> 1) & 1) << 10) | (((f >> 2) & 1) << 20);
+    int total;
+    const int ex = block_exclusive_scan(packed, warp_tot, &total);
+    const int cell = row * p.H + col;
+    if (f & 1) st.label_mat[base + cell] = run_root + (ex & 1023) + 1;
+    if (f & 2) {
+      const int pos = run_keep + ((ex >> 10) & 1023);
+      const float4 pt = st.full_cloud[base + cell];
+      st.seg_cloud[base + pos] = pt;
+      st.seg_range[base + pos] = st.range_mat[base + cell];
+      st.seg_col[base + pos] = (uint32_t)col;
+      st.seg_ground[base + pos] = st.ground_mat[base + cell] == 1 ? 1 : 0;
+      // adjustDistortion's sequential halfPassed flag (featureAssociation.cpp:162,173-187): the flag
+      // flips at the FIRST segmented point whose branch-1 orientation is more than pi past the start;
+      // record candidates here, k_feature_prep reads the minimum.
+      float ori = -ll_atan2f(pt.y, pt.x);  // point.x = seg.y, point.z = seg.x after the axis swap
+      if ((double)ori < (double)start_ori - LL_PI / 2)
+        ori = (float)((double)ori + 2 * LL_PI);
+      else if ((double)ori > (double)start_ori + LL_PI * 3 / 2)
+        ori = (float)((double)ori - 2 * LL_PI);
+      if ((double)(ori - start_ori) > LL_PI) atomicMin(st.half_idx + s, pos);
+    }
+    if (f & 4) {
+      const int pos = run_out + ((ex >> 20) & 1023);
+      if (pos < st.cap_outlier) st.outlier_cloud[(size_t)s * st.cap_outlier + pos] = st.full_cloud[base + cell];
+    }
+    run_root += total & 1023;
+    run_keep += (total >> 10) & 1023;
+    run_out += (total >> 20) & 1023;
+  }
+  if (threadIdx.x == 0) {
+    st.start_ring[s * p.V + row] = keep_before_row - 1 + 5;  // imageProjection.cpp:361
+    st.end_ring[s * p.V + row] = run_keep - 1 - 5;           // imageProjection.cpp:395
+    if (row == p.V - 1) {
+      st.seg_count[s] = run_keep;
+      st.outlier_count[s] = min(run_out, st.cap_outlier);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_label_final(DevState st) {
+  const DevParams& p = st.p;
+  const int s = blockIdx.y;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= p.N) return;
+  const size_t base = (size_t)s * p.N;
+  const int par = st.parent[base + cell];
+  if (par < 0) return;  // label stays -1
+  const bool feas = feasible_root(st, base, par);
+  if (par == cell) {
+    if (!feas) st.label_mat[base + cell] = LL_INVALID_LABEL;  // feasible roots were numbered by k_seg_emit
+  } else {
+    // labels of feasible roots are not written in this kernel, so this read does not race
+    st.label_mat[base + cell] = feas ? st.label_mat[base + par] : LL_INVALID_LABEL;
+  }
+}
+
+}  // namespace
+
+void launch_segmentation(LaunchCtx& ctx, DevState& st) {
+  const DevParams& p = st.p;
+  const dim3 grid_rows(p.V, p.B);
+  const dim3 grid_cells((p.N + 255) / 256, p.B);
+  k_ccl_rows<<<grid_rows, 256, p.H * sizeof(int), ctx.stream>>>(st);
+  ctx.count("k_ccl_rows");
+  k_ccl_merge<<<grid_cells, 256, 0, ctx.stream>>>(st);
+  ctx.count("k_ccl_merge");
+  k_ccl_flatten<<<grid_cells, 256, 0, ctx.stream>>>(st);
+  ctx.count("k_ccl_flatten");
+  k_seg_count<<<grid_rows, 256, 0, ctx.stream>>>(st);
+  ctx.count("k_seg_count");
+  k_seg_emit<<<grid_rows, 256, 0, ctx.stream>>>(st);
+  ctx.count("k_seg_emit");
+  k_label_final<<<grid_cells, 256, 0, ctx.stream>>>(st);
+  ctx.count("k_label_final");
+}
