@@ -115,6 +115,7 @@ typedef enum ll_buffer {
   LL_BUF_MAP_ITERS = 32,             /* i32[2] iterations run, rows in the last iteration */
   LL_BUF_OUTLIER_LAST = 33,          /* pt[O] outlier cloud after adjustOutlierCloud (featureAssociation.cpp:1273-1283) */
   LL_BUF_SURF_LESS_FLAT_RAW_COUNT = 34, /* i32[V] less-flat points per ring before the 0.2 m VoxelGrid */
+  LL_BUF_MAP_TRACE = 35, /* f64[10][34] per scan-to-map iteration: 21 J^T J (upper), 6 J^T r, rows, 6 step X */
   LL_BUF_COUNT_
 } ll_buffer;
 
@@ -198,6 +199,12 @@ int ll_synchronize(ll_handle* h);
  * ll_enable_stage_timing(h, 1) before the call; synchronises the stream. */
 int ll_enable_stage_timing(ll_handle* h, int enable);
 int ll_get_stage_times_ms(ll_handle* h, float* ms5);
+
+/* Per-kernel device time: select one kernel by name (e.g. "k_extract_features"; NULL = none) and every
+ * later launch of it is bracketed by a CUDA event pair on the handle's stream (up to 4096 launches).
+ * ll_get_kernel_time returns the summed duration and the number of launches since ll_time_kernel. */
+int ll_time_kernel(ll_handle* h, const char* kernel_name);
+int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches);
 
 #ifdef __cplusplus
 }

@@ -21,8 +21,15 @@
 
 #if defined(__CUDACC__)
 #define LLM_HD __host__ __device__ inline
+/* The three solvers are kept out of line in device code: nvcc 12.9's optimiser (cicc -O3) was
+ * observed to miscompile colpiv_qr_solve<6,6> when it is inlined into a kernel that builds the
+ * matrix from shared-memory doubles (tools/test_smallmat2.cu reproduces it: wrong X at -O3,
+ * right X with -Xcicc -O1, with -G, or out of line).  Out of line the body is compiled once,
+ * in one context, which is the context tests/test_gpu_mapping.py checks against the CPU. */
+#define LLM_SOLVER __host__ __device__ __noinline__
 #else
 #define LLM_HD inline
+#define LLM_SOLVER inline
 #endif
 
 namespace llm {
@@ -53,7 +60,7 @@ LLM_HD void make_householder(float* x, int n, int st, float* tau, float* beta) {
 /* Least-squares / square solve of A(RxC) x = b by column-pivoted Householder QR
  * (Eigen ColPivHouseholderQR::compute + solve).  A is destroyed. */
 template <int R, int C>
-LLM_HD void colpiv_qr_solve(float* A, const float* b_in, float* x) {
+LLM_SOLVER void colpiv_qr_solve(float* A, const float* b_in, float* x) {
   const int size = R < C ? R : C;
   const float eps = FLT_EPSILON;
   float h[C];
@@ -172,7 +179,7 @@ LLM_HD void make_givens(float p, float q, float* c, float* s) {
  * lower triangle of M (row-major NxN).  evals ascending; eigenvector k is COLUMN k
  * of V, i.e. V[r*N + k]. */
 template <int N>
-LLM_HD void self_adjoint_eigen(const float* M, float* evals, float* V) {
+LLM_SOLVER void self_adjoint_eigen(const float* M, float* evals, float* V) {
   float a[N * N];
   float scale = 0.f;
   for (int r = 0; r < N; ++r)
@@ -320,7 +327,7 @@ LLM_HD void self_adjoint_eigen(const float* M, float* evals, float* V) {
 /* Inverse by Gauss-Jordan with partial pivoting (only reached when an LM stage is
  * degenerate: matP = V^-1 * V2, featureAssociation.cpp:891). Returns false if singular. */
 template <int N>
-LLM_HD bool invert(const float* M, float* Inv) {
+LLM_SOLVER bool invert(const float* M, float* Inv) {
   float a[N * N];
   for (int i = 0; i < N * N; ++i) { a[i] = M[i]; Inv[i] = 0.f; }
   for (int i = 0; i < N; ++i) Inv[i * N + i] = 1.f;
@@ -350,7 +357,7 @@ LLM_HD bool invert(const float* M, float* Inv) {
  * mapOptmization.cpp:1262-1292: at iteration 0 find eigenvalues below `thr` scanning
  * from the largest down, zero the matching ROWS of V2 (sic), P = V^-1 * V2. */
 template <int N>
-LLM_HD bool degeneracy_projector(const float* AtA, float thr, float* P) {
+LLM_SOLVER bool degeneracy_projector(const float* AtA, float thr, float* P) {
   float ev[N], V[N * N], V2[N * N], Vi[N * N];
   self_adjoint_eigen<N>(AtA, ev, V);
   for (int i = 0; i < N * N; ++i) V2[i] = V[i];

@@ -25,6 +25,7 @@ BUFFERS = {
     "MAP_SURF": (28, np.float32, 4), "SCAN_CORNER_DS": (29, np.float32, 4), "SCAN_SURF_TOTAL_DS": (30, np.float32, 4),
     "TRANSFORM_TOBE_MAPPED": (31, np.float32, 1), "MAP_ITERS": (32, np.int32, 1),
     "OUTLIER_LAST": (33, np.float32, 4), "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
+    "MAP_TRACE": (35, np.float64, 1),
 }
 
 EXPORTS = [
@@ -32,7 +33,7 @@ EXPORTS = [
     "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
     "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
     "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_download", "ll_upload", "ll_synchronize",
-    "ll_enable_stage_timing", "ll_get_stage_times_ms",
+    "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
 ]
 
 _lib = None
@@ -74,6 +75,8 @@ def load_library(path=None):
     lib.ll_upload.argtypes = [vp, ip, ip, vp, sz]
     lib.ll_enable_stage_timing.argtypes = [vp, ip]
     lib.ll_get_stage_times_ms.argtypes = [vp, vp]
+    lib.ll_time_kernel.argtypes = [vp, C.c_char_p]
+    lib.ll_get_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     if path == LIB_CUDA:
         _lib = lib
     return lib
@@ -203,3 +206,12 @@ class LegoLoam:
         ms = np.zeros(5, np.float32)
         self._ck(self.lib.ll_get_stage_times_ms(self.h, ms.ctypes.data), "ll_get_stage_times_ms")
         return ms
+
+    def time_kernel(self, name):
+        self._ck(self.lib.ll_time_kernel(self.h, name.encode() if name else None), "ll_time_kernel")
+
+    def kernel_time(self):
+        """(total milliseconds, launches) of the kernel selected with time_kernel()."""
+        ms, n = C.c_double(0), C.c_int(0)
+        self._ck(self.lib.ll_get_kernel_time(self.h, C.byref(ms), C.byref(n)), "ll_get_kernel_time")
+        return ms.value, n.value

@@ -205,6 +205,12 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.map_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.map_flags, (size_t)B * 4));
   CK(dev_alloc(h, &st.map_matP, (size_t)B * 36));
   CK(dev_alloc(h, &st.map_partials, (size_t)B * st.map_max_blocks * 28));
+  CK(dev_alloc(h, &st.map_trace, (size_t)B * 10 * 34));
+  st.vox_cap = N + st.cap_outlier;
+  CK(dev_alloc(h, &st.vox_key0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_key1, (size_t)B * 3 * st.vox_cap, false));
+  CK(dev_alloc(h, &st.vox_val0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_val1, (size_t)B * 3 * st.vox_cap, false));
+  CK(dev_alloc(h, &st.vox_tmp_surf, BN, false)); CK(dev_alloc(h, &st.vox_tmp_out, (size_t)B * st.cap_outlier, false));
+  CK(dev_alloc(h, &st.vox_tmp_counts, (size_t)B * 2));
   for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->ev[i]));
   CK(cudaStreamSynchronize(h->ctx.stream));
   *out = h;
@@ -219,6 +225,11 @@ int ll_destroy(ll_handle* h) {
   if (h->h_n_in) cudaFreeHost(h->h_n_in);
   for (int i = 0; i < 16; ++i) cudaEventDestroy(h->slot_ev[i]);
   for (int i = 0; i < 6; ++i) cudaEventDestroy(h->ev[i]);
+  if (h->ctx.ev_start) {
+    for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { cudaEventDestroy(h->ctx.ev_start[i]); cudaEventDestroy(h->ctx.ev_stop[i]); }
+    delete[] h->ctx.ev_start;
+    delete[] h->ctx.ev_stop;
+  }
   if (h->own_stream) cudaStreamDestroy(h->ctx.stream);
   delete h;
   return LL_OK;
@@ -414,6 +425,36 @@ int ll_get_poses(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   return LL_OK;
 }
 
+int ll_time_kernel(ll_handle* h, const char* kernel_name) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  LaunchCtx& c = h->ctx;
+  CK(cudaStreamSynchronize(c.stream));
+  if (!c.ev_start) {
+    c.ev_start = new cudaEvent_t[LaunchCtx::kMaxTimed];
+    c.ev_stop = new cudaEvent_t[LaunchCtx::kMaxTimed];
+    for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { CK(cudaEventCreate(&c.ev_start[i])); CK(cudaEventCreate(&c.ev_stop[i])); }
+  }
+  c.timed_used = 0;
+  memset(c.timed_name, 0, sizeof(c.timed_name));
+  if (kernel_name) strncpy(c.timed_name, kernel_name, sizeof(c.timed_name) - 1);
+  return LL_OK;
+}
+
+int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches) {
+  if (!h || !total_ms || !launches) return LL_ERR_INVALID_ARG;
+  LaunchCtx& c = h->ctx;
+  CK(cudaStreamSynchronize(c.stream));
+  double tot = 0.0;
+  for (int i = 0; i < c.timed_used; ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c.ev_start[i], c.ev_stop[i]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = c.timed_used;
+  return LL_OK;
+}
+
 int ll_enable_stage_timing(ll_handle* h, int enable) {
   if (!h) return LL_ERR_INVALID_ARG;
   h->timing = enable != 0;
@@ -486,6 +527,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_SCAN_SURF_TOTAL_DS: COUNTED(st.scan_surf_ds, 16, N, st.scan_ds_counts + seq * 2 + 1); break;
     case LL_BUF_TRANSFORM_TOBE_MAPPED: src = st.transform_tobe_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_MAP_ITERS: src = st.map_iters + seq * 2; elem = 4; n = 2; break;
+    case LL_BUF_MAP_TRACE: src = st.map_trace + (size_t)seq * 340; elem = 8; n = 340; break;
     case LL_BUF_OUTLIER_LAST: COUNTED(st.outlier_last, 16, (size_t)st.cap_outlier, st.odom_flags + seq * 4 + 3); break;
     case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: {
       // gathered from the per-ring counters (stride 8)

@@ -474,8 +474,7 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
   const DevParams& p = st.p;
   {
     dim3 grid((p.N + FP_THREADS - 1) / FP_THREADS, p.B);
-    k_feature_prep<<<grid, FP_THREADS, 0, ctx.stream>>>(st);
-    ctx.count("k_feature_prep");
+    LL_LAUNCH(ctx, "k_feature_prep", k_feature_prep<<<grid, FP_THREADS, 0, ctx.stream>>>(st));
   }
   {
     const int P = next_pow2(p.H / 6 + 2);
@@ -488,9 +487,7 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
       configured = smem;
     }
     dim3 grid(p.V, p.B);
-    k_extract_features<<<grid, EX_THREADS, smem, ctx.stream>>>(st, P, sort_cap);
-    ctx.count("k_extract_features");
-    k_feature_compact<<<grid, 256, 0, ctx.stream>>>(st);
-    ctx.count("k_feature_compact");
+    LL_LAUNCH(ctx, "k_extract_features", k_extract_features<<<grid, EX_THREADS, smem, ctx.stream>>>(st, P, sort_cap));
+    LL_LAUNCH(ctx, "k_feature_compact", k_feature_compact<<<grid, 256, 0, ctx.stream>>>(st));
   }
 }

@@ -78,12 +78,8 @@ __global__ void __launch_bounds__(256) k_grid_fill(BuildArgs a) {
 void launch_grid_build(LaunchCtx& ctx, HashGrid& g, int B, const float4* pts, int stride, const int* counts,
                        int count_stride, int count_off, const int* enable, int enable_stride) {
   BuildArgs a{g, pts, stride, counts, count_stride, count_off, enable, enable_stride};
-  k_grid_clear<<<dim3((g.tbl + 255) / 256, B), 256, 0, ctx.stream>>>(a);
-  ctx.count("k_grid_clear");
-  k_grid_count<<<dim3((g.cap + 255) / 256, B), 256, 0, ctx.stream>>>(a);
-  ctx.count("k_grid_count");
-  k_grid_scan<<<B, 1024, 0, ctx.stream>>>(a);
-  ctx.count("k_grid_scan");
-  k_grid_fill<<<dim3((g.cap + 255) / 256, B), 256, 0, ctx.stream>>>(a);
-  ctx.count("k_grid_fill");
+  LL_LAUNCH(ctx, "k_grid_clear", k_grid_clear<<<dim3((g.tbl + 255) / 256, B), 256, 0, ctx.stream>>>(a));
+  LL_LAUNCH(ctx, "k_grid_count", k_grid_count<<<dim3((g.cap + 255) / 256, B), 256, 0, ctx.stream>>>(a));
+  LL_LAUNCH(ctx, "k_grid_scan", k_grid_scan<<<B, 1024, 0, ctx.stream>>>(a));
+  LL_LAUNCH(ctx, "k_grid_fill", k_grid_fill<<<dim3((g.cap + 255) / 256, B), 256, 0, ctx.stream>>>(a));
 }

@@ -96,9 +96,6 @@ struct DevState {
   int* last_counts;     // [B][2]
   float4* outlier_last; // [B][cap_outlier]
   HashGrid grid_corner_last, grid_surf_last;  // index the clouds the "kd-trees" were last built on
-  float4* tree_corner;  // [B][120V] copy of the cloud the corner tree was built on (see odometry.cu)
-  float4* tree_surf;    // [B][N]
-  int* tree_counts;     // [B][2]
   float* transform_cur;  // [B][6]
   float* transform_sum;  // [B][6]
   int* odom_iters;       // [B][2]
@@ -117,7 +114,14 @@ struct DevState {
   int* map_iters;                                // [B][2]
   int* map_flags;                                // [B][4]: 0 isDegenerate, 1 converged/done
   float* map_matP;                               // [B][36]
+  // VoxelGrid scratch for downsampleCurrentScan (voxelgrid.cu)
+  unsigned *vox_key0, *vox_key1, *vox_val0, *vox_val1;  // [B][3][vox_cap]
+  float4* vox_tmp_surf;                          // [B][N]  laserCloudSurfLastDS
+  float4* vox_tmp_out;                           // [B][cap_outlier] laserCloudOutlierLastDS
+  int* vox_tmp_counts;                           // [B][2]
+  int vox_cap;
   double* map_partials;                          // [B][max_blocks][28]
+  double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)
   int* map_rows;                                 // [B][max_blocks]
   int map_max_blocks;
 };

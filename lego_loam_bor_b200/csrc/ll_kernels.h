@@ -7,13 +7,35 @@
 struct DevState;
 struct HashGrid;
 
+// Every kernel launch of the library goes through LL_LAUNCH: it counts launches (the bench's
+// "gpu_launches"), records the first launch error, and -- for ONE selected kernel name -- brackets
+// each launch with a CUDA event pair on the launching stream so that bench.py can report that
+// kernel's average duration inside the timed region (roofline.achieved).
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   cudaError_t first_error = cudaSuccess;
   const char* first_error_kernel = nullptr;
+  // per-kernel timing
+  static const int kMaxTimed = 4096;
+  char timed_name[64] = {0};
+  cudaEvent_t* ev_start = nullptr;
+  cudaEvent_t* ev_stop = nullptr;
+  int timed_used = 0;
+  bool timing_now = false;
+  inline bool is_timed(const char* name) const {
+    if (!timed_name[0] || !ev_start) return false;
+    int i = 0;
+    while (timed_name[i] && name[i] && timed_name[i] == name[i]) ++i;
+    return timed_name[i] == 0 && name[i] == 0;
+  }
+  inline void pre(const char* name) {
+    timing_now = is_timed(name) && timed_used < kMaxTimed;
+    if (timing_now) cudaEventRecord(ev_start[timed_used], stream);
+  }
   inline void count(const char* name) {
     ++launches;
+    if (timing_now) { cudaEventRecord(ev_stop[timed_used], stream); ++timed_used; timing_now = false; }
     const cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess && first_error == cudaSuccess) {
       first_error = e;
@@ -21,6 +43,13 @@ struct LaunchCtx {
     }
   }
 };
+
+#define LL_LAUNCH(ctx, name, ...) \
+  do {                            \
+    (ctx).pre(name);              \
+    __VA_ARGS__;                  \
+    (ctx).count(name);            \
+  } while (0)
 
 // projection.cu: projectPointCloud + groundRemoval (+ resets, start/end angle)
 void launch_projection(LaunchCtx& ctx, DevState& st);

@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
   const int rows = (int)tot[27];
   st.map_iters[s * 2 + 0] = iter + 1;
   st.map_iters[s * 2 + 1] = rows;
+  double* trace = st.map_trace + ((size_t)s * 10 + iter) * 34;
+  for (int i = 0; i < 28; ++i) trace[i] = tot[i];
+  for (int i = 28; i < 34; ++i) trace[i] = 0.0;
   if (rows < 50) return;  // LMOptimization returns false: keep iterating (mapOptmization.cpp:1208-1210)
   float AtA[36], AtB[6], A2[36], X[6];
   int k = 0;
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
     }
   }
   for (int i = 0; i < 6; ++i) T[i] += X[i];
+  for (int i = 0; i < 6; ++i) trace[28 + i] = (double)X[i];
   const float r2d = 57.29578f;  // pcl::rad2deg(float)
   const double r0 = (double)(X[0] * r2d), r1 = (double)(X[1] * r2d), r2 = (double)(X[2] * r2d);
   const double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
@@ -244,16 +248,10 @@ void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
   // kd-tree builds of every mapping cycle (mapOptmization.cpp:1317-1318)
   launch_grid_build(ctx, st.grid_map_corner, p.B, st.map_corner, st.cap_map_corner, st.map_counts, 2, 0, nullptr, 0);
   launch_grid_build(ctx, st.grid_map_surf, p.B, st.map_surf, st.cap_map_surf, st.map_counts, 2, 1, nullptr, 0);
-  k_map_begin<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st);
-  ctx.count("k_map_begin");
+  LL_LAUNCH(ctx, "k_map_begin", k_map_begin<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
   for (int iter = 0; iter < 10; ++iter) {
-    k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st);
-    ctx.count("k_map_iter");
-    k_map_solve<<<p.B, 32, 0, ctx.stream>>>(st, iter);
-    ctx.count("k_map_solve");
+    LL_LAUNCH(ctx, "k_map_iter", k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_map_solve", k_map_solve<<<p.B, 32, 0, ctx.stream>>>(st, iter));
   }
 }
 
-void launch_downsample_current_scan(LaunchCtx& ctx, DevState& st) {
-  (void)ctx; (void)st;  // implemented in voxelgrid.cu
-}

@@ -518,19 +518,13 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
 void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
   const DevParams& p = st.p;
   if (!first_frame) {
-    k_odom_search<STAGE_SURF><<<dim3((p.cap_flat * 32 + 255) / 256, p.B), 256, 0, ctx.stream>>>(st);
-    ctx.count("k_odom_search_surf");
-    k_odom_lm<STAGE_SURF><<<p.B, LM_THREADS, 0, ctx.stream>>>(st);
-    ctx.count("k_odom_lm_surf");
-    k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp * 32 + 255) / 256, p.B), 256, 0, ctx.stream>>>(st);
-    ctx.count("k_odom_search_corner");
-    k_odom_lm<STAGE_CORNER><<<p.B, LM_THREADS, 0, ctx.stream>>>(st);
-    ctx.count("k_odom_lm_corner");
-    k_odom_finish<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st);
-    ctx.count("k_odom_finish");
+    LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<dim3((p.cap_flat * 32 + 255) / 256, p.B), 256, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_lm_surf", k_odom_lm<STAGE_SURF><<<p.B, LM_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp * 32 + 255) / 256, p.B), 256, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_lm_corner", k_odom_lm<STAGE_CORNER><<<p.B, LM_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_finish", k_odom_finish<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
   }
-  k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0);
-  ctx.count("k_publish_clouds_last");
+  LL_LAUNCH(ctx, "k_publish_clouds_last", k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0));
   launch_grid_build(ctx, st.grid_corner_last, p.B, st.corner_last, p.cap_less_sharp, st.last_counts, 2, 0,
                     st.odom_flags + 2, 4);
   launch_grid_build(ctx, st.grid_surf_last, p.B, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4);

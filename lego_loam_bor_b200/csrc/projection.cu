@@ -148,12 +148,10 @@ void launch_projection(LaunchCtx& ctx, DevState& st) {
   const DevParams& p = st.p;
   {
     dim3 grid((p.max_pts + 255) / 256, p.B);
-    k_project_scatter<<<grid, 256, 0, ctx.stream>>>(st);
-    ctx.count("k_project_scatter");
+    LL_LAUNCH(ctx, "k_project_scatter", k_project_scatter<<<grid, 256, 0, ctx.stream>>>(st));
   }
   {
     dim3 grid((p.H + 127) / 128, (p.V + GG_ROWS - 1) / GG_ROWS, p.B);
-    k_gather_ground<<<grid, 128, 0, ctx.stream>>>(st);
-    ctx.count("k_gather_ground");
+    LL_LAUNCH(ctx, "k_gather_ground", k_gather_ground<<<grid, 128, 0, ctx.stream>>>(st));
   }
 }

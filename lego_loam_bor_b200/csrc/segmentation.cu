@@ -303,16 +303,10 @@ void launch_segmentation(LaunchCtx& ctx, DevState& st) {
   const DevParams& p = st.p;
   const dim3 grid_rows(p.V, p.B);
   const dim3 grid_cells((p.N + 255) / 256, p.B);
-  k_ccl_rows<<<grid_rows, 256, p.H * sizeof(int), ctx.stream>>>(st);
-  ctx.count("k_ccl_rows");
-  k_ccl_merge<<<grid_cells, 256, 0, ctx.stream>>>(st);
-  ctx.count("k_ccl_merge");
-  k_ccl_flatten<<<grid_cells, 256, 0, ctx.stream>>>(st);
-  ctx.count("k_ccl_flatten");
-  k_seg_count<<<grid_rows, 256, 0, ctx.stream>>>(st);
-  ctx.count("k_seg_count");
-  k_seg_emit<<<grid_rows, 256, 0, ctx.stream>>>(st);
-  ctx.count("k_seg_emit");
-  k_label_final<<<grid_cells, 256, 0, ctx.stream>>>(st);
-  ctx.count("k_label_final");
+  LL_LAUNCH(ctx, "k_ccl_rows", k_ccl_rows<<<grid_rows, 256, p.H * sizeof(int), ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_ccl_merge", k_ccl_merge<<<grid_cells, 256, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_ccl_flatten", k_ccl_flatten<<<grid_cells, 256, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_seg_count", k_seg_count<<<grid_rows, 256, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_seg_emit", k_seg_emit<<<grid_rows, 256, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_label_final", k_label_final<<<grid_cells, 256, 0, ctx.stream>>>(st));
 }

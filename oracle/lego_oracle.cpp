@@ -155,6 +155,7 @@ struct lo_handle {
   bool mapDegenerate;
   float matP6[36];
   int map_iters[2];
+  double map_trace[340];
   std::vector<P4> moOri, moCoeff;
   double timers[5];
 
@@ -196,6 +197,7 @@ struct lo_handle {
     for (int i = 0; i < 36; ++i) matP6[i] = 0.f; /* mapOptmization.cpp:223 matP.setZero() */
     mapDegenerate = false;
     odom_iters[0] = odom_iters[1] = 0; map_iters[0] = map_iters[1] = 0;
+    for (int i = 0; i < 340; ++i) map_trace[i] = 0.0;
     lessFlatRawCount.assign(V, 0);
     for (int i = 0; i < 5; ++i) timers[i] = 0;
   }
@@ -1037,6 +1039,9 @@ struct lo_handle {
     float srz = sin_(transformTobeMapped[2]); float crz = cos_(transformTobeMapped[2]);
     int laserCloudSelNum = moOri.size();
     map_iters[1] = laserCloudSelNum;
+    double* trace = map_trace + 34 * iterCount;
+    for (int i = 0; i < 34; ++i) trace[i] = 0.0;
+    trace[27] = laserCloudSelNum;
     if (laserCloudSelNum < 50) return false;
     std::vector<float> matA(laserCloudSelNum * 6), matB(laserCloudSelNum);
     for (int i = 0; i < laserCloudSelNum; i++) {
@@ -1058,6 +1063,8 @@ struct lo_handle {
     }
     float AtA[36], AtB[6], X[6], AtAc[36];
     normal_equations<6>(matA, matB, laserCloudSelNum, AtA, AtB);
+    { int k = 0; for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) trace[k++] = AtA[r * 6 + c];
+      for (int r = 0; r < 6; ++r) trace[21 + r] = AtB[r]; }
     for (int i = 0; i < 36; ++i) AtAc[i] = AtA[i];
     llm::colpiv_qr_solve<6, 6>(AtAc, AtB, X);
     if (iterCount == 0) mapDegenerate = llm::degeneracy_projector<6>(AtA, 100.f, matP6);
@@ -1071,6 +1078,7 @@ struct lo_handle {
       }
     }
     for (int i = 0; i < 6; ++i) transformTobeMapped[i] += X[i];
+    for (int i = 0; i < 6; ++i) trace[28 + i] = X[i];
     const float r2d = 57.29578f; /* pcl::rad2deg(float) */
     float deltaR = sqrt(pow(X[0] * r2d, 2) + pow(X[1] * r2d, 2) + pow(X[2] * r2d, 2));
     float deltaT = sqrt(pow(X[3] * 100, 2) + pow(X[4] * 100, 2) + pow(X[5] * 100, 2));
@@ -1214,6 +1222,7 @@ int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n
     case LL_BUF_SCAN_SURF_TOTAL_DS: return copy_out(h->scanSurfTotalDS.data(), h->scanSurfTotalDS.size(), dst, dst_bytes, n);
     case LL_BUF_TRANSFORM_TOBE_MAPPED: return copy_out(h->transformTobeMapped, 6, dst, dst_bytes, n);
     case LL_BUF_MAP_ITERS: return copy_out(h->map_iters, 2, dst, dst_bytes, n);
+    case LL_BUF_MAP_TRACE: return copy_out(h->map_trace, 340, dst, dst_bytes, n);
     case LL_BUF_OUTLIER_LAST: return copy_out(h->outlierLast.data(), h->outlierLast.size(), dst, dst_bytes, n);
     case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: return copy_out(h->lessFlatRawCount.data(), h->lessFlatRawCount.size(), dst, dst_bytes, n);
     default: return LL_ERR_INVALID_ARG;

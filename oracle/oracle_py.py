@@ -27,6 +27,7 @@ BUFFERS = {
     "MAP_SURF": (28,) + PT[1:], "SCAN_CORNER_DS": (29,) + PT[1:], "SCAN_SURF_TOTAL_DS": (30,) + PT[1:],
     "TRANSFORM_TOBE_MAPPED": (31, np.float32, 1), "MAP_ITERS": (32, np.int32, 1),
     "OUTLIER_LAST": (33,) + PT[1:], "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
+    "MAP_TRACE": (35, np.float64, 1),
 }
 
 
