@@ -116,6 +116,8 @@ typedef enum ll_buffer {
   LL_BUF_OUTLIER_LAST = 33,          /* pt[O] outlier cloud after adjustOutlierCloud (featureAssociation.cpp:1273-1283) */
   LL_BUF_SURF_LESS_FLAT_RAW_COUNT = 34, /* i32[V] less-flat points per ring before the 0.2 m VoxelGrid */
   LL_BUF_MAP_TRACE = 35, /* f64[10][34] per scan-to-map iteration: 21 J^T J (upper), 6 J^T r, rows, 6 step X */
+  LL_BUF_TRANSFORM_BEF_MAPPED = 36, /* f32[6] */
+  LL_BUF_TRANSFORM_AFT_MAPPED = 37, /* f32[6] */
   LL_BUF_COUNT_
 } ll_buffer;
 
@@ -170,13 +172,22 @@ int ll_map_downsample_current_scan(ll_handle* h);
 /* transformTobeMapped initial guess, f32[batch][6] host (result of
  * transformAssociateToMap, mapOptmization.cpp:264-387, computed by the host class). */
 int ll_map_set_initial_guess(ll_handle* h, const float* transform_tobe_mapped);
+/* Same as ll_map_set_initial_guess but only enqueues the copy (the host buffer must stay valid and
+ * unchanged until the stream has consumed it; use pinned memory to keep it asynchronous). */
+int ll_map_set_initial_guess_async(ll_handle* h, const float* transform_tobe_mapped);
+/* Odometry -> map pose chain kept on the device (MapOptimization::transformAssociateToMap and
+ * transformUpdate, mapOptmization.cpp:264-395).  ll_map_set_poses seeds transformAftMapped /
+ * transformBefMapped (f32[batch][6] host); ll_map_predict_pose computes transformTobeMapped from them and
+ * the current odometry pose; ll_scan_to_map ends with transformUpdate. */
+int ll_map_set_poses(ll_handle* h, const float* transform_aft_mapped, const float* transform_bef_mapped);
+int ll_map_predict_pose(ll_handle* h);
 /* kd-tree replacement build + <=10 x (cornerOptimization, surfOptimization,
  * LMOptimization) (mapOptmization.cpp:1028-1332) for all sequences. */
 int ll_scan_to_map(ll_handle* h);
 
 /* One full frame for every sequence: ll_image_projection + ll_feature_association,
- * and every mapping_frequency_divider-th odometry frame also
- * ll_map_downsample_current_scan + ll_scan_to_map when a local map is set. */
+ * and every mapping_frequency_divider-th odometry frame also ll_map_downsample_current_scan +
+ * ll_map_predict_pose + ll_scan_to_map when a local map is set.  Returns 1 on such frames, else 0. */
 int ll_process_scans(ll_handle* h);
 
 /* ---- results ------------------------------------------------------------------- */
@@ -205,6 +216,9 @@ int ll_get_stage_times_ms(ll_handle* h, float* ms5);
  * ll_get_kernel_time returns the summed duration and the number of launches since ll_time_kernel. */
 int ll_time_kernel(ll_handle* h, const char* kernel_name);
 int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches);
+/* With ll_time_kernel(h, "*") every kernel is timed; this writes one text line per kernel name,
+ * "name total_ms launches\n", into buf (NUL-terminated). */
+int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

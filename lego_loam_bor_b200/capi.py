@@ -25,15 +25,18 @@ BUFFERS = {
     "MAP_SURF": (28, np.float32, 4), "SCAN_CORNER_DS": (29, np.float32, 4), "SCAN_SURF_TOTAL_DS": (30, np.float32, 4),
     "TRANSFORM_TOBE_MAPPED": (31, np.float32, 1), "MAP_ITERS": (32, np.int32, 1),
     "OUTLIER_LAST": (33, np.float32, 4), "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
-    "MAP_TRACE": (35, np.float64, 1),
+    "MAP_TRACE": (35, np.float64, 1), "TRANSFORM_BEF_MAPPED": (36, np.float32, 1),
+    "TRANSFORM_AFT_MAPPED": (37, np.float32, 1),
 }
 
 EXPORTS = [
     "ll_default_params", "ll_create", "ll_destroy", "ll_reset", "ll_last_error", "ll_kernel_launches",
     "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
     "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
+    "ll_map_set_initial_guess_async", "ll_map_set_poses", "ll_map_predict_pose",
     "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_download", "ll_upload", "ll_synchronize",
     "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
+    "ll_get_kernel_time_table",
 ]
 
 _lib = None
@@ -64,8 +67,10 @@ def load_library(path=None):
     lib.ll_kernel_launches.restype = C.c_int64
     lib.ll_set_scans_host.argtypes = [vp, vp, vp, ip]
     lib.ll_set_scans_device.argtypes = [vp, vp, vp, ip]
+    lib.ll_map_set_initial_guess_async.argtypes = [vp, vp]
+    lib.ll_map_set_poses.argtypes = [vp, vp, vp]
     for name in ("ll_image_projection", "ll_feature_association", "ll_map_downsample_current_scan",
-                 "ll_scan_to_map", "ll_process_scans", "ll_synchronize"):
+                 "ll_scan_to_map", "ll_process_scans", "ll_synchronize", "ll_map_predict_pose"):
         getattr(lib, name).argtypes = [vp]
     lib.ll_map_set_local.argtypes = [vp, ip, vp, ip, vp, ip]
     lib.ll_map_set_scan.argtypes = [vp, ip, vp, ip, vp, ip]
@@ -77,6 +82,7 @@ def load_library(path=None):
     lib.ll_get_stage_times_ms.argtypes = [vp, vp]
     lib.ll_time_kernel.argtypes = [vp, C.c_char_p]
     lib.ll_get_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.ll_get_kernel_time_table.argtypes = [vp, C.c_char_p, sz]
     if path == LIB_CUDA:
         _lib = lib
     return lib
@@ -169,6 +175,14 @@ class LegoLoam:
         t = np.ascontiguousarray(t, np.float32).reshape(self.batch, 6)
         self._ck(self.lib.ll_map_set_initial_guess(self.h, t.ctypes.data), "ll_map_set_initial_guess")
 
+    def map_set_poses(self, aft, bef):
+        aft = np.ascontiguousarray(aft, np.float32).reshape(self.batch, 6)
+        bef = np.ascontiguousarray(bef, np.float32).reshape(self.batch, 6)
+        self._ck(self.lib.ll_map_set_poses(self.h, aft.ctypes.data, bef.ctypes.data), "ll_map_set_poses")
+
+    def map_predict_pose(self):
+        self._ck(self.lib.ll_map_predict_pose(self.h), "ll_map_predict_pose")
+
     def scan_to_map(self):
         self._ck(self.lib.ll_scan_to_map(self.h), "ll_scan_to_map")
 
@@ -215,3 +229,13 @@ class LegoLoam:
         ms, n = C.c_double(0), C.c_int(0)
         self._ck(self.lib.ll_get_kernel_time(self.h, C.byref(ms), C.byref(n)), "ll_get_kernel_time")
         return ms.value, n.value
+
+    def kernel_time_table(self):
+        """After time_kernel("*"): {kernel name: (total ms, launches)}."""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.ll_get_kernel_time_table(self.h, buf, len(buf)), "ll_get_kernel_time_table")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out

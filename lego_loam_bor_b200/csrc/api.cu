@@ -202,6 +202,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.scan_corner_ds, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.scan_surf_ds, BN));
   CK(dev_alloc(h, &st.scan_ds_counts, (size_t)B * 2));
   CK(dev_alloc(h, &st.transform_tobe_mapped, (size_t)B * 6));
+  CK(dev_alloc(h, &st.transform_bef_mapped, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_aft_mapped, (size_t)B * 6));
   CK(dev_alloc(h, &st.map_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.map_flags, (size_t)B * 4));
   CK(dev_alloc(h, &st.map_matP, (size_t)B * 36));
   CK(dev_alloc(h, &st.map_partials, (size_t)B * st.map_max_blocks * 28));
@@ -229,6 +230,7 @@ int ll_destroy(ll_handle* h) {
     for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { cudaEventDestroy(h->ctx.ev_start[i]); cudaEventDestroy(h->ctx.ev_stop[i]); }
     delete[] h->ctx.ev_start;
     delete[] h->ctx.ev_stop;
+    delete[] h->ctx.ev_name;
   }
   if (h->own_stream) cudaStreamDestroy(h->ctx.stream);
   delete h;
@@ -250,6 +252,7 @@ int ll_reset(ll_handle* h) {
   CK(cudaMemsetAsync(st.smooth_ind, 0, BN * 4, sm));
   CK(cudaMemsetAsync(st.transform_cur, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_sum, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm));
+  CK(cudaMemsetAsync(st.transform_bef_mapped, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_aft_mapped, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.last_counts, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_flags, 0, (size_t)p.B * 16, sm));
   CK(cudaMemsetAsync(st.odom_iters, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_matP, 0, (size_t)p.B * 36, sm));
   CK(cudaMemsetAsync(st.map_flags, 0, (size_t)p.B * 16, sm)); CK(cudaMemsetAsync(st.map_matP, 0, (size_t)p.B * 144, sm));
@@ -382,6 +385,26 @@ int ll_map_set_initial_guess(ll_handle* h, const float* t) {
   return LL_OK;
 }
 
+int ll_map_set_initial_guess_async(ll_handle* h, const float* t) {
+  if (!h || !t) return LL_ERR_INVALID_ARG;
+  CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_map_set_poses(ll_handle* h, const float* aft, const float* bef) {
+  if (!h || !aft || !bef) return LL_ERR_INVALID_ARG;
+  CK(cudaMemcpyAsync(h->st.transform_aft_mapped, aft, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaMemcpyAsync(h->st.transform_bef_mapped, bef, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_map_predict_pose(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  launch_map_predict_pose(h->ctx, h->st);
+  return check_stream(h, "ll_map_predict_pose");
+}
+
 int ll_scan_to_map(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (!h->map_set) { h->err = "ll_scan_to_map: no local map set"; return LL_ERR_STATE; }
@@ -397,6 +420,8 @@ int ll_process_scans(ll_handle* h) {
   if (rc < 0) return rc;
   if (rc == 1 && h->map_set) {
     rc = ll_map_downsample_current_scan(h);
+    if (rc < 0) return rc;
+    rc = ll_map_predict_pose(h);
     if (rc < 0) return rc;
     rc = ll_scan_to_map(h);
     if (rc < 0) return rc;
@@ -432,6 +457,7 @@ int ll_time_kernel(ll_handle* h, const char* kernel_name) {
   if (!c.ev_start) {
     c.ev_start = new cudaEvent_t[LaunchCtx::kMaxTimed];
     c.ev_stop = new cudaEvent_t[LaunchCtx::kMaxTimed];
+    c.ev_name = new const char*[LaunchCtx::kMaxTimed];
     for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { CK(cudaEventCreate(&c.ev_start[i])); CK(cudaEventCreate(&c.ev_stop[i])); }
   }
   c.timed_used = 0;
@@ -452,6 +478,33 @@ int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches) {
   }
   *total_ms = tot;
   *launches = c.timed_used;
+  return LL_OK;
+}
+
+int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap) {
+  if (!h || !buf || cap < 2) return LL_ERR_INVALID_ARG;
+  LaunchCtx& c = h->ctx;
+  CK(cudaStreamSynchronize(c.stream));
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int> cnt;
+  for (int i = 0; i < c.timed_used; ++i) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c.ev_start[i], c.ev_stop[i]));
+    size_t k = 0;
+    for (; k < names.size(); ++k) if (names[k] == c.ev_name[i]) break;
+    if (k == names.size()) { names.push_back(c.ev_name[i]); ms.push_back(0.0); cnt.push_back(0); }
+    ms[k] += t;
+    cnt[k] += 1;
+  }
+  std::string out;
+  char line[160];
+  for (size_t k = 0; k < names.size(); ++k) {
+    snprintf(line, sizeof(line), "%s %.6f %d\n", names[k].c_str(), ms[k], cnt[k]);
+    out += line;
+  }
+  if (out.size() + 1 > cap) return LL_ERR_CAPACITY;
+  memcpy(buf, out.c_str(), out.size() + 1);
   return LL_OK;
 }
 
@@ -528,6 +581,8 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_TRANSFORM_TOBE_MAPPED: src = st.transform_tobe_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_MAP_ITERS: src = st.map_iters + seq * 2; elem = 4; n = 2; break;
     case LL_BUF_MAP_TRACE: src = st.map_trace + (size_t)seq * 340; elem = 8; n = 340; break;
+    case LL_BUF_TRANSFORM_BEF_MAPPED: src = st.transform_bef_mapped + seq * 6; elem = 4; n = 6; break;
+    case LL_BUF_TRANSFORM_AFT_MAPPED: src = st.transform_aft_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_OUTLIER_LAST: COUNTED(st.outlier_last, 16, (size_t)st.cap_outlier, st.odom_flags + seq * 4 + 3); break;
     case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: {
       // gathered from the per-ring counters (stride 8)

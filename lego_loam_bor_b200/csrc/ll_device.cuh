@@ -111,6 +111,8 @@ struct DevState {
   float4* scan_corner_ds; float4* scan_surf_ds;  // [B][120V], [B][N]
   int* scan_ds_counts;                           // [B][2]
   float* transform_tobe_mapped;                  // [B][6]
+  float* transform_bef_mapped;                   // [B][6]
+  float* transform_aft_mapped;                   // [B][6]
   int* map_iters;                                // [B][2]
   int* map_flags;                                // [B][4]: 0 isDegenerate, 1 converged/done
   float* map_matP;                               // [B][36]

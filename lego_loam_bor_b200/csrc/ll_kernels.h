@@ -21,10 +21,12 @@ struct LaunchCtx {
   char timed_name[64] = {0};
   cudaEvent_t* ev_start = nullptr;
   cudaEvent_t* ev_stop = nullptr;
+  const char** ev_name = nullptr;  // kernel name of every recorded launch
   int timed_used = 0;
   bool timing_now = false;
   inline bool is_timed(const char* name) const {
     if (!timed_name[0] || !ev_start) return false;
+    if (timed_name[0] == '*' && timed_name[1] == 0) return true;  // "*": every kernel
     int i = 0;
     while (timed_name[i] && name[i] && timed_name[i] == name[i]) ++i;
     return timed_name[i] == 0 && name[i] == 0;
@@ -35,7 +37,12 @@ struct LaunchCtx {
   }
   inline void count(const char* name) {
     ++launches;
-    if (timing_now) { cudaEventRecord(ev_stop[timed_used], stream); ++timed_used; timing_now = false; }
+    if (timing_now) {
+      cudaEventRecord(ev_stop[timed_used], stream);
+      ev_name[timed_used] = name;
+      ++timed_used;
+      timing_now = false;
+    }
     const cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess && first_error == cudaSuccess) {
       first_error = e;
@@ -64,4 +71,5 @@ void launch_grid_build(LaunchCtx& ctx, HashGrid& g, int B, const float4* pts, in
                        int count_stride, int count_off, const int* enable /* [B] or null */, int enable_stride);
 // mapping.cu: scan2MapOptimization and downsampleCurrentScan
 void launch_scan_to_map(LaunchCtx& ctx, DevState& st);
+void launch_map_predict_pose(LaunchCtx& ctx, DevState& st);
 void launch_downsample_current_scan(LaunchCtx& ctx, DevState& st);

@@ -241,7 +241,81 @@ __global__ void k_map_begin(DevState st) {
   st.map_iters[s * 2 + 1] = 0;
 }
 
+// MapOptimization::transformAssociateToMap (mapOptmization.cpp:264-387), one thread per sequence.
+__global__ void k_map_associate(DevState st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= st.p.B) return;
+  const float* tS = st.transform_sum + s * 6;
+  const float* tB = st.transform_bef_mapped + s * 6;
+  const float* tA = st.transform_aft_mapped + s * 6;
+  float* tT = st.transform_tobe_mapped + s * 6;
+  float sbcx, cbcx, sbcy, cbcy, sbcz, cbcz, sblx, cblx, sbly, cbly, sblz, cblz, salx, calx, saly, caly, salz, calz;
+  ll_sincosf(tS[0], &sbcx, &cbcx); ll_sincosf(tS[1], &sbcy, &cbcy); ll_sincosf(tS[2], &sbcz, &cbcz);
+  ll_sincosf(tB[0], &sblx, &cblx); ll_sincosf(tB[1], &sbly, &cbly); ll_sincosf(tB[2], &sblz, &cblz);
+  ll_sincosf(tA[0], &salx, &calx); ll_sincosf(tA[1], &saly, &caly); ll_sincosf(tA[2], &salz, &calz);
+  float x1 = cbcy * (tB[3] - tS[3]) - sbcy * (tB[5] - tS[5]);
+  float y1 = tB[4] - tS[4];
+  float z1 = sbcy * (tB[3] - tS[3]) + cbcy * (tB[5] - tS[5]);
+  float x2 = x1;
+  float y2 = cbcx * y1 + sbcx * z1;
+  float z2 = -sbcx * y1 + cbcx * z1;
+  const float inc3 = cbcz * x2 + sbcz * y2;
+  const float inc4 = -sbcz * x2 + cbcz * y2;
+  const float inc5 = z2;
+  const float srx = -sbcx * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz) -
+                    cbcx * sbcy * (calx * calz * (cbly * sblz - cblz * sblx * sbly) - calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) -
+                    cbcx * cbcy * (calx * salz * (cblz * sbly - cbly * sblx * sblz) - calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx);
+  const float t0 = -ll_asinf(srx);
+  const float srycrx = sbcx * (cblx * cblz * (caly * salz - calz * salx * saly) - cblx * sblz * (caly * calz + salx * saly * salz) + calx * saly * sblx) -
+                       cbcx * cbcy * ((caly * calz + salx * saly * salz) * (cblz * sbly - cbly * sblx * sblz) +
+                                      (caly * salz - calz * salx * saly) * (sbly * sblz + cbly * cblz * sblx) - calx * cblx * cbly * saly) +
+                       cbcx * sbcy * ((caly * calz + salx * saly * salz) * (cbly * cblz + sblx * sbly * sblz) +
+                                      (caly * salz - calz * salx * saly) * (cbly * sblz - cblz * sblx * sbly) + calx * cblx * saly * sbly);
+  const float crycrx = sbcx * (cblx * sblz * (calz * saly - caly * salx * salz) - cblx * cblz * (saly * salz + caly * calz * salx) + calx * caly * sblx) +
+                       cbcx * cbcy * ((saly * salz + caly * calz * salx) * (sbly * sblz + cbly * cblz * sblx) +
+                                      (calz * saly - caly * salx * salz) * (cblz * sbly - cbly * sblx * sblz) + calx * caly * cblx * cbly) -
+                       cbcx * sbcy * ((saly * salz + caly * calz * salx) * (cbly * sblz - cblz * sblx * sbly) +
+                                      (calz * saly - caly * salx * salz) * (cbly * cblz + sblx * sbly * sblz) - calx * caly * cblx * sbly);
+  float st0, ct0;
+  ll_sincosf(t0, &st0, &ct0);
+  const float t1 = ll_atan2f(srycrx / ct0, crycrx / ct0);
+  const float srzcrx = (cbcz * sbcy - cbcy * sbcx * sbcz) * (calx * salz * (cblz * sbly - cbly * sblx * sblz) - calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx) -
+                       (cbcy * cbcz + sbcx * sbcy * sbcz) * (calx * calz * (cbly * sblz - cblz * sblx * sbly) - calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) +
+                       cbcx * sbcz * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz);
+  const float crzcrx = (cbcy * sbcz - cbcz * sbcx * sbcy) * (calx * calz * (cbly * sblz - cblz * sblx * sbly) - calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) -
+                       (sbcy * sbcz + cbcy * cbcz * sbcx) * (calx * salz * (cblz * sbly - cbly * sblx * sblz) - calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx) +
+                       cbcx * cbcz * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz);
+  const float t2 = ll_atan2f(srzcrx / ct0, crzcrx / ct0);
+  float st1, ct1, st2, ct2;
+  ll_sincosf(t1, &st1, &ct1);
+  ll_sincosf(t2, &st2, &ct2);
+  x1 = ct2 * inc3 - st2 * inc4;
+  y1 = st2 * inc3 + ct2 * inc4;
+  z1 = inc5;
+  x2 = x1;
+  y2 = ct0 * y1 - st0 * z1;
+  z2 = st0 * y1 + ct0 * z1;
+  tT[0] = t0; tT[1] = t1; tT[2] = t2;
+  tT[3] = tA[3] - (ct1 * x2 + st1 * z2);
+  tT[4] = tA[4] - y2;
+  tT[5] = tA[5] - (-st1 * x2 + ct1 * z2);
+}
+
+// MapOptimization::transformUpdate (mapOptmization.cpp:389-395), inside the guard of :1316
+__global__ void k_map_update(DevState st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= st.p.B || !map_guard(st, s)) return;
+  for (int i = 0; i < 6; ++i) {
+    st.transform_bef_mapped[s * 6 + i] = st.transform_sum[s * 6 + i];
+    st.transform_aft_mapped[s * 6 + i] = st.transform_tobe_mapped[s * 6 + i];
+  }
+}
+
 }  // namespace
+
+void launch_map_predict_pose(LaunchCtx& ctx, DevState& st) {
+  LL_LAUNCH(ctx, "k_map_associate", k_map_associate<<<(st.p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
+}
 
 void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
   const DevParams& p = st.p;
@@ -253,5 +327,6 @@ void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
     LL_LAUNCH(ctx, "k_map_iter", k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st));
     LL_LAUNCH(ctx, "k_map_solve", k_map_solve<<<p.B, 32, 0, ctx.stream>>>(st, iter));
   }
+  LL_LAUNCH(ctx, "k_map_update", k_map_update<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
 }
 

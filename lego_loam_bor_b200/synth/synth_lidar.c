@@ -113,18 +113,15 @@ void synth_pose(const SynthConfig* cfg, int seq, int frame, double* pose6) {
   pose6[5] = phi + M_PI / 2.0;
 }
 
-static double ray_box(const double o[3], const double d[3], const Box* b) {
-  double tmin = 0.0, tmax = 1e30;
+/* slab test with a precomputed reciprocal direction (inf where the direction component is 0) */
+static inline double ray_box(const double o[3], const double inv[3], const Box* b, double tbest) {
+  double tmin = 0.0, tmax = tbest;
   for (int a = 0; a < 3; ++a) {
-    if (fabs(d[a]) < 1e-12) {
-      if (o[a] < b->lo[a] || o[a] > b->hi[a]) return -1.0;
-    } else {
-      double t1 = (b->lo[a] - o[a]) / d[a], t2 = (b->hi[a] - o[a]) / d[a];
-      if (t1 > t2) { double t = t1; t1 = t2; t2 = t; }
-      if (t1 > tmin) tmin = t1;
-      if (t2 < tmax) tmax = t2;
-      if (tmin > tmax) return -1.0;
-    }
+    double t1 = (b->lo[a] - o[a]) * inv[a], t2 = (b->hi[a] - o[a]) * inv[a];
+    if (t1 > t2) { const double t = t1; t1 = t2; t2 = t; }
+    if (t1 > tmin) tmin = t1;
+    if (t2 < tmax) tmax = t2;
+    if (!(tmin <= tmax)) return -1.0;
   }
   return tmin > 0.0 ? tmin : -1.0;
 }
@@ -158,8 +155,10 @@ int synth_scan(const SynthConfig* cfg, int seq, int frame, float* out_xyzi) {
                             R[2][0] * ds[0] + R[2][1] * ds[1] + R[2][2] * ds[2]};
       double t = 1e30;
       if (dw[2] < -1e-9) t = (GROUND_Z - o[2]) / dw[2];
+      double inv[3];
+      for (int a = 0; a < 3; ++a) inv[a] = fabs(dw[a]) < 1e-12 ? (dw[a] < 0 ? -1e300 : 1e300) : 1.0 / dw[a];
       for (int b = 0; b < nb; ++b) {
-        const double tb = ray_box(o, dw, &boxes[b]);
+        const double tb = ray_box(o, inv, &boxes[b], t);
         if (tb > 0.0 && tb < t) t = tb;
       }
       if (t >= 1e29) continue;

@@ -151,7 +151,7 @@ struct lo_handle {
   /* ---- MapOptimization scan-to-map slice (mapOptimization.h) ---- */
   std::vector<P4> mapCorner, mapSurf, scanCornerDS, scanSurfTotalDS;
   std::unique_ptr<oknn::KdTree> kdCornerMap, kdSurfMap;
-  float transformTobeMapped[6];
+  float transformTobeMapped[6], transformBefMapped[6], transformAftMapped[6], transformIncre[6];
   bool mapDegenerate;
   float matP6[36];
   int map_iters[2];
@@ -188,7 +188,10 @@ struct lo_handle {
     cloudCurvature.assign(N, 0.f); cloudNeighborPicked.assign(N, 0); cloudLabel.assign(N, 0);
     searchCornerInd1.assign(N, 0.f); searchCornerInd2.assign(N, 0.f);
     searchSurfInd1.assign(N, 0.f); searchSurfInd2.assign(N, 0.f); searchSurfInd3.assign(N, 0.f);
-    for (int i = 0; i < 6; ++i) { transformCur[i] = 0; transformSum[i] = 0; transformTobeMapped[i] = 0; }
+    for (int i = 0; i < 6; ++i) {
+      transformCur[i] = 0; transformSum[i] = 0; transformTobeMapped[i] = 0;
+      transformBefMapped[i] = 0; transformAftMapped[i] = 0; transformIncre[i] = 0;
+    }
     systemInitedLM = false; isDegenerate = false; cycle_count = 0;
     cornerLast.clear(); surfLast.clear(); outlierLast.clear(); cornerLastNum = surfLastNum = 0;
     kdCornerLast.reset(new oknn::KdTree()); kdSurfLast.reset(new oknn::KdTree());
@@ -949,6 +952,68 @@ struct lo_handle {
     po->i = pi->i;
   }
 
+
+  /* mapOptmization.cpp:264-387.  MapOptimization::transformSum is the odometry pose that arrives through
+   * nav_msgs::Odometry and a tf RPY->quaternion->RPY round trip (featureAssociation.cpp:1287-1297,
+   * utility.h:96-110; tf is not vendored): restated as the identity on FeatureAssociation's transformSum. */
+  void transformAssociateToMap() {
+    const float* tS = transformSum;
+    float x1 = cos_(tS[1]) * (transformBefMapped[3] - tS[3]) - sin_(tS[1]) * (transformBefMapped[5] - tS[5]);
+    float y1 = transformBefMapped[4] - tS[4];
+    float z1 = sin_(tS[1]) * (transformBefMapped[3] - tS[3]) + cos_(tS[1]) * (transformBefMapped[5] - tS[5]);
+    float x2 = x1;
+    float y2 = cos_(tS[0]) * y1 + sin_(tS[0]) * z1;
+    float z2 = -sin_(tS[0]) * y1 + cos_(tS[0]) * z1;
+    transformIncre[3] = cos_(tS[2]) * x2 + sin_(tS[2]) * y2;
+    transformIncre[4] = -sin_(tS[2]) * x2 + cos_(tS[2]) * y2;
+    transformIncre[5] = z2;
+    float sbcx = sin_(tS[0]), cbcx = cos_(tS[0]), sbcy = sin_(tS[1]), cbcy = cos_(tS[1]), sbcz = sin_(tS[2]), cbcz = cos_(tS[2]);
+    float sblx = sin_(transformBefMapped[0]), cblx = cos_(transformBefMapped[0]);
+    float sbly = sin_(transformBefMapped[1]), cbly = cos_(transformBefMapped[1]);
+    float sblz = sin_(transformBefMapped[2]), cblz = cos_(transformBefMapped[2]);
+    float salx = sin_(transformAftMapped[0]), calx = cos_(transformAftMapped[0]);
+    float saly = sin_(transformAftMapped[1]), caly = cos_(transformAftMapped[1]);
+    float salz = sin_(transformAftMapped[2]), calz = cos_(transformAftMapped[2]);
+    float srx = -sbcx * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz) -
+                cbcx * sbcy * (calx * calz * (cbly * sblz - cblz * sblx * sbly) - calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) -
+                cbcx * cbcy * (calx * salz * (cblz * sbly - cbly * sblx * sblz) - calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx);
+    transformTobeMapped[0] = -asin_(srx);
+    float srycrx = sbcx * (cblx * cblz * (caly * salz - calz * salx * saly) - cblx * sblz * (caly * calz + salx * saly * salz) + calx * saly * sblx) -
+                   cbcx * cbcy * ((caly * calz + salx * saly * salz) * (cblz * sbly - cbly * sblx * sblz) +
+                                  (caly * salz - calz * salx * saly) * (sbly * sblz + cbly * cblz * sblx) - calx * cblx * cbly * saly) +
+                   cbcx * sbcy * ((caly * calz + salx * saly * salz) * (cbly * cblz + sblx * sbly * sblz) +
+                                  (caly * salz - calz * salx * saly) * (cbly * sblz - cblz * sblx * sbly) + calx * cblx * saly * sbly);
+    float crycrx = sbcx * (cblx * sblz * (calz * saly - caly * salx * salz) - cblx * cblz * (saly * salz + caly * calz * salx) + calx * caly * sblx) +
+                   cbcx * cbcy * ((saly * salz + caly * calz * salx) * (sbly * sblz + cbly * cblz * sblx) +
+                                  (calz * saly - caly * salx * salz) * (cblz * sbly - cbly * sblx * sblz) + calx * caly * cblx * cbly) -
+                   cbcx * sbcy * ((saly * salz + caly * calz * salx) * (cbly * sblz - cblz * sblx * sbly) +
+                                  (calz * saly - caly * salx * salz) * (cbly * cblz + sblx * sbly * sblz) - calx * caly * cblx * sbly);
+    transformTobeMapped[1] = atan2_(srycrx / cos_(transformTobeMapped[0]), crycrx / cos_(transformTobeMapped[0]));
+    float srzcrx = (cbcz * sbcy - cbcy * sbcx * sbcz) * (calx * salz * (cblz * sbly - cbly * sblx * sblz) - calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx) -
+                   (cbcy * cbcz + sbcx * sbcy * sbcz) * (calx * calz * (cbly * sblz - cblz * sblx * sbly) - calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) +
+                   cbcx * sbcz * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz);
+    float crzcrx = (cbcy * sbcz - cbcz * sbcx * sbcy) * (calx * calz * (cbly * sblz - cblz * sblx * sbly) - calx * salz * (cbly * cblz + sblx * sbly * sblz) + cblx * salx * sbly) -
+                   (sbcy * sbcz + cbcy * cbcz * sbcx) * (calx * salz * (cblz * sbly - cbly * sblx * sblz) - calx * calz * (sbly * sblz + cbly * cblz * sblx) + cblx * cbly * salx) +
+                   cbcx * cbcz * (salx * sblx + calx * cblx * salz * sblz + calx * calz * cblx * cblz);
+    transformTobeMapped[2] = atan2_(srzcrx / cos_(transformTobeMapped[0]), crzcrx / cos_(transformTobeMapped[0]));
+    x1 = cos_(transformTobeMapped[2]) * transformIncre[3] - sin_(transformTobeMapped[2]) * transformIncre[4];
+    y1 = sin_(transformTobeMapped[2]) * transformIncre[3] + cos_(transformTobeMapped[2]) * transformIncre[4];
+    z1 = transformIncre[5];
+    x2 = x1;
+    y2 = cos_(transformTobeMapped[0]) * y1 - sin_(transformTobeMapped[0]) * z1;
+    z2 = sin_(transformTobeMapped[0]) * y1 + cos_(transformTobeMapped[0]) * z1;
+    transformTobeMapped[3] = transformAftMapped[3] - (cos_(transformTobeMapped[1]) * x2 + sin_(transformTobeMapped[1]) * z2);
+    transformTobeMapped[4] = transformAftMapped[4] - y2;
+    transformTobeMapped[5] = transformAftMapped[5] - (-sin_(transformTobeMapped[1]) * x2 + cos_(transformTobeMapped[1]) * z2);
+  }
+
+  void transformUpdate() { /* mapOptmization.cpp:389-395 */
+    for (int i = 0; i < 6; i++) {
+      transformBefMapped[i] = transformSum[i];
+      transformAftMapped[i] = transformTobeMapped[i];
+    }
+  }
+
   void cornerOptimization(int) { /* mapOptmization.cpp:1028-1134 */
     updatePointAssociateToMapSinCos();
     const std::vector<P4>& mp = kdCornerMap->cloud();
@@ -1098,6 +1163,7 @@ struct lo_handle {
         map_iters[0] = iterCount + 1;
         if (LMOptimization(iterCount) == true) break;
       }
+      transformUpdate();
     }
   }
 
@@ -1179,6 +1245,11 @@ int lo_map_set_initial_guess(lo_handle* h, const float* t6) {
   for (int i = 0; i < 6; ++i) h->transformTobeMapped[i] = t6[i];
   return 0;
 }
+int lo_map_set_poses(lo_handle* h, const float* aft6, const float* bef6) {
+  for (int i = 0; i < 6; ++i) { h->transformAftMapped[i] = aft6[i]; h->transformBefMapped[i] = bef6[i]; }
+  return 0;
+}
+int lo_map_predict_pose(lo_handle* h) { h->transformAssociateToMap(); return 0; }
 int lo_scan_to_map(lo_handle* h) {
   double t0 = now_s();
   h->scan2MapOptimization();
@@ -1223,6 +1294,8 @@ int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n
     case LL_BUF_TRANSFORM_TOBE_MAPPED: return copy_out(h->transformTobeMapped, 6, dst, dst_bytes, n);
     case LL_BUF_MAP_ITERS: return copy_out(h->map_iters, 2, dst, dst_bytes, n);
     case LL_BUF_MAP_TRACE: return copy_out(h->map_trace, 340, dst, dst_bytes, n);
+    case LL_BUF_TRANSFORM_BEF_MAPPED: return copy_out(h->transformBefMapped, 6, dst, dst_bytes, n);
+    case LL_BUF_TRANSFORM_AFT_MAPPED: return copy_out(h->transformAftMapped, 6, dst, dst_bytes, n);
     case LL_BUF_OUTLIER_LAST: return copy_out(h->outlierLast.data(), h->outlierLast.size(), dst, dst_bytes, n);
     case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: return copy_out(h->lessFlatRawCount.data(), h->lessFlatRawCount.size(), dst, dst_bytes, n);
     default: return LL_ERR_INVALID_ARG;

@@ -36,6 +36,9 @@ int lo_map_set_local(lo_handle* h, const float* corner, int nc, const float* sur
 int lo_map_set_scan(lo_handle* h, const float* corner, int nc, const float* surf_total, int ns);
 int lo_map_downsample_current_scan(lo_handle* h);
 int lo_map_set_initial_guess(lo_handle* h, const float* t6);
+/* transformAftMapped / transformBefMapped (mapOptimization.h), then transformAssociateToMap */
+int lo_map_set_poses(lo_handle* h, const float* aft6, const float* bef6);
+int lo_map_predict_pose(lo_handle* h);
 int lo_scan_to_map(lo_handle* h);
 int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n_elems);
 int lo_upload(lo_handle* h, int buffer, const void* src, size_t n_elems);

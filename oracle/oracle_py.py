@@ -27,7 +27,8 @@ BUFFERS = {
     "MAP_SURF": (28,) + PT[1:], "SCAN_CORNER_DS": (29,) + PT[1:], "SCAN_SURF_TOTAL_DS": (30,) + PT[1:],
     "TRANSFORM_TOBE_MAPPED": (31, np.float32, 1), "MAP_ITERS": (32, np.int32, 1),
     "OUTLIER_LAST": (33,) + PT[1:], "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
-    "MAP_TRACE": (35, np.float64, 1),
+    "MAP_TRACE": (35, np.float64, 1), "TRANSFORM_BEF_MAPPED": (36, np.float32, 1),
+    "TRANSFORM_AFT_MAPPED": (37, np.float32, 1),
 }
 
 
@@ -61,6 +62,8 @@ def load(prefer_ref=True):
         lib.lo_map_downsample_current_scan.argtypes = [C.c_void_p]
         lib.lo_map_set_initial_guess.argtypes = [C.c_void_p, C.c_void_p]
         lib.lo_scan_to_map.argtypes = [C.c_void_p]
+        lib.lo_map_set_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.lo_map_predict_pose.argtypes = [C.c_void_p]
         lib.lo_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.lo_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         lib.lo_voxel_grid.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
@@ -132,6 +135,15 @@ class Oracle:
     def map_set_initial_guess(self, t6):
         t6 = np.ascontiguousarray(t6, np.float32)
         return self.lib.lo_map_set_initial_guess(self.h, t6.ctypes.data)
+
+    def map_set_poses(self, aft6, bef6):
+        aft6 = np.ascontiguousarray(aft6, np.float32)
+        bef6 = np.ascontiguousarray(bef6, np.float32)
+        return self.lib.lo_map_set_poses(self.h, aft6.ctypes.data, bef6.ctypes.data)
+
+    def map_predict_pose(self):
+        self._select()
+        return self.lib.lo_map_predict_pose(self.h)
 
     def scan_to_map(self):
         self._select()

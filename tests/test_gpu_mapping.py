@@ -77,3 +77,51 @@ def test_scan_to_map_vlp16(built):
 
 def test_scan_to_map_64_beam(built):
     _run("C", [1])
+
+
+def test_full_pipeline_with_pose_chain(built):
+    """ll_process_scans end to end (every stage, mapping every 5th odometry frame, odometry -> map pose
+    chain on the device) against the oracle driven the same way, free-running over 12 frames."""
+    from lego_loam_bor_b200 import synth
+    from lego_loam_bor_b200.capi import LegoLoam
+    from oracle.oracle_py import Oracle
+    seqs = [0, 4]
+    n_frames = 12
+    p, cfg, scans = make_scans("A", seqs, range(n_frames))
+    gpu = LegoLoam(p, batch=len(seqs))
+    oracles = [Oracle(p) for _ in seqs]
+    aft = np.zeros((len(seqs), 6), np.float32)
+    for k, s in enumerate(seqs):
+        x, y, z, roll, pitch, yaw = synth.pose(cfg, s, 0)
+        aft[k] = [0, yaw, 0, y, z, x]
+        cm, sm = synth.local_map(cfg, s, 1, 0.2), synth.local_map(cfg, s, 0, 0.4)
+        gpu.map_set_local(k, cm, sm)
+        oracles[k].map_set_local(cm, sm)
+        oracles[k].map_set_poses(aft[k], np.zeros(6, np.float32))
+    gpu.map_set_poses(aft, np.zeros_like(aft))
+    cycles = 0
+    for f in range(n_frames):
+        gpu.set_scans_host([scans[(s, f)] for s in seqs])
+        rc = gpu.process_scans()
+        for k, s in enumerate(seqs):
+            o = oracles[k]
+            o.image_projection(scans[(s, f)])
+            if o.feature_association() == 1:
+                assert rc == 1
+                o.map_downsample_current_scan()
+                o.map_predict_pose()
+                o.scan_to_map()
+            else:
+                assert rc == 0
+        cycles += rc
+        for k in range(len(seqs)):
+            for name in ("TRANSFORM_SUM", "TRANSFORM_TOBE_MAPPED", "TRANSFORM_AFT_MAPPED", "TRANSFORM_BEF_MAPPED"):
+                a, b = gpu.download(name, k), oracles[k].download(name)
+                assert np.all(np.abs(a[:3] - b[:3]) <= POSE_TOL_RAD), f"frame {f} {name} rot {a} vs {b}"
+                assert np.all(np.abs(a[3:] - b[3:]) <= POSE_TOL_M), f"frame {f} {name} trans {a} vs {b}"
+    assert cycles == 2
+    # the map-frame pose must track the synthetic ground truth to a few centimetres
+    for k, s in enumerate(seqs):
+        x, y, z, roll, pitch, yaw = synth.pose(cfg, s, 10)  # last mapped frame
+        a = gpu.download("TRANSFORM_AFT_MAPPED", k)
+        assert abs(a[3] - y) < 0.1 and abs(a[5] - x) < 0.1 and abs(a[4] - z) < 0.1, (a, (x, y, z))
