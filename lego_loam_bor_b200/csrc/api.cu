@@ -67,9 +67,13 @@ int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell) {
   g->cell = cell;
   g->inv_cell = 1.0f / cell;
   g->cap = cap;
-  g->tbl = next_pow2(cap < 1024 ? 2048 : 2 * cap);
+  g->tbl = next_pow2(cap < 4096 ? 4096 : cap);  // buckets >= points: a low load factor keeps empty cells cheap
+  g->ntiles = g->tbl / 4096;
   CK(dev_alloc(h, &g->cell_start, (size_t)B * (g->tbl + 1)));
   CK(dev_alloc(h, &g->cursor, (size_t)B * g->tbl));
+  CK(dev_alloc(h, &g->cnt, (size_t)B * g->tbl));
+  CK(dev_alloc(h, &g->occ, (size_t)B * (g->tbl / 32)));
+  CK(dev_alloc(h, &g->tile_tot, (size_t)B * g->ntiles));
   CK(dev_alloc(h, &g->sorted, (size_t)B * cap));
   CK(dev_alloc(h, &g->count, (size_t)B));
   return LL_OK;
@@ -180,9 +184,9 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.outlier_cloud, (size_t)B * st.cap_outlier)); CK(dev_alloc(h, &st.outlier_count, B));
   CK(dev_alloc(h, &st.curvature, BN)); CK(dev_alloc(h, &st.picked, BN)); CK(dev_alloc(h, &st.cloud_label, BN));
   CK(dev_alloc(h, &st.smooth_val, BN)); CK(dev_alloc(h, &st.smooth_ind, BN));
-  CK(dev_alloc(h, &st.st_sharp, (size_t)B * V * 12)); CK(dev_alloc(h, &st.st_sharp_ind, (size_t)B * V * 12));
-  CK(dev_alloc(h, &st.st_less_sharp, (size_t)B * V * 120)); CK(dev_alloc(h, &st.st_less_sharp_ind, (size_t)B * V * 120));
-  CK(dev_alloc(h, &st.st_flat, (size_t)B * V * 24)); CK(dev_alloc(h, &st.st_flat_ind, (size_t)B * V * 24));
+  CK(dev_alloc(h, &st.st_sharp_ind, (size_t)B * V * 12)); CK(dev_alloc(h, &st.scan_list, BN));
+  CK(dev_alloc(h, &st.st_less_sharp_ind, (size_t)B * V * 120));
+  CK(dev_alloc(h, &st.st_flat_ind, (size_t)B * V * 24));
   CK(dev_alloc(h, &st.st_less_flat, BN)); CK(dev_alloc(h, &st.ring_counts, (size_t)B * V * 8));
   CK(dev_alloc(h, &st.corner_sharp, (size_t)B * p.cap_sharp)); CK(dev_alloc(h, &st.corner_sharp_ind, (size_t)B * p.cap_sharp));
   CK(dev_alloc(h, &st.corner_less_sharp, (size_t)B * p.cap_less_sharp));
@@ -207,6 +211,9 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.map_matP, (size_t)B * 36));
   CK(dev_alloc(h, &st.map_partials, (size_t)B * st.map_max_blocks * 28));
   CK(dev_alloc(h, &st.map_trace, (size_t)B * 10 * 34));
+  st.map_knn_cap = p.cap_less_sharp + N;
+  CK(dev_alloc(h, &st.map_knn, (size_t)B * st.map_knn_cap * 5, false));
+  CK(dev_alloc(h, &st.map_knn_state, (size_t)B * st.map_knn_cap, false));
   st.vox_cap = N + st.cap_outlier;
   CK(dev_alloc(h, &st.vox_key0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_key1, (size_t)B * 3 * st.vox_cap, false));
   CK(dev_alloc(h, &st.vox_val0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_val1, (size_t)B * 3 * st.vox_cap, false));
@@ -258,6 +265,8 @@ int ll_reset(ll_handle* h) {
   CK(cudaMemsetAsync(st.map_flags, 0, (size_t)p.B * 16, sm)); CK(cudaMemsetAsync(st.map_matP, 0, (size_t)p.B * 144, sm));
   CK(cudaMemsetAsync(st.map_iters, 0, (size_t)p.B * 8, sm));
   CK(cudaMemsetAsync(st.grid_corner_last.cell_start, 0, (size_t)p.B * (st.grid_corner_last.tbl + 1) * 4, sm));
+  CK(cudaMemsetAsync(st.grid_corner_last.occ, 0, (size_t)p.B * (st.grid_corner_last.tbl / 32) * 4, sm));
+  CK(cudaMemsetAsync(st.grid_surf_last.occ, 0, (size_t)p.B * (st.grid_surf_last.tbl / 32) * 4, sm));
   CK(cudaMemsetAsync(st.grid_surf_last.cell_start, 0, (size_t)p.B * (st.grid_surf_last.tbl + 1) * 4, sm));
   h->frames = 0;
   h->odom_cycles = 0;

@@ -126,78 +126,46 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-#define EX_THREADS 256
+#define SORT_THREADS 256
 
-// dynamic shared memory layout (ints unless noted), L = span length <= H + 16, P = padded sextant size:
-//   curv[L] float | col[L] | picked[L] u8 | ground[L] u8 | label[L] i8 | keys[max(6P, pow2(H))] u64 | list[6][P+1] | lfpos[H]
-__global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, int P, int sort_cap) {
-  extern __shared__ unsigned long long sh_raw[];
-  __shared__ int warp_tot[33];
+// ---- 1. per-ring sextant sort ------------------------------------------------------------------
+// One block per (ring, sequence).  std::sort(cloudSmoothness + sp, cloudSmoothness + ep, by_value)
+// for the six sextants (featureAssociation.cpp:275-286) as one bitonic network over 6 padded segments
+// in shared memory; the sorted (value, ind) pairs go back in place (the array persists across frames),
+// and a packed "scan list" is emitted for the greedy pass: entry k of [sp, ep] = ind | edge_ok << 31 |
+// flat_ok << 30, so that pass needs nothing but cloudNeighborPicked to test a candidate.
+__global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int P) {
+  extern __shared__ unsigned long long keys[];  // [6][P]
   __shared__ int sh_sp[6], sh_ep[6];
-  __shared__ int sh_counts[8];
-  __shared__ int sh_imn[3], sh_imx[3];
   const DevParams& p = st.p;
   const int ring = blockIdx.x, s = blockIdx.y;
   const size_t base = (size_t)s * p.N;
-  const int S = st.seg_count[s];
   const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
-  const int a = start - 4, b = end + 6;  // this ring's points are [a, b)
-  const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
-  const int L = max(0, span_hi - span_lo);
-  const int Lcap = p.H + 16;
-  // carve shared memory
-  unsigned long long* keys = sh_raw;                          // [sort_cap]
-  float* sm_curv = (float*)(keys + sort_cap);                 // [Lcap]
-  int* sm_col = (int*)(sm_curv + Lcap);                       // [Lcap]
-  int* sm_list = sm_col + Lcap;                               // [6][P+1]
-  int* sm_lfpos = sm_list + 6 * (P + 1);                      // [H]
-  unsigned char* sm_picked = (unsigned char*)(sm_lfpos + p.H);  // [Lcap]
-  unsigned char* sm_ground = sm_picked + Lcap;                  // [Lcap]
-  signed char* sm_label = (signed char*)(sm_ground + Lcap);     // [Lcap]
-
-  float4* o_sharp = st.st_sharp + ((size_t)s * p.V + ring) * 12;
-  int* o_sharp_i = st.st_sharp_ind + ((size_t)s * p.V + ring) * 12;
-  float4* o_lsharp = st.st_less_sharp + ((size_t)s * p.V + ring) * 120;
-  int* o_lsharp_i = st.st_less_sharp_ind + ((size_t)s * p.V + ring) * 120;
-  float4* o_flat = st.st_flat + ((size_t)s * p.V + ring) * 24;
-  int* o_flat_i = st.st_flat_ind + ((size_t)s * p.V + ring) * 24;
-  float4* o_lflat = st.st_less_flat + ((size_t)s * p.V + ring) * p.H;
-  int* o_counts = st.ring_counts + ((size_t)s * p.V + ring) * 8;
-
-  if (threadIdx.x < 8) sh_counts[threadIdx.x] = 0;
   if (threadIdx.x < 6) {
     const int j = threadIdx.x;
-    // featureAssociation.cpp:275-281 (integer division as written)
     sh_sp[j] = (start * (6 - j) + end * j) / 6;
     sh_ep[j] = (start * (5 - j) + end * (j + 1)) / 6 - 1;
   }
-  for (int t = threadIdx.x; t < L; t += EX_THREADS) {
-    const int g = span_lo + t;
-    sm_curv[t] = st.curvature[base + g];
-    sm_col[t] = (int)st.seg_col[base + g];
-    sm_picked[t] = (unsigned char)(st.picked[base + g] != 0);
-    sm_ground[t] = st.seg_ground[base + g];
-    sm_label[t] = (signed char)st.cloud_label[base + g];
-  }
-  for (int t = threadIdx.x; t < 6 * P; t += EX_THREADS) keys[t] = ~0ull;
+  for (int t = threadIdx.x; t < 6 * P; t += SORT_THREADS) keys[t] = ~0ull;
   __syncthreads();
-  // ---- sort keys: sextant j occupies keys[j*P .. j*P + (ep-sp)) ----
+  bool any = false;
   for (int j = 0; j < 6; ++j) {
     const int sp = sh_sp[j], ep = sh_ep[j];
     if (sp >= ep) continue;
-    for (int t = threadIdx.x; t < ep - sp; t += EX_THREADS) {
+    any = true;
+    for (int t = threadIdx.x; t < ep - sp; t += SORT_THREADS) {
       const float v = st.smooth_val[base + sp + t];
       const int ind = st.smooth_ind[base + sp + t];
-      keys[j * P + t] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)ind;  // values are >= 0
+      keys[j * P + t] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)ind;  // curvature >= 0
     }
   }
+  if (!any) return;
   __syncthreads();
   bitonic_sort_u64(keys, P, 6 * P);
-  // write the sorted order back (std::sort is in place, featureAssociation.cpp:285) and build scan lists
   for (int j = 0; j < 6; ++j) {
     const int sp = sh_sp[j], ep = sh_ep[j];
     if (sp >= ep) continue;
-    for (int t = threadIdx.x; t <= ep - sp; t += EX_THREADS) {
+    for (int t = threadIdx.x; t <= ep - sp; t += SORT_THREADS) {
       int ind;
       if (t < ep - sp) {
         const unsigned long long k = keys[j * P + t];
@@ -207,128 +175,182 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, in
       } else {
         ind = st.smooth_ind[base + ep];  // position ep is scanned but not sorted (sic)
       }
-      sm_list[j * (P + 1) + t] = ind;
+      const float c = st.curvature[base + ind];
+      const bool ground = st.seg_ground[base + ind] != 0;
+      unsigned e = (unsigned)ind;
+      if (c > p.edge_threshold && !ground) e |= 0x80000000u;   // featureAssociation.cpp:291-293
+      if (c < p.surf_threshold && ground) e |= 0x40000000u;    // featureAssociation.cpp:333-335
+      st.scan_list[base + sp + t] = e;
     }
   }
-  __syncthreads();
+}
 
-  // ---- greedy picks, one warp, sextants strictly in order ----
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int n_sharp = 0, n_lsharp = 0, n_flat = 0;
-    const int colsz = p.N;  // segInfo.segmentedCloudColInd.size()
-    auto in_span = [&](int g) { return g >= span_lo && g < span_hi; };
-    auto get_picked = [&](int g) -> int { return in_span(g) ? (int)sm_picked[g - span_lo] : st.picked[base + g]; };
-    auto set_picked = [&](int g) { if (in_span(g)) sm_picked[g - span_lo] = 1; else st.picked[base + g] = 1; };
-    auto get_curv = [&](int g) -> float { return in_span(g) ? sm_curv[g - span_lo] : st.curvature[base + g]; };
-    auto get_ground = [&](int g) -> int { return in_span(g) ? (int)sm_ground[g - span_lo] : (int)st.seg_ground[base + g]; };
-    auto get_col = [&](int g) -> int { return in_span(g) ? sm_col[g - span_lo] : (int)st.seg_col[base + g]; };
-    auto set_label = [&](int g, int v) { if (in_span(g)) sm_label[g - span_lo] = (signed char)v; else st.cloud_label[base + g] = v; };
-    auto mark_neighbors = [&](int ind) {  // featureAssociation.cpp:306-326 (lane 0 only)
-      set_picked(ind);
-      for (int l = 1; l <= 5; l++) {
-        if (ind + l >= colsz) continue;
-        const int cdiff = abs(get_col(ind + l) - get_col(ind + l - 1));
-        if (cdiff > 10) break;
-        set_picked(ind + l);
-      }
-      for (int l = -1; l >= -5; l--) {
-        if (ind + l < 0) continue;
-        const int cdiff = abs(get_col(ind + l) - get_col(ind + l + 1));
-        if (cdiff > 10) break;
-        set_picked(ind + l);
-      }
-    };
-    for (int j = 0; j < 6; ++j) {
-      const int sp = sh_sp[j], ep = sh_ep[j];
-      if (sp >= ep) continue;
-      const int len = ep - sp + 1;
-      const int* list = sm_list + j * (P + 1);
-      // descending scan for edge points (featureAssociation.cpp:288-328)
-      int largest = 0;
-      int top = len - 1;
-      while (top >= 0 && largest < 20) {
-        const int t = top - lane;
-        bool cand = false;
-        int ind = 0;
-        if (t >= 0) {
-          ind = list[t];
-          cand = get_picked(ind) == 0 && get_curv(ind) > p.edge_threshold && get_ground(ind) == 0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m == 0) { top -= 32; continue; }
-        const int w = __ffs(m) - 1;
-        const int pick = __shfl_sync(0xffffffffu, ind, w);
-        largest++;
-        if (lane == 0) {
-          const float4 pt = st.seg_cloud[base + pick];
-          if (largest <= 2) {
-            set_label(pick, 2);
-            o_sharp[n_sharp] = pt; o_sharp_i[n_sharp] = pick;
-            o_lsharp[n_lsharp] = pt; o_lsharp_i[n_lsharp] = pick;
-          } else {
-            set_label(pick, 1);
-            o_lsharp[n_lsharp] = pt; o_lsharp_i[n_lsharp] = pick;
-          }
-          mark_neighbors(pick);
-        }
-        if (largest <= 2) n_sharp++;
-        n_lsharp++;
-        __syncwarp();
-        top = top - w - 1;
-      }
-      // ascending scan for flat points (featureAssociation.cpp:330-368)
-      int smallest = 0;
-      int bot = 0;
-      while (bot < len) {
-        const int t = bot + lane;
-        bool cand = false;
-        int ind = 0;
-        if (t < len) {
-          ind = list[t];
-          cand = get_picked(ind) == 0 && get_curv(ind) < p.surf_threshold && get_ground(ind) != 0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m == 0) { bot += 32; continue; }
-        const int w = __ffs(m) - 1;
-        const int pick = __shfl_sync(0xffffffffu, ind, w);
-        smallest++;
-        if (lane == 0) {
-          set_label(pick, -1);
-          o_flat[n_flat] = st.seg_cloud[base + pick];
-          o_flat_i[n_flat] = pick;
-          if (smallest < 4) mark_neighbors(pick);  // the 4th pick breaks before the suppression (sic, :339-342)
-        }
-        n_flat++;
-        __syncwarp();
-        if (smallest >= 4) break;
-        bot = bot + w + 1;
-      }
+// ---- 2. greedy picks ----------------------------------------------------------------------------
+// One WARP per (ring, sequence); the six sextants of a ring must run in order because a pick
+// suppresses up to 5 neighbours on either side, across sextant boundaries.  Each step tests 32
+// consecutive scan-list entries at once; the only mutable state is cloudNeighborPicked, kept as
+// bytes in shared memory for the ring's span (other indices go to global memory).
+#define PICK_WARPS 4
+
+__global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
+  extern __shared__ unsigned char sh_picked_all[];  // [PICK_WARPS][H + 32]
+  const DevParams& p = st.p;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ring = blockIdx.x * PICK_WARPS + wid, s = blockIdx.y;
+  if (ring >= p.V) return;
+  const size_t base = (size_t)s * p.N;
+  const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
+  const int a = start - 4, b = end + 6;  // this ring's points are [a, b)
+  const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
+  const int L = max(0, span_hi - span_lo);
+  unsigned char* sm_picked = sh_picked_all + (size_t)wid * (p.H + 32);
+  for (int t = lane; t < L; t += 32) sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
+  __syncwarp();
+  const size_t rs = (size_t)s * p.V + ring;
+  int* o_sharp_i = st.st_sharp_ind + rs * 12;
+  int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
+  int* o_flat_i = st.st_flat_ind + rs * 24;
+  int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+  const int colsz = p.N;  // segInfo.segmentedCloudColInd.size()
+  auto in_span = [&](int g) { return g >= span_lo && g < span_hi; };
+  auto get_picked = [&](int g) -> int { return in_span(g) ? (int)sm_picked[g - span_lo] : st.picked[base + g]; };
+  auto set_picked = [&](int g) { if (in_span(g)) sm_picked[g - span_lo] = 1; else st.picked[base + g] = 1; };
+  // featureAssociation.cpp:306-326 / 344-366: lanes 1..5 handle ind+1..ind+5, lanes 6..10 handle ind-1..ind-5
+  auto mark_neighbors = [&](int ind) {
+    int g = -1;          // index this lane may mark
+    bool bad = false;    // column gap > 10 right before it (stops the loop)
+    bool skip = true;    // `continue` cases: out of range
+    if (lane >= 1 && lane <= 5) {
+      g = ind + lane;
+      if (g < colsz) { skip = false; bad = abs((int)st.seg_col[base + g] - (int)st.seg_col[base + g - 1]) > 10; }
+    } else if (lane >= 6 && lane <= 10) {
+      g = ind - (lane - 5);
+      if (g >= 0) { skip = false; bad = abs((int)st.seg_col[base + g] - (int)st.seg_col[base + g + 1]) > 10; }
     }
-    if (lane == 0) { sh_counts[0] = n_sharp; sh_counts[1] = n_lsharp; sh_counts[2] = n_flat; }
+    const unsigned bm = __ballot_sync(0xffffffffu, bad);
+    const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
+    const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
+    if (lane == 0) set_picked(ind);
+    if (!skip && lane >= 1 && lane <= 5 && lane < stop_f) set_picked(g);
+    if (!skip && lane >= 6 && lane <= 10 && lane < stop_b) set_picked(g);
+    __syncwarp();
+  };
+  for (int j = 0; j < 6; ++j) {
+    const int sp = (start * (6 - j) + end * j) / 6;
+    const int ep = (start * (5 - j) + end * (j + 1)) / 6 - 1;
+    if (sp >= ep) continue;
+    const unsigned* list = st.scan_list + base + sp;
+    const int len = ep - sp + 1;
+    // descending scan for edge points (featureAssociation.cpp:288-328)
+    int largest = 0;
+    int top = len - 1;
+    while (top >= 0 && largest < 20) {
+      const int t = top - lane;
+      bool cand = false;
+      int ind = 0;
+      if (t >= 0) {
+        const unsigned e = list[t];
+        ind = (int)(e & 0x3fffffffu);
+        cand = (e & 0x80000000u) && get_picked(ind) == 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      if (m == 0) { top -= 32; continue; }
+      const int w = __ffs(m) - 1;
+      const int pick = __shfl_sync(0xffffffffu, ind, w);
+      largest++;
+      if (lane == 0) {
+        if (largest <= 2) {
+          st.cloud_label[base + pick] = 2;
+          o_sharp_i[n_sharp] = pick;
+        } else {
+          st.cloud_label[base + pick] = 1;
+        }
+        o_lsharp_i[n_lsharp] = pick;
+      }
+      if (largest <= 2) n_sharp++;
+      n_lsharp++;
+      mark_neighbors(pick);
+      top = top - w - 1;
+    }
+    // ascending scan for flat points (featureAssociation.cpp:330-368)
+    int smallest = 0;
+    int bot = 0;
+    while (bot < len) {
+      const int t = bot + lane;
+      bool cand = false;
+      int ind = 0;
+      if (t < len) {
+        const unsigned e = list[t];
+        ind = (int)(e & 0x3fffffffu);
+        cand = (e & 0x40000000u) && get_picked(ind) == 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      if (m == 0) { bot += 32; continue; }
+      const int w = __ffs(m) - 1;
+      const int pick = __shfl_sync(0xffffffffu, ind, w);
+      smallest++;
+      if (lane == 0) {
+        st.cloud_label[base + pick] = -1;
+        o_flat_i[n_flat] = pick;
+      }
+      n_flat++;
+      if (smallest >= 4) break;  // the 4th pick breaks before the suppression (sic, :339-342)
+      mark_neighbors(pick);
+      bot = bot + w + 1;
+    }
+  }
+  __syncwarp();
+  // persist cloudNeighborPicked for this ring's own range (entries are only ever set to 1 here)
+  for (int t = lane; t < L; t += 32) {
+    const int g = span_lo + t;
+    if (g >= a - 1 && g < b && sm_picked[t]) st.picked[base + g] = 1;
+  }
+  if (lane == 0) {
+    int* o_counts = st.ring_counts + rs * 8;
+    o_counts[0] = n_sharp;
+    o_counts[1] = n_lsharp;
+    o_counts[2] = n_flat;
+  }
+}
+
+// ---- 3. less-flat collection + per-ring VoxelGrid ----------------------------------------------
+#define LF_THREADS 256
+
+__global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
+  extern __shared__ unsigned long long lf_keys[];  // [pow2(H)] then int lfpos[H]
+  __shared__ int warp_tot[33];
+  __shared__ int sh_sp[6], sh_ep[6];
+  __shared__ int sh_imn[3], sh_imx[3];
+  const DevParams& p = st.p;
+  const int ring = blockIdx.x, s = blockIdx.y;
+  const size_t base = (size_t)s * p.N;
+  int hp2 = 1;
+  while (hp2 < p.H) hp2 <<= 1;
+  unsigned long long* keys = lf_keys;
+  int* sm_lfpos = (int*)(lf_keys + hp2);
+  const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
+  const size_t rs = (size_t)s * p.V + ring;
+  float4* o_lflat = st.st_less_flat + rs * p.H;
+  int* o_counts = st.ring_counts + rs * 8;
+  if (threadIdx.x < 6) {
+    const int j = threadIdx.x;
+    sh_sp[j] = (start * (6 - j) + end * j) / 6;
+    sh_ep[j] = (start * (5 - j) + end * (j + 1)) / 6 - 1;
   }
   __syncthreads();
-  // persist the mutated per-point state of this ring's span (only entries this block may have changed)
-  for (int t = threadIdx.x; t < L; t += EX_THREADS) {
-    const int g = span_lo + t;
-    if (g >= a - 1 && g < b) {
-      if (sm_picked[t]) st.picked[base + g] = 1;
-      st.cloud_label[base + g] = (int)sm_label[t];
-    }
-  }
-  // ---- less-flat collection (featureAssociation.cpp:370-374): by POSITION k over the active sextants ----
+  // less-flat collection (featureAssociation.cpp:370-374): by POSITION k over the active sextants
   int n_raw = 0;
   {
     const int k_lo = sh_sp[0], k_hi = sh_ep[5];
     int run = 0;
-    for (int k0 = k_lo; k0 <= k_hi; k0 += EX_THREADS) {
+    for (int k0 = k_lo; k0 <= k_hi; k0 += LF_THREADS) {
       const int k = k0 + threadIdx.x;
       int f = 0;
-      if (k <= k_hi) {
+      if (k <= k_hi && k >= 0 && k < p.N) {
         bool active = false;
 #pragma unroll
         for (int j = 0; j < 6; ++j) active = active || (sh_sp[j] < sh_ep[j] && k >= sh_sp[j] && k <= sh_ep[j]);
-        if (active && k >= span_lo && k < span_hi && sm_label[k - span_lo] <= 0) f = 1;
+        if (active && st.cloud_label[base + k] <= 0) f = 1;
       }
       int total;
       const int ex = block_exclusive_scan(f, warp_tot, &total);
@@ -338,14 +360,14 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, in
     n_raw = run;
   }
   __syncthreads();
-  // ---- pcl::VoxelGrid, leaf 0.2 (featureAssociation.cpp:101,377-381; algorithm: SURVEY.md section 8 f1) ----
+  // pcl::VoxelGrid, leaf 0.2 (featureAssociation.cpp:101,377-381; algorithm: SURVEY.md section 8 f1)
   int n_ds = 0;
   if (n_raw > 0) {
     const float inv = 1.0f / 0.2f;
     if (threadIdx.x < 3) { sh_imn[threadIdx.x] = f2ord(FLT_MAX); sh_imx[threadIdx.x] = f2ord(-FLT_MAX); }
     __syncthreads();
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int t = threadIdx.x; t < n_raw; t += EX_THREADS) {
+    for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) {
       const float4 q = st.seg_cloud[base + sm_lfpos[t]];
       mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
       mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
@@ -374,14 +396,14 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, in
     const long long dz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
     if (dx * dy * dz > 2147483647LL) {
       // PCL refuses to filter (index overflow) and returns the input unchanged
-      for (int t = threadIdx.x; t < n_raw; t += EX_THREADS) o_lflat[t] = st.seg_cloud[base + sm_lfpos[t]];
+      for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) o_lflat[t] = st.seg_cloud[base + sm_lfpos[t]];
       n_ds = n_raw;
     } else {
       const int minb0 = (int)floorf(bmn[0] * inv), minb1 = (int)floorf(bmn[1] * inv), minb2 = (int)floorf(bmn[2] * inv);
       const int div0 = (int)floorf(bmx[0] * inv) - minb0 + 1, div1 = (int)floorf(bmx[1] * inv) - minb1 + 1;
       int n2 = 1;
       while (n2 < n_raw) n2 <<= 1;
-      for (int t = threadIdx.x; t < n2; t += EX_THREADS) {
+      for (int t = threadIdx.x; t < n2; t += LF_THREADS) {
         unsigned long long k = ~0ull;
         if (t < n_raw) {
           const float4 q = st.seg_cloud[base + sm_lfpos[t]];
@@ -396,7 +418,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, in
       __syncthreads();
       bitonic_sort_u64(keys, n2, n2);
       int run = 0;
-      for (int t0 = 0; t0 < n_raw; t0 += EX_THREADS) {
+      for (int t0 = 0; t0 < n_raw; t0 += LF_THREADS) {
         const int t = t0 + threadIdx.x;
         int head = 0;
         if (t < n_raw) head = (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
@@ -420,19 +442,16 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract_features(DevState st, in
     }
   }
   if (threadIdx.x == 0) {
-    o_counts[0] = sh_counts[0];
-    o_counts[1] = sh_counts[1];
-    o_counts[2] = sh_counts[2];
     o_counts[3] = n_ds;
     o_counts[4] = n_raw;
   }
-  (void)S;
 }
 
 __global__ void __launch_bounds__(256) k_feature_compact(DevState st) {
   __shared__ int sh_off[4];
   const DevParams& p = st.p;
   const int ring = blockIdx.x, s = blockIdx.y;
+  const size_t base = (size_t)s * p.N;
   if (threadIdx.x < 4) sh_off[threadIdx.x] = 0;
   __syncthreads();
   if (threadIdx.x < ring) {
@@ -446,16 +465,19 @@ __global__ void __launch_bounds__(256) k_feature_compact(DevState st) {
   const int* rc = st.ring_counts + ((size_t)s * p.V + ring) * 8;
   const size_t rs = (size_t)s * p.V + ring;
   for (int t = threadIdx.x; t < rc[0]; t += blockDim.x) {
-    st.corner_sharp[(size_t)s * p.cap_sharp + sh_off[0] + t] = st.st_sharp[rs * 12 + t];
-    st.corner_sharp_ind[(size_t)s * p.cap_sharp + sh_off[0] + t] = st.st_sharp_ind[rs * 12 + t];
+    const int ind = st.st_sharp_ind[rs * 12 + t];
+    st.corner_sharp[(size_t)s * p.cap_sharp + sh_off[0] + t] = st.seg_cloud[base + ind];
+    st.corner_sharp_ind[(size_t)s * p.cap_sharp + sh_off[0] + t] = ind;
   }
   for (int t = threadIdx.x; t < rc[1]; t += blockDim.x) {
-    st.corner_less_sharp[(size_t)s * p.cap_less_sharp + sh_off[1] + t] = st.st_less_sharp[rs * 120 + t];
-    st.corner_less_sharp_ind[(size_t)s * p.cap_less_sharp + sh_off[1] + t] = st.st_less_sharp_ind[rs * 120 + t];
+    const int ind = st.st_less_sharp_ind[rs * 120 + t];
+    st.corner_less_sharp[(size_t)s * p.cap_less_sharp + sh_off[1] + t] = st.seg_cloud[base + ind];
+    st.corner_less_sharp_ind[(size_t)s * p.cap_less_sharp + sh_off[1] + t] = ind;
   }
   for (int t = threadIdx.x; t < rc[2]; t += blockDim.x) {
-    st.surf_flat[(size_t)s * p.cap_flat + sh_off[2] + t] = st.st_flat[rs * 24 + t];
-    st.surf_flat_ind[(size_t)s * p.cap_flat + sh_off[2] + t] = st.st_flat_ind[rs * 24 + t];
+    const int ind = st.st_flat_ind[rs * 24 + t];
+    st.surf_flat[(size_t)s * p.cap_flat + sh_off[2] + t] = st.seg_cloud[base + ind];
+    st.surf_flat_ind[(size_t)s * p.cap_flat + sh_off[2] + t] = ind;
   }
   for (int t = threadIdx.x; t < rc[3]; t += blockDim.x)
     st.surf_less_flat[(size_t)s * p.N + sh_off[3] + t] = st.st_less_flat[rs * p.H + t];
@@ -476,18 +498,30 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
     dim3 grid((p.N + FP_THREADS - 1) / FP_THREADS, p.B);
     LL_LAUNCH(ctx, "k_feature_prep", k_feature_prep<<<grid, FP_THREADS, 0, ctx.stream>>>(st));
   }
+  const dim3 grid_rings(p.V, p.B);
   {
     const int P = next_pow2(p.H / 6 + 2);
-    const int sort_cap = max(6 * P, next_pow2(p.H));
-    const int Lcap = p.H + 16;
-    const size_t smem = (size_t)sort_cap * 8 + (size_t)Lcap * 4 * 2 + (size_t)6 * (P + 1) * 4 + (size_t)p.H * 4 + (size_t)Lcap * 3 + 16;
+    const size_t smem = (size_t)6 * P * 8;
     static size_t configured = 0;
     if (smem > configured) {
-      cudaFuncSetAttribute(k_extract_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_feature_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;
     }
-    dim3 grid(p.V, p.B);
-    LL_LAUNCH(ctx, "k_extract_features", k_extract_features<<<grid, EX_THREADS, smem, ctx.stream>>>(st, P, sort_cap));
-    LL_LAUNCH(ctx, "k_feature_compact", k_feature_compact<<<grid, 256, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_feature_sort", k_feature_sort<<<grid_rings, SORT_THREADS, smem, ctx.stream>>>(st, P));
   }
+  {
+    const size_t smem = (size_t)PICK_WARPS * (p.H + 32);
+    LL_LAUNCH(ctx, "k_feature_pick",
+              k_feature_pick<<<dim3((p.V + PICK_WARPS - 1) / PICK_WARPS, p.B), PICK_WARPS * 32, smem, ctx.stream>>>(st));
+  }
+  {
+    const size_t smem = (size_t)next_pow2(p.H) * 8 + (size_t)p.H * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaFuncSetAttribute(k_feature_lessflat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    LL_LAUNCH(ctx, "k_feature_lessflat", k_feature_lessflat<<<grid_rings, LF_THREADS, smem, ctx.stream>>>(st));
+  }
+  LL_LAUNCH(ctx, "k_feature_compact", k_feature_compact<<<grid_rings, 256, 0, ctx.stream>>>(st));
 }

@@ -32,6 +32,7 @@ __device__ __forceinline__ void warp_nn1(const HashGrid& g, int s, float qx, flo
                                          float* out_d2, int* out_idx) {
   const int lane = threadIdx.x & 31;
   const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+  const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
   const float4* pts = g.sorted + (size_t)s * g.cap;
   const int cx = grid_cell(qx, g.inv_cell), cy = grid_cell(qy, g.inv_cell), cz = grid_cell(qz, g.inv_cell);
   float best = max_d2;
@@ -45,6 +46,7 @@ __device__ __forceinline__ void warp_nn1(const HashGrid& g, int s, float qx, flo
       const int dy = rem / side - r, dx = rem % side - r;
       if (max(max(abs(dx), abs(dy)), abs(dz)) != r) continue;  // inner cells were visited at smaller r
       const uint32_t h = grid_hash(cx + dx, cy + dy, cz + dz, g.tbl);
+      if (!((occ[h >> 5] >> (h & 31)) & 1u)) continue;  // empty bucket
       const int b0 = cs[h], b1 = cs[h + 1];
       for (int k = b0; k < b1; ++k) {
         const float4 q = pts[k];

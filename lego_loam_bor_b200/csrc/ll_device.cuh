@@ -21,6 +21,10 @@
 struct HashGrid {
   int* cell_start;   // [B][tbl+1] exclusive prefix of bucket counts
   int* cursor;       // [B][tbl]   fill cursors
+  int* cnt;          // [B][tbl]   bucket counters (zero at rest)
+  unsigned* occ;     // [B][tbl/32] bit h set <=> bucket h is not empty (tested before touching cell_start)
+  int* tile_tot;     // [B][ntiles] per-tile counter sums of the scan
+  int ntiles;        // tbl / 4096
   float4* sorted;    // [B][cap]   points bucket by bucket; .w carries the original index (int bits)
   int* count;        // [B]        points indexed
   float inv_cell;    // 1 / cell size
@@ -78,10 +82,11 @@ struct DevState {
   int* cloud_label;            // [B][N] cloudLabel (persistent)
   float* smooth_val;           // [B][N] cloudSmoothness[].value (persistent, sorted in place)
   int* smooth_ind;             // [B][N] cloudSmoothness[].ind
+  unsigned* scan_list;         // [B][N] per sextant [sp, ep]: ind | edge candidate << 31 | flat candidate << 30
   // per-ring staging written by the extraction kernel
-  float4* st_sharp;  int* st_sharp_ind;       // [B][V][12]
-  float4* st_less_sharp; int* st_less_sharp_ind;  // [B][V][120]
-  float4* st_flat; int* st_flat_ind;          // [B][V][24]
+  int* st_sharp_ind;       // [B][V][12]
+  int* st_less_sharp_ind;  // [B][V][120]
+  int* st_flat_ind;        // [B][V][24]
   float4* st_less_flat;                       // [B][V][H]
   int* ring_counts;                           // [B][V][8]: sharp, lessSharp, flat, lessFlatDS, lessFlatRaw
   // compacted feature clouds of the current frame
@@ -122,6 +127,9 @@ struct DevState {
   float4* vox_tmp_out;                           // [B][cap_outlier] laserCloudOutlierLastDS
   int* vox_tmp_counts;                           // [B][2]
   int vox_cap;
+  int* map_knn;                                  // [B][map_knn_cap][5] neighbour indices of every scan point (-1: none)
+  float4* map_knn_state;                         // [B][map_knn_cap] query position of the last full search + squared 6th-NN distance
+  int map_knn_cap;
   double* map_partials;                          // [B][max_blocks][28]
   double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)
   int* map_rows;                                 // [B][max_blocks]
@@ -174,6 +182,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int* t
 }
 
 __device__ __forceinline__ uint32_t grid_hash(int ix, int iy, int iz, int tbl) {
-  const uint32_t h = (uint32_t)ix * 73856093u ^ (uint32_t)iy * 19349663u ^ (uint32_t)iz * 83492791u;
-  return (h ^ (h >> 15)) & (uint32_t)(tbl - 1);
+  // multiply-add of the three cell coordinates followed by a full avalanche (lowbias32): neighbouring
+  // cells land in unrelated buckets, so an empty neighbour cell rarely aliases an occupied bucket
+  uint32_t h = (uint32_t)ix * 0x9E3779B1u + (uint32_t)iy * 0x85EBCA77u + (uint32_t)iz * 0xC2B2AE3Du;
+  h ^= h >> 16;
+  h *= 0x7feb352du;
+  h ^= h >> 15;
+  h *= 0x846ca68bu;
+  h ^= h >> 16;
+  return h & (uint32_t)(tbl - 1);
 }

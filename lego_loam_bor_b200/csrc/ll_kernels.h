@@ -66,9 +66,10 @@ void launch_segmentation(LaunchCtx& ctx, DevState& st);
 void launch_feature_extraction(LaunchCtx& ctx, DevState& st);
 // odometry.cu: first-frame initialisation / updateTransformation + integrateTransformation + publishCloudsLast
 void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame);
-// hashgrid.cu: build the k-NN structure over `pts` ([B][stride] points, counts[B*count_stride + count_off])
-void launch_grid_build(LaunchCtx& ctx, HashGrid& g, int B, const float4* pts, int stride, const int* counts,
-                       int count_stride, int count_off, const int* enable /* [B] or null */, int enable_stride);
+// hashgrid.cu: build the k-NN structures over two clouds at once ([B][stride] points, counts[s*cstride+coff])
+void launch_grid_build2(LaunchCtx& ctx, int B, HashGrid& g0, const float4* pts0, int stride0, const int* counts0,
+                        int cstride0, int coff0, HashGrid& g1, const float4* pts1, int stride1, const int* counts1,
+                        int cstride1, int coff1, const int* enable /* [B*enable_stride] or null */, int enable_stride);
 // mapping.cu: scan2MapOptimization and downsampleCurrentScan
 void launch_scan_to_map(LaunchCtx& ctx, DevState& st);
 void launch_map_predict_pose(LaunchCtx& ctx, DevState& st);

@@ -5,11 +5,11 @@
 //       last-frame cloud (hash grid instead of the kd-tree) and the reference's ring-window scans,
 //       with its loop bounds and visiting-order tie-breaks.  Runs for LM
 //       iteration 0 of each stage for all sequences at once.
-//   k_odom_lm<SURF|CORNER>      one block per sequence: the whole <=25-iteration LM loop of one stage
-//       without host round trips.  Per iteration: residual + Jacobian row per feature, J^T J / J^T r
+//   k_odom_lm<SURF|CORNER>      one block per sequence: five LM iterations of one stage per launch
+//       (5 launches per stage, no-ops once converged), no host round trips.  Per iteration: residual + Jacobian row per feature, J^T J / J^T r
 //       as exact double products reduced by warp shuffles + a fixed-order cross-warp sum, 3x3
 //       column-pivoted Householder solve, degeneracy test at iteration 0, convergence test.
-//       Correspondences are refreshed in-kernel at iterations 5, 10, 15, 20 (featureAssociation.cpp:511).
+//       Correspondences are refreshed by k_odom_search before iterations 0, 5, 10, 15, 20 (featureAssociation.cpp:511).
 //   k_odom_finish               integrateTransformation (one thread per sequence)
 //   k_publish_clouds_last       TransformToEnd on the less-sharp / less-flat clouds into the
 //       "last" buffers, adjustOutlierCloud, counts and the kd-tree-rebuild condition.
@@ -187,14 +187,14 @@ template <int STAGE>
 __global__ void __launch_bounds__(256) k_odom_search(DevState st) {
   const DevParams& p = st.p;
   const int s = blockIdx.y;
-  if (!odom_guard(st, s)) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (!odom_guard(st, s) || st.odom_flags[s * 4 + 1]) return;  // flag 1: this stage has converged
   const int n = st.feat_counts[s * 4 + (STAGE == STAGE_SURF ? 2 : 0)];
-  if (warp >= n) return;
   float T[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) T[k] = st.transform_cur[s * 6 + k];
-  warp_find_correspondence<STAGE>(st, s, warp, T, threadIdx.x & 31);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps)
+    warp_find_correspondence<STAGE>(st, s, i, T, threadIdx.x & 31);
 }
 
 // One accepted correspondence -> one row [a0 a1 a2 | b] of the 3-column system.
@@ -335,8 +335,11 @@ __device__ __forceinline__ Row3 corner_row(const DevState& st, int s, int i, con
 #define LM_THREADS 512
 #define LM_WARPS (LM_THREADS / 32)
 
+// Iterations [it_begin, it_begin + 5) of one LM stage; the correspondences were refreshed by
+// k_odom_search right before (featureAssociation.cpp:511: every 5th iteration).  A sequence that has
+// converged (or failed the guard) turns the remaining launches of its stage into no-ops.
 template <int STAGE>
-__global__ void __launch_bounds__(LM_THREADS) k_odom_lm(DevState st) {
+__global__ void __launch_bounds__(LM_THREADS) k_odom_lm(DevState st, int it_begin) {
   __shared__ float sT[6];
   __shared__ double sh_part[LM_WARPS][10];
   __shared__ int sh_state[4];  // 0: stop flag, 1: iterations run
@@ -344,23 +347,19 @@ __global__ void __launch_bounds__(LM_THREADS) k_odom_lm(DevState st) {
   const int s = blockIdx.x;
   const bool surf = (STAGE == STAGE_SURF);
   if (!odom_guard(st, s)) {
-    if (threadIdx.x == 0) st.odom_iters[s * 2 + STAGE] = 0;
+    if (threadIdx.x == 0 && it_begin == 0) st.odom_iters[s * 2 + STAGE] = 0;
     return;
   }
+  if (st.odom_flags[s * 4 + 1]) return;
   const int n = st.feat_counts[s * 4 + (surf ? 2 : 0)];
   if (threadIdx.x < 6) sT[threadIdx.x] = st.transform_cur[s * 6 + threadIdx.x];
-  if (threadIdx.x == 0) { sh_state[0] = 0; sh_state[1] = 0; }
+  if (threadIdx.x == 0) { sh_state[0] = 0; sh_state[1] = it_begin; }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int iter = 0; iter < 25; ++iter) {
+  for (int iter = it_begin; iter < it_begin + 5; ++iter) {
     float T[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) T[k] = sT[k];
-    if (iter > 0 && iter % 5 == 0) {
-      // refresh correspondences (iteration 0 was done by k_odom_search with the same transform)
-      for (int i = wid; i < n; i += LM_WARPS) warp_find_correspondence<STAGE>(st, s, i, T, lane);
-      __syncthreads();
-    }
     double acc[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) acc[k] = 0.0;
@@ -433,7 +432,15 @@ __global__ void __launch_bounds__(LM_THREADS) k_odom_lm(DevState st) {
     if (sh_state[0]) break;
   }
   if (threadIdx.x < 6) st.transform_cur[s * 6 + threadIdx.x] = sT[threadIdx.x];
-  if (threadIdx.x == 0) st.odom_iters[s * 2 + STAGE] = sh_state[1];
+  if (threadIdx.x == 0) {
+    st.odom_iters[s * 2 + STAGE] = sh_state[1];
+    if (sh_state[0]) st.odom_flags[s * 4 + 1] = 1;
+  }
+}
+
+__global__ void k_odom_stage_begin(DevState st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < st.p.B) st.odom_flags[s * 4 + 1] = 0;
 }
 
 __device__ __forceinline__ void accumulate_rotation(float cx, float cy, float cz, float lx, float ly, float lz,
@@ -518,14 +525,23 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
 void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
   const DevParams& p = st.p;
   if (!first_frame) {
-    LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<dim3((p.cap_flat * 32 + 255) / 256, p.B), 256, 0, ctx.stream>>>(st));
-    LL_LAUNCH(ctx, "k_odom_lm_surf", k_odom_lm<STAGE_SURF><<<p.B, LM_THREADS, 0, ctx.stream>>>(st));
-    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp * 32 + 255) / 256, p.B), 256, 0, ctx.stream>>>(st));
-    LL_LAUNCH(ctx, "k_odom_lm_corner", k_odom_lm<STAGE_CORNER><<<p.B, LM_THREADS, 0, ctx.stream>>>(st));
+    const dim3 g_surf(24, p.B), g_corner(24, p.B);  // 24 x 8 warps per sequence, each looping over its feature points
+    const int g_seq = (p.B + 63) / 64;
+    // surf stage: <= 25 iterations = 5 x (search, 5 LM iterations)   (featureAssociation.cpp:1216-1224)
+    LL_LAUNCH(ctx, "k_odom_stage_begin", k_odom_stage_begin<<<g_seq, 64, 0, ctx.stream>>>(st));
+    for (int c = 0; c < 5; ++c) {
+      LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<g_surf, 256, 0, ctx.stream>>>(st));
+      LL_LAUNCH(ctx, "k_odom_lm_surf", k_odom_lm<STAGE_SURF><<<p.B, LM_THREADS, 0, ctx.stream>>>(st, 5 * c));
+    }
+    // corner stage (featureAssociation.cpp:1226-1234)
+    LL_LAUNCH(ctx, "k_odom_stage_begin", k_odom_stage_begin<<<g_seq, 64, 0, ctx.stream>>>(st));
+    for (int c = 0; c < 5; ++c) {
+      LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<g_corner, 256, 0, ctx.stream>>>(st));
+      LL_LAUNCH(ctx, "k_odom_lm_corner", k_odom_lm<STAGE_CORNER><<<p.B, LM_THREADS, 0, ctx.stream>>>(st, 5 * c));
+    }
     LL_LAUNCH(ctx, "k_odom_finish", k_odom_finish<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
   }
   LL_LAUNCH(ctx, "k_publish_clouds_last", k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0));
-  launch_grid_build(ctx, st.grid_corner_last, p.B, st.corner_last, p.cap_less_sharp, st.last_counts, 2, 0,
-                    st.odom_flags + 2, 4);
-  launch_grid_build(ctx, st.grid_surf_last, p.B, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4);
+  launch_grid_build2(ctx, p.B, st.grid_corner_last, st.corner_last, p.cap_less_sharp, st.last_counts, 2, 0,
+                     st.grid_surf_last, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4);
 }

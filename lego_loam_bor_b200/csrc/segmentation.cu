@@ -126,7 +126,19 @@ __global__ void __launch_bounds__(256) k_ccl_merge(DevState st) {
   const float r = range[cell];
   if (row + 1 < p.V) {
     const int up = cell + p.H;
-    if (__ldcg(parent + up) >= 0 && seg_edge(r, range[up], p.sin_ay, p.cos_ay, p.seg_tan_theta)) uf_union(parent, cell, up);
+    const int pu = __ldcg(parent + up);
+    if (pu >= 0 && seg_edge(r, range[up], p.sin_ay, p.cos_ay, p.seg_tan_theta)) {
+      // The same two horizontal runs usually overlap over many columns; only the leftmost column of an
+      // overlap has to union them.  Skip when the left neighbours are in the same two components and
+      // are vertically connected themselves (that column, or one further left, does the union).
+      bool skip = false;
+      if (col > 0) {
+        const int pl = __ldcg(parent + cell - 1), plu = __ldcg(parent + up - 1);
+        skip = pl >= 0 && plu >= 0 && pl == __ldcg(parent + cell) && plu == pu &&
+               seg_edge(range[cell - 1], range[up - 1], p.sin_ay, p.cos_ay, p.seg_tan_theta);
+      }
+      if (!skip) uf_union(parent, cell, up);
+    }
   }
   if (col == p.H - 1 && p.H > 1) {
     const int w = cell - col;  // column 0 of the same row (imageProjection.cpp:446-451)
