@@ -71,6 +71,24 @@ def local_maps(cfg, seq):
 
 
 # --------------------------------------------------------------------------------------------
+# multi-GPU: independent sequences are sharded over ranks, no data-path collective (replicas only)
+
+
+def shard_sequences(rank, batch, unique=0):
+    """Sequence ids of the `batch` slots of `rank` (weak scaling: every rank owns its own sequences).
+    With unique < batch the rank's distinct sequences are replicated over its slots."""
+    u = unique or batch
+    return [rank * batch + (k % u) for k in range(batch)]
+
+
+def aggregate_throughput(world, batch, steps, local_ms, reduce_max=None):
+    """Whole-job scans/s: all ranks' scans divided by the slowest rank's device time.
+    reduce_max: callable mapping a local float to the max over ranks (identity for one rank)."""
+    worst_ms = reduce_max(local_ms) if reduce_max else local_ms
+    return world * batch * steps / (worst_ms * 1e-3), worst_ms
+
+
+# --------------------------------------------------------------------------------------------
 # clocks
 
 
@@ -277,7 +295,7 @@ def main():
     use_map = not args.no_map
     prof_steps = 5                               # one mapping cycle with every kernel timed (picks the roofline kernel)
     n_frames = 1 + args.warmup + prof_steps + args.steps
-    seq_ids = [rank * B + (k % U) for k in range(B)]   # weak scaling: every rank has its own sequences
+    seq_ids = shard_sequences(rank, B, U)   # weak scaling: every rank has its own sequences
     cfg, scans, counts, N, gen_s = gen_dataset(params, seq_ids, n_frames)
     stride = N
     # pinned host dataset [F][B][stride][4] and a device-resident copy
@@ -399,9 +417,8 @@ def main():
     times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
-    value = world * B * args.steps / (dev_ms * 1e-3)
-    e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    value, dev_ms = aggregate_throughput(world, B, args.steps, float(times[0]))
+    e2e_value, e2e_ms = aggregate_throughput(world, B, e2e_steps, float(times[1]))
 
     if rank == 0:
         peaks = {}

@@ -35,8 +35,9 @@ BUFFERS = {
 def build(force=False):
     """make port (+ ref when /root/reference is present).  Prebuilt files are used as they are
     when the sources are not newer (the GPU box has no /root/reference)."""
-    target = "all" if os.path.exists(os.path.join(REFERENCE, "LeGO-LOAM/include/lego_loam/nanoflann.hpp")) else "port"
-    args = ["make", "-C", HERE, target] + (["-B"] if force else [])
+    have_ref = os.path.exists(os.path.join(REFERENCE, "LeGO-LOAM/include/lego_loam/nanoflann.hpp"))
+    targets = ["all"] if have_ref else ["port", "smallmat"]
+    args = ["make", "-C", HERE] + targets + (["-B"] if force else [])
     subprocess.check_call(args, stdout=subprocess.DEVNULL)
 
 
