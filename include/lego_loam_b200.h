@@ -118,6 +118,8 @@ typedef enum ll_buffer {
   LL_BUF_MAP_TRACE = 35, /* f64[10][34] per scan-to-map iteration: 21 J^T J (upper), 6 J^T r, rows, 6 step X */
   LL_BUF_TRANSFORM_BEF_MAPPED = 36, /* f32[6] */
   LL_BUF_TRANSFORM_AFT_MAPPED = 37, /* f32[6] */
+  LL_BUF_SCAN_SURF_DS = 38,    /* pt[..] laserCloudSurfLastDS (before the outlier cloud is appended) */
+  LL_BUF_SCAN_OUTLIER_DS = 39, /* pt[..] laserCloudOutlierLastDS */
   LL_BUF_COUNT_
 } ll_buffer;
 

@@ -25,13 +25,18 @@ def needs_build():
     if not os.path.exists(LIB_CUDA):
         return True
     t = os.path.getmtime(LIB_CUDA)
+    from ._paths import PKG
     deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
-        glob.glob(os.path.join(INCLUDE, "*.h"))
+        glob.glob(os.path.join(INCLUDE, "*.h")) + glob.glob(os.path.join(PKG, "host", "*.cpp")) + \
+        glob.glob(os.path.join(PKG, "host", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        from ._paths import PKG
+        if not os.path.exists(os.path.join(PKG, "host", "sequence_driver")):
+            build_host()
         return LIB_CUDA
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -57,7 +62,19 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed; see " + log_path)
     subprocess.check_call([nvcc, "-shared", "-o", LIB_CUDA] + objs + ["-lcudart"])
+    build_host()
     return LIB_CUDA
+
+
+def build_host():
+    """The C++ host mirror of the reference's stage classes + the bag-less sequence driver."""
+    from ._paths import PKG
+    host = os.path.join(PKG, "host")
+    exe = os.path.join(host, "sequence_driver")
+    srcs = [os.path.join(host, "lego_loam_host.cpp"), os.path.join(host, "sequence_driver.cpp")]
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-g", "-pthread", "-I", INCLUDE] + srcs +
+                          ["-L", PKG, "-llego_loam_b200", "-Wl,-rpath," + PKG, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe])
+    return exe
 
 
 if __name__ == "__main__":

@@ -417,6 +417,7 @@ int ll_map_predict_pose(ll_handle* h) {
 int ll_scan_to_map(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (!h->map_set) { h->err = "ll_scan_to_map: no local map set"; return LL_ERR_STATE; }
+  if (h->st.cap_map_corner == 0 || h->st.cap_map_surf == 0) return LL_OK;  // empty maps: the guard of :1316 fails for every sequence
   launch_scan_to_map(h->ctx, h->st);
   return check_stream(h, "ll_scan_to_map");
 }
@@ -590,6 +591,8 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_TRANSFORM_TOBE_MAPPED: src = st.transform_tobe_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_MAP_ITERS: src = st.map_iters + seq * 2; elem = 4; n = 2; break;
     case LL_BUF_MAP_TRACE: src = st.map_trace + (size_t)seq * 340; elem = 8; n = 340; break;
+    case LL_BUF_SCAN_SURF_DS: COUNTED(st.vox_tmp_surf, 16, N, st.vox_tmp_counts + seq * 2 + 0); break;
+    case LL_BUF_SCAN_OUTLIER_DS: COUNTED(st.vox_tmp_out, 16, (size_t)st.cap_outlier, st.vox_tmp_counts + seq * 2 + 1); break;
     case LL_BUF_TRANSFORM_BEF_MAPPED: src = st.transform_bef_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_TRANSFORM_AFT_MAPPED: src = st.transform_aft_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_OUTLIER_LAST: COUNTED(st.outlier_last, 16, (size_t)st.cap_outlier, st.odom_flags + seq * 4 + 3); break;

@@ -1,0 +1,69 @@
+// sequence_driver.cpp -- bag-less replacement of the reference's main.cpp bag loop (main.cpp:37-47,72-76):
+// builds the two channels and the three stage objects and feeds a recorded sequence of scans to
+// ImageProjection::cloudHandler, one message at a time, with blocking channels (the reference's
+// deterministic rosbag mode).
+//
+//   sequence_driver <config: A|B|C|T> <scans.bin> <poses.out>
+//
+// scans.bin: int32 n_frames, then per frame: int32 n_points, n_points * 4 float32 (x, y, z, intensity).
+// poses.out: per frame one text line: frame, transformSum[6], transformAftMapped[6], key frames, map cycles.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "lego_loam_host.h"
+
+using namespace lego_loam;
+
+static LegoLoamParams config(const char* name) {
+  LegoLoamParams p;
+  ll_default_params(&p);
+  if (!strcmp(name, "B")) { p.num_vertical_scans = 32; p.ground_scan_index = 15; }
+  else if (!strcmp(name, "C")) { p.num_vertical_scans = 64; p.num_horizontal_scans = 2048; p.ground_scan_index = 31; p.vertical_angle_bottom = -16.6f; p.vertical_angle_top = 16.6f; }
+  else if (!strcmp(name, "T")) { p.num_horizontal_scans = 450; }
+  return p;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 4) { fprintf(stderr, "usage: %s <A|B|C|T> <scans.bin> <poses.out>\n", argv[0]); return 2; }
+  const LegoLoamParams params = config(argv[1]);
+  FILE* f = fopen(argv[2], "rb");
+  if (!f) { fprintf(stderr, "Unable to open [%s]\n", argv[2]); return 1; }  // main.cpp:32-33
+  int32_t n_frames = 0;
+  if (fread(&n_frames, 4, 1, f) != 1) return 1;
+  FILE* out = fopen(argv[3], "w");
+  if (!out) return 1;
+  try {
+    std::shared_ptr<Device> dev(new Device(params));
+    Channel<ProjectionOut> projection_out_channel(true);
+    Channel<AssociationOut> association_out_channel(true);  // bag mode: blocking (main.cpp:38)
+    ImageProjection IP(params, dev, projection_out_channel);
+    FeatureAssociation FA(params, dev, projection_out_channel, association_out_channel);
+    MapOptimization MO(params, dev, association_out_channel);
+    std::vector<float> scan;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n_frames; ++i) {
+      int32_t n = 0;
+      if (fread(&n, 4, 1, f) != 1) break;
+      scan.resize((size_t)n * 4);
+      if (n && fread(scan.data(), 16, n, f) != (size_t)n) break;
+      IP.cloudHandler(scan.data(), n, 0.1 * i);
+      dev->waitIdle();
+      float ts[6], am[6];
+      FA.transformSum(ts);
+      MO.transformAftMapped(am);
+      fprintf(out, "%d %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %.9g %zu %zu\n", i, ts[0], ts[1], ts[2], ts[3], ts[4],
+              ts[5], am[0], am[1], am[2], am[3], am[4], am[5], MO.keyFrames(), MO.cycles());
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "Entire sequence processed at %.1fX speed (%d scans, %.3f s)\n", 0.1 * n_frames / sec, n_frames, sec);  // main.cpp:99-102
+  } catch (const std::exception& e) {
+    fprintf(stderr, "fatal: %s\n", e.what());
+    return 1;
+  }
+  fclose(out);
+  fclose(f);
+  return 0;
+}
