@@ -332,9 +332,15 @@ def main():
         gpu.set_scans_device(devdata.data_ptr() + f * frame_bytes, counts[f], stride)
         gpu.process_scans()
 
-    def step_host(f):
+    def upload(f):
         gpu.set_scans_host_ptr(host.data_ptr() + f * frame_bytes, counts[f], stride)
+
+    def step_host(f):
+        """Scan f was staged by upload(f).  Enqueue its processing, stage scan f+1 (its H2D copy overlaps the
+        kernels of scan f: the library double-buffers the input), then read the poses back (synchronises)."""
         gpu.process_scans()
+        if f + 1 < n_frames:
+            upload(f + 1)
         return gpu.poses()
 
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
@@ -392,10 +398,11 @@ def main():
     if use_map:
         seed_map_poses()
     f = 0
+    upload(f)
     step_host(f); f += 1
     for _ in range(min(args.warmup, 3)):
         step_host(f); f += 1
-    e2e_steps = min(args.steps, n_frames - f)
+    e2e_steps = min(args.steps, n_frames - f - 1)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)

@@ -141,7 +141,9 @@ int64_t ll_kernel_launches(const ll_handle* h);
 
 /* Host scans: xyzi[batch][stride_points][4] floats, n_points[batch] valid points each
  * (NaN points must already be removed, as pcl::removeNaNFromPointCloud does).
- * Copies host->device on the handle's stream (async if the memory is pinned). */
+ * Copies host->device on the handle's own copy stream into one of two input buffers (async if the
+ * memory is pinned): the next ll_image_projection consumes it, and calling ll_set_scans_host for scan
+ * f+1 before reading back the results of scan f overlaps that copy with the kernels of scan f. */
 int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, int stride_points);
 /* Same, for scans that already live in device memory (no copy is made; the buffer
  * must stay valid until the next ll_image_projection has been enqueued). */

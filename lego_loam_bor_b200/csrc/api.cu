@@ -27,7 +27,16 @@ struct ll_handle {
   cudaEvent_t slot_ev[16];
   bool slot_used[16] = {false};
   int slot = 0;
-  float4* in_owned = nullptr; // device input buffer used by ll_set_scans_host
+  // ll_set_scans_host double-buffers the input on its own copy stream, so the H2D copy of scan f+1
+  // overlaps the kernels of scan f when the caller sets the next scan before reading back the pose
+  float4* in_buf[2] = {nullptr, nullptr};
+  int* n_in_buf[2] = {nullptr, nullptr};
+  int* n_in_default = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied[2], consumed[2];
+  bool consumed_valid[2] = {false, false};
+  int wr = 0;        // buffer the next ll_set_scans_host writes
+  int pending = -1;  // buffer waiting to be consumed by ll_image_projection
   bool timing = false;
   cudaEvent_t ev[6];
   float stage_ms[5];
@@ -79,7 +88,7 @@ int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell) {
   return LL_OK;
 }
 
-int stage_counts(ll_handle* h, const int32_t* n_points, int stride_points, const char* who) {
+int stage_counts(ll_handle* h, const int32_t* n_points, int stride_points, const char* who, int* dst, cudaStream_t stream) {
   DevState& st = h->st;
   const int B = st.p.B;
   const int slot = h->slot;
@@ -90,8 +99,8 @@ int stage_counts(ll_handle* h, const int32_t* n_points, int stride_points, const
     if (n_points[s] < 0 || n_points[s] > stride_points) { h->err = std::string(who) + ": n_points out of range"; return LL_ERR_INVALID_ARG; }
     stage[s] = n_points[s];
   }
-  CK(cudaMemcpyAsync(st.n_in, stage, sizeof(int32_t) * B, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaEventRecord(h->slot_ev[slot], h->ctx.stream));
+  CK(cudaMemcpyAsync(dst, stage, sizeof(int32_t) * B, cudaMemcpyHostToDevice, stream));
+  CK(cudaEventRecord(h->slot_ev[slot], stream));
   h->slot_used[slot] = true;
   return LL_OK;
 }
@@ -167,8 +176,15 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   st.cap_map_corner = 0; st.cap_map_surf = 0;
   st.map_max_blocks = 96;
   const size_t BN = (size_t)B * N;
-  CK(dev_alloc(h, &st.n_in, B));
-  CK(dev_alloc(h, &h->in_owned, (size_t)B * max_points, false));
+  CK(dev_alloc(h, &h->n_in_default, B));
+  st.n_in = h->n_in_default;
+  for (int b = 0; b < 2; ++b) {
+    CK(dev_alloc(h, &h->in_buf[b], (size_t)B * max_points, false));
+    CK(dev_alloc(h, &h->n_in_buf[b], B));
+    CK(cudaEventCreateWithFlags(&h->copied[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->consumed[b], cudaEventDisableTiming));
+  }
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CK(cudaMallocHost((void**)&h->h_n_in, sizeof(int32_t) * B * 16));
   for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&h->slot_ev[i], cudaEventDisableTiming));
   CK(dev_alloc(h, &st.winner, BN));
@@ -183,7 +199,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.seg_count, B));
   CK(dev_alloc(h, &st.outlier_cloud, (size_t)B * st.cap_outlier)); CK(dev_alloc(h, &st.outlier_count, B));
   CK(dev_alloc(h, &st.curvature, BN)); CK(dev_alloc(h, &st.picked, BN)); CK(dev_alloc(h, &st.cloud_label, BN));
-  CK(dev_alloc(h, &st.smooth_val, BN)); CK(dev_alloc(h, &st.smooth_ind, BN));
+  CK(dev_alloc(h, &st.slot4, (size_t)B * 2)); CK(dev_alloc(h, &st.sext_off, (size_t)B * V * 16));
   CK(dev_alloc(h, &st.st_sharp_ind, (size_t)B * V * 12)); CK(dev_alloc(h, &st.scan_list, BN));
   CK(dev_alloc(h, &st.st_less_sharp_ind, (size_t)B * V * 120));
   CK(dev_alloc(h, &st.st_flat_ind, (size_t)B * V * 24));
@@ -232,6 +248,8 @@ int ll_destroy(ll_handle* h) {
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_n_in) cudaFreeHost(h->h_n_in);
   for (int i = 0; i < 16; ++i) cudaEventDestroy(h->slot_ev[i]);
+  for (int b = 0; b < 2; ++b) { cudaEventDestroy(h->copied[b]); cudaEventDestroy(h->consumed[b]); }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < 6; ++i) cudaEventDestroy(h->ev[i]);
   if (h->ctx.ev_start) {
     for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { cudaEventDestroy(h->ctx.ev_start[i]); cudaEventDestroy(h->ctx.ev_stop[i]); }
@@ -255,8 +273,7 @@ int ll_reset(ll_handle* h) {
   cudaStream_t sm = h->ctx.stream;
   // featureAssociation.cpp:96-157 initializationValue
   CK(cudaMemsetAsync(st.curvature, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.picked, 0, BN * 4, sm));
-  CK(cudaMemsetAsync(st.cloud_label, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.smooth_val, 0, BN * 4, sm));
-  CK(cudaMemsetAsync(st.smooth_ind, 0, BN * 4, sm));
+  CK(cudaMemsetAsync(st.cloud_label, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.slot4, 0, (size_t)p.B * 8, sm));
   CK(cudaMemsetAsync(st.transform_cur, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_sum, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.transform_bef_mapped, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_aft_mapped, 0, (size_t)p.B * 24, sm));
@@ -279,15 +296,19 @@ int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, 
   DevState& st = h->st;
   const int B = st.p.B;
   if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_host: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
-  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_host"); if (rc) return rc; }
+  const int b = h->wr;
+  // the buffer may still be read by the projection kernels of two scans ago
+  if (h->consumed_valid[b]) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[b], 0));
+  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_host", h->n_in_buf[b], h->copy_stream); if (rc) return rc; }
   // one copy per sequence of just the valid points (no batched-memcpy API is used)
   for (int s = 0; s < B; ++s) {
     if (n_points[s] == 0) continue;
-    CK(cudaMemcpyAsync(h->in_owned + (size_t)s * st.p.max_pts, xyzi + (size_t)s * stride_points * 4,
-                       (size_t)n_points[s] * 16, cudaMemcpyHostToDevice, h->ctx.stream));
+    CK(cudaMemcpyAsync(h->in_buf[b] + (size_t)s * st.p.max_pts, xyzi + (size_t)s * stride_points * 4,
+                       (size_t)n_points[s] * 16, cudaMemcpyHostToDevice, h->copy_stream));
   }
-  st.in_pts = h->in_owned;
-  st.in_stride = st.p.max_pts;
+  CK(cudaEventRecord(h->copied[b], h->copy_stream));
+  h->pending = b;
+  h->wr ^= 1;
   return LL_OK;
 }
 
@@ -295,18 +316,33 @@ int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_po
   if (!h || !xyzi_dev || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
   DevState& st = h->st;
   if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_device: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
-  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_device"); if (rc) return rc; }
+  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_device", h->n_in_default, h->ctx.stream); if (rc) return rc; }
+  st.n_in = h->n_in_default;
   st.in_pts = (const float4*)xyzi_dev;
   st.in_stride = stride_points;
+  h->pending = -1;
   return LL_OK;
 }
 
 int ll_image_projection(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  const int pb = h->pending;
+  if (pb >= 0) {
+    // scans staged by ll_set_scans_host: the kernels wait for that copy only
+    CK(cudaStreamWaitEvent(h->ctx.stream, h->copied[pb], 0));
+    h->st.in_pts = h->in_buf[pb];
+    h->st.n_in = h->n_in_buf[pb];
+    h->st.in_stride = h->st.p.max_pts;
+    h->pending = -1;
+  }
   if (!h->st.in_pts) { h->err = "ll_image_projection: no scans set"; return LL_ERR_STATE; }
   h->st.frame_tag += 1;
   if (h->timing) cudaEventRecord(h->ev[0], h->ctx.stream);
   launch_projection(h->ctx, h->st);
+  if (pb >= 0) {
+    CK(cudaEventRecord(h->consumed[pb], h->ctx.stream));  // the input buffer is only read by the projection kernels
+    h->consumed_valid[pb] = true;
+  }
   if (h->timing) cudaEventRecord(h->ev[1], h->ctx.stream);
   launch_segmentation(h->ctx, h->st);
   if (h->timing) cudaEventRecord(h->ev[2], h->ctx.stream);

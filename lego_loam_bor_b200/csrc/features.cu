@@ -1,6 +1,7 @@
 // features.cu -- FeatureAssociation::adjustDistortion / calculateSmoothness / markOccludedPoints /
 // extractFeatures (reference: LeGO-LOAM/src/featureAssociation.cpp:161-383).
 //
+//   (cloudSmoothness is not materialised: see k_feature_sort)
 //   k_feature_prep     one thread per segmented point.  adjustDistortion with the sequential
 //       halfPassed flag resolved from the first-trigger index found by k_seg_emit; the 11-tap
 //       curvature stencil over the FLATTENED range array from a shared-memory tile with a 6-point
@@ -94,8 +95,6 @@ __global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
     st.curvature[base + i] = curv;
     st.picked[base + i] = mark ? 1 : 0;
     st.cloud_label[base + i] = 0;
-    st.smooth_val[base + i] = curv;
-    st.smooth_ind[base + i] = i;
   } else if (mark) {
     st.picked[base + i] = 1;  // outside [5, S-5) the array is never reset
   }
@@ -128,59 +127,89 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 
 #define SORT_THREADS 256
 
-// ---- 1. per-ring sextant sort ------------------------------------------------------------------
-// One block per (ring, sequence).  std::sort(cloudSmoothness + sp, cloudSmoothness + ep, by_value)
-// for the six sextants (featureAssociation.cpp:275-286) as one bitonic network over 6 padded segments
-// in shared memory; the sorted (value, ind) pairs go back in place (the array persists across frames),
-// and a packed "scan list" is emitted for the greedy pass: entry k of [sp, ep] = ind | edge_ok << 31 |
-// flat_ok << 30, so that pass needs nothing but cloudNeighborPicked to test a candidate.
-__global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int P) {
-  extern __shared__ unsigned long long keys[];  // [6][P]
+// ---- 1. per-ring candidate sort ----------------------------------------------------------------
+// One block per (ring, sequence).  The reference sorts each sextant of cloudSmoothness by curvature
+// (std::sort(begin + sp, begin + ep), featureAssociation.cpp:275-286) and then scans it downwards for
+// edge points and upwards for flat points.  Only elements that can pass the tests of :291-293 /
+// :333-335 (curvature vs threshold, ground flag) can ever be picked, so only those are sorted, all
+// twelve lists of the ring in ONE bitonic network with the composite key
+//   [list = sextant*2 + (0 edge | 1 flat)] [visit order] [index tie-break]
+// where the visit order is ~curvature for edge lists (descending scan), curvature for flat lists,
+// and the unsorted element at position ep (the reference's sort excludes ep but both scans include
+// it) gets the first / last slot.  Output: scan_list[ring range] = picked
+// candidates in visiting order + the 13 list offsets.
+// cloudSmoothness itself is not stored: for k in [5, S-5) its entry is (curvature[k], k) by
+// construction (featureAssociation.cpp:220-221); the one stale entry that can ever be read, position
+// 4, is carried in `slot4` and updated to the minimum of the sorted
+// range that contains it, which is what the reference's in-place sort leaves there.
+__global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int cap2) {
+  extern __shared__ unsigned long long keys[];  // [cap2]
   __shared__ int sh_sp[6], sh_ep[6];
+  __shared__ int sh_cnt[12];
+  __shared__ int sh_n;
+  __shared__ unsigned long long sh_slot_min;
   const DevParams& p = st.p;
   const int ring = blockIdx.x, s = blockIdx.y;
   const size_t base = (size_t)s * p.N;
   const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
+  const int a = start - 4;
+  int* offs = st.sext_off + ((size_t)s * p.V + ring) * 16;
   if (threadIdx.x < 6) {
     const int j = threadIdx.x;
     sh_sp[j] = (start * (6 - j) + end * j) / 6;
     sh_ep[j] = (start * (5 - j) + end * (j + 1)) / 6 - 1;
   }
-  for (int t = threadIdx.x; t < 6 * P; t += SORT_THREADS) keys[t] = ~0ull;
+  if (threadIdx.x < 12) sh_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { sh_n = 0; sh_slot_min = ~0ull; }
   __syncthreads();
-  bool any = false;
+  const unsigned slot_val = st.slot4[s * 2 + 0];
+  const int slot_ind = (int)st.slot4[s * 2 + 1];
+  bool slot_in_sorted_range = false;
   for (int j = 0; j < 6; ++j) {
     const int sp = sh_sp[j], ep = sh_ep[j];
     if (sp >= ep) continue;
-    any = true;
-    for (int t = threadIdx.x; t < ep - sp; t += SORT_THREADS) {
-      const float v = st.smooth_val[base + sp + t];
-      const int ind = st.smooth_ind[base + sp + t];
-      keys[j * P + t] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)ind;  // curvature >= 0
+    if (sp == 4) slot_in_sorted_range = true;
+    for (int k = sp + threadIdx.x; k <= ep; k += SORT_THREADS) {
+      unsigned vb;
+      int ind;
+      if (k == 4) { vb = slot_val; ind = slot_ind; }
+      else { vb = __float_as_uint(st.curvature[base + k]); ind = k; }
+      if (sp == 4 && k < ep) atomicMin(&sh_slot_min, ((unsigned long long)vb << 32) | (unsigned)ind);
+      const float c = (k == 4) ? st.curvature[base + ind] : __uint_as_float(vb);
+      const bool ground = st.seg_ground[base + ind] != 0;
+      const bool edge_ok = c > p.edge_threshold && !ground;   // featureAssociation.cpp:291-293
+      const bool flat_ok = c < p.surf_threshold && ground;    // featureAssociation.cpp:333-335
+      if (!edge_ok && !flat_ok) continue;
+      const int list = j * 2 + (edge_ok ? 0 : 1);
+      unsigned order;
+      if (k == ep) order = edge_ok ? 0u : 0xffffffffu;        // position ep: scanned first (down) / last (up)
+      else order = edge_ok ? ~vb : vb;
+      const unsigned tb = edge_ok ? (0x1fffffu - (unsigned)ind) : (unsigned)ind;
+      const int slot = atomicAdd(&sh_n, 1);
+      atomicAdd(&sh_cnt[list], 1);
+      keys[slot] = ((unsigned long long)list << 53) | ((unsigned long long)order << 21) | tb;
     }
   }
-  if (!any) return;
   __syncthreads();
-  bitonic_sort_u64(keys, P, 6 * P);
-  for (int j = 0; j < 6; ++j) {
-    const int sp = sh_sp[j], ep = sh_ep[j];
-    if (sp >= ep) continue;
-    for (int t = threadIdx.x; t <= ep - sp; t += SORT_THREADS) {
-      int ind;
-      if (t < ep - sp) {
-        const unsigned long long k = keys[j * P + t];
-        ind = (int)(unsigned)(k & 0xffffffffull);
-        st.smooth_val[base + sp + t] = __uint_as_float((unsigned)(k >> 32));
-        st.smooth_ind[base + sp + t] = ind;
-      } else {
-        ind = st.smooth_ind[base + ep];  // position ep is scanned but not sorted (sic)
-      }
-      const float c = st.curvature[base + ind];
-      const bool ground = st.seg_ground[base + ind] != 0;
-      unsigned e = (unsigned)ind;
-      if (c > p.edge_threshold && !ground) e |= 0x80000000u;   // featureAssociation.cpp:291-293
-      if (c < p.surf_threshold && ground) e |= 0x40000000u;    // featureAssociation.cpp:333-335
-      st.scan_list[base + sp + t] = e;
+  const int n = sh_n;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int t = n + threadIdx.x; t < n2; t += SORT_THREADS) keys[t] = ~0ull;
+  __syncthreads();
+  if (n > 1) bitonic_sort_u64(keys, n2, n2);
+  for (int t = threadIdx.x; t < n; t += SORT_THREADS) {
+    const unsigned long long k = keys[t];
+    const int list = (int)(k >> 53);
+    const unsigned tb = (unsigned)(k & 0x1fffffull);
+    st.scan_list[base + a + t] = (list & 1) ? tb : (0x1fffffu - tb);
+  }
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int l = 0; l < 12; ++l) { offs[l] = run; run += sh_cnt[l]; }
+    offs[12] = run;
+    if (slot_in_sorted_range && sh_slot_min != ~0ull) {
+      st.slot4[s * 2 + 0] = (unsigned)(sh_slot_min >> 32);
+      st.slot4[s * 2 + 1] = (unsigned)(sh_slot_min & 0xffffffffull);
     }
   }
 }
@@ -188,8 +217,9 @@ __global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int 
 // ---- 2. greedy picks ----------------------------------------------------------------------------
 // One WARP per (ring, sequence); the six sextants of a ring must run in order because a pick
 // suppresses up to 5 neighbours on either side, across sextant boundaries.  Each step tests 32
-// consecutive scan-list entries at once; the only mutable state is cloudNeighborPicked, kept as
-// bytes in shared memory for the ring's span (other indices go to global memory).
+// consecutive candidates of the pre-sorted list at once; the only mutable state is
+// cloudNeighborPicked, kept as bytes in shared memory for the ring's span (other indices go to
+// global memory).
 #define PICK_WARPS 4
 
 __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
@@ -207,6 +237,7 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
   for (int t = lane; t < L; t += 32) sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
   __syncwarp();
   const size_t rs = (size_t)s * p.V + ring;
+  const int* offs = st.sext_off + rs * 16;
   int* o_sharp_i = st.st_sharp_ind + rs * 12;
   int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
   int* o_flat_i = st.st_flat_ind + rs * 24;
@@ -236,67 +267,68 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
     __syncwarp();
   };
   for (int j = 0; j < 6; ++j) {
-    const int sp = (start * (6 - j) + end * j) / 6;
-    const int ep = (start * (5 - j) + end * (j + 1)) / 6 - 1;
-    if (sp >= ep) continue;
-    const unsigned* list = st.scan_list + base + sp;
-    const int len = ep - sp + 1;
-    // descending scan for edge points (featureAssociation.cpp:288-328)
-    int largest = 0;
-    int top = len - 1;
-    while (top >= 0 && largest < 20) {
-      const int t = top - lane;
-      bool cand = false;
-      int ind = 0;
-      if (t >= 0) {
-        const unsigned e = list[t];
-        ind = (int)(e & 0x3fffffffu);
-        cand = (e & 0x80000000u) && get_picked(ind) == 0;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, cand);
-      if (m == 0) { top -= 32; continue; }
-      const int w = __ffs(m) - 1;
-      const int pick = __shfl_sync(0xffffffffu, ind, w);
-      largest++;
-      if (lane == 0) {
-        if (largest <= 2) {
-          st.cloud_label[base + pick] = 2;
-          o_sharp_i[n_sharp] = pick;
-        } else {
-          st.cloud_label[base + pick] = 1;
+    // edge candidates of sextant j in descending-curvature visiting order (featureAssociation.cpp:288-328)
+    {
+      const unsigned* list = st.scan_list + base + a + offs[2 * j];
+      const int len = offs[2 * j + 1] - offs[2 * j];
+      int largest = 0;
+      int pos = 0;
+      while (pos < len && largest < 20) {
+        const int t = pos + lane;
+        bool cand = false;
+        int ind = 0;
+        if (t < len) {
+          ind = (int)list[t];
+          cand = get_picked(ind) == 0;
         }
-        o_lsharp_i[n_lsharp] = pick;
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m == 0) { pos += 32; continue; }
+        const int w = __ffs(m) - 1;
+        const int pick = __shfl_sync(0xffffffffu, ind, w);
+        largest++;
+        if (lane == 0) {
+          if (largest <= 2) {
+            st.cloud_label[base + pick] = 2;
+            o_sharp_i[n_sharp] = pick;
+          } else {
+            st.cloud_label[base + pick] = 1;
+          }
+          o_lsharp_i[n_lsharp] = pick;
+        }
+        if (largest <= 2) n_sharp++;
+        n_lsharp++;
+        mark_neighbors(pick);
+        pos = pos + w + 1;
       }
-      if (largest <= 2) n_sharp++;
-      n_lsharp++;
-      mark_neighbors(pick);
-      top = top - w - 1;
     }
-    // ascending scan for flat points (featureAssociation.cpp:330-368)
-    int smallest = 0;
-    int bot = 0;
-    while (bot < len) {
-      const int t = bot + lane;
-      bool cand = false;
-      int ind = 0;
-      if (t < len) {
-        const unsigned e = list[t];
-        ind = (int)(e & 0x3fffffffu);
-        cand = (e & 0x40000000u) && get_picked(ind) == 0;
+    // flat candidates in ascending-curvature visiting order (featureAssociation.cpp:330-368)
+    {
+      const unsigned* list = st.scan_list + base + a + offs[2 * j + 1];
+      const int len = offs[2 * j + 2] - offs[2 * j + 1];
+      int smallest = 0;
+      int pos = 0;
+      while (pos < len) {
+        const int t = pos + lane;
+        bool cand = false;
+        int ind = 0;
+        if (t < len) {
+          ind = (int)list[t];
+          cand = get_picked(ind) == 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (m == 0) { pos += 32; continue; }
+        const int w = __ffs(m) - 1;
+        const int pick = __shfl_sync(0xffffffffu, ind, w);
+        smallest++;
+        if (lane == 0) {
+          st.cloud_label[base + pick] = -1;
+          o_flat_i[n_flat] = pick;
+        }
+        n_flat++;
+        if (smallest >= 4) break;  // the 4th pick breaks before the suppression (sic, :339-342)
+        mark_neighbors(pick);
+        pos = pos + w + 1;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, cand);
-      if (m == 0) { bot += 32; continue; }
-      const int w = __ffs(m) - 1;
-      const int pick = __shfl_sync(0xffffffffu, ind, w);
-      smallest++;
-      if (lane == 0) {
-        st.cloud_label[base + pick] = -1;
-        o_flat_i[n_flat] = pick;
-      }
-      n_flat++;
-      if (smallest >= 4) break;  // the 4th pick breaks before the suppression (sic, :339-342)
-      mark_neighbors(pick);
-      bot = bot + w + 1;
     }
   }
   __syncwarp();
@@ -500,14 +532,14 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
   }
   const dim3 grid_rings(p.V, p.B);
   {
-    const int P = next_pow2(p.H / 6 + 2);
-    const size_t smem = (size_t)6 * P * 8;
+    const int cap2 = next_pow2(p.H);
+    const size_t smem = (size_t)cap2 * 8;
     static size_t configured = 0;
     if (smem > configured) {
       cudaFuncSetAttribute(k_feature_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;
     }
-    LL_LAUNCH(ctx, "k_feature_sort", k_feature_sort<<<grid_rings, SORT_THREADS, smem, ctx.stream>>>(st, P));
+    LL_LAUNCH(ctx, "k_feature_sort", k_feature_sort<<<grid_rings, SORT_THREADS, smem, ctx.stream>>>(st, cap2));
   }
   {
     const size_t smem = (size_t)PICK_WARPS * (p.H + 32);

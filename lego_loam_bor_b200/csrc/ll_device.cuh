@@ -80,9 +80,9 @@ struct DevState {
   float* curvature;            // [B][N] cloudCurvature (persistent)
   int* picked;                 // [B][N] cloudNeighborPicked (persistent)
   int* cloud_label;            // [B][N] cloudLabel (persistent)
-  float* smooth_val;           // [B][N] cloudSmoothness[].value (persistent, sorted in place)
-  int* smooth_ind;             // [B][N] cloudSmoothness[].ind
-  unsigned* scan_list;         // [B][N] per sextant [sp, ep]: ind | edge candidate << 31 | flat candidate << 30
+  unsigned* slot4;             // [B][2] the one stale cloudSmoothness entry that is ever read (position 4): value bits, ind
+  unsigned* scan_list;         // [B][N] per ring: its 12 candidate lists (edge/flat per sextant) in visiting order
+  int* sext_off;               // [B][V][16] offsets of those 12 lists inside the ring's range (+ end)
   // per-ring staging written by the extraction kernel
   int* st_sharp_ind;       // [B][V][12]
   int* st_less_sharp_ind;  // [B][V][120]
