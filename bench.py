@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=11, help="frames per sequence of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--time-kernel", default="", help="kernel to report in `roofline` (default: the slowest)")
+    ap.add_argument("--streams", type=int, default=1, help="split the batch over this many handles / CUDA streams")
     return ap.parse_args()
 
 
@@ -254,7 +255,7 @@ def workload_config(args, params, batch, where):
     return {"workload": f"{params.num_vertical_scans}x{params.num_horizontal_scans} synthetic lidar, {batch} independent "
                         f"sequences per {'GPU' if where == 'gpu' else 'host'}, full hot path per scan (projection, ground, "
                         "segmentation, features, scan-to-scan LM" + ("" if args.no_map else ", scan-to-map every 5th scan vs synthetic local map") + ")",
-            "sensor": args.config, "batch_per_gpu": batch, "parallelism": f"replicas x{args.gpus} (independent sequences, no collective)",
+            "sensor": args.config, "batch_per_gpu": batch, "streams_per_gpu": args.streams, "parallelism": f"replicas x{args.gpus} (independent sequences, no collective)",
             "l2": "every step reads a distinct set of scans (inputs per step ~ L2 size, dataset >> L2); no reuse between steps"}
 
 
@@ -309,7 +310,25 @@ def main():
     del scans
     devdata = host.to(dev, non_blocking=False)
     stream = torch.cuda.Stream(device=dev)
-    gpu = LegoLoam(params, batch=B, max_points=stride, device=local_rank, stream=stream.cuda_stream)
+    sub_streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else [stream]
+    if args.streams > 1:
+        from lego_loam_bor_b200.capi import LegoLoamStreams
+        gpu = LegoLoamStreams(params, B, args.streams, max_points=stride, device=local_rank,
+                              streams=[s.cuda_stream for s in sub_streams])
+    else:
+        gpu = LegoLoam(params, batch=B, max_points=stride, device=local_rank, stream=stream.cuda_stream)
+
+    def fork(ev):
+        """timed regions are bracketed on `stream`; the per-handle streams start after ev and are joined before the end event"""
+        if args.streams > 1:
+            for ss in sub_streams:
+                ss.wait_event(ev)
+
+    def join():
+        if args.streams > 1:
+            for ss in sub_streams:
+                stream.wait_stream(ss)
+
     if use_map:
         for k, s in enumerate(seq_ids):
             cm, sm = local_maps(cfg, s)
@@ -370,8 +389,10 @@ def main():
     t_begin = time.time()
     with torch.cuda.stream(stream):
         ev0.record(stream)
+        fork(ev0)
         for _ in range(args.steps):
             step_device(f); f += 1
+        join()
         ev1.record(stream)
     torch.cuda.synchronize(dev)
     t_end = time.time()
@@ -410,9 +431,11 @@ def main():
     h2d = 0
     with torch.cuda.stream(stream):
         e0.record(stream)
+        fork(e0)
         for _ in range(e2e_steps):
             h2d += int(counts[f].sum()) * 16 + B * 4
             step_host(f); f += 1
+        join()
         e1.record(stream)
     torch.cuda.synchronize(dev)
     e2e_ms = e0.elapsed_time(e1)

@@ -240,3 +240,82 @@ class LegoLoam:
             name, ms, n = line.split()
             out[name] = (float(ms), int(n))
         return out
+
+
+class LegoLoamStreams:
+    """`batch` independent sequences split over `n_streams` handles, each with its own CUDA stream.
+
+    Sequences never interact, so the sub-batches may run concurrently: while the few slow sequences of
+    one sub-batch finish their LM iterations (kernels that occupy a handful of SMs), the wide kernels of the
+    other sub-batches fill the rest of the GPU.  Same call surface as `LegoLoam`; `streams` are the raw
+    cudaStream_t handles (e.g. from torch.cuda.Stream().cuda_stream) or None to let each handle create one."""
+
+    def __init__(self, params, batch, n_streams, max_points=None, device=0, streams=None):
+        if batch % n_streams:
+            raise ValueError("batch must be a multiple of n_streams")
+        self.batch, self.n, self.sub = batch, n_streams, batch // n_streams
+        self.parts = [LegoLoam(params, self.sub, max_points, device, streams[i] if streams else None)
+                      for i in range(n_streams)]
+        self.max_points = self.parts[0].max_points
+
+    def _loc(self, seq):
+        return self.parts[seq // self.sub], seq % self.sub
+
+    def reset(self):
+        for p in self.parts:
+            p.reset()
+
+    def set_scans_device(self, dev_ptr, counts, stride):
+        for i, p in enumerate(self.parts):
+            p.set_scans_device(dev_ptr + i * self.sub * stride * 16, counts[i * self.sub:(i + 1) * self.sub], stride)
+
+    def set_scans_host_ptr(self, ptr, counts, stride):
+        for i, p in enumerate(self.parts):
+            p.set_scans_host_ptr(ptr + i * self.sub * stride * 16, counts[i * self.sub:(i + 1) * self.sub], stride)
+
+    def process_scans(self):
+        return [p.process_scans() for p in self.parts][0]
+
+    def map_set_local(self, seq, corner, surf):
+        p, k = self._loc(seq)
+        p.map_set_local(k, corner, surf)
+
+    def map_set_poses(self, aft, bef):
+        aft = np.ascontiguousarray(aft, np.float32).reshape(self.batch, 6)
+        bef = np.ascontiguousarray(bef, np.float32).reshape(self.batch, 6)
+        for i, p in enumerate(self.parts):
+            p.map_set_poses(aft[i * self.sub:(i + 1) * self.sub], bef[i * self.sub:(i + 1) * self.sub])
+
+    def poses(self):
+        out = [p.poses() for p in self.parts]
+        return tuple(np.concatenate([o[j] for o in out]) for j in range(3))
+
+    def synchronize(self):
+        for p in self.parts:
+            p.synchronize()
+
+    def download(self, name, seq=0):
+        p, k = self._loc(seq)
+        return p.download(name, k)
+
+    def kernel_launches(self):
+        return sum(p.kernel_launches() for p in self.parts)
+
+    def time_kernel(self, name):
+        for p in self.parts:
+            p.time_kernel(name)
+
+    def kernel_time(self):
+        ms, n = 0.0, 0
+        for p in self.parts:
+            a, b = p.kernel_time()
+            ms, n = ms + a, n + b
+        return ms, n
+
+    def kernel_time_table(self):
+        out = {}
+        for p in self.parts:
+            for k, (ms, n) in p.kernel_time_table().items():
+                a, b = out.get(k, (0.0, 0))
+                out[k] = (a + ms, b + n)
+        return out

@@ -118,6 +118,22 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int n 
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void bitonic_sort_t(T* key, int n /* pow2 */) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+        if (l > i) {
+          const T a = key[i], b = key[l];
+          if (a > b) { key[i] = b; key[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // order-preserving float <-> int map (an involution), for shared-memory atomicMin/Max on floats
 __device__ __forceinline__ int f2ord(float f) {
   const int i = __float_as_int(f);
@@ -433,37 +449,68 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
     } else {
       const int minb0 = (int)floorf(bmn[0] * inv), minb1 = (int)floorf(bmn[1] * inv), minb2 = (int)floorf(bmn[2] * inv);
       const int div0 = (int)floorf(bmx[0] * inv) - minb0 + 1, div1 = (int)floorf(bmx[1] * inv) - minb1 + 1;
-      int n2 = 1;
-      while (n2 < n_raw) n2 <<= 1;
-      for (int t = threadIdx.x; t < n2; t += LF_THREADS) {
-        unsigned long long k = ~0ull;
-        if (t < n_raw) {
-          const float4 q = st.seg_cloud[base + sm_lfpos[t]];
-          const int i0 = (int)floorf(q.x * inv) - minb0;
-          const int i1 = (int)floorf(q.y * inv) - minb1;
-          const int i2 = (int)floorf(q.z * inv) - minb2;
-          const int idx = i0 + i1 * div0 + i2 * div0 * div1;
-          k = ((unsigned long long)(unsigned)idx << 32) | (unsigned)t;  // stable: ties keep input order
-        }
-        keys[t] = k;
+      // Consecutive points of a ring mostly share a voxel, so the sort runs over RUNS of equal voxel
+      // index (key = voxel index major, first input position minor) instead of over points; runs of the
+      // same voxel end up adjacent and in input order, so each voxel's float sums keep the input order.
+      int pos_bits = 0;
+      while ((1 << pos_bits) < n_raw) ++pos_bits;
+      int* sm_vox = sm_lfpos + p.H;              // [H] voxel index of every collected point
+      int* sm_runend = sm_vox + p.H;             // [H] end position (exclusive) of the run starting at position t
+      for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) {
+        const float4 q = st.seg_cloud[base + sm_lfpos[t]];
+        const int i0 = (int)floorf(q.x * inv) - minb0;
+        const int i1 = (int)floorf(q.y * inv) - minb1;
+        const int i2 = (int)floorf(q.z * inv) - minb2;
+        sm_vox[t] = i0 + i1 * div0 + i2 * div0 * div1;
       }
       __syncthreads();
-      bitonic_sort_u64(keys, n2, n2);
+      // run heads -> compact run keys
+      int n_runs = 0;
+      {
+        int run = 0;
+        for (int t0 = 0; t0 < n_raw; t0 += LF_THREADS) {
+          const int t = t0 + threadIdx.x;
+          int head = 0;
+          if (t < n_raw) head = (t == 0) || (sm_vox[t] != sm_vox[t - 1]);
+          int total;
+          const int ex = block_exclusive_scan(head, warp_tot, &total);
+          if (head) keys[run + ex] = ((unsigned long long)(unsigned)sm_vox[t] << pos_bits) | (unsigned)t;
+          run += total;
+        }
+        n_runs = run;
+      }
+      __syncthreads();
+      // run ends: the next run head in input order (keys are still in input order here)
+      for (int r = threadIdx.x; r < n_runs; r += LF_THREADS) {
+        const unsigned pos_mask0 = (1u << pos_bits) - 1u;
+        const int startp = (int)((unsigned)keys[r] & pos_mask0);
+        const int endp = (r + 1 < n_runs) ? (int)((unsigned)keys[r + 1] & pos_mask0) : n_raw;
+        sm_runend[startp] = endp;
+      }
+      int n2 = 1;
+      while (n2 < n_runs) n2 <<= 1;
+      for (int t = n_runs + threadIdx.x; t < n2; t += LF_THREADS) keys[t] = ~0ull;
+      __syncthreads();
+      if (n_runs > 1) bitonic_sort_t<unsigned long long>(keys, n2);
+      const unsigned pos_mask = (1u << pos_bits) - 1u;
       int run = 0;
-      for (int t0 = 0; t0 < n_raw; t0 += LF_THREADS) {
+      for (int t0 = 0; t0 < n_runs; t0 += LF_THREADS) {
         const int t = t0 + threadIdx.x;
         int head = 0;
-        if (t < n_raw) head = (t == 0) || ((keys[t] >> 32) != (keys[t - 1] >> 32));
+        if (t < n_runs) head = (t == 0) || ((unsigned)(keys[t] >> pos_bits) != (unsigned)(keys[t - 1] >> pos_bits));
         int total;
         const int ex = block_exclusive_scan(head, warp_tot, &total);
         if (head) {
-          const unsigned vox = (unsigned)(keys[t] >> 32);
+          const unsigned vox = (unsigned)(keys[t] >> pos_bits);
           float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
           int cnt = 0;
-          for (int u = t; u < n_raw && (unsigned)(keys[u] >> 32) == vox; ++u) {
-            const float4 q = st.seg_cloud[base + sm_lfpos[(int)(keys[u] & 0xffffffffull)]];
-            cx += q.x; cy += q.y; cz += q.z; ci += q.w;
-            ++cnt;
+          for (int u = t; u < n_runs && (unsigned)(keys[u] >> pos_bits) == vox; ++u) {
+            const int ps = (int)((unsigned)keys[u] & pos_mask), pe = sm_runend[ps];
+            for (int v = ps; v < pe; ++v) {
+              const float4 q = st.seg_cloud[base + sm_lfpos[v]];
+              cx += q.x; cy += q.y; cz += q.z; ci += q.w;
+              ++cnt;
+            }
           }
           const float fc = (float)cnt;
           o_lflat[run + ex] = make_float4(cx / fc, cy / fc, cz / fc, ci / fc);
@@ -547,7 +594,7 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
               k_feature_pick<<<dim3((p.V + PICK_WARPS - 1) / PICK_WARPS, p.B), PICK_WARPS * 32, smem, ctx.stream>>>(st));
   }
   {
-    const size_t smem = (size_t)next_pow2(p.H) * 8 + (size_t)p.H * 4;
+    const size_t smem = (size_t)next_pow2(p.H) * 8 + (size_t)p.H * 4 * 3;
     static size_t configured = 0;
     if (smem > configured) {
       cudaFuncSetAttribute(k_feature_lessflat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

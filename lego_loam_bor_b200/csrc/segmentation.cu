@@ -121,24 +121,27 @@ __global__ void __launch_bounds__(256) k_ccl_merge(DevState st) {
   if (cell >= p.N) return;
   int* parent = st.parent + (size_t)s * p.N;
   const float* range = st.range_mat + (size_t)s * p.N;
-  if (__ldcg(parent + cell) < 0) return;
   const int row = cell / p.H, col = cell - row * p.H;
+  const bool has_up = row + 1 < p.V;
+  const bool has_left = col > 0;
+  // all first-touch loads are issued together (coalesced rows); stale values are harmless, see below
+  const int up = has_up ? cell + p.H : cell;
+  const int pc = parent[cell];
+  const int pu = parent[up];
   const float r = range[cell];
-  if (row + 1 < p.V) {
-    const int up = cell + p.H;
-    const int pu = __ldcg(parent + up);
-    if (pu >= 0 && seg_edge(r, range[up], p.sin_ay, p.cos_ay, p.seg_tan_theta)) {
-      // The same two horizontal runs usually overlap over many columns; only the leftmost column of an
-      // overlap has to union them.  Skip when the left neighbours are in the same two components and
-      // are vertically connected themselves (that column, or one further left, does the union).
-      bool skip = false;
-      if (col > 0) {
-        const int pl = __ldcg(parent + cell - 1), plu = __ldcg(parent + up - 1);
-        skip = pl >= 0 && plu >= 0 && pl == __ldcg(parent + cell) && plu == pu &&
-               seg_edge(range[cell - 1], range[up - 1], p.sin_ay, p.cos_ay, p.seg_tan_theta);
-      }
-      if (!skip) uf_union(parent, cell, up);
-    }
+  const float ru = range[up];
+  const int pl = has_left ? parent[cell - 1] : -1;
+  const int plu = has_left ? parent[up - 1] : -1;
+  const float rl = has_left ? range[cell - 1] : 0.f;
+  const float rlu = has_left ? range[up - 1] : 0.f;
+  if (pc < 0) return;
+  if (has_up && pu >= 0 && seg_edge(r, ru, p.sin_ay, p.cos_ay, p.seg_tan_theta)) {
+    // The same two horizontal runs usually overlap over many columns; only the leftmost column of an
+    // overlap has to union them.  Skip when the left neighbours are in the same two components (equal
+    // parents, at whatever time they were read, imply equal components) and are vertically connected
+    // themselves: that column, or one further left, does the union.
+    const bool skip = pl >= 0 && plu >= 0 && pl == pc && plu == pu && seg_edge(rl, rlu, p.sin_ay, p.cos_ay, p.seg_tan_theta);
+    if (!skip) uf_union(parent, cell, up);
   }
   if (col == p.H - 1 && p.H > 1) {
     const int w = cell - col;  // column 0 of the same row (imageProjection.cpp:446-451)
