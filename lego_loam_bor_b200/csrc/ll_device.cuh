@@ -127,8 +127,7 @@ struct DevState {
   float4* vox_tmp_out;                           // [B][cap_outlier] laserCloudOutlierLastDS
   int* vox_tmp_counts;                           // [B][2]
   int vox_cap;
-  int* map_knn;                                  // [B][map_knn_cap][5] neighbour indices of every scan point (-1: none)
-  float4* map_knn_state;                         // [B][map_knn_cap] query position of the last full search + squared 6th-NN distance
+  float4* map_knn_rec;                           // [B][map_knn_cap][6] per query: 5 neighbours (x,y,z,index) + (p0, bound)
   int map_knn_cap;
   double* map_partials;                          // [B][max_blocks][28]
   double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)

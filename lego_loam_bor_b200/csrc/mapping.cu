@@ -4,7 +4,7 @@
 //
 //   grid build (hashgrid.cu)  replaces the two kd-tree builds of every mapping cycle (:1317-1318);
 //       cell = 1 m = the acceptance radius of :1036,1144, so a 27-cell lookup is exact.
-//   k_map_knn    one warp per down-sampled scan point: pointAssociateToMap + exact 5-NN (27 cells in parallel)
+//   k_map_knn    one thread per down-sampled scan point: pointAssociateToMap + exact 5-NN with provable reuse
 //   k_map_iter   one thread per down-sampled scan point: line fit
 //       (3x3 symmetric eigen-solve) or plane fit (5x3 column-pivoted QR), residual + 6-column
 //       Jacobian row, J^T J / J^T r partial sums (exact double products) per block.
@@ -20,7 +20,7 @@
 namespace {
 
 #define MAP_BLOCKS 96
-#define KNN_BLOCKS 64
+#define KNN_BLOCKS 112
 #define MAP_THREADS 128
 #define MAP_NACC 28  // 21 upper-triangle J^T J + 6 J^T r + row count
 
@@ -52,12 +52,8 @@ __device__ __forceinline__ float4 point_associate_to_map(const MapPose& m, const
 }
 
 // cornerOptimization body for one point; returns false if rejected
-__device__ __forceinline__ bool corner_fit(const DevState& st, int s, const float4 sel, const int* idx, float4* coeff) {
-  if (idx[4] < 0) return false;  // pointSearchSqDis[4] < 1.0 failed
-  const float4* mp = st.map_corner + (size_t)s * st.cap_map_corner;
-  float4 q[5];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) q[j] = mp[idx[j]];
+__device__ __forceinline__ bool corner_fit(const float4 sel, const float4* q, float4* coeff) {
+  if (__float_as_int(q[4].w) < 0) return false;  // pointSearchSqDis[4] < 1.0 failed
   float cx = 0, cy = 0, cz = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) { cx += q[j].x; cy += q[j].y; cz += q[j].z; }
@@ -99,12 +95,8 @@ __device__ __forceinline__ bool corner_fit(const DevState& st, int s, const floa
 }
 
 // surfOptimization body for one point
-__device__ __forceinline__ bool surf_fit(const DevState& st, int s, const float4 sel, const int* idx, float4* coeff) {
-  if (idx[4] < 0) return false;
-  const float4* mp = st.map_surf + (size_t)s * st.cap_map_surf;
-  float4 q[5];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) q[j] = mp[idx[j]];
+__device__ __forceinline__ bool surf_fit(const float4 sel, const float4* q, float4* coeff) {
+  if (__float_as_int(q[4].w) < 0) return false;
   float matA0[15], matX0[3];
   const float matB0[5] = {-1, -1, -1, -1, -1};
 #pragma unroll
@@ -126,126 +118,29 @@ __device__ __forceinline__ bool surf_fit(const DevState& st, int s, const float4
 }
 
 
-// Exact 5-NN of every down-sampled scan point in the local map.
+// Exact 5-NN of every down-sampled scan point in the local map, one THREAD per query.
 //
-// Phase 1 (one thread per query) tries to REUSE the neighbours of the previous LM iteration: the last
-// full search left the query position p0 and the squared distance d6 to the 6th nearest point (or 1 m,
-// the reach of the 27-cell block).  If the query has moved by |delta| and the five old neighbours are
-// now all closer than sqrt(d6) - |delta| (minus a float-safety margin), no other map point can have
-// entered the top five (triangle inequality), so only their order has to be recomputed.
-// Phase 2 (one warp per remaining query) is the full search: the candidates of the 27 buckets are
-// flattened over the 32 lanes, every lane keeps its six best, six rounds of warp arg-min merge them.
-#define KNN_THREADS 256
-#define KNN_WARPS (KNN_THREADS / 32)
+// Per query a 96-byte record is kept: the five neighbours with their coordinates (x, y, z, index), in
+// ascending (d2, index) order, and (p0, bound): the query position of the last full search and the
+// squared distance to the 6th nearest map point there (or 1 m, the reach of the 27-cell block).
+// In later LM iterations the search is skipped when it provably cannot change: if the query moved by
+// |delta| since p0, every map point outside the record is at least sqrt(bound) - |delta| away, so if
+// all five recorded neighbours are closer than that (minus a float-safety margin) they still are the
+// exact 5-NN (triangle inequality) and only their order is refreshed.
+// The full search visits the 27 buckets around the query (occupancy bitmap first), keeps a sorted
+// top-6 in registers; consecutive queries are consecutive voxels of the VoxelGrid output, so
+// neighbouring threads walk the same buckets and share them through L1.
+#define KNN_THREADS 128
 
-struct Cand {
-  float d2;
-  int idx;
-};
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
-#define KNN_SLOTS 8                 // candidates a lane can hold per pass (32 * 8 = 256 per pass)
-#define KNN_NS (KNN_SLOTS + 1)      // + one slot that carries the best six between passes (lanes 0..5)
-
-// Removes and returns the warp-wide minimum (d2, idx) over all slots of all lanes; every slot holding
-// that index is invalidated, which also removes the duplicates that hash collisions can produce.
-// Squared distances are >= 0, so their bit patterns order like unsigned integers and the minimum is
-// one __reduce_min_sync.
-__device__ __forceinline__ void knn_extract_min(unsigned (&kd)[KNN_NS], int (&ki)[KNN_NS], unsigned* out_d, int* out_i) {
-  unsigned m = kd[0];
-#pragma unroll
-  for (int i = 1; i < KNN_NS; ++i) m = min(m, kd[i]);
-  const unsigned wm = __reduce_min_sync(0xffffffffu, m);
-  int mi = 0x7fffffff;
-#pragma unroll
-  for (int i = 0; i < KNN_NS; ++i)
-    if (kd[i] == wm) mi = min(mi, ki[i]);
-  const int wi = __reduce_min_sync(0xffffffffu, mi);
-#pragma unroll
-  for (int i = 0; i < KNN_NS; ++i)
-    if (ki[i] == wi) { kd[i] = 0xffffffffu; ki[i] = 0x7fffffff; }
-  *out_d = wm;
-  *out_i = wi;
-}
-
-__device__ __forceinline__ void knn_full_search(const DevState& st, int s, int q, bool corner, const float4 sel, int lane) {
-  const HashGrid& g = corner ? st.grid_map_corner : st.grid_map_surf;
-  const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
-  const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
-  const float4* pts = g.sorted + (size_t)s * g.cap;
-  const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
-  int b0 = 0, len = 0;
-  if (lane < 27) {
-    const uint32_t h = grid_hash(cx + (lane % 3 - 1), cy + ((lane % 9) / 3 - 1), cz + (lane / 9 - 1), g.tbl);
-    if ((occ[h >> 5] >> (h & 31)) & 1u) {
-      b0 = cs[h];
-      len = cs[h + 1] - b0;
-    }
-  }
-  // inclusive scan of the bucket lengths over the lanes: candidate t lives in the first lane with inc > t
-  int inc = len;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  const int total = __shfl_sync(0xffffffffu, inc, 31);
-  const int start_of_mine = b0 - (inc - len);  // bucket start minus exclusive prefix: element k = start + t
-  unsigned kd[KNN_NS];
-  int ki[KNN_NS];
-#pragma unroll
-  for (int i = 0; i < KNN_NS; ++i) { kd[i] = 0xffffffffu; ki[i] = 0x7fffffff; }
-  unsigned res_d = 0xffffffffu;  // lane r < 6 ends up with the r-th nearest
-  int res_i = 0x7fffffff;
-  for (int pass0 = 0; pass0 == 0 || pass0 < total; pass0 += 32 * KNN_SLOTS) {
-#pragma unroll
-    for (int i = 0; i < KNN_SLOTS; ++i) {
-      const int t = pass0 + i * 32 + lane;
-      int lo = 0;
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int probe = __shfl_sync(0xffffffffu, inc, lo + step - 1);
-        if (probe <= t) lo += step;
-      }
-      const int base_k = __shfl_sync(0xffffffffu, start_of_mine, lo);
-      if (t < total) {
-        const float4 c = pts[base_k + t];
-        const float dd = nn_dist2(sel.x, sel.y, sel.z, c);
-        if (dd < 1.0f) { kd[i] = __float_as_uint(dd); ki[i] = __float_as_int(c.w); }
-      }
-    }
-    // carried best six of the earlier passes re-enter through the spare slot of lanes 0..5
-    kd[KNN_SLOTS] = res_d;
-    ki[KNN_SLOTS] = res_i;
-    res_d = 0xffffffffu;
-    res_i = 0x7fffffff;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      unsigned wd;
-      int wi;
-      knn_extract_min(kd, ki, &wd, &wi);
-      if (lane == r) { res_d = wd; res_i = wi; }
-    }
-#pragma unroll
-    for (int i = 0; i < KNN_NS; ++i) { kd[i] = 0xffffffffu; ki[i] = 0x7fffffff; }
-  }
-  const size_t qo = (size_t)s * st.map_knn_cap + q;
-  if (lane < 5) st.map_knn[qo * 5 + lane] = (res_i == 0x7fffffff) ? -1 : res_i;
-  const unsigned d6u = __shfl_sync(0xffffffffu, res_d, 5);
-  const int i6 = __shfl_sync(0xffffffffu, res_i, 5);
-  if (lane == 0) {
-    const float d6 = (i6 == 0x7fffffff) ? 1.0f : fminf(__uint_as_float(d6u), 1.0f);
-    st.map_knn_state[qo] = make_float4(sel.x, sel.y, sel.z, d6);
-  }
-}
-
-__global__ void __launch_bounds__(KNN_THREADS) k_map_knn(DevState st, int iter) {
+__global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int iter) {
   __shared__ int sh_need[KNN_THREADS];
   __shared__ int sh_n;
+  __shared__ int2 sh_bucket[27][KNN_THREADS];  // per thread: its non-empty buckets (start, end), column-major: no bank conflicts
   const DevParams& p = st.p;
   const int s = blockIdx.y;
   if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nc = st.scan_ds_counts[s * 2 + 0], ns = st.scan_ds_counts[s * 2 + 1];
   const int nq = nc + ns;
   float T[6];
@@ -255,57 +150,123 @@ __global__ void __launch_bounds__(KNN_THREADS) k_map_knn(DevState st, int iter) 
   for (int qbase = blockIdx.x * KNN_THREADS; qbase < nq; qbase += gridDim.x * KNN_THREADS) {
     if (threadIdx.x == 0) sh_n = 0;
     __syncthreads();
-    const int q = qbase + threadIdx.x;
-    if (q < nq) {
-      bool need = true;
-      if (iter > 0) {
-        const bool corner = q < nc;
-        const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
-        const float4 sel = point_associate_to_map(mp, ori);
-        const size_t qo = (size_t)s * st.map_knn_cap + q;
-        const float4 stt = st.map_knn_state[qo];
-        int idx[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) idx[i] = st.map_knn[qo * 5 + i];
-        if (idx[4] >= 0) {
-          const float4* mpts = corner ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
+    // ---- phase 1: one thread per query, try to keep the recorded neighbours ----
+    {
+      const int q = qbase + threadIdx.x;
+      if (q < nq) {
+        bool need = true;
+        if (iter > 0) {
+          const bool corner = q < nc;
+          const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
+          const float4 sel = point_associate_to_map(mp, ori);
+          float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * 6;
+          const float4 stt = rec[5];
+          float4 c[5];
           float d2[5];
-          float dmax = 0.f;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            d2[i] = nn_dist2(sel.x, sel.y, sel.z, mpts[idx[i]]);
-            dmax = fmaxf(dmax, d2[i]);
+          for (int i = 0; i < 5; ++i) c[i] = rec[i];
+          if (__float_as_int(c[4].w) >= 0) {
+            float dmax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { d2[i] = nn_dist2(sel.x, sel.y, sel.z, c[i]); dmax = fmaxf(dmax, d2[i]); }
+            const float dx = sel.x - stt.x, dy = sel.y - stt.y, dz = sel.z - stt.z;
+            const float delta = sqrtf(dx * dx + dy * dy + dz * dz);
+            if (sqrtf(dmax) + delta + 1e-4f < sqrtf(stt.w)) {
+              // same five neighbours; restore the ascending (d2, index) order of a fresh search
+#pragma unroll
+              for (int a = 1; a < 5; ++a) {
+#pragma unroll
+                for (int b = a; b > 0; --b) {
+                  if (cand_less(d2[b], __float_as_int(c[b].w), d2[b - 1], __float_as_int(c[b - 1].w))) {
+                    const float td = d2[b]; d2[b] = d2[b - 1]; d2[b - 1] = td;
+                    const float4 tc = c[b]; c[b] = c[b - 1]; c[b - 1] = tc;
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 5; ++i) rec[i] = c[i];
+              need = false;
+            }
           }
-          const float dx = sel.x - stt.x, dy = sel.y - stt.y, dz = sel.z - stt.z;
-          const float delta = sqrtf(dx * dx + dy * dy + dz * dz);
-          if (sqrtf(dmax) + delta + 1e-4f < sqrtf(stt.w)) {
-            // same five neighbours; restore the ascending (d2, idx) order of a fresh search
+        }
+        if (need) sh_need[atomicAdd(&sh_n, 1)] = q;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: full search of the remaining queries, packed onto consecutive threads ----
+    const int n_need = sh_n;
+    for (int w = threadIdx.x; w < n_need; w += KNN_THREADS) {
+      const int q = sh_need[w];
+      const bool corner = q < nc;
+      const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
+      const float4 sel = point_associate_to_map(mp, ori);
+      const HashGrid& g = corner ? st.grid_map_corner : st.grid_map_surf;
+      const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+      const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
+      const float4* pts = g.sorted + (size_t)s * g.cap;
+      const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
+      // 2a: the non-empty buckets among the 27 cells.  Fully unrolled so that the 27 bitmap loads (and then
+      // the cell_start loads of the occupied ones) are independent and in flight together: this kernel is
+      // bound by memory latency, not by bandwidth or issue rate.
+      uint32_t hh[27];
+      unsigned occw[27];
 #pragma unroll
-            for (int a = 1; a < 5; ++a) {
+      for (int t = 0; t < 27; ++t) {
+        hh[t] = grid_hash(cx + (t % 3 - 1), cy + ((t % 9) / 3 - 1), cz + (t / 9 - 1), g.tbl);
+        occw[t] = occ[hh[t] >> 5];
+      }
+      int nb = 0;
 #pragma unroll
-              for (int b = a; b > 0; --b) {
-                if (cand_less(d2[b], idx[b], d2[b - 1], idx[b - 1])) {
-                  const float td = d2[b]; d2[b] = d2[b - 1]; d2[b - 1] = td;
-                  const int ti = idx[b]; idx[b] = idx[b - 1]; idx[b - 1] = ti;
+      for (int t = 0; t < 27; ++t) {
+        if ((occw[t] >> (hh[t] & 31)) & 1u) {
+          sh_bucket[nb++][threadIdx.x] = make_int2(cs[hh[t]], cs[hh[t] + 1]);
+        }
+      }
+      // 2b: candidates of the concatenated buckets, four independent loads per step.  A point is a candidate
+      // if it is closer than 1 m (such a point necessarily lies in one of the 27 cells); two of the 27 cells can
+      // share a bucket (hash collision), so an index that is already in the list is skipped.
+      float bd[6];
+      int bi[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { bd[i] = 1.0f; bi[i] = 0x7fffffff; }
+      for (int u = 0; u < nb; ++u) {
+        const int2 be = sh_bucket[u][threadIdx.x];
+        for (int k = be.x; k < be.y; k += 4) {
+          float4 cpt[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) cpt[v] = pts[min(k + v, be.y - 1)];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (k + v >= be.y) continue;
+            float cd = nn_dist2(sel.x, sel.y, sel.z, cpt[v]);
+            if (cd < bd[5]) {
+              int ci = __float_as_int(cpt[v].w);
+              bool dup = false;
+#pragma unroll
+              for (int i = 0; i < 6; ++i) dup = dup || (bi[i] == ci);
+              if (!dup) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                  if (cand_less(cd, ci, bd[i], bi[i])) {
+                    const float td = bd[i]; const int ti = bi[i];
+                    bd[i] = cd; bi[i] = ci;
+                    cd = td; ci = ti;
+                  }
                 }
               }
             }
-#pragma unroll
-            for (int i = 0; i < 5; ++i) st.map_knn[qo * 5 + i] = idx[i];
-            need = false;
           }
         }
       }
-      if (need) sh_need[atomicAdd(&sh_n, 1)] = q;
-    }
-    __syncthreads();
-    const int n_need = sh_n;
-    for (int i = wid; i < n_need; i += KNN_WARPS) {
-      const int qq = sh_need[i];
-      const bool corner = qq < nc;
-      const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + qq] : st.scan_surf_ds[(size_t)s * p.N + (qq - nc)];
-      const float4 sel = point_associate_to_map(mp, ori);
-      knn_full_search(st, s, qq, corner, sel, lane);
+      const float4* mpts = corner ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
+      float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * 6;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (bi[i] != 0x7fffffff) { c = mpts[bi[i]]; c.w = __int_as_float(bi[i]); }
+        rec[i] = c;
+      }
+      rec[5] = make_float4(sel.x, sel.y, sel.z, bd[5]);  // bd[5] = min(6th nearest d2, 1)
     }
     __syncthreads();
   }
@@ -331,13 +292,13 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st) {
     const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
     const float4 sel = point_associate_to_map(mp, ori);
     float4 cf;
-    int idx[5];
+    float4 nb[5];
     {
-      const int* kn = st.map_knn + ((size_t)s * st.map_knn_cap + q) * 5;
+      const float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * 6;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) idx[i] = kn[i];
+      for (int i = 0; i < 5; ++i) nb[i] = rec[i];
     }
-    const bool ok = corner ? corner_fit(st, s, sel, idx, &cf) : surf_fit(st, s, sel, idx, &cf);
+    const bool ok = corner ? corner_fit(sel, nb, &cf) : surf_fit(sel, nb, &cf);
     if (!ok) continue;
     // mapOptmization.cpp:1223-1255
     const float arx = (crx * sry * srz * ori.x + crx * crz * sry * ori.y - srx * sry * ori.z) * cf.x +
