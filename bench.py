@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=11, help="frames per sequence of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--time-kernel", default="", help="kernel to report in `roofline` (default: the slowest)")
-    ap.add_argument("--streams", type=int, default=1, help="split the batch over this many handles / CUDA streams")
+    ap.add_argument("--streams", type=int, default=4, help="split the batch over this many handles / CUDA streams")
     return ap.parse_args()
 
 
