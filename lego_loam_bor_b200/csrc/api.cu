@@ -72,11 +72,14 @@ int next_pow2(int v) {
   return n;
 }
 
-int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell) {
+int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell, int expected_points = 0) {
   g->cell = cell;
   g->inv_cell = 1.0f / cell;
   g->cap = cap;
-  g->tbl = next_pow2(cap < 4096 ? 4096 : cap);  // buckets >= points: a low load factor keeps empty cells cheap
+  // buckets ~ 1..2x the points actually indexed: a low load factor keeps empty cells cheap, but every
+  // build scans the whole table, so it is sized from the expected fill rather than from the capacity
+  const int want = expected_points > 0 ? expected_points : cap;
+  g->tbl = next_pow2(want < 4096 ? 4096 : want);
   g->ntiles = g->tbl / 4096;
   CK(dev_alloc(h, &g->cell_start, (size_t)B * (g->tbl + 1)));
   CK(dev_alloc(h, &g->cursor, (size_t)B * g->tbl));
@@ -212,11 +215,12 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.corner_last, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.surf_last, BN));
   CK(dev_alloc(h, &st.last_counts, (size_t)B * 2));
   CK(dev_alloc(h, &st.outlier_last, (size_t)B * st.cap_outlier));
-  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f); if (rc) return rc; }
-  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp / 2); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f, N / 3); if (rc) return rc; }
   CK(dev_alloc(h, &st.transform_cur, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_sum, (size_t)B * 6));
   CK(dev_alloc(h, &st.odom_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.odom_flags, (size_t)B * 4));
   CK(dev_alloc(h, &st.odom_matP, (size_t)B * 9));
+  CK(dev_alloc(h, &st.win_tab, (size_t)B * 2 * 2 * (LL_MAX_RINGS + 8)));
   CK(dev_alloc(h, &st.corr_surf, (size_t)B * p.cap_flat * 3)); CK(dev_alloc(h, &st.corr_corner, (size_t)B * p.cap_sharp * 2));
   CK(dev_alloc(h, &st.map_counts, (size_t)B * 2));
   CK(dev_alloc(h, &st.scan_corner_ds, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.scan_surf_ds, BN));

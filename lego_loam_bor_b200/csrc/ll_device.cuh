@@ -106,6 +106,7 @@ struct DevState {
   int* odom_iters;       // [B][2]
   int* odom_flags;       // [B][4]: 0 isDegenerate, 1 systemInitedLM
   float* odom_matP;      // [B][9]
+  int* win_tab;          // [B][2 clouds][2][LL_MAX_RINGS+8] break positions of the ring-window scans
   int* corr_surf;        // [B][24V][3] closest / ring-window indices (pointSearchSurfInd1..3)
   int* corr_corner;      // [B][12V][2]
   // ---- MapOptimization scan-to-map ----

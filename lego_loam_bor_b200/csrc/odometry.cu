@@ -118,18 +118,21 @@ __device__ __forceinline__ void warp_find_correspondence(const DevState& st, int
     closest = nidx;
     const int cs = (int)last[closest].w;
     OrdMin m2{p.nearest_feature_dist_sqr, 0, -1}, m3{p.nearest_feature_dist_sqr, 0, -1};
-    // upward scan; bounded by the CURRENT frame's feature count (sic, featureAssociation.cpp:522,661)
-    const int jend = min(cur_n, last_n);
+    // The reference scans upwards from closest+1 until the first point whose ring id exceeds cs + 2.5 and
+    // downwards from closest-1 until the first id below cs - 2.5 (featureAssociation.cpp:522-563,661-712).
+    // Ring ids are non-decreasing along the cloud up to a -1 wobble (negative relTime truncates to ring-1),
+    // which is enough to make those break positions a function of cs alone: the first index of the WHOLE
+    // cloud with id >= cs+3 and the last index with id <= cs-3 (tables built by k_window_tables).
+    const int* tab = st.win_tab + ((size_t)s * 2 + (surf ? 1 : 0)) * 2 * (LL_MAX_RINGS + 8);
+    const int up_break = tab[min(max(cs + 3, 0), LL_MAX_RINGS + 7)];
+    const int dn_break = (cs - 3 >= 0) ? tab[(LL_MAX_RINGS + 8) + min(cs - 3, LL_MAX_RINGS + 7)] : -1;
+    // upward scan; also bounded by the CURRENT frame's feature count (sic, featureAssociation.cpp:522,661)
+    const int jend = min(min(cur_n, last_n), up_break);
     for (int b0 = closest + 1; b0 < jend; b0 += 32) {
       const int j = b0 + lane;
-      const bool valid = j < jend;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) q = last[j];
-      const int id = (int)q.w;
-      const bool brk = valid && (id > cs + 2);  // int(I) > closestPointScan + 2.5
-      const unsigned bm = __ballot_sync(0xffffffffu, brk);
-      const int nproc = bm ? (__ffs(bm) - 1) : 32;
-      if (valid && lane < nproc) {
+      if (j < jend) {
+        const float4 q = last[j];
+        const int id = (int)q.w;
         const float d2 = sq_dist_ref(q, sel);
         const int ord = j - closest;
         if (surf) {
@@ -138,18 +141,12 @@ __device__ __forceinline__ void warp_find_correspondence(const DevState& st, int
           if (id > cs) ordmin_update(m2, d2, ord, j);
         }
       }
-      if (bm) break;
     }
-    for (int b0 = closest - 1; b0 >= 0; b0 -= 32) {
+    for (int b0 = closest - 1; b0 > dn_break; b0 -= 32) {
       const int j = b0 - lane;
-      const bool valid = j >= 0;
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) q = last[j];
-      const int id = (int)q.w;
-      const bool brk = valid && (id < cs - 2);  // int(I) < closestPointScan - 2.5
-      const unsigned bm = __ballot_sync(0xffffffffu, brk);
-      const int nproc = bm ? (__ffs(bm) - 1) : 32;
-      if (valid && lane < nproc) {
+      if (j > dn_break) {
+        const float4 q = last[j];
+        const int id = (int)q.w;
         const float d2 = sq_dist_ref(q, sel);
         const int ord = 0x40000000 + (closest - j);
         if (surf) {
@@ -158,7 +155,6 @@ __device__ __forceinline__ void warp_find_correspondence(const DevState& st, int
           if (id < cs) ordmin_update(m2, d2, ord, j);
         }
       }
-      if (bm) break;
     }
     ordmin_warp_reduce(m2);
     ind2 = m2.idx;
@@ -520,6 +516,35 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   }
 }
 
+// Break positions of the ring-window scans, per (sequence, cloud): tab[v] = first index whose ring id
+// is >= v, tab2[v] = last index whose ring id is <= v (see warp_find_correspondence).
+__global__ void __launch_bounds__(256) k_window_tables(DevState st) {
+  __shared__ int first_eq[LL_MAX_RINGS + 8], last_eq[LL_MAX_RINGS + 8];
+  const DevParams& p = st.p;
+  const int s = blockIdx.x, cloud = blockIdx.y;  // cloud 0: corner_last, 1: surf_last
+  const int R = LL_MAX_RINGS + 8;
+  const float4* pts = cloud ? st.surf_last + (size_t)s * p.N : st.corner_last + (size_t)s * p.cap_less_sharp;
+  const int n = st.last_counts[s * 2 + cloud];
+  for (int t = threadIdx.x; t < R; t += blockDim.x) { first_eq[t] = 0x7fffffff; last_eq[t] = -1; }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int id = min(max((int)pts[j].w, 0), R - 1);
+    // neighbours with the same id make most of these atomics redundant: only run boundaries matter
+    const int idp = j > 0 ? min(max((int)pts[j - 1].w, 0), R - 1) : -1;
+    const int idn = j + 1 < n ? min(max((int)pts[j + 1].w, 0), R - 1) : -1;
+    if (idp != id) atomicMin(&first_eq[id], j);
+    if (idn != id) atomicMax(&last_eq[id], j);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* tab = st.win_tab + ((size_t)s * 2 + cloud) * 2 * R;
+    int run = n;  // "no such index": the scan runs to the end of the cloud
+    for (int v = R - 1; v >= 0; --v) { run = min(run, first_eq[v]); tab[v] = run; }
+    int runl = -1;
+    for (int v = 0; v < R; ++v) { runl = max(runl, last_eq[v]); tab[R + v] = runl; }
+  }
+}
+
 }  // namespace
 
 void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
@@ -542,6 +567,7 @@ void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
     LL_LAUNCH(ctx, "k_odom_finish", k_odom_finish<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
   }
   LL_LAUNCH(ctx, "k_publish_clouds_last", k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0));
+  LL_LAUNCH(ctx, "k_window_tables", k_window_tables<<<dim3(p.B, 2), 256, 0, ctx.stream>>>(st));
   launch_grid_build2(ctx, p.B, st.grid_corner_last, st.corner_last, p.cap_less_sharp, st.last_counts, 2, 0,
                      st.grid_surf_last, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4);
 }
