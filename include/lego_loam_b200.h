@@ -120,6 +120,8 @@ typedef enum ll_buffer {
   LL_BUF_TRANSFORM_AFT_MAPPED = 37, /* f32[6] */
   LL_BUF_SCAN_SURF_DS = 38,    /* pt[..] laserCloudSurfLastDS (before the outlier cloud is appended) */
   LL_BUF_SCAN_OUTLIER_DS = 39, /* pt[..] laserCloudOutlierLastDS */
+  LL_BUF_STAGE_CLOCKS = 40,    /* i64[16] profiling aid: nanoseconds the two scan-to-scan LM stages of the last frame spent per phase
+                                  (stage*8 + {0 total, 1 prologue, 2 re-search, 3 rows + reduction, 4 solve, 5 re-searched points}) */
   LL_BUF_COUNT_
 } ll_buffer;
 

@@ -27,7 +27,7 @@ BUFFERS = {
     "OUTLIER_LAST": (33, np.float32, 4), "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
     "MAP_TRACE": (35, np.float64, 1), "TRANSFORM_BEF_MAPPED": (36, np.float32, 1),
     "TRANSFORM_AFT_MAPPED": (37, np.float32, 1), "SCAN_SURF_DS": (38, np.float32, 4),
-    "SCAN_OUTLIER_DS": (39, np.float32, 4),
+    "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
 }
 
 EXPORTS = [

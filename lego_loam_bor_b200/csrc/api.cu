@@ -72,7 +72,7 @@ int next_pow2(int v) {
   return n;
 }
 
-int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell, int expected_points = 0) {
+int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell, int expected_points = 0, bool ring_sig = false) {
   g->cell = cell;
   g->inv_cell = 1.0f / cell;
   g->cap = cap;
@@ -88,6 +88,8 @@ int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell, int expect
   CK(dev_alloc(h, &g->tile_tot, (size_t)B * g->ntiles));
   CK(dev_alloc(h, &g->sorted, (size_t)B * cap));
   CK(dev_alloc(h, &g->count, (size_t)B));
+  g->sig = nullptr;
+  if (ring_sig) CK(dev_alloc(h, &g->sig, (size_t)B * g->tbl));
   return LL_OK;
 }
 
@@ -214,14 +216,18 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.surf_less_flat, BN)); CK(dev_alloc(h, &st.feat_counts, (size_t)B * 4));
   CK(dev_alloc(h, &st.corner_last, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.surf_last, BN));
   CK(dev_alloc(h, &st.last_counts, (size_t)B * 2));
+  CK(dev_alloc(h, &st.win_first, (size_t)2 * B * 2 * (LL_MAX_RINGS + 8))); CK(dev_alloc(h, &st.win_last, (size_t)2 * B * 2 * (LL_MAX_RINGS + 8)));
+  CK(cudaMemsetAsync(st.win_first, 0x7f, (size_t)2 * B * 2 * (LL_MAX_RINGS + 8) * 4, h->ctx.stream));
+  CK(cudaMemsetAsync(st.win_last, 0xff, (size_t)2 * B * 2 * (LL_MAX_RINGS + 8) * 4, h->ctx.stream));
+  CK(dev_alloc(h, &st.odom_ga, (size_t)B * p.cap_flat)); CK(dev_alloc(h, &st.odom_ok, (size_t)B * p.cap_flat));
+  CK(dev_alloc(h, &st.stage_clocks, (size_t)B * 16)); CK(dev_alloc(h, &st.odom_cl, (size_t)B * p.cap_flat));
+  CK(dev_alloc(h, &st.odom_gb, (size_t)B * p.cap_sharp)); CK(dev_alloc(h, &st.odom_s0, (size_t)B * p.cap_flat));
   CK(dev_alloc(h, &st.outlier_last, (size_t)B * st.cap_outlier));
-  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp / 2); if (rc) return rc; }
-  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f, N / 3); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp / 2, true); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f, N / 3, true); if (rc) return rc; }
   CK(dev_alloc(h, &st.transform_cur, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_sum, (size_t)B * 6));
   CK(dev_alloc(h, &st.odom_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.odom_flags, (size_t)B * 4));
   CK(dev_alloc(h, &st.odom_matP, (size_t)B * 9));
-  CK(dev_alloc(h, &st.win_tab, (size_t)B * 2 * 2 * (LL_MAX_RINGS + 8)));
-  CK(dev_alloc(h, &st.corr_surf, (size_t)B * p.cap_flat * 3)); CK(dev_alloc(h, &st.corr_corner, (size_t)B * p.cap_sharp * 2));
   CK(dev_alloc(h, &st.map_counts, (size_t)B * 2));
   CK(dev_alloc(h, &st.scan_corner_ds, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.scan_surf_ds, BN));
   CK(dev_alloc(h, &st.scan_ds_counts, (size_t)B * 2));
@@ -288,6 +294,10 @@ int ll_reset(ll_handle* h) {
   CK(cudaMemsetAsync(st.grid_corner_last.occ, 0, (size_t)p.B * (st.grid_corner_last.tbl / 32) * 4, sm));
   CK(cudaMemsetAsync(st.grid_surf_last.occ, 0, (size_t)p.B * (st.grid_surf_last.tbl / 32) * 4, sm));
   CK(cudaMemsetAsync(st.grid_surf_last.cell_start, 0, (size_t)p.B * (st.grid_surf_last.tbl + 1) * 4, sm));
+  CK(cudaMemsetAsync(st.win_first, 0x7f, (size_t)2 * p.B * 2 * (LL_MAX_RINGS + 8) * 4, sm));
+  CK(cudaMemsetAsync(st.win_last, 0xff, (size_t)2 * p.B * 2 * (LL_MAX_RINGS + 8) * 4, sm));
+  CK(cudaMemsetAsync(st.grid_corner_last.sig, 0, (size_t)p.B * st.grid_corner_last.tbl * 4, sm));
+  CK(cudaMemsetAsync(st.grid_surf_last.sig, 0, (size_t)p.B * st.grid_surf_last.tbl * 4, sm));
   h->frames = 0;
   h->odom_cycles = 0;
   h->handed_to_mapping = false;
@@ -629,6 +639,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_SCAN_SURF_TOTAL_DS: COUNTED(st.scan_surf_ds, 16, N, st.scan_ds_counts + seq * 2 + 1); break;
     case LL_BUF_TRANSFORM_TOBE_MAPPED: src = st.transform_tobe_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_MAP_ITERS: src = st.map_iters + seq * 2; elem = 4; n = 2; break;
+    case LL_BUF_STAGE_CLOCKS: src = st.stage_clocks + (size_t)seq * 16; elem = 8; n = 16; break;
     case LL_BUF_MAP_TRACE: src = st.map_trace + (size_t)seq * 340; elem = 8; n = 340; break;
     case LL_BUF_SCAN_SURF_DS: COUNTED(st.vox_tmp_surf, 16, N, st.vox_tmp_counts + seq * 2 + 0); break;
     case LL_BUF_SCAN_OUTLIER_DS: COUNTED(st.vox_tmp_out, 16, (size_t)st.cap_outlier, st.vox_tmp_counts + seq * 2 + 1); break;

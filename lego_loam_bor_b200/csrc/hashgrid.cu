@@ -24,6 +24,7 @@ struct BuildArgs {
   BuildJob job[2];
   const int* enable;
   int enable_stride;
+  int pack_ring;  // sorted.w = index | (ring id + 1) << 24 instead of the plain index (scan-to-scan clouds)
 };
 
 __device__ __forceinline__ bool seq_enabled(const BuildArgs& a, int s) { return a.enable == nullptr || a.enable[s * a.enable_stride] != 0; }
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(GS_THREADS) k_grid_scan(BuildArgs a) {
   int* cnt = j.g.cnt + (size_t)s * j.g.tbl + (size_t)tile * GS_TILE;
   const int4 v = reinterpret_cast<const int4*>(cnt)[threadIdx.x];
   reinterpret_cast<int4*>(cnt)[threadIdx.x] = make_int4(0, 0, 0, 0);
+  if (j.g.sig) reinterpret_cast<int4*>(j.g.sig + (size_t)s * j.g.tbl + (size_t)tile * GS_TILE)[threadIdx.x] = make_int4(0, 0, 0, 0);
   {
     // occupancy bitmap: 4 buckets per thread, 8 threads per 32-bit word
     unsigned bits = (v.x > 0 ? 1u : 0u) | (v.y > 0 ? 2u : 0u) | (v.z > 0 ? 4u : 0u) | (v.w > 0 ? 8u : 0u);
@@ -112,19 +114,26 @@ __global__ void __launch_bounds__(256) k_grid_fill(BuildArgs a) {
   const float4 q = j.pts[(size_t)s * j.stride + i];
   const uint32_t h = grid_hash(grid_cell(q.x, j.g.inv_cell), grid_cell(q.y, j.g.inv_cell), grid_cell(q.z, j.g.inv_cell), j.g.tbl);
   const int pos = atomicAdd(j.g.cursor + (size_t)s * j.g.tbl + h, 1);
-  j.g.sorted[(size_t)s * j.g.cap + pos] = make_float4(q.x, q.y, q.z, __int_as_float(i));
+  int w = i;
+  if (a.pack_ring) {
+    const int idp = min(max((int)q.w + 1, 0), 255);  // ring id = int(intensity), -1..254
+    w |= idp << 24;
+    if (j.g.sig) atomicOr(j.g.sig + (size_t)s * j.g.tbl + h, 1u << (idp & 31));
+  }
+  j.g.sorted[(size_t)s * j.g.cap + pos] = make_float4(q.x, q.y, q.z, __int_as_float(w));
 }
 
 }  // namespace
 
 void launch_grid_build2(LaunchCtx& ctx, int B, HashGrid& g0, const float4* pts0, int stride0, const int* counts0,
                         int cstride0, int coff0, HashGrid& g1, const float4* pts1, int stride1, const int* counts1,
-                        int cstride1, int coff1, const int* enable, int enable_stride) {
+                        int cstride1, int coff1, const int* enable, int enable_stride, bool pack_ring) {
   BuildArgs a;
   a.job[0] = BuildJob{g0, pts0, stride0, counts0, cstride0, coff0};
   a.job[1] = BuildJob{g1, pts1, stride1, counts1, cstride1, coff1};
   a.enable = enable;
   a.enable_stride = enable_stride;
+  a.pack_ring = pack_ring ? 1 : 0;
   const int cap = g0.cap > g1.cap ? g0.cap : g1.cap;
   const int ntiles = g0.ntiles > g1.ntiles ? g0.ntiles : g1.ntiles;
   LL_LAUNCH(ctx, "k_grid_count", k_grid_count<<<dim3((cap + 255) / 256, B, 2), 256, 0, ctx.stream>>>(a));

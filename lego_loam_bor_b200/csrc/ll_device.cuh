@@ -23,6 +23,7 @@ struct HashGrid {
   int* cursor;       // [B][tbl]   fill cursors
   int* cnt;          // [B][tbl]   bucket counters (zero at rest)
   unsigned* occ;     // [B][tbl/32] bit h set <=> bucket h is not empty (tested before touching cell_start)
+  unsigned* sig;     // [B][tbl] or null: bit ((ring id + 1) & 31) set for every ring id present in the bucket
   int* tile_tot;     // [B][ntiles] per-tile counter sums of the scan
   int ntiles;        // tbl / 4096
   float4* sorted;    // [B][cap]   points bucket by bucket; .w carries the original index (int bits)
@@ -99,16 +100,22 @@ struct DevState {
   float4* corner_last;  // [B][120V]
   float4* surf_last;    // [B][N]
   int* last_counts;     // [B][2]
+  int* win_first;       // [2 frame parities][B][2 clouds][LL_MAX_RINGS+8] first index of a run of each ring id
+  int* win_last;        // same shape: last index of a run of each ring id
+  // correspondences of LM iteration 0 of the current stage (k_odom_search -> k_odom_stage), stride 24V
+  float4* odom_ga;      // [B][24V] SURF: unit plane through the three correspondences; CORNER: first line point
+  float4* odom_gb;      // [B][12V] CORNER: second line point
+  float4* odom_s0;      // [B][24V] transformed feature point at search time (x, y, z), slack
+  uint8_t* odom_ok;     // [B][24V]
+  int* odom_cl;         // [B][24V] closest point (index into the last-frame cloud) or -1
+  long long* stage_clocks;  // [B][16] see LL_BUF_STAGE_CLOCKS
   float4* outlier_last; // [B][cap_outlier]
   HashGrid grid_corner_last, grid_surf_last;  // index the clouds the "kd-trees" were last built on
   float* transform_cur;  // [B][6]
   float* transform_sum;  // [B][6]
   int* odom_iters;       // [B][2]
-  int* odom_flags;       // [B][4]: 0 isDegenerate, 1 systemInitedLM
+  int* odom_flags;       // [B][4]: 0 isDegenerate, 2 grids index the current last-frame clouds, 3 outlier count
   float* odom_matP;      // [B][9]
-  int* win_tab;          // [B][2 clouds][2][LL_MAX_RINGS+8] break positions of the ring-window scans
-  int* corr_surf;        // [B][24V][3] closest / ring-window indices (pointSearchSurfInd1..3)
-  int* corr_corner;      // [B][12V][2]
   // ---- MapOptimization scan-to-map ----
   float4* map_corner; float4* map_surf;   // [B][cap_map_corner], [B][cap_map_surf]
   int* map_counts;                        // [B][2]

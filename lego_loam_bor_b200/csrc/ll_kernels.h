@@ -69,7 +69,8 @@ void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame);
 // hashgrid.cu: build the k-NN structures over two clouds at once ([B][stride] points, counts[s*cstride+coff])
 void launch_grid_build2(LaunchCtx& ctx, int B, HashGrid& g0, const float4* pts0, int stride0, const int* counts0,
                         int cstride0, int coff0, HashGrid& g1, const float4* pts1, int stride1, const int* counts1,
-                        int cstride1, int coff1, const int* enable /* [B*enable_stride] or null */, int enable_stride);
+                        int cstride1, int coff1, const int* enable /* [B*enable_stride] or null */, int enable_stride,
+                        bool pack_ring = false /* sorted.w = index | (int(intensity) + 1) << 24 */);
 // mapping.cu: scan2MapOptimization and downsampleCurrentScan
 void launch_scan_to_map(LaunchCtx& ctx, DevState& st);
 void launch_map_predict_pose(LaunchCtx& ctx, DevState& st);

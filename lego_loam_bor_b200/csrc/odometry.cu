@@ -1,27 +1,36 @@
 // odometry.cu -- scan-to-scan LM odometry of FeatureAssociation
 // (reference: LeGO-LOAM/src/featureAssociation.cpp:388-500, 503-1032, 1181-1270, 1329-1359).
 //
-//   k_odom_search<SURF|CORNER>  one warp per feature point: TransformToStart, exact 1-NN in the
-//       last-frame cloud (hash grid instead of the kd-tree) and the reference's ring-window scans,
-//       with its loop bounds and visiting-order tie-breaks.  Runs for LM
-//       iteration 0 of each stage for all sequences at once.
-//   k_odom_lm<SURF|CORNER>      one block per sequence: five LM iterations of one stage per launch
-//       (5 launches per stage, no-ops once converged), no host round trips.  Per iteration: residual + Jacobian row per feature, J^T J / J^T r
-//       as exact double products reduced by warp shuffles + a fixed-order cross-warp sum, 3x3
-//       column-pivoted Householder solve, degeneracy test at iteration 0, convergence test.
-//       Correspondences are refreshed by k_odom_search before iterations 0, 5, 10, 15, 20 (featureAssociation.cpp:511).
-//   k_odom_finish               integrateTransformation (one thread per sequence)
+//   k_odom_search_surf          wide correspondence search of LM iteration 0 of the surf stage: a group of 8 lanes per
+//       flat point, all sequences at once.  TransformToStart, exact 1-NN in the last-frame cloud (hash grid
+//       instead of the kd-tree), then the reference's ring-window scans restated as a second walk over the
+//       same hash grid with the window as a predicate (index range from the ring break tables, ring-id group,
+//       buckets pre-filtered by a ring signature) and the reference's "first strictly smaller wins" rule as
+//       a lexicographic (distance, visiting order) minimum.
+//   k_odom_stage<SURF|CORNER>   one block per sequence runs a whole LM stage of updateTransformation
+//       (featureAssociation.cpp:1213-1235): up to 25 iterations with the 3x3 solve, the degeneracy test and
+//       the convergence test, without a host or kernel boundary in between.  The features of the sequence
+//       and the geometry derived from their correspondences (plane / line end points) live in shared memory
+//       for the whole stage.  The CORNER stage searches in-block (its clouds are small: 1-NN on the hash
+//       grid, window scans linearly); the SURF stage starts from k_odom_search_surf's result and searches
+//       in-block only at iterations 5, 10, ... (rare).
+//       LM iteration: residual + Jacobian row per feature, J^T J / J^T r as exact double products,
+//       warp shuffles + one cross-warp sum, 3x3 column-pivoted Householder solve by one thread.
+//       The CORNER launch ends with integrateTransformation (featureAssociation.cpp:1241-1270).
 //   k_publish_clouds_last       TransformToEnd on the less-sharp / less-flat clouds into the
-//       "last" buffers, adjustOutlierCloud, counts and the kd-tree-rebuild condition.
+//       "last" buffers, adjustOutlierCloud, counts, the kd-tree-rebuild condition and the ring run boundaries
+//       the window break tables are made of.
 #include "../../include/ll_smallmat.h"
 #include "hashgrid.cuh"
 #include "ll_kernels.h"
+#include "shell_offsets.cuh"
 
 namespace {
 
 enum { STAGE_SURF = 0, STAGE_CORNER = 1 };
 
-__device__ __forceinline__ float4 transform_to_start(const float4 pi, const float* T) {
+// (out of line: the double-precision sin/cos expansions are long, and the stage kernels call this from several places)
+__device__ __noinline__ float4 transform_to_start(const float4 pi, const float* T) {
   // featureAssociation.cpp:388-418
   const float s = 10 * (pi.w - (float)(int)pi.w);
   const float ry = s * T[1], rx = s * T[0], rz = s * T[2];
@@ -79,99 +88,31 @@ __device__ __forceinline__ float sq_dist_ref(const float4 a, const float4 b) {
   return (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z);
 }
 
-// running minimum with the reference's "first strictly smaller wins" rule, expressed as a
-// lexicographic (distance, visiting order) minimum so that a warp can evaluate it in parallel
-struct OrdMin {
-  float d2;
-  int ord;
-  int idx;
+// Running minimum with a tie-break key, plus the smallest distance among all OTHER candidates seen (`second`,
+// not limited by the acceptance cap the minimum starts from).  With key = visiting order this is the reference's
+// "first strictly smaller wins" rule as a lexicographic (distance, order) minimum that lanes can evaluate in
+// parallel; with key = point index it is the 1-NN with ties to the lowest index.  `second` is what lets a later
+// LM iteration prove that the minimum cannot have changed (see CorrS::slack).
+#define BEST_NONE 0x7fffffff
+struct Best {
+  float d2;      // starts at the acceptance cap: only strictly smaller distances are accepted
+  int key;       // BEST_NONE: no candidate accepted yet
+  int w;         // payload (packed grid word or cloud index)
+  float second;
 };
-__device__ __forceinline__ void ordmin_update(OrdMin& m, float d2, int ord, int idx) {
-  if (d2 < m.d2 || (d2 == m.d2 && m.idx >= 0 && ord < m.ord)) { m.d2 = d2; m.ord = ord; m.idx = idx; }
-}
-__device__ __forceinline__ void ordmin_warp_reduce(OrdMin& m) {
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, m.d2, o);
-    const int oo = __shfl_xor_sync(0xffffffffu, m.ord, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, m.idx, o);
-    if (oi >= 0 && (m.idx < 0 || od < m.d2 || (od == m.d2 && oo < m.ord))) { m.d2 = od; m.ord = oo; m.idx = oi; }
+__device__ __forceinline__ Best best_init(float cap) { return Best{cap, BEST_NONE, -1, FLT_MAX}; }
+__device__ __forceinline__ void best_update(Best& m, float d2, int key, int w) {
+  if (d2 < m.d2 || (d2 == m.d2 && m.key != BEST_NONE && key < m.key)) {
+    if (m.key != BEST_NONE) m.second = fminf(m.second, m.d2);
+    m.d2 = d2; m.key = key; m.w = w;
+  } else {
+    m.second = fminf(m.second, d2);
   }
 }
-
-// Correspondence search for one feature point, executed by one warp.
-// SURF: featureAssociation.cpp:649-718; CORNER: featureAssociation.cpp:511-568.
-template <int STAGE>
-__device__ __forceinline__ void warp_find_correspondence(const DevState& st, int s, int i, const float* T, int lane) {
-  const DevParams& p = st.p;
-  const bool surf = (STAGE == STAGE_SURF);
-  const float4* cur = surf ? st.surf_flat + (size_t)s * p.cap_flat : st.corner_sharp + (size_t)s * p.cap_sharp;
-  const float4* last = surf ? st.surf_last + (size_t)s * p.N : st.corner_last + (size_t)s * p.cap_less_sharp;
-  const int cur_n = st.feat_counts[s * 4 + (surf ? 2 : 0)];
-  const int last_n = st.last_counts[s * 2 + (surf ? 1 : 0)];
-  const HashGrid& g = surf ? st.grid_surf_last : st.grid_corner_last;
-  const float4 sel = transform_to_start(cur[i], T);
-  float nd2;
-  int nidx;
-  warp_nn1(g, s, sel.x, sel.y, sel.z, p.nearest_feature_dist_sqr, &nd2, &nidx);
-  int closest = -1, ind2 = -1, ind3 = -1;
-  if (nidx >= 0 && nidx < last_n) {  // nd2 < nearest_feature_dist_sqr by construction
-    closest = nidx;
-    const int cs = (int)last[closest].w;
-    OrdMin m2{p.nearest_feature_dist_sqr, 0, -1}, m3{p.nearest_feature_dist_sqr, 0, -1};
-    // The reference scans upwards from closest+1 until the first point whose ring id exceeds cs + 2.5 and
-    // downwards from closest-1 until the first id below cs - 2.5 (featureAssociation.cpp:522-563,661-712).
-    // Ring ids are non-decreasing along the cloud up to a -1 wobble (negative relTime truncates to ring-1),
-    // which is enough to make those break positions a function of cs alone: the first index of the WHOLE
-    // cloud with id >= cs+3 and the last index with id <= cs-3 (tables built by k_window_tables).
-    const int* tab = st.win_tab + ((size_t)s * 2 + (surf ? 1 : 0)) * 2 * (LL_MAX_RINGS + 8);
-    const int up_break = tab[min(max(cs + 3, 0), LL_MAX_RINGS + 7)];
-    const int dn_break = (cs - 3 >= 0) ? tab[(LL_MAX_RINGS + 8) + min(cs - 3, LL_MAX_RINGS + 7)] : -1;
-    // upward scan; also bounded by the CURRENT frame's feature count (sic, featureAssociation.cpp:522,661)
-    const int jend = min(min(cur_n, last_n), up_break);
-    for (int b0 = closest + 1; b0 < jend; b0 += 32) {
-      const int j = b0 + lane;
-      if (j < jend) {
-        const float4 q = last[j];
-        const int id = (int)q.w;
-        const float d2 = sq_dist_ref(q, sel);
-        const int ord = j - closest;
-        if (surf) {
-          if (id <= cs) ordmin_update(m2, d2, ord, j); else ordmin_update(m3, d2, ord, j);
-        } else {
-          if (id > cs) ordmin_update(m2, d2, ord, j);
-        }
-      }
-    }
-    for (int b0 = closest - 1; b0 > dn_break; b0 -= 32) {
-      const int j = b0 - lane;
-      if (j > dn_break) {
-        const float4 q = last[j];
-        const int id = (int)q.w;
-        const float d2 = sq_dist_ref(q, sel);
-        const int ord = 0x40000000 + (closest - j);
-        if (surf) {
-          if (id >= cs) ordmin_update(m2, d2, ord, j); else ordmin_update(m3, d2, ord, j);
-        } else {
-          if (id < cs) ordmin_update(m2, d2, ord, j);
-        }
-      }
-    }
-    ordmin_warp_reduce(m2);
-    ind2 = m2.idx;
-    if (surf) {
-      ordmin_warp_reduce(m3);
-      ind3 = m3.idx;
-    }
-  }
-  if (lane == 0) {
-    if (surf) {
-      int* c = st.corr_surf + ((size_t)s * p.cap_flat + i) * 3;
-      c[0] = closest; c[1] = ind2; c[2] = ind3;
-    } else {
-      int* c = st.corr_corner + ((size_t)s * p.cap_sharp + i) * 2;
-      c[0] = closest; c[1] = ind2;
-    }
-  }
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 __device__ __forceinline__ bool odom_guard(const DevState& st, int s) {
@@ -179,18 +120,306 @@ __device__ __forceinline__ bool odom_guard(const DevState& st, int s) {
   return !(st.last_counts[s * 2 + 0] < 10 || st.last_counts[s * 2 + 1] < 100);
 }
 
-template <int STAGE>
-__global__ void __launch_bounds__(256) k_odom_search(DevState st) {
-  const DevParams& p = st.p;
-  const int s = blockIdx.y;
-  if (!odom_guard(st, s) || st.odom_flags[s * 4 + 1]) return;  // flag 1: this stage has converged
-  const int n = st.feat_counts[s * 4 + (STAGE == STAGE_SURF ? 2 : 0)];
+#define LM_THREADS 512
+#define LM_WARPS (LM_THREADS / 32)
+#define WIN_R (LL_MAX_RINGS + 8)
+
+// Break positions of the ring-window scans.  The reference walks upwards from closest+1 until the first
+// point whose ring id exceeds cs + 2.5 and downwards from closest-1 until the first id below cs - 2.5
+// (featureAssociation.cpp:522-563,661-712).  Ring ids are non-decreasing along the cloud up to a -1 wobble
+// (a negative relTime truncates to ring-1), which makes those break positions a function of cs alone: the
+// first index of the WHOLE cloud with id >= cs+3 and the last index with id <= cs-3.
+struct WinTables {
+  int up_tab[WIN_R];   // up_tab[v]: first index of the last-frame cloud whose ring id is >= v (cloud size if none)
+  int dn_tab[WIN_R];   // dn_tab[v]: last index whose ring id is <= v (-1 if none)
+};
+
+// Shared state of one stage of one sequence.
+struct StageShared {
+  WinTables win;
   float T[6];
+  double part[LM_WARPS][10];
+  int stop, iters;
+};
+
+// win_first / win_last hold, per ring id, the first / last index of a run of that id (k_publish_clouds_last);
+// the tables are their suffix minimum / prefix maximum.  Called by all threads of the block, ends with a barrier.
+__device__ __forceinline__ void build_window_tables(WinTables& w, const DevState& st, int s, int cloud, int n) {
+  const int par = (int)((st.frame_tag - 1u) & 1u);  // written while the previous frame was published
+  const int* first = st.win_first + (((size_t)par * st.p.B + s) * 2 + cloud) * WIN_R;
+  const int* lastv = st.win_last + (((size_t)par * st.p.B + s) * 2 + cloud) * WIN_R;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int carry = n;
+    for (int base = WIN_R - 1; base >= 0; base -= 32) {
+      const int v = base - lane;
+      int x = v >= 0 ? first[v] : 0x7fffffff;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = min(x, y);
+      }
+      x = min(x, carry);
+      if (v >= 0) w.up_tab[v] = x;
+      carry = __shfl_sync(0xffffffffu, x, 31);
+    }
+    carry = -1;
+    for (int base = 0; base < WIN_R; base += 32) {
+      const int v = base + lane;
+      int x = v < WIN_R ? lastv[v] : -1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = max(x, y);
+      }
+      x = max(x, carry);
+      if (v < WIN_R) w.dn_tab[v] = x;
+      carry = __shfl_sync(0xffffffffu, x, 31);
+    }
+  }
+  __syncthreads();
+}
+
+#define SG 32                      // lanes that cooperate on the search of one feature point (a warp: sub-warp groups
+                                   // would run their data-dependent loops one after the other anyway)
+#define SLACK_HORIZON 0.2f         // cells farther than the current minimum + this are not visited; caps CorrS::slack at half of it
+#define LM_GROUPS (LM_THREADS / SG)
+#define SEARCH_THREADS 256
+#define SEARCH_GROUPS (SEARCH_THREADS / SG)
+
+// Warp-wide reduction of Best (all 32 lanes; SG == 32): hardware integer min-reductions on the distance bits
+// (non-negative floats order like unsigned ints) and on the tie-break key, payload from the winning lane.
+__device__ __forceinline__ void best_group_reduce(unsigned gmask, Best& m) {
+  const unsigned mybits = m.key != BEST_NONE ? __float_as_uint(m.d2) : 0xffffffffu;
+  const unsigned minbits = __reduce_min_sync(gmask, mybits);
+  if (minbits == 0xffffffffu) {  // no lane has a candidate: only the runner-up distances need merging
+    m.second = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(m.second)));
+    return;
+  }
+  const unsigned mykey = mybits == minbits ? (unsigned)m.key : 0xffffffffu;
+  const unsigned minkey = __reduce_min_sync(gmask, mykey);
+  const bool holds = mybits == minbits && (unsigned)m.key == minkey;  // lanes holding the winning candidate (same key => same candidate)
+  const int src = __ffs(__ballot_sync(gmask, holds)) - 1;
+  const int ww = __shfl_sync(gmask, m.w, src);
+  // runner-up: every lane's `second`, plus the minimum of the lanes that hold a different candidate
+  const float mine = (holds || m.key == BEST_NONE) ? m.second : fminf(m.second, m.d2);
+  m.second = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(mine)));
+  m.d2 = __uint_as_float(minbits); m.key = (int)minkey; m.w = ww;
+}
+
+// The SG lanes of a group visit the buckets of shell r (cells at Chebyshev distance r from (cx,cy,cz)).  Cells are
+// tested SG at a time, one per lane (occupancy bit, optional ring signature, bucket range); the non-empty buckets
+// are then walked one after the other with their points spread over the lanes, so that long buckets (clustered
+// edge points) do not serialise on one lane.  `want` != 0 restricts the visit to buckets whose ring signature
+// intersects it.  f(point) is called for every stored point of the visited buckets (by some lane of the group);
+// aliasing buckets only add candidates.
+template <typename F>
+__device__ __forceinline__ void group_visit_shell(const HashGrid& g, const int* __restrict__ cs, const unsigned* __restrict__ occ,
+                                                  const unsigned* __restrict__ sig, unsigned want, const float4* __restrict__ pts,
+                                                  int cx, int cy, int cz, int r, int gl, unsigned gmask, float qx, float qy, float qz,
+                                                  float bound2, F&& f) {
+  // bound2: cells whose box is farther than sqrt(bound2) from the query (qx, qy, qz) are skipped
+  const int side = 2 * r + 1;
+  const bool tabled = r <= LL_SHELL_TABLE_R;
+  const int t_begin = tabled ? k_shell_start[r] : 0;
+  const int t_end = tabled ? k_shell_start[r + 1] : side * side * side;
+  for (int t0 = t_begin; t0 < t_end; t0 += SG) {  // uniform over the group
+    const int t = t0 + gl;
+    int b0 = 0, b1 = 0;
+    if (t < t_end) {
+      int dx, dy, dz;
+      if (tabled) {
+        const int o = k_shell_ofs[t];
+        dx = (o & 15) - 8; dy = ((o >> 4) & 15) - 8; dz = (o >> 8) - 8;
+      } else {  // beyond the table: enumerate the cube and skip its interior
+        dz = t / (side * side) - r;
+        const int rem = t % (side * side);
+        dy = rem / side - r; dx = rem % side - r;
+      }
+      bool visit = tabled || max(max(abs(dx), abs(dy)), abs(dz)) == r;
+      if (visit && r > 0) {
+        // distance from the query to the cell's box, shrunk a little so that rounding in grid_cell() cannot matter
+        const float tol = 1e-3f * g.cell;
+        const float lx = (float)(cx + dx) * g.cell, ly = (float)(cy + dy) * g.cell, lz = (float)(cz + dz) * g.cell;
+        const float gx = fmaxf(fmaxf(lx - qx, qx - (lx + g.cell)) - tol, 0.f);
+        const float gy = fmaxf(fmaxf(ly - qy, qy - (ly + g.cell)) - tol, 0.f);
+        const float gz = fmaxf(fmaxf(lz - qz, qz - (lz + g.cell)) - tol, 0.f);
+        visit = gx * gx + gy * gy + gz * gz < bound2;
+      }
+      if (visit) {
+        const uint32_t h = grid_hash(cx + dx, cy + dy, cz + dz, g.tbl);
+        if ((__ldg(occ + (h >> 5)) >> (h & 31)) & 1u) {
+          if (want == 0u || (__ldg(sig + h) & want)) { b0 = __ldg(cs + h); b1 = __ldg(cs + h + 1); }
+        }
+      }
+    }
+    unsigned m = __ballot_sync(gmask, b1 > b0) & gmask;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int sb0 = __shfl_sync(gmask, b0, src), sb1 = __shfl_sync(gmask, b1, src);
+      for (int k = sb0 + gl; k < sb1; k += SG) f(__ldg(pts + k));
+    }
+  }
+}
+
+// Result of a correspondence search.  slack (metres): if the transformed feature point moves by less than
+// `slack` from where it was searched, closest / ind2 / ind3 provably stay what they are: every other candidate
+// of each of the three minima is more than 2 * slack farther away than the winner (triangle inequality on both),
+// the winners stay inside the acceptance radius, an empty minimum stays empty, and the window (a function of the
+// closest point's ring) stays the same.  slack <= 0: nothing can be proved.
+struct CorrS {
+  int closest, ind2, ind3;
+  float slack;
+};
+
+// Correspondence search for one feature point by a group of SG lanes (all lanes pass the same `sel` and get the
+// same result).  SURF: featureAssociation.cpp:649-718; CORNER: featureAssociation.cpp:511-568.
+// fresh: the hash grid indexes the current last-frame cloud and its sorted points carry index | (ring id + 1) << 24
+// in .w, so the ring-window scans of the SURF stage become a second walk over the grid with the window as a
+// predicate; the CORNER windows are a few hundred points and are scanned linearly like the reference does.
+// !fresh: the grid still indexes an OLDER cloud (the reference rebuilds its kd-trees only when both last-frame
+// clouds are large enough, featureAssociation.cpp:1356, while the clouds are always swapped): the 1-NN runs on
+// the stale grid and the window scans run linearly over the current cloud, as in the reference.  Rare.
+template <int STAGE>
+__device__ __forceinline__ CorrS group_search(const DevState& st, const WinTables& win, int s, const float4 sel, int cur_n, int last_n,
+                                              const float4* __restrict__ last, bool fresh, int gl, unsigned gmask, int seed = -1) {
+  const DevParams& p = st.p;
+  const bool surf = (STAGE == STAGE_SURF);
+  const HashGrid& g = surf ? st.grid_surf_last : st.grid_corner_last;
+  const int* cs_tab = g.cell_start + (size_t)s * (g.tbl + 1);
+  const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
+  const unsigned* sig = g.sig + (size_t)s * g.tbl;
+  const float4* pts = g.sorted + (size_t)s * g.cap;
+  const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
+  const float cap = p.nearest_feature_dist_sqr;
+  const float lim = sqrtf(cap);
+  const int rmax = (int)ceilf(lim * g.inv_cell);
+  CorrS c{-1, -1, -1, 0.f};
+  // ---- exact 1-NN with d2 < nearest_feature_dist_sqr; ties: lowest index ----
+  Best nn = best_init(cap);
+  if (fresh && seed >= 0 && seed < last_n) {
+    // re-search: the previous closest point is a candidate that usually is, or is next to, the new one; starting
+    // from it lets the walk skip every cell that is farther away
+    const float4 q = last[seed];
+    best_update(nn, nn_dist2(sel.x, sel.y, sel.z, q), seed, seed | (min(max((int)q.w + 1, 0), 255) << 24));
+  }
+  float seen2 = 0.f;  // everything closer than sqrt(seen2) has been visited
+  for (int r = 0; r <= rmax; ++r) {
+    Best t = best_init(cap);
+    const float hb = sqrtf(nn.d2) + SLACK_HORIZON;
+    group_visit_shell(g, cs_tab, occ, sig, 0u, pts, cx, cy, cz, r, gl, gmask, sel.x, sel.y, sel.z, hb * hb, [&](const float4 q) {
+      const int w = __float_as_int(q.w);
+      best_update(t, nn_dist2(sel.x, sel.y, sel.z, q), w & 0xffffff, w);
+    });
+    best_group_reduce(gmask, t);
+    // merge the shell into the running result (both are uniform over the group)
+    float sec = fminf(nn.second, t.second);
+    if (t.key != BEST_NONE && (nn.key == BEST_NONE || t.d2 < nn.d2 || (t.d2 == nn.d2 && t.key < nn.key))) {
+      if (nn.key != BEST_NONE) sec = fminf(sec, nn.d2);
+      nn.d2 = t.d2; nn.key = t.key; nn.w = t.w;
+    } else if (t.key != BEST_NONE && !(t.key == nn.key && t.w == nn.w)) {
+      sec = fminf(sec, t.d2);
+    }
+    nn.second = sec;
+    const float reach = (float)r * g.cell;
+    seen2 = reach * reach * 0.9999f;
+    if (nn.d2 < seen2) break;  // nothing outside the visited block can be closer
+  }
+  const int closest = nn.key;
+  if (nn.key == BEST_NONE || closest >= last_n) return c;
+  c.closest = closest;
+  const float sq1 = sqrtf(nn.d2);
+  // runner-ups closer than min(reach of the visited block, the final pruning horizon) have all been visited
+  float slack = fminf(lim - sq1, 0.5f * (fminf(sqrtf(fminf(nn.second, seen2)), sq1 + SLACK_HORIZON - 0.01f) - sq1));
+  const int csr = fresh ? (int)((unsigned)nn.w >> 24) - 1 : (int)last[closest].w;  // closestPointScan
+  const int up_break = win.up_tab[min(max(csr + 3, 0), WIN_R - 1)];
+  const int dn_break = (csr - 3 >= 0) ? win.dn_tab[min(csr - 3, WIN_R - 1)] : -1;
+  // the upward scan is also bounded by the CURRENT frame's feature count (sic, featureAssociation.cpp:522,661)
+  const int jend = min(min(cur_n, last_n), up_break);
+  Best m2 = best_init(cap), m3 = best_init(cap);
+  float wseen2 = FLT_MAX;  // window candidates closer than sqrt(wseen2) have all been visited
+  if (fresh && surf) {
+    // SURF windows span thousands of points: walk the grid instead.  Ring ids csr-2 .. csr+2 as signature bits of (id + 1) & 31
+    unsigned want = 0u;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) T[k] = st.transform_cur[s * 6 + k];
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps)
-    warp_find_correspondence<STAGE>(st, s, i, T, threadIdx.x & 31);
+    for (int d = -2; d <= 2; ++d) want |= 1u << ((csr + 1 + d) & 31);
+    float wb = lim + SLACK_HORIZON;  // pruning horizon: the farther of the two current minima + SLACK_HORIZON
+    for (int r = 0; r <= rmax; ++r) {
+      group_visit_shell(g, cs_tab, occ, sig, want, pts, cx, cy, cz, r, gl, gmask, sel.x, sel.y, sel.z, wb * wb, [&](const float4 q) {
+        const int w = __float_as_int(q.w);
+        const int j = w & 0xffffff;
+        const int id = (int)((unsigned)w >> 24) - 1;
+        if (j == closest) return;
+        const bool up = j > closest;
+        if (up ? (j >= jend) : (j <= dn_break)) return;
+        const float d2 = nn_dist2(sel.x, sel.y, sel.z, q);  // == (q - sel)^2 summed left to right
+        const int ord = up ? (j - closest) : (0x40000000 + (closest - j));
+        const bool same = up ? (id <= csr) : (id >= csr);
+        if (same) best_update(m2, d2, ord, j); else best_update(m3, d2, ord, j);
+      });
+      Best t2 = m2, t3 = m3;
+      best_group_reduce(gmask, t2);
+      best_group_reduce(gmask, t3);
+      const float reach = (float)r * g.cell;
+      wseen2 = reach * reach * 0.9999f;
+      wb = sqrtf(fmaxf(t2.d2, t3.d2)) + SLACK_HORIZON;  // d2 is the cap while a minimum is still empty
+      const bool done2 = t2.key != BEST_NONE && t2.d2 < wseen2;
+      const bool done3 = t3.key != BEST_NONE && t3.d2 < wseen2;
+      if ((done2 && done3) || r == rmax) {
+        m2 = t2; m3 = t3;
+        // skipped cells were farther than (the larger minimum at that time + SLACK_HORIZON) >= the final horizon
+        wseen2 = fminf(wseen2, (wb - 0.5f * SLACK_HORIZON) * (wb - 0.5f * SLACK_HORIZON));
+        break;
+      }
+    }
+  } else {
+    // candidates of the upward scan have id > csr (CORNER) and those of the downward scan id < csr, so the same-ring
+    // runs next to the closest point can be skipped there: ids below csr + 1 end before up_tab[csr + 1]
+    const int up0 = surf ? closest + 1 : max(closest + 1, win.up_tab[min(max(csr + 1, 0), WIN_R - 1)]);
+    const int dn0 = surf ? closest - 1 : min(closest - 1, (csr - 1 >= 0) ? win.dn_tab[min(csr - 1, WIN_R - 1)] : -1);
+    for (int j = up0 + gl; j < jend; j += SG) {
+      const float4 q = last[j];
+      const int id = (int)q.w;
+      const float d2 = sq_dist_ref(q, sel);
+      const int ord = j - closest;
+      if (surf) {
+        if (id <= csr) best_update(m2, d2, ord, j); else best_update(m3, d2, ord, j);
+      } else if (id > csr) {
+        best_update(m2, d2, ord, j);
+      }
+    }
+    for (int j = dn0 - gl; j > dn_break; j -= SG) {
+      const float4 q = last[j];
+      const int id = (int)q.w;
+      const float d2 = sq_dist_ref(q, sel);
+      const int ord = 0x40000000 + (closest - j);
+      if (surf) {
+        if (id >= csr) best_update(m2, d2, ord, j); else best_update(m3, d2, ord, j);
+      } else if (id < csr) {
+        best_update(m2, d2, ord, j);
+      }
+    }
+    best_group_reduce(gmask, m2);
+    if (surf) best_group_reduce(gmask, m3);
+  }
+  // slack of the window minima: a found one must keep its lead and stay inside the radius, an empty one must stay empty
+  if (m2.key != BEST_NONE) {
+    const float sq = sqrtf(m2.d2);
+    slack = fminf(slack, fminf(lim - sq, 0.5f * (sqrtf(fminf(m2.second, wseen2)) - sq)));
+    c.ind2 = m2.w;
+  } else {
+    slack = fminf(slack, sqrtf(fminf(m2.second, wseen2)) - lim);
+  }
+  if (surf) {
+    if (m3.key != BEST_NONE) {
+      const float sq = sqrtf(m3.d2);
+      slack = fminf(slack, fminf(lim - sq, 0.5f * (sqrtf(fminf(m3.second, wseen2)) - sq)));
+      c.ind3 = m3.w;
+    } else {
+      slack = fminf(slack, sqrtf(fminf(m3.second, wseen2)) - lim);
+    }
+  }
+  c.slack = fresh ? slack : 0.f;
+  return c;
 }
 
 // One accepted correspondence -> one row [a0 a1 a2 | b] of the 3-column system.
@@ -253,24 +482,13 @@ __device__ __forceinline__ CornerCoef make_corner_coef(const float* T) {
   return c;
 }
 
-// featureAssociation.cpp:721-777 + 834-857
-__device__ __forceinline__ Row3 surf_row(const DevState& st, int s, int i, const float* T, const SurfCoef& k, int iter) {
-  const DevParams& p = st.p;
+
+// featureAssociation.cpp:721-777 + 834-857; `pl` = the unit plane (pa, pb, pc, pd) through the three
+// correspondences, which the reference recomputes every iteration from the same three points
+__device__ __forceinline__ Row3 surf_row(const float4 ori, const float4 sel, const float4 pl, const SurfCoef& k, int iter) {
   Row3 r;
   r.ok = false;
-  const int* c = st.corr_surf + ((size_t)s * p.cap_flat + i) * 3;
-  const int i1 = c[0], i2 = c[1], i3 = c[2];
-  if (!(i2 >= 0 && i3 >= 0)) return r;
-  const float4 ori = st.surf_flat[(size_t)s * p.cap_flat + i];
-  const float4 sel = transform_to_start(ori, T);
-  const float4* last = st.surf_last + (size_t)s * p.N;
-  const float4 t1 = last[i1], t2 = last[i2], t3 = last[i3];
-  float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
-  float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
-  float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
-  float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
-  const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
-  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+  const float pa = pl.x, pb = pl.y, pc = pl.z, pd = pl.w;
   const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
   float w = 1;
   if (iter >= 5) {
@@ -290,18 +508,21 @@ __device__ __forceinline__ Row3 surf_row(const DevState& st, int s, int i, const
   return r;
 }
 
+__device__ __forceinline__ float4 surf_plane(const float4 t1, const float4 t2, const float4 t3) {
+  // featureAssociation.cpp:734-747
+  float pa = (t2.y - t1.y) * (t3.z - t1.z) - (t3.y - t1.y) * (t2.z - t1.z);
+  float pb = (t2.z - t1.z) * (t3.x - t1.x) - (t3.z - t1.z) * (t2.x - t1.x);
+  float pc = (t2.x - t1.x) * (t3.y - t1.y) - (t3.x - t1.x) * (t2.y - t1.y);
+  float pd = -(pa * t1.x + pb * t1.y + pc * t1.z);
+  const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+  return make_float4(pa, pb, pc, pd);
+}
+
 // featureAssociation.cpp:571-635 + 960-978
-__device__ __forceinline__ Row3 corner_row(const DevState& st, int s, int i, const float* T, const CornerCoef& k, int iter) {
-  const DevParams& p = st.p;
+__device__ __forceinline__ Row3 corner_row(const float4 ori, const float4 sel, const float4 t1, const float4 t2, const CornerCoef& k, int iter) {
   Row3 r;
   r.ok = false;
-  const int* c = st.corr_corner + ((size_t)s * p.cap_sharp + i) * 2;
-  const int i1 = c[0], i2 = c[1];
-  if (!(i2 >= 0)) return r;
-  const float4 ori = st.corner_sharp[(size_t)s * p.cap_sharp + i];
-  const float4 sel = transform_to_start(ori, T);
-  const float4* last = st.corner_last + (size_t)s * p.cap_less_sharp;
-  const float4 t1 = last[i1], t2 = last[i2];
   const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
   const float x1 = t1.x, y1 = t1.y, z1 = t1.z;
   const float x2 = t2.x, y2 = t2.y, z2 = t2.z;
@@ -328,117 +549,6 @@ __device__ __forceinline__ Row3 corner_row(const DevState& st, int s, int i, con
   return r;
 }
 
-#define LM_THREADS 512
-#define LM_WARPS (LM_THREADS / 32)
-
-// Iterations [it_begin, it_begin + 5) of one LM stage; the correspondences were refreshed by
-// k_odom_search right before (featureAssociation.cpp:511: every 5th iteration).  A sequence that has
-// converged (or failed the guard) turns the remaining launches of its stage into no-ops.
-template <int STAGE>
-__global__ void __launch_bounds__(LM_THREADS) k_odom_lm(DevState st, int it_begin) {
-  __shared__ float sT[6];
-  __shared__ double sh_part[LM_WARPS][10];
-  __shared__ int sh_state[4];  // 0: stop flag, 1: iterations run
-  const DevParams& p = st.p;
-  const int s = blockIdx.x;
-  const bool surf = (STAGE == STAGE_SURF);
-  if (!odom_guard(st, s)) {
-    if (threadIdx.x == 0 && it_begin == 0) st.odom_iters[s * 2 + STAGE] = 0;
-    return;
-  }
-  if (st.odom_flags[s * 4 + 1]) return;
-  const int n = st.feat_counts[s * 4 + (surf ? 2 : 0)];
-  if (threadIdx.x < 6) sT[threadIdx.x] = st.transform_cur[s * 6 + threadIdx.x];
-  if (threadIdx.x == 0) { sh_state[0] = 0; sh_state[1] = it_begin; }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int iter = it_begin; iter < it_begin + 5; ++iter) {
-    float T[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) T[k] = sT[k];
-    double acc[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
-    SurfCoef ks;
-    CornerCoef kc;
-    if (surf) ks = make_surf_coef(T); else kc = make_corner_coef(T);
-    for (int i = threadIdx.x; i < n; i += LM_THREADS) {
-      const Row3 r = surf ? surf_row(st, s, i, T, ks, iter) : corner_row(st, s, i, T, kc, iter);
-      if (r.ok) {
-        const double a0 = r.a0, a1 = r.a1, a2 = r.a2, b = r.b;
-        acc[0] += a0 * a0; acc[1] += a0 * a1; acc[2] += a0 * a2;
-        acc[3] += a1 * a1; acc[4] += a1 * a2; acc[5] += a2 * a2;
-        acc[6] += a0 * b; acc[7] += a1 * b; acc[8] += a2 * b;
-        acc[9] += 1.0;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] = warp_sum_d(acc[k]);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 10; ++k) sh_part[wid][k] = acc[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double tot[10];
-      for (int k = 0; k < 10; ++k) {
-        double v = 0.0;
-        for (int w = 0; w < LM_WARPS; ++w) v += sh_part[w][k];
-        tot[k] = v;
-      }
-      sh_state[1] = iter + 1;
-      const int rows = (int)tot[9];
-      if (rows >= 10) {  // featureAssociation.cpp:1222,1232
-        float AtA[9] = {(float)tot[0], (float)tot[1], (float)tot[2], (float)tot[1], (float)tot[3],
-                        (float)tot[4], (float)tot[2], (float)tot[4], (float)tot[5]};
-        float AtB[3] = {(float)tot[6], (float)tot[7], (float)tot[8]};
-        float A2[9], X[3];
-        for (int k = 0; k < 9; ++k) A2[k] = AtA[k];
-        llm::colpiv_qr_solve<3, 3>(A2, AtB, X);
-        float* matP = st.odom_matP + s * 9;
-        if (iter == 0) st.odom_flags[s * 4 + 0] = llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0;
-        if (st.odom_flags[s * 4 + 0]) {
-          const float X2[3] = {X[0], X[1], X[2]};
-          for (int r = 0; r < 3; ++r) X[r] = matP[r * 3 + 0] * X2[0] + matP[r * 3 + 1] * X2[1] + matP[r * 3 + 2] * X2[2];
-        }
-        if (surf) {
-          sT[0] += X[0]; sT[2] += X[1]; sT[4] += X[2];
-        } else {
-          sT[1] += X[0]; sT[3] += X[1]; sT[5] += X[2];
-        }
-        for (int k = 0; k < 6; ++k)
-          if (sT[k] != sT[k]) sT[k] = 0;
-        const float RAD2DEG = (float)(180.0 / LL_PI);
-        float deltaR, deltaT;
-        if (surf) {
-          const double r0 = (double)(RAD2DEG * X[0]), r1 = (double)(RAD2DEG * X[1]);
-          deltaR = (float)sqrt(r0 * r0 + r1 * r1);
-          const double t0 = (double)(X[2] * 100);
-          deltaT = (float)sqrt(t0 * t0);
-        } else {
-          const double r0 = (double)(RAD2DEG * X[0]);
-          deltaR = (float)sqrt(r0 * r0);
-          const double t0 = (double)(X[1] * 100), t1 = (double)(X[2] * 100);
-          deltaT = (float)sqrt(t0 * t0 + t1 * t1);
-        }
-        if ((double)deltaR < 0.1 && (double)deltaT < 0.1) sh_state[0] = 1;
-      }
-    }
-    __syncthreads();
-    if (sh_state[0]) break;
-  }
-  if (threadIdx.x < 6) st.transform_cur[s * 6 + threadIdx.x] = sT[threadIdx.x];
-  if (threadIdx.x == 0) {
-    st.odom_iters[s * 2 + STAGE] = sh_state[1];
-    if (sh_state[0]) st.odom_flags[s * 4 + 1] = 1;
-  }
-}
-
-__global__ void k_odom_stage_begin(DevState st) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < st.p.B) st.odom_flags[s * 4 + 1] = 0;
-}
-
 __device__ __forceinline__ void accumulate_rotation(float cx, float cy, float cz, float lx, float ly, float lz,
                                                     float* ox, float* oy, float* oz) {
   // featureAssociation.cpp:474-500
@@ -456,10 +566,8 @@ __device__ __forceinline__ void accumulate_rotation(float cx, float cy, float cz
   *oz = ll_atan2f(srzcrx / cox, crzcrx / cox);
 }
 
-__global__ void k_odom_finish(DevState st) {
-  // integrateTransformation, featureAssociation.cpp:1241-1270
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= st.p.B) return;
+// integrateTransformation, featureAssociation.cpp:1241-1270 (one thread)
+__device__ __forceinline__ void integrate_transformation(const DevState& st, int s) {
   float* Tc = st.transform_cur + s * 6;
   float* Ts = st.transform_sum + s * 6;
   float rx, ry, rz;
@@ -492,13 +600,35 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   for (int k = 0; k < 6; ++k) T[k] = st.transform_cur[s * 6 + k];
   const int n_corner = st.feat_counts[s * 4 + 1];
   const int n_surf = st.feat_counts[s * 4 + 3];
+  // window tables are double buffered by frame parity: this frame fills one half (reset while the previous
+  // frame was published, or by ll_reset) and resets the other half for the next frame
+  const int par = (int)(st.frame_tag & 1u);
+  int* wfirst = st.win_first + ((size_t)par * p.B + s) * 2 * WIN_R;
+  int* wlast = st.win_last + ((size_t)par * p.B + s) * 2 * WIN_R;
+  if (i < 2 * WIN_R) {
+    st.win_first[((size_t)(par ^ 1) * p.B + s) * 2 * WIN_R + i] = 0x7fffffff;
+    st.win_last[((size_t)(par ^ 1) * p.B + s) * 2 * WIN_R + i] = -1;
+  }
   if (i < n_corner) {
     const float4 q = st.corner_less_sharp[(size_t)s * p.cap_less_sharp + i];
     st.corner_last[(size_t)s * p.cap_less_sharp + i] = first_frame ? q : transform_to_end(q, T);
+    // ring run boundaries of the new last-frame cloud: id = int(intensity) is the same before and after TransformToEnd
+    const float4* src = st.corner_less_sharp + (size_t)s * p.cap_less_sharp;
+    const int id = min(max((int)q.w, 0), WIN_R - 1);
+    const int idp = i > 0 ? min(max((int)src[i - 1].w, 0), WIN_R - 1) : -1;
+    const int idn = i + 1 < n_corner ? min(max((int)src[i + 1].w, 0), WIN_R - 1) : -1;
+    if (idp != id) atomicMin(wfirst + id, i);
+    if (idn != id) atomicMax(wlast + id, i);
   }
   if (i < n_surf) {
     const float4 q = st.surf_less_flat[(size_t)s * p.N + i];
     st.surf_last[(size_t)s * p.N + i] = first_frame ? q : transform_to_end(q, T);
+    const float4* src = st.surf_less_flat + (size_t)s * p.N;
+    const int id = min(max((int)q.w, 0), WIN_R - 1);
+    const int idp = i > 0 ? min(max((int)src[i - 1].w, 0), WIN_R - 1) : -1;
+    const int idn = i + 1 < n_surf ? min(max((int)src[i + 1].w, 0), WIN_R - 1) : -1;
+    if (idp != id) atomicMin(wfirst + WIN_R + id, i);
+    if (idn != id) atomicMax(wlast + WIN_R + id, i);
   }
   if (!first_frame) {
     const int n_out = st.outlier_count[s];
@@ -516,58 +646,271 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   }
 }
 
-// Break positions of the ring-window scans, per (sequence, cloud): tab[v] = first index whose ring id
-// is >= v, tab2[v] = last index whose ring id is <= v (see warp_find_correspondence).
-__global__ void __launch_bounds__(256) k_window_tables(DevState st) {
-  __shared__ int first_eq[LL_MAX_RINGS + 8], last_eq[LL_MAX_RINGS + 8];
-  const DevParams& p = st.p;
-  const int s = blockIdx.x, cloud = blockIdx.y;  // cloud 0: corner_last, 1: surf_last
-  const int R = LL_MAX_RINGS + 8;
-  const float4* pts = cloud ? st.surf_last + (size_t)s * p.N : st.corner_last + (size_t)s * p.cap_less_sharp;
-  const int n = st.last_counts[s * 2 + cloud];
-  for (int t = threadIdx.x; t < R; t += blockDim.x) { first_eq[t] = 0x7fffffff; last_eq[t] = -1; }
-  __syncthreads();
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    const int id = min(max((int)pts[j].w, 0), R - 1);
-    // neighbours with the same id make most of these atomics redundant: only run boundaries matter
-    const int idp = j > 0 ? min(max((int)pts[j - 1].w, 0), R - 1) : -1;
-    const int idn = j + 1 < n ? min(max((int)pts[j + 1].w, 0), R - 1) : -1;
-    if (idp != id) atomicMin(&first_eq[id], j);
-    if (idn != id) atomicMax(&last_eq[id], j);
+// Geometry of one feature point's correspondences as the LM rows need it: SURF: the unit plane through the
+// three points (featureAssociation.cpp:734-747, recomputed by the reference in every iteration from the same
+// three points); CORNER: the two line points.
+template <int STAGE>
+__device__ __forceinline__ bool corr_geometry(const CorrS& c, const float4* __restrict__ last, float4* ga, float4* gb) {
+  if (STAGE == STAGE_SURF) {
+    if (!(c.ind2 >= 0 && c.ind3 >= 0)) return false;
+    *ga = surf_plane(last[c.closest], last[c.ind2], last[c.ind3]);
+    return true;
   }
-  __syncthreads();
+  if (!(c.ind2 >= 0)) return false;
+  *ga = last[c.closest];
+  *gb = last[c.ind2];
+  return true;
+}
+
+// Correspondences of LM iteration 0 of one stage for all sequences (a group of SG lanes per feature point).
+template <int STAGE>
+__global__ void __launch_bounds__(SEARCH_THREADS) k_odom_search(DevState st) {
+  __shared__ WinTables win;
+  const DevParams& p = st.p;
+  const bool surf = (STAGE == STAGE_SURF);
+  const int s = blockIdx.y;
+  if (!odom_guard(st, s)) return;
+  const int n = st.feat_counts[s * 4 + (surf ? 2 : 0)];
+  if (blockIdx.x * SEARCH_GROUPS >= n) return;
+  const int last_n = st.last_counts[s * 2 + (surf ? 1 : 0)];
+  const bool fresh = st.odom_flags[s * 4 + 2] != 0;
+  build_window_tables(win, st, s, surf ? 1 : 0, last_n);
+  float T[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) T[k] = st.transform_cur[s * 6 + k];
+  const int lane = threadIdx.x & 31;
+  const int gl = threadIdx.x & (SG - 1), grp = threadIdx.x / SG;
+  const unsigned gmask = SG == 32 ? 0xffffffffu : ((1u << (SG & 31)) - 1u) << (lane & ~(SG - 1));
+  const int i = blockIdx.x * SEARCH_GROUPS + grp;
+  if (i >= n) return;
+  const int cap = surf ? p.cap_flat : p.cap_sharp;
+  const float4* cur = surf ? st.surf_flat + (size_t)s * p.cap_flat : st.corner_sharp + (size_t)s * p.cap_sharp;
+  const float4* last = surf ? st.surf_last + (size_t)s * p.N : st.corner_last + (size_t)s * p.cap_less_sharp;
+  float4 sel;
+  if (gl == 0) sel = transform_to_start(cur[i], T);
+  sel.x = __shfl_sync(gmask, sel.x, 0, SG);
+  sel.y = __shfl_sync(gmask, sel.y, 0, SG);
+  sel.z = __shfl_sync(gmask, sel.z, 0, SG);
+  const CorrS c = group_search<STAGE>(st, win, s, sel, n, last_n, last, fresh, gl, gmask);
+  if (gl == 0) {
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+    const bool ok = corr_geometry<STAGE>(c, last, &ga, &gb);
+    const size_t o = (size_t)s * cap + i;
+    st.odom_ok[(size_t)s * p.cap_flat + i] = ok ? 1 : 0;
+    st.odom_ga[(size_t)s * p.cap_flat + i] = ga;
+    if (!surf) st.odom_gb[o] = gb;
+    st.odom_s0[(size_t)s * p.cap_flat + i] = make_float4(sel.x, sel.y, sel.z, c.slack);
+    st.odom_cl[(size_t)s * p.cap_flat + i] = c.closest;
+  }
+}
+
+// One LM stage of one sequence.  Dynamic shared memory: float4 ori[cap], ga[cap], s0[cap], gb[cap] (corner only),
+// unsigned short list[cap], unsigned char ok[cap]; cap = 24V (SURF) or 12V (CORNER).
+template <int STAGE>
+__global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
+  extern __shared__ float4 sh_dyn[];
+  __shared__ StageShared sh;
+  __shared__ int sh_nlist;
+  const DevParams& p = st.p;
+  const int s = blockIdx.x;
+  const bool surf = (STAGE == STAGE_SURF);
+  const int cap = surf ? p.cap_flat : p.cap_sharp;
+  float4* sh_ori = sh_dyn;
+  float4* sh_ga = sh_dyn + cap;                       // SURF: unit plane; CORNER: tripod1
+  float4* sh_s0 = sh_dyn + 2 * cap;                   // where the point was when it was searched (x, y, z), slack
+  float4* sh_gb = sh_dyn + 3 * cap;                   // CORNER: tripod2
+  int* sh_cl = reinterpret_cast<int*>(sh_dyn + (surf ? 3 : 4) * cap);  // closest point of the last search (-1: none)
+  unsigned short* sh_list = reinterpret_cast<unsigned short*>(sh_cl + cap);
+  unsigned char* sh_ok = reinterpret_cast<unsigned char*>(sh_list + cap);
+  const bool guard = odom_guard(st, s);
+  long long clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // thread 0 only: LL_BUF_STAGE_CLOCKS
+  const long long t_begin = global_ns();
+  long long t_mark = t_begin;
+#define STAGE_CLOCK(slot) do { if (threadIdx.x == 0) { const long long t__ = global_ns(); clk[slot] += t__ - t_mark; t_mark = t__; } } while (0)
+  if (!guard) {
+    if (threadIdx.x == 0) {
+      st.odom_iters[s * 2 + STAGE] = 0;
+      if (!surf) integrate_transformation(st, s);  // runs whether or not updateTransformation returned early
+    }
+    return;
+  }
+  const float4* cur = surf ? st.surf_flat + (size_t)s * p.cap_flat : st.corner_sharp + (size_t)s * p.cap_sharp;
+  const float4* last = surf ? st.surf_last + (size_t)s * p.N : st.corner_last + (size_t)s * p.cap_less_sharp;
+  const int n = st.feat_counts[s * 4 + (surf ? 2 : 0)];
+  const int last_n = st.last_counts[s * 2 + (surf ? 1 : 0)];
+  const bool fresh = st.odom_flags[s * 4 + 2] != 0;  // the grids index the current last-frame clouds
+  if (threadIdx.x < 6) sh.T[threadIdx.x] = st.transform_cur[s * 6 + threadIdx.x];
+  if (threadIdx.x == 0) { sh.stop = 0; sh.iters = 0; }
+  // iteration 0 correspondences come from k_odom_search
+  for (int i = threadIdx.x; i < n; i += LM_THREADS) {
+    sh_ori[i] = cur[i];
+    sh_ga[i] = st.odom_ga[(size_t)s * p.cap_flat + i];
+    sh_s0[i] = st.odom_s0[(size_t)s * p.cap_flat + i];
+    sh_ok[i] = st.odom_ok[(size_t)s * p.cap_flat + i];
+    sh_cl[i] = st.odom_cl[(size_t)s * p.cap_flat + i];
+    if (!surf) sh_gb[i] = st.odom_gb[(size_t)s * cap + i];
+  }
+  build_window_tables(sh.win, st, s, surf ? 1 : 0, last_n);  // ends with a barrier
+  STAGE_CLOCK(1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gl = threadIdx.x & (SG - 1), grp = threadIdx.x / SG;
+  const unsigned gmask = SG == 32 ? 0xffffffffu : ((1u << (SG & 31)) - 1u) << (lane & ~(SG - 1));
+  for (int iter = 0; iter < 25; ++iter) {
+    float T[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) T[k] = sh.T[k];
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+    SurfCoef ks;
+    CornerCoef kc;
+    if (surf) ks = make_surf_coef(T); else kc = make_corner_coef(T);
+    if (iter % 5 == 0 && iter > 0) {
+      // Correspondences are refreshed every 5th iteration (featureAssociation.cpp:511,649).  A point that has moved by
+      // less than its slack since it was searched keeps its correspondences (CorrS::slack); the others are searched again.
+      if (threadIdx.x == 0) sh_nlist = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += LM_THREADS) {
+        const float4 sel = transform_to_start(sh_ori[i], T);
+        const float4 s0 = sh_s0[i];
+        const float dx = sel.x - s0.x, dy = sel.y - s0.y, dz = sel.z - s0.z;
+        const float moved = sqrtf(dx * dx + dy * dy + dz * dz);
+        if (!(moved + 1e-4f < s0.w)) {
+          sh_list[atomicAdd(&sh_nlist, 1)] = (unsigned short)i;
+          sh_ga[i] = sel;  // its geometry is about to be replaced: carry the transformed point to the search
+        }
+      }
+      __syncthreads();
+      const int nlist = sh_nlist;
+      if (threadIdx.x == 0) clk[5] += nlist;
+      for (int l0 = 0; l0 < nlist; l0 += LM_GROUPS) {
+        const int l = l0 + grp;  // uniform within a group
+        if (l >= nlist) continue;
+        const int i = sh_list[l];
+        const float4 sel = sh_ga[i];
+        __syncwarp(gmask);  // every lane has read it before lane 0 overwrites it below
+        const CorrS c = group_search<STAGE>(st, sh.win, s, sel, n, last_n, last, fresh, gl, gmask, sh_cl[i]);
+        if (gl == 0) {
+          float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+          sh_cl[i] = c.closest;
+          sh_ok[i] = corr_geometry<STAGE>(c, last, &ga, &gb) ? 1 : 0;
+          sh_ga[i] = ga;
+          if (!surf) sh_gb[i] = gb;
+          sh_s0[i] = make_float4(sel.x, sel.y, sel.z, c.slack);
+        }
+      }
+      __syncthreads();
+      STAGE_CLOCK(2);
+    }
+    for (int i = threadIdx.x; i < n; i += LM_THREADS) {
+      if (!sh_ok[i]) continue;
+      const float4 ori = sh_ori[i];
+      const float4 sel = transform_to_start(ori, T);
+      const Row3 r = surf ? surf_row(ori, sel, sh_ga[i], ks, iter) : corner_row(ori, sel, sh_ga[i], sh_gb[i], kc, iter);
+      if (r.ok) {
+        const double a0 = r.a0, a1 = r.a1, a2 = r.a2, b = r.b;
+        acc[0] += a0 * a0; acc[1] += a0 * a1; acc[2] += a0 * a2;
+        acc[3] += a1 * a1; acc[4] += a1 * a2; acc[5] += a2 * a2;
+        acc[6] += a0 * b; acc[7] += a1 * b; acc[8] += a2 * b;
+        acc[9] += 1.0;
+      }
+    }
+    STAGE_CLOCK(6);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = warp_sum_d(acc[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) sh.part[wid][k] = acc[k];
+    }
+    __syncthreads();
+    STAGE_CLOCK(3);
+    if (wid == 0) {
+      double v = 0.0;
+      if (lane < 10)
+        for (int w = 0; w < LM_WARPS; ++w) v += sh.part[w][lane];
+      double tot[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) tot[k] = __shfl_sync(0xffffffffu, v, k);
+      if (lane == 0) {
+        sh.iters = iter + 1;
+        const int rows = (int)tot[9];
+        if (rows >= 10) {  // featureAssociation.cpp:1222,1232
+          float AtA[9] = {(float)tot[0], (float)tot[1], (float)tot[2], (float)tot[1], (float)tot[3],
+                          (float)tot[4], (float)tot[2], (float)tot[4], (float)tot[5]};
+          float AtB[3] = {(float)tot[6], (float)tot[7], (float)tot[8]};
+          float A2[9], X[3];
+          for (int k = 0; k < 9; ++k) A2[k] = AtA[k];
+          llm::colpiv_qr_solve<3, 3>(A2, AtB, X);
+          float* matP = st.odom_matP + s * 9;
+          if (iter == 0) st.odom_flags[s * 4 + 0] = llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0;
+          if (st.odom_flags[s * 4 + 0]) {
+            const float X2[3] = {X[0], X[1], X[2]};
+            for (int r = 0; r < 3; ++r) X[r] = matP[r * 3 + 0] * X2[0] + matP[r * 3 + 1] * X2[1] + matP[r * 3 + 2] * X2[2];
+          }
+          if (surf) {
+            sh.T[0] += X[0]; sh.T[2] += X[1]; sh.T[4] += X[2];
+          } else {
+            sh.T[1] += X[0]; sh.T[3] += X[1]; sh.T[5] += X[2];
+          }
+          for (int k = 0; k < 6; ++k)
+            if (sh.T[k] != sh.T[k]) sh.T[k] = 0;
+          const float RAD2DEG = (float)(180.0 / LL_PI);
+          float deltaR, deltaT;
+          if (surf) {
+            const double r0 = (double)(RAD2DEG * X[0]), r1 = (double)(RAD2DEG * X[1]);
+            deltaR = (float)sqrt(r0 * r0 + r1 * r1);
+            const double t0 = (double)(X[2] * 100);
+            deltaT = (float)sqrt(t0 * t0);
+          } else {
+            const double r0 = (double)(RAD2DEG * X[0]);
+            deltaR = (float)sqrt(r0 * r0);
+            const double t0 = (double)(X[1] * 100), t1 = (double)(X[2] * 100);
+            deltaT = (float)sqrt(t0 * t0 + t1 * t1);
+          }
+          if ((double)deltaR < 0.1 && (double)deltaT < 0.1) sh.stop = 1;
+        }
+      }
+    }
+    __syncthreads();
+    STAGE_CLOCK(4);
+    if (sh.stop) break;
+  }
   if (threadIdx.x == 0) {
-    int* tab = st.win_tab + ((size_t)s * 2 + cloud) * 2 * R;
-    int run = n;  // "no such index": the scan runs to the end of the cloud
-    for (int v = R - 1; v >= 0; --v) { run = min(run, first_eq[v]); tab[v] = run; }
-    int runl = -1;
-    for (int v = 0; v < R; ++v) { runl = max(runl, last_eq[v]); tab[R + v] = runl; }
+    long long* out = st.stage_clocks + (size_t)s * 16 + STAGE * 8;
+    out[0] = global_ns() - t_begin;
+    for (int k = 1; k < 8; ++k) out[k] = clk[k];
+  }
+  if (threadIdx.x < 6) st.transform_cur[s * 6 + threadIdx.x] = sh.T[threadIdx.x];
+  if (threadIdx.x == 0) st.odom_iters[s * 2 + STAGE] = sh.iters;
+  if (!surf) {
+    __syncthreads();  // transform_cur of this sequence is complete (same block)
+    if (threadIdx.x == 0) integrate_transformation(st, s);
   }
 }
 
 }  // namespace
 
+static size_t stage_smem(const DevParams& p, bool surf) {
+  const size_t cap = surf ? p.cap_flat : p.cap_sharp;
+  return cap * (surf ? 3 : 4) * sizeof(float4) + cap * 4 + cap * 2 + ((cap + 15) / 16) * 16;
+}
+
 void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
   const DevParams& p = st.p;
   if (!first_frame) {
-    const dim3 g_surf(24, p.B), g_corner(24, p.B);  // 24 x 8 warps per sequence, each looping over its feature points
-    const int g_seq = (p.B + 63) / 64;
-    // surf stage: <= 25 iterations = 5 x (search, 5 LM iterations)   (featureAssociation.cpp:1216-1224)
-    LL_LAUNCH(ctx, "k_odom_stage_begin", k_odom_stage_begin<<<g_seq, 64, 0, ctx.stream>>>(st));
-    for (int c = 0; c < 5; ++c) {
-      LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<g_surf, 256, 0, ctx.stream>>>(st));
-      LL_LAUNCH(ctx, "k_odom_lm_surf", k_odom_lm<STAGE_SURF><<<p.B, LM_THREADS, 0, ctx.stream>>>(st, 5 * c));
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_odom_stage<STAGE_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(k_odom_stage<STAGE_CORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = true;
     }
-    // corner stage (featureAssociation.cpp:1226-1234)
-    LL_LAUNCH(ctx, "k_odom_stage_begin", k_odom_stage_begin<<<g_seq, 64, 0, ctx.stream>>>(st));
-    for (int c = 0; c < 5; ++c) {
-      LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<g_corner, 256, 0, ctx.stream>>>(st));
-      LL_LAUNCH(ctx, "k_odom_lm_corner", k_odom_lm<STAGE_CORNER><<<p.B, LM_THREADS, 0, ctx.stream>>>(st, 5 * c));
-    }
-    LL_LAUNCH(ctx, "k_odom_finish", k_odom_finish<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
+    // surf stage then corner stage (featureAssociation.cpp:1216-1234), then integrateTransformation
+    LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<dim3((p.cap_flat + SEARCH_GROUPS - 1) / SEARCH_GROUPS, p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_stage_surf", k_odom_stage<STAGE_SURF><<<p.B, LM_THREADS, stage_smem(p, true), ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp + SEARCH_GROUPS - 1) / SEARCH_GROUPS, p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_stage_corner", k_odom_stage<STAGE_CORNER><<<p.B, LM_THREADS, stage_smem(p, false), ctx.stream>>>(st));
   }
   LL_LAUNCH(ctx, "k_publish_clouds_last", k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0));
-  LL_LAUNCH(ctx, "k_window_tables", k_window_tables<<<dim3(p.B, 2), 256, 0, ctx.stream>>>(st));
   launch_grid_build2(ctx, p.B, st.grid_corner_last, st.corner_last, p.cap_less_sharp, st.last_counts, 2, 0,
-                     st.grid_surf_last, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4);
+                     st.grid_surf_last, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4, /*pack_ring=*/true);
 }
