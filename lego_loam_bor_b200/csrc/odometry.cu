@@ -214,12 +214,13 @@ __device__ __forceinline__ void best_group_reduce(unsigned gmask, Best& m) {
 template <typename F>
 __device__ __forceinline__ void group_visit_shell(const HashGrid& g, const int* __restrict__ cs, const unsigned* __restrict__ occ,
                                                   const unsigned* __restrict__ sig, unsigned want, const float4* __restrict__ pts,
-                                                  int cx, int cy, int cz, int r, int gl, unsigned gmask, float qx, float qy, float qz,
-                                                  float bound2, F&& f) {
+                                                  int cx, int cy, int cz, int r_lo, int r, int gl, unsigned gmask, float qx, float qy,
+                                                  float qz, float bound2, F&& f) {
+  // shells r_lo .. r in one pass (r_lo < r only inside the offset table)
   // bound2: cells whose box is farther than sqrt(bound2) from the query (qx, qy, qz) are skipped
   const int side = 2 * r + 1;
   const bool tabled = r <= LL_SHELL_TABLE_R;
-  const int t_begin = tabled ? k_shell_start[r] : 0;
+  const int t_begin = tabled ? k_shell_start[r_lo] : 0;
   const int t_end = tabled ? k_shell_start[r + 1] : side * side * side;
   for (int t0 = t_begin; t0 < t_end; t0 += SG) {  // uniform over the group
     const int t = t0 + gl;
@@ -235,7 +236,7 @@ __device__ __forceinline__ void group_visit_shell(const HashGrid& g, const int* 
         dy = rem / side - r; dx = rem % side - r;
       }
       bool visit = tabled || max(max(abs(dx), abs(dy)), abs(dz)) == r;
-      if (visit && r > 0) {
+      if (visit && (dx | dy | dz) != 0) {
         // distance from the query to the cell's box, shrunk a little so that rounding in grid_cell() cannot matter
         const float tol = 1e-3f * g.cell;
         const float lx = (float)(cx + dx) * g.cell, ly = (float)(cy + dy) * g.cell, lz = (float)(cz + dz) * g.cell;
@@ -306,7 +307,10 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
   for (int r = 0; r <= rmax; ++r) {
     Best t = best_init(cap);
     const float hb = sqrtf(nn.d2) + SLACK_HORIZON;
-    group_visit_shell(g, cs_tab, occ, sig, 0u, pts, cx, cy, cz, r, gl, gmask, sel.x, sel.y, sel.z, hb * hb, [&](const float4 q) {
+    // a seeded search already has a tight bound: its first pass covers the whole 3x3x3 block (one round of dependent loads less)
+    const int r_lo = r;
+    if (r == 0 && nn.key != BEST_NONE && rmax >= 1 && LL_SHELL_TABLE_R >= 1) r = 1;
+    group_visit_shell(g, cs_tab, occ, sig, 0u, pts, cx, cy, cz, r_lo, r, gl, gmask, sel.x, sel.y, sel.z, hb * hb, [&](const float4 q) {
       const int w = __float_as_int(q.w);
       best_update(t, nn_dist2(sel.x, sel.y, sel.z, q), w & 0xffffff, w);
     });
@@ -344,7 +348,7 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
     for (int d = -2; d <= 2; ++d) want |= 1u << ((csr + 1 + d) & 31);
     float wb = lim + SLACK_HORIZON;  // pruning horizon: the farther of the two current minima + SLACK_HORIZON
     for (int r = 0; r <= rmax; ++r) {
-      group_visit_shell(g, cs_tab, occ, sig, want, pts, cx, cy, cz, r, gl, gmask, sel.x, sel.y, sel.z, wb * wb, [&](const float4 q) {
+      group_visit_shell(g, cs_tab, occ, sig, want, pts, cx, cy, cz, r, r, gl, gmask, sel.x, sel.y, sel.z, wb * wb, [&](const float4 q) {
         const int w = __float_as_int(q.w);
         const int j = w & 0xffffff;
         const int id = (int)((unsigned)w >> 24) - 1;
@@ -665,13 +669,15 @@ __device__ __forceinline__ bool corr_geometry(const CorrS& c, const float4* __re
 // Correspondences of LM iteration 0 of one stage for all sequences (a group of SG lanes per feature point).
 template <int STAGE>
 __global__ void __launch_bounds__(SEARCH_THREADS) k_odom_search(DevState st) {
+  // feature points per warp: the long SURF searches want as many warps in flight as possible
+  constexpr int SEARCH_QPW = STAGE == STAGE_SURF ? 1 : 4;
   __shared__ WinTables win;
   const DevParams& p = st.p;
   const bool surf = (STAGE == STAGE_SURF);
   const int s = blockIdx.y;
   if (!odom_guard(st, s)) return;
   const int n = st.feat_counts[s * 4 + (surf ? 2 : 0)];
-  if (blockIdx.x * SEARCH_GROUPS >= n) return;
+  if (blockIdx.x * SEARCH_GROUPS * SEARCH_QPW >= n) return;
   const int last_n = st.last_counts[s * 2 + (surf ? 1 : 0)];
   const bool fresh = st.odom_flags[s * 4 + 2] != 0;
   build_window_tables(win, st, s, surf ? 1 : 0, last_n);
@@ -681,26 +687,33 @@ __global__ void __launch_bounds__(SEARCH_THREADS) k_odom_search(DevState st) {
   const int lane = threadIdx.x & 31;
   const int gl = threadIdx.x & (SG - 1), grp = threadIdx.x / SG;
   const unsigned gmask = SG == 32 ? 0xffffffffu : ((1u << (SG & 31)) - 1u) << (lane & ~(SG - 1));
-  const int i = blockIdx.x * SEARCH_GROUPS + grp;
-  if (i >= n) return;
   const int cap = surf ? p.cap_flat : p.cap_sharp;
   const float4* cur = surf ? st.surf_flat + (size_t)s * p.cap_flat : st.corner_sharp + (size_t)s * p.cap_sharp;
   const float4* last = surf ? st.surf_last + (size_t)s * p.N : st.corner_last + (size_t)s * p.cap_less_sharp;
-  float4 sel;
-  if (gl == 0) sel = transform_to_start(cur[i], T);
-  sel.x = __shfl_sync(gmask, sel.x, 0, SG);
-  sel.y = __shfl_sync(gmask, sel.y, 0, SG);
-  sel.z = __shfl_sync(gmask, sel.z, 0, SG);
-  const CorrS c = group_search<STAGE>(st, win, s, sel, n, last_n, last, fresh, gl, gmask);
-  if (gl == 0) {
-    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
-    const bool ok = corr_geometry<STAGE>(c, last, &ga, &gb);
-    const size_t o = (size_t)s * cap + i;
-    st.odom_ok[(size_t)s * p.cap_flat + i] = ok ? 1 : 0;
-    st.odom_ga[(size_t)s * p.cap_flat + i] = ga;
-    if (!surf) st.odom_gb[o] = gb;
-    st.odom_s0[(size_t)s * p.cap_flat + i] = make_float4(sel.x, sel.y, sel.z, c.slack);
-    st.odom_cl[(size_t)s * p.cap_flat + i] = c.closest;
+  // a warp takes SEARCH_QPW consecutive feature points: their TransformToStart (long double-precision chains) run
+  // side by side on the first lanes, then the warp searches them one after the other
+  const int i_base = (blockIdx.x * SEARCH_GROUPS + grp) * SEARCH_QPW;
+  if (i_base >= n) return;
+  float4 mysel = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gl < SEARCH_QPW && i_base + gl < n) mysel = transform_to_start(cur[i_base + gl], T);
+  for (int q = 0; q < SEARCH_QPW; ++q) {
+    const int i = i_base + q;
+    if (i >= n) break;
+    float4 sel;
+    sel.x = __shfl_sync(gmask, mysel.x, q, SG);
+    sel.y = __shfl_sync(gmask, mysel.y, q, SG);
+    sel.z = __shfl_sync(gmask, mysel.z, q, SG);
+    sel.w = 0.f;
+    const CorrS c = group_search<STAGE>(st, win, s, sel, n, last_n, last, fresh, gl, gmask);
+    if (gl == 0) {
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+      const bool ok = corr_geometry<STAGE>(c, last, &ga, &gb);
+      st.odom_ok[(size_t)s * p.cap_flat + i] = ok ? 1 : 0;
+      st.odom_ga[(size_t)s * p.cap_flat + i] = ga;
+      if (!surf) st.odom_gb[(size_t)s * cap + i] = gb;
+      st.odom_s0[(size_t)s * p.cap_flat + i] = make_float4(sel.x, sel.y, sel.z, c.slack);
+      st.odom_cl[(size_t)s * p.cap_flat + i] = c.closest;
+    }
   }
 }
 
@@ -710,7 +723,7 @@ template <int STAGE>
 __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
   extern __shared__ float4 sh_dyn[];
   __shared__ StageShared sh;
-  __shared__ int sh_nlist;
+  __shared__ int sh_nlist, sh_next;
   const DevParams& p = st.p;
   const int s = blockIdx.x;
   const bool surf = (STAGE == STAGE_SURF);
@@ -768,7 +781,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
     if (iter % 5 == 0 && iter > 0) {
       // Correspondences are refreshed every 5th iteration (featureAssociation.cpp:511,649).  A point that has moved by
       // less than its slack since it was searched keeps its correspondences (CorrS::slack); the others are searched again.
-      if (threadIdx.x == 0) sh_nlist = 0;
+      if (threadIdx.x == 0) { sh_nlist = 0; sh_next = 0; }
       __syncthreads();
       for (int i = threadIdx.x; i < n; i += LM_THREADS) {
         const float4 sel = transform_to_start(sh_ori[i], T);
@@ -777,17 +790,20 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
         const float moved = sqrtf(dx * dx + dy * dy + dz * dz);
         if (!(moved + 1e-4f < s0.w)) {
           sh_list[atomicAdd(&sh_nlist, 1)] = (unsigned short)i;
-          sh_ga[i] = sel;  // its geometry is about to be replaced: carry the transformed point to the search
+          sh_s0[i] = sel;  // position and slack of the old search are dead now: carry the transformed point to the new one
         }
       }
       __syncthreads();
       const int nlist = sh_nlist;
       if (threadIdx.x == 0) clk[5] += nlist;
-      for (int l0 = 0; l0 < nlist; l0 += LM_GROUPS) {
-        const int l = l0 + grp;  // uniform within a group
-        if (l >= nlist) continue;
+      // searches differ a lot in length: warps take the next list entry when they are done with one
+      for (;;) {
+        int l = 0;
+        if (gl == 0) l = atomicAdd(&sh_next, 1);
+        l = __shfl_sync(gmask, l, 0, SG);
+        if (l >= nlist) break;
         const int i = sh_list[l];
-        const float4 sel = sh_ga[i];
+        const float4 sel = sh_s0[i];
         __syncwarp(gmask);  // every lane has read it before lane 0 overwrites it below
         const CorrS c = group_search<STAGE>(st, sh.win, s, sel, n, last_n, last, fresh, gl, gmask, sh_cl[i]);
         if (gl == 0) {
@@ -907,7 +923,7 @@ void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
     // surf stage then corner stage (featureAssociation.cpp:1216-1234), then integrateTransformation
     LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<dim3((p.cap_flat + SEARCH_GROUPS - 1) / SEARCH_GROUPS, p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
     LL_LAUNCH(ctx, "k_odom_stage_surf", k_odom_stage<STAGE_SURF><<<p.B, LM_THREADS, stage_smem(p, true), ctx.stream>>>(st));
-    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp + SEARCH_GROUPS - 1) / SEARCH_GROUPS, p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp + SEARCH_GROUPS * 4 - 1) / (SEARCH_GROUPS * 4), p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
     LL_LAUNCH(ctx, "k_odom_stage_corner", k_odom_stage<STAGE_CORNER><<<p.B, LM_THREADS, stage_smem(p, false), ctx.stream>>>(st));
   }
   LL_LAUNCH(ctx, "k_publish_clouds_last", k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0));
