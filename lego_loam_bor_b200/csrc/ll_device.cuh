@@ -135,7 +135,8 @@ struct DevState {
   float4* vox_tmp_out;                           // [B][cap_outlier] laserCloudOutlierLastDS
   int* vox_tmp_counts;                           // [B][2]
   int vox_cap;
-  float4* map_knn_rec;                           // [B][map_knn_cap][6] per query: 5 neighbours (x,y,z,index) + (p0, bound)
+  float4* map_knn_rec;                           // [B][map_knn_cap][11] per query: 10 nearest map points (x,y,z,index) + (p0, bound)
+  int* map_knn_sel;                              // [B][map_knn_cap] positions of the current 5-NN inside the record (5 x 4 bits), bit 31 valid
   int map_knn_cap;
   double* map_partials;                          // [B][max_blocks][28]
   double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)

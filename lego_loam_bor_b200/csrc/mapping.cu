@@ -9,8 +9,8 @@
 //       (3x3 symmetric eigen-solve) or plane fit (5x3 column-pivoted QR), residual + 6-column
 //       Jacobian row, J^T J / J^T r partial sums (exact double products) per block.
 //   k_map_solve  one block per sequence: fixed-order sum of the partials, 6x6 solve, degeneracy
-//       projection, pose update and convergence flag.  Ten (iter, solve) pairs are enqueued; a
-//       converged sequence makes its remaining pairs no-ops, so there is no host round trip.
+//       projection, pose update and convergence flag.  Ten (knn, iter, solve) triples are enqueued; a
+//       converged sequence makes its remaining launches no-ops, so there is no host round trip.
 //   k_voxel_*    pcl::VoxelGrid on whole clouds for downsampleCurrentScan (one block per sequence
 //       and cloud: stable LSD radix sort by voxel index in shared/global memory, sequential centroids).
 #include "../../include/ll_smallmat.h"
@@ -120,21 +120,24 @@ __device__ __forceinline__ bool surf_fit(const float4 sel, const float4* q, floa
 
 // Exact 5-NN of every down-sampled scan point in the local map, one THREAD per query.
 //
-// Per query a 96-byte record is kept: the five neighbours with their coordinates (x, y, z, index), in
-// ascending (d2, index) order, and (p0, bound): the query position of the last full search and the
-// squared distance to the 6th nearest map point there (or 1 m, the reach of the 27-cell block).
-// In later LM iterations the search is skipped when it provably cannot change: if the query moved by
-// |delta| since p0, every map point outside the record is at least sqrt(bound) - |delta| away, so if
-// all five recorded neighbours are closer than that (minus a float-safety margin) they still are the
-// exact 5-NN (triangle inequality) and only their order is refreshed.
-// The full search visits the 27 buckets around the query (occupancy bitmap first), keeps a sorted
-// top-6 in registers; consecutive queries are consecutive voxels of the VoxelGrid output, so
-// neighbouring threads walk the same buckets and share them through L1.
+// Per query a record of KNN_K + 1 float4 is kept: the KNN_K nearest map points of the last full search with their
+// coordinates (x, y, z, index), ascending by (d2, index), and (p0, bound): the query position of that search and the
+// squared distance to the (KNN_K+1)-th nearest map point there (or 1 m, the reach of the 27-cell block).
+// In later LM iterations the query has moved by |delta| since p0, so every map point outside the record is at least
+// sqrt(bound) - |delta| away; if the five nearest of the RECORDED points are closer than that (minus a float-safety
+// margin) they are the exact 5-NN (triangle inequality) and no search is needed.  Their positions inside the record,
+// in ascending (d2, index) order, go to the selection word k_map_iter reads (5 x 4 bits, bit 31 = all five closer
+// than 1 m, mapOptmization.cpp:1036,1144).
+// The full search visits the 27 buckets around the query (occupancy bitmap first) and keeps a sorted top-(KNN_K+1)
+// in registers; consecutive queries are consecutive voxels of the VoxelGrid output, so neighbouring threads walk the
+// same buckets and share them through L1.
 #define KNN_THREADS 128
+#define KNN_K 10
+#define KNN_REC (KNN_K + 1)
 
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
-__global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int iter) {
+__global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int iter) {
   __shared__ int sh_need[KNN_THREADS];
   __shared__ int sh_n;
   __shared__ int2 sh_bucket[27][KNN_THREADS];  // per thread: its non-empty buckets (start, end), column-major: no bank conflicts
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int ite
   for (int qbase = blockIdx.x * KNN_THREADS; qbase < nq; qbase += gridDim.x * KNN_THREADS) {
     if (threadIdx.x == 0) sh_n = 0;
     __syncthreads();
-    // ---- phase 1: one thread per query, try to keep the recorded neighbours ----
+    // ---- phase 1: one thread per query, try to select the five nearest among the recorded candidates ----
     {
       const int q = qbase + threadIdx.x;
       if (q < nq) {
@@ -159,32 +162,35 @@ __global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int ite
           const bool corner = q < nc;
           const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
           const float4 sel = point_associate_to_map(mp, ori);
-          float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * 6;
-          const float4 stt = rec[5];
-          float4 c[5];
-          float d2[5];
+          const float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
+          const float4 stt = rec[KNN_K];
+          float d5[5];
+          int i5[5], p5[5];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) c[i] = rec[i];
-          if (__float_as_int(c[4].w) >= 0) {
-            float dmax = 0.f;
+          for (int i = 0; i < 5; ++i) { d5[i] = FLT_MAX; i5[i] = 0x7fffffff; p5[i] = 0; }
 #pragma unroll
-            for (int i = 0; i < 5; ++i) { d2[i] = nn_dist2(sel.x, sel.y, sel.z, c[i]); dmax = fmaxf(dmax, d2[i]); }
+          for (int c = 0; c < KNN_K; ++c) {
+            const float4 cp = rec[c];
+            const int ci0 = __float_as_int(cp.w);
+            if (ci0 < 0) continue;  // fewer than KNN_K points within reach at p0
+            float cd = nn_dist2(sel.x, sel.y, sel.z, cp);
+            int ci = ci0, cpos = c;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              if (cand_less(cd, ci, d5[i], i5[i])) {
+                const float td = d5[i]; const int ti = i5[i], tp = p5[i];
+                d5[i] = cd; i5[i] = ci; p5[i] = cpos;
+                cd = td; ci = ti; cpos = tp;
+              }
+            }
+          }
+          if (i5[4] != 0x7fffffff) {
             const float dx = sel.x - stt.x, dy = sel.y - stt.y, dz = sel.z - stt.z;
             const float delta = sqrtf(dx * dx + dy * dy + dz * dz);
-            if (sqrtf(dmax) + delta + 1e-4f < sqrtf(stt.w)) {
-              // same five neighbours; restore the ascending (d2, index) order of a fresh search
-#pragma unroll
-              for (int a = 1; a < 5; ++a) {
-#pragma unroll
-                for (int b = a; b > 0; --b) {
-                  if (cand_less(d2[b], __float_as_int(c[b].w), d2[b - 1], __float_as_int(c[b - 1].w))) {
-                    const float td = d2[b]; d2[b] = d2[b - 1]; d2[b - 1] = td;
-                    const float4 tc = c[b]; c[b] = c[b - 1]; c[b - 1] = tc;
-                  }
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 5; ++i) rec[i] = c[i];
+            if (sqrtf(d5[4]) + delta + 1e-4f < sqrtf(stt.w)) {
+              // d5[4] < bound <= 1: all five are inside the acceptance radius
+              st.map_knn_sel[(size_t)s * st.map_knn_cap + q] =
+                  (int)(0x80000000u | (unsigned)p5[0] | ((unsigned)p5[1] << 4) | ((unsigned)p5[2] << 8) | ((unsigned)p5[3] << 12) | ((unsigned)p5[4] << 16));
               need = false;
             }
           }
@@ -205,30 +211,31 @@ __global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int ite
       const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
       const float4* pts = g.sorted + (size_t)s * g.cap;
       const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
-      // 2a: the non-empty buckets among the 27 cells.  Fully unrolled so that the 27 bitmap loads (and then
-      // the cell_start loads of the occupied ones) are independent and in flight together: this kernel is
-      // bound by memory latency, not by bandwidth or issue rate.
-      uint32_t hh[27];
-      unsigned occw[27];
-#pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        hh[t] = grid_hash(cx + (t % 3 - 1), cy + ((t % 9) / 3 - 1), cz + (t / 9 - 1), g.tbl);
-        occw[t] = occ[hh[t] >> 5];
-      }
+      // 2a: the non-empty buckets among the 27 cells, nine at a time so that the bitmap loads (and then the
+      // cell_start loads of the occupied ones) are independent and in flight together: this kernel is bound by
+      // memory latency, not by bandwidth or issue rate.
       int nb = 0;
 #pragma unroll
-      for (int t = 0; t < 27; ++t) {
-        if ((occw[t] >> (hh[t] & 31)) & 1u) {
-          sh_bucket[nb++][threadIdx.x] = make_int2(cs[hh[t]], cs[hh[t] + 1]);
+      for (int z = 0; z < 3; ++z) {
+        uint32_t hh[9];
+        unsigned occw[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          hh[t] = grid_hash(cx + (t % 3 - 1), cy + (t / 3 - 1), cz + (z - 1), g.tbl);
+          occw[t] = occ[hh[t] >> 5];
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          if ((occw[t] >> (hh[t] & 31)) & 1u) sh_bucket[nb++][threadIdx.x] = make_int2(cs[hh[t]], cs[hh[t] + 1]);
         }
       }
       // 2b: candidates of the concatenated buckets, four independent loads per step.  A point is a candidate
       // if it is closer than 1 m (such a point necessarily lies in one of the 27 cells); two of the 27 cells can
       // share a bucket (hash collision), so an index that is already in the list is skipped.
-      float bd[6];
-      int bi[6];
+      float bd[KNN_REC];
+      int bi[KNN_REC];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { bd[i] = 1.0f; bi[i] = 0x7fffffff; }
+      for (int i = 0; i < KNN_REC; ++i) { bd[i] = 1.0f; bi[i] = 0x7fffffff; }
       for (int u = 0; u < nb; ++u) {
         const int2 be = sh_bucket[u][threadIdx.x];
         for (int k = be.x; k < be.y; k += 4) {
@@ -239,14 +246,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int ite
           for (int v = 0; v < 4; ++v) {
             if (k + v >= be.y) continue;
             float cd = nn_dist2(sel.x, sel.y, sel.z, cpt[v]);
-            if (cd < bd[5]) {
+            if (cd < bd[KNN_K]) {
               int ci = __float_as_int(cpt[v].w);
               bool dup = false;
 #pragma unroll
-              for (int i = 0; i < 6; ++i) dup = dup || (bi[i] == ci);
+              for (int i = 0; i < KNN_REC; ++i) dup = dup || (bi[i] == ci);
               if (!dup) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
+                for (int i = 0; i < KNN_REC; ++i) {
                   if (cand_less(cd, ci, bd[i], bi[i])) {
                     const float td = bd[i]; const int ti = bi[i];
                     bd[i] = cd; bi[i] = ci;
@@ -259,14 +266,16 @@ __global__ void __launch_bounds__(KNN_THREADS, 8) k_map_knn(DevState st, int ite
         }
       }
       const float4* mpts = corner ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
-      float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * 6;
+      float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
+      for (int i = 0; i < KNN_K; ++i) {
         float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         if (bi[i] != 0x7fffffff) { c = mpts[bi[i]]; c.w = __int_as_float(bi[i]); }
         rec[i] = c;
       }
-      rec[5] = make_float4(sel.x, sel.y, sel.z, bd[5]);  // bd[5] = min(6th nearest d2, 1)
+      rec[KNN_K] = make_float4(sel.x, sel.y, sel.z, bd[KNN_K]);  // bd[KNN_K] = min((KNN_K+1)-th nearest d2, 1)
+      // a fresh record is already in ascending order
+      st.map_knn_sel[(size_t)s * st.map_knn_cap + q] = (int)((bi[4] != 0x7fffffff ? 0x80000000u : 0u) | 0x43210u);
     }
     __syncthreads();
   }
@@ -294,9 +303,11 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st) {
     float4 cf;
     float4 nb[5];
     {
-      const float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * 6;
+      const float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
+      const unsigned selw = (unsigned)st.map_knn_sel[(size_t)s * st.map_knn_cap + q];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) nb[i] = rec[i];
+      for (int i = 0; i < 5; ++i) nb[i] = rec[(selw >> (4 * i)) & 15u];
+      if (!(selw >> 31)) nb[4].w = __int_as_float(-1);  // fewer than five map points within 1 m: rejected by the fits
     }
     const bool ok = corner ? corner_fit(sel, nb, &cf) : surf_fit(sel, nb, &cf);
     if (!ok) continue;
@@ -334,6 +345,9 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st) {
   }
 }
 
+// One block per sequence: fixed-order sum of the partials, 6x6 solve (LMOptimization, mapOptmization.cpp:1257-1312),
+// degeneracy projection, pose update and convergence flag.  (Folding this into the last-finishing block of k_map_iter
+// was tried and gave wrong solves; it stays a launch of its own.)
 __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
   __shared__ double tot[MAP_NACC];
   const int s = blockIdx.x;
@@ -346,7 +360,7 @@ __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
   }
   __syncwarp();
   if (threadIdx.x != 0) return;
-  float* T = st.transform_tobe_mapped + s * 6;
+  float* Tm = st.transform_tobe_mapped + s * 6;
   const int rows = (int)tot[27];
   st.map_iters[s * 2 + 0] = iter + 1;
   st.map_iters[s * 2 + 1] = rows;
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
       X[r] = v;
     }
   }
-  for (int i = 0; i < 6; ++i) T[i] += X[i];
+  for (int i = 0; i < 6; ++i) Tm[i] += X[i];
   for (int i = 0; i < 6; ++i) trace[28 + i] = (double)X[i];
   const float r2d = 57.29578f;  // pcl::rad2deg(float)
   const double r0 = (double)(X[0] * r2d), r1 = (double)(X[1] * r2d), r2 = (double)(X[2] * r2d);
