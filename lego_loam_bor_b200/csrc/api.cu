@@ -199,7 +199,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.tile_counts, (size_t)B * V * 4));
   CK(dev_alloc(h, &st.orientation, (size_t)B * 4)); CK(dev_alloc(h, &st.half_idx, B));
   CK(dev_alloc(h, &st.seg_cloud, BN)); CK(dev_alloc(h, &st.seg_range, BN));
-  CK(dev_alloc(h, &st.seg_col, BN)); CK(dev_alloc(h, &st.seg_ground, BN));
+  CK(dev_alloc(h, &st.seg_col, BN)); CK(dev_alloc(h, &st.seg_ground, BN)); CK(dev_alloc(h, &st.seg_ori, BN));
   CK(dev_alloc(h, &st.start_ring, (size_t)B * V)); CK(dev_alloc(h, &st.end_ring, (size_t)B * V));
   CK(dev_alloc(h, &st.seg_count, B));
   CK(dev_alloc(h, &st.outlier_cloud, (size_t)B * st.cap_outlier)); CK(dev_alloc(h, &st.outlier_count, B));

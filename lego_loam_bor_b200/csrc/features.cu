@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
     const int half = st.half_idx[s];
     const float4 sp = st.seg_cloud[base + i];
     const float px = sp.y, py = sp.z, pz = sp.x;
-    float ori = -ll_atan2f(px, pz);
+    // -atan2(point.x, point.z) of the axis-swapped point = -atan2(seg.y, seg.x): k_seg_emit needed the same value to find
+    // the halfPassed trigger and left it in seg_ori (a double-precision atan2 per point is most of this kernel otherwise)
+    float ori = st.seg_ori[base + i];
     if (i <= half) {
       if ((double)ori < (double)start_ori - LL_PI / 2)
         ori = (float)((double)ori + 2 * LL_PI);
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int 
 #define PICK_WARPS 4
 
 __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
-  extern __shared__ unsigned char sh_picked_all[];  // [PICK_WARPS][H + 32]
+  extern __shared__ unsigned char sh_picked_all[];  // [PICK_WARPS][H + 32] picked bytes, then [PICK_WARPS][H + 32] u16 column indices
   const DevParams& p = st.p;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ring = blockIdx.x * PICK_WARPS + wid, s = blockIdx.y;
@@ -250,7 +252,13 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
   const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
   const int L = max(0, span_hi - span_lo);
   unsigned char* sm_picked = sh_picked_all + (size_t)wid * (p.H + 32);
-  for (int t = lane; t < L; t += 32) sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
+  // segmentedCloudColInd of the span (columns < H <= 65535): the neighbour suppression of every pick reads up to
+  // twelve of them, and a pick is a chain of dependent steps, so they must not come from global memory
+  unsigned short* sm_col = reinterpret_cast<unsigned short*>(sh_picked_all + (size_t)PICK_WARPS * (p.H + 32)) + (size_t)wid * (p.H + 32);
+  for (int t = lane; t < L; t += 32) {
+    sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
+    sm_col[t] = (unsigned short)st.seg_col[base + span_lo + t];
+  }
   __syncwarp();
   const size_t rs = (size_t)s * p.V + ring;
   const int* offs = st.sext_off + rs * 16;
@@ -262,6 +270,7 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
   auto in_span = [&](int g) { return g >= span_lo && g < span_hi; };
   auto get_picked = [&](int g) -> int { return in_span(g) ? (int)sm_picked[g - span_lo] : st.picked[base + g]; };
   auto set_picked = [&](int g) { if (in_span(g)) sm_picked[g - span_lo] = 1; else st.picked[base + g] = 1; };
+  auto get_col = [&](int g) -> int { return in_span(g) ? (int)sm_col[g - span_lo] : (int)st.seg_col[base + g]; };
   // featureAssociation.cpp:306-326 / 344-366: lanes 1..5 handle ind+1..ind+5, lanes 6..10 handle ind-1..ind-5
   auto mark_neighbors = [&](int ind) {
     int g = -1;          // index this lane may mark
@@ -269,10 +278,10 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
     bool skip = true;    // `continue` cases: out of range
     if (lane >= 1 && lane <= 5) {
       g = ind + lane;
-      if (g < colsz) { skip = false; bad = abs((int)st.seg_col[base + g] - (int)st.seg_col[base + g - 1]) > 10; }
+      if (g < colsz) { skip = false; bad = abs(get_col(g) - get_col(g - 1)) > 10; }
     } else if (lane >= 6 && lane <= 10) {
       g = ind - (lane - 5);
-      if (g >= 0) { skip = false; bad = abs((int)st.seg_col[base + g] - (int)st.seg_col[base + g + 1]) > 10; }
+      if (g >= 0) { skip = false; bad = abs(get_col(g) - get_col(g + 1)) > 10; }
     }
     const unsigned bm = __ballot_sync(0xffffffffu, bad);
     const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
@@ -589,7 +598,7 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
     LL_LAUNCH(ctx, "k_feature_sort", k_feature_sort<<<grid_rings, SORT_THREADS, smem, ctx.stream>>>(st, cap2));
   }
   {
-    const size_t smem = (size_t)PICK_WARPS * (p.H + 32);
+    const size_t smem = (size_t)PICK_WARPS * (p.H + 32) * 3;
     LL_LAUNCH(ctx, "k_feature_pick",
               k_feature_pick<<<dim3((p.V + PICK_WARPS - 1) / PICK_WARPS, p.B), PICK_WARPS * 32, smem, ctx.stream>>>(st));
   }

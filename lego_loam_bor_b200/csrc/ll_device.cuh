@@ -71,6 +71,7 @@ struct DevState {
   float* seg_range;            // [B][N]
   uint32_t* seg_col;           // [B][N]
   uint8_t* seg_ground;         // [B][N]
+  float* seg_ori;              // [B][N] -atan2(y, x) of every segmented point (adjustDistortion's raw orientation)
   int* start_ring;             // [B][V]
   int* end_ring;               // [B][V]
   int* seg_count;              // [B]

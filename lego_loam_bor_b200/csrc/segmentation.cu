@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
       // flips at the FIRST segmented point whose branch-1 orientation is more than pi past the start;
       // record candidates here, k_feature_prep reads the minimum.
       float ori = -ll_atan2f(pt.y, pt.x);  // point.x = seg.y, point.z = seg.x after the axis swap
+      st.seg_ori[base + pos] = ori;        // adjustDistortion's raw orientation, reused by k_feature_prep
       if ((double)ori < (double)start_ori - LL_PI / 2)
         ori = (float)((double)ori + 2 * LL_PI);
       else if ((double)ori > (double)start_ori + LL_PI * 3 / 2)
