@@ -148,16 +148,20 @@ def algorithmic_bytes(kernel, st):
         "k_project_scatter": 16 * n_in + 8 * n_in,
         "k_gather_ground": 29 * N + 16 * g * N,
         "k_ccl_rows": 12 * N, "k_ccl_merge": 8 * N, "k_ccl_flatten": 8 * N,
-        "k_seg_count": 5 * N, "k_seg_emit": 5 * N + 45 * S, "k_label_final": 8 * N,
-        "k_feature_prep": 61 * S,
-        "k_extract_features": 53 * S + 16 * lf,
+        "k_seg_count": 5 * N, "k_seg_emit": 5 * N + 45 * S + 4 * S, "k_label_final": 8 * N,
+        "k_feature_prep": 61 * S + 4 * S,
+        "k_feature_sort": 21 * S, "k_feature_pick": 8 * S, "k_feature_lessflat": 24 * S + 16 * lf,
         "k_feature_compact": 32 * lf + 20 * (ls + ff + fs),
+        # correspondence search: feature point in, geometry out, the last-frame cloud read once
         "k_odom_search_surf": ff * 96 + lf * 16, "k_odom_search_corner": fs * 80 + ls * 16,
-        "k_odom_lm_surf": ff * 32 * 2, "k_odom_lm_corner": fs * 32 * 2,
+        # LM stage: features + their correspondence geometry once per launch (they then live in shared memory)
+        "k_odom_stage_surf": ff * 69, "k_odom_stage_corner": fs * 85,
         "k_publish_clouds_last": 32 * (lf + ls + out),
-        "k_grid_clear": 0, "k_grid_count": 16 * (lf + ls), "k_grid_scan": 0, "k_grid_fill": 32 * (lf + ls),
+        "k_grid_count": 16 * (lf + ls), "k_grid_tile_sums": 0, "k_grid_scan": 0, "k_grid_fill": 32 * (lf + ls),
         "k_voxel_grid": 16 * (lf + ls + out) * 2, "k_voxel_grid_total": 16 * qs * 2,
-        "k_map_iter": (qs + qc) * 96 + (ms + mc) * 16, "k_map_solve": 0,
+        # 5-NN: query + 10-candidate record written (full search) or read (reuse) + the map read once
+        "k_map_knn": (qs + qc) * (16 + 176) + (ms + mc) * 16,
+        "k_map_iter": (qs + qc) * (16 + 4 + 5 * 16), "k_map_solve": 0,
     }
     return float(table.get(kernel, 0))
 
@@ -260,6 +264,60 @@ def workload_config(args, params, batch, where):
 
 
 # --------------------------------------------------------------------------------------------
+
+
+def kernel_rooflines(alone, st, sub, peak):
+    """Every kernel timed ALONE on the GPU (one sub-batch of `sub` sequences per launch): average launch duration, achieved
+    algorithmic GB/s and fraction of the measured HBM peak; `psf_mean_frac` is the time-weighted mean over the
+    projection / segmentation / feature kernels (the group north_star's 60 % target is about)."""
+    out, t_psf, b_psf = {}, 0.0, 0.0
+    for k, (ms, n) in sorted(alone.items(), key=lambda kv: -kv[1][0]):
+        if n == 0:
+            continue
+        us = 1e3 * ms / n
+        alg = algorithmic_bytes(k, st) * sub
+        gbs = alg / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        out[k] = {"avg_us": round(us, 1), "launches": n, "alg_MB": round(alg / 1e6, 2), "GBps": round(gbs, 1),
+                  "frac": round(gbs / peak, 4) if peak else None}
+        if k in PSF_KERNELS:
+            t_psf += us
+            b_psf += alg
+    out["psf_mean_frac"] = round(b_psf / (t_psf * 1e-6) / 1e9 / peak, 4) if t_psf > 0 and peak else None
+    out["sequences_per_launch"] = sub
+    return out
+
+
+PSF_KERNELS = ["k_project_scatter", "k_gather_ground", "k_ccl_rows", "k_ccl_merge", "k_ccl_flatten", "k_seg_count",
+               "k_seg_emit", "k_label_final", "k_feature_prep", "k_feature_sort", "k_feature_pick", "k_feature_lessflat",
+               "k_feature_compact"]
+
+
+def single_sequence_latency(params, devdata, counts, stride, n_frames, B, dev, torch, local_map=None, aft0=None):
+    """p50 / p95 device latency of one scan of ONE sequence (batch 1, one stream; BASELINE.json configs[3]):
+    the projection..odometry chain of every scan, scan-to-map on every 5th."""
+    from lego_loam_bor_b200.capi import LegoLoam
+    stream = torch.cuda.Stream(device=dev)
+    one = LegoLoam(params, batch=1, max_points=stride, device=dev.index, stream=stream.cuda_stream)
+    if local_map is not None:
+        one.map_set_local(0, *local_map)
+        one.map_set_poses(aft0, np.zeros((1, 6), np.float32))
+    frame_bytes = B * stride * 16
+    evs = []
+    with torch.cuda.stream(stream):
+        for f in range(n_frames):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            one.set_scans_device(devdata.data_ptr() + f * frame_bytes, counts[f][:1], stride)
+            e0.record(stream)
+            one.process_scans()
+            e1.record(stream)
+            evs.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    ms = np.array([a.elapsed_time(b) for a, b in evs[3:]])  # first frame only initialises; two more to warm up
+    one.close()
+    return {"batch": 1, "scans": int(len(ms)), "p50_ms": float(np.percentile(ms, 50)), "p95_ms": float(np.percentile(ms, 95)),
+            "mean_ms": float(ms.mean()),
+            "note": "device time per scan of one sequence, one stream; every 5th scan also runs scan-to-map"
+                    + ("" if local_map is not None else " (disabled: --no-map)")}
 
 
 def main():
@@ -414,6 +472,33 @@ def main():
     odom_iters = np.mean([gpu.download("ODOM_ITERS", k) for k in sample_seqs], axis=0)
     map_iters = np.mean([gpu.download("MAP_ITERS", k) for k in sample_seqs], axis=0) if use_map else [0, 0]
 
+    # ---- per-kernel pass: the sub-batches one after the other, so that every launch runs alone on the GPU ----
+    gpu.time_kernel("*")
+    psf_steps = 3
+    f_psf = f - psf_steps  # re-run the last frames (results are not used)
+    gpu.reset()
+    if use_map:
+        seed_map_poses()
+    parts = getattr(gpu, "parts", [gpu])
+    sub = B // len(parts)
+    for ff in range(max(0, f_psf - 2), f_psf + psf_steps):
+        if ff == f_psf:
+            gpu.time_kernel("*")
+        for i, part in enumerate(parts):
+            part.set_scans_device(devdata.data_ptr() + ff * frame_bytes + i * sub * stride * 16, counts[ff][i * sub:(i + 1) * sub], stride)
+            part.process_scans()
+            part.synchronize()
+    alone = gpu.kernel_time_table()
+    gpu.time_kernel("")
+    latency = None
+    if rank == 0:
+        aft0 = None
+        if use_map:
+            x, y, z, roll, pitch, yaw = synth.pose(cfg, seq_ids[0], 0)
+            aft0 = np.array([[0, yaw, 0, y, z, x]], np.float32)
+        latency = single_sequence_latency(params, devdata, counts, stride, n_frames, B, dev, torch,
+                                          local_maps(cfg, seq_ids[0]) if use_map else None, aft0)
+
     # ---- end-to-end: same C ABI, pinned host scans, H2D + pose D2H inside the timed region ----
     gpu.reset()
     if use_map:
@@ -466,7 +551,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, params, B, "gpu"),
-            "p50_scan_latency_ms": dev_ms / args.steps,
+            "p50_scan_latency_ms": latency["p50_ms"] if latency else None, "latency_single_sequence": latency,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, e2e_steps),
                     "d2h_bytes_per_step": B * 6 * 4 * 3, "steps": e2e_steps, "ms_per_step": e2e_ms / max(1, e2e_steps)},
             "gpu_launches": int(gpu_launches),
@@ -474,6 +559,7 @@ def main():
                          "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "avg_launch_us": per_launch_s * 1e6, "launches_timed": k_n,
                          "kernel_time_share_profiling_pass": shares},
+            "kernel_rooflines": kernel_rooflines(alone, st, sub, peak),
             "clocks": clocks,
             "stats": {**{k: round(v, 1) for k, v in st.items()}, "odom_iters": [float(x) for x in odom_iters],
                       "map_iters_rows": [float(x) for x in map_iters], "launches_per_step": launches_per_step,

@@ -8,3 +8,10 @@ for k, v in r['kernel_time_share_profiling_pass'].items():
     print(f"  {k:26s} {v:.3f}  ~{v * d['ms_per_step'] * 1000:7.1f} us/step")
 print(d['stats'])
 if 'cpu_baseline' in d: print(d['cpu_baseline'])
+if 'kernel_rooflines' in d:
+    kr = d['kernel_rooflines']
+    print("kernels timed alone (%s sequences per launch): psf_mean_frac %s" % (kr.get('sequences_per_launch'), kr.get('psf_mean_frac')))
+    for k, v in kr.items():
+        if isinstance(v, dict):
+            print(f"  {k:26s} {v['avg_us']:8.1f} us  {v['GBps']:8.1f} GB/s  frac {v['frac']}")
+if d.get('latency_single_sequence'): print(d['latency_single_sequence'])
