@@ -14,17 +14,60 @@
 
 namespace {
 
+// ---- discrete decisions without the exact (double-precision) inverse trigonometry -----------------------------
+// Row, column and the ground flag are step functions of one angle each, and every step of their evaluation (float
+// add / divide, double subtract / divide / round, truncation) is monotonic in that angle.  CUDA's asinf / atan2f are
+// within a few ulp of the true value (2 and 3 ulp in the CUDA C Programming Guide) and the reference value -- the
+// correctly rounded float, ll_asinf / ll_atan2f -- within 0.5 ulp, so if the step function gives the same result FAST_ULPS
+// ulps below and above the fast value, it gives that result for the reference value too.  Only the (rare) angles next to
+// a step pay for the exact evaluation.
+#define FAST_ULPS 16
+
+__device__ __forceinline__ float step_ulps(float v, int n) {
+  int b = __float_as_int(v);
+  int o = b >= 0 ? b : (int)(0x80000000u - (unsigned)b);  // order-preserving integer image of the float
+  o += n;
+  b = o >= 0 ? o : (int)(0x80000000u - (unsigned)o);
+  return __int_as_float(b);
+}
+
+// imageProjection.cpp:193-196 as a monotonic class: -1 below the image, V above, else the row
+__device__ __forceinline__ int row_class(const DevParams& p, float va) {
+  const float rowf = (va + p.ang_bottom) / p.ang_res_y;
+  if (!(rowf > -2147483648.f)) return -1;
+  if (!(rowf < 2147483648.f)) return p.V;
+  const int r = (int)rowf;  // C truncation toward zero (imageProjection.cpp:193)
+  return r < 0 ? -1 : (r >= p.V ? p.V : r);
+}
+
+// imageProjection.cpp:200 before the wrap, evaluated in double because of M_PI_2 and * 0.5 (non-increasing in ha)
+__device__ __forceinline__ double col_value(const DevParams& p, float ha) {
+  return -round(((double)ha - LL_PI_2) / (double)p.ang_res_x) + p.H * 0.5;
+}
+
 __device__ __forceinline__ bool project_cell(const DevParams& p, const float4 pt, int* row, int* col, float* range_out) {
   const float range = sqrtf(pt.x * pt.x + pt.y * pt.y + pt.z * pt.z);
-  const float va = ll_asinf(pt.z / range);
-  const float rowf = (va + p.ang_bottom) / p.ang_res_y;
-  if (!(rowf == rowf)) return false;
-  if (!(rowf > -2147483648.f && rowf < 2147483648.f)) return false;
-  const int r = (int)rowf;  // C truncation toward zero (imageProjection.cpp:193)
+  const float q = pt.z / range;
+  int r;
+  {
+    const float vf = asinf(q);
+    const int r_lo = row_class(p, step_ulps(vf, -FAST_ULPS)), r_hi = row_class(p, step_ulps(vf, FAST_ULPS));
+    if (vf == vf && r_lo == r_hi) {
+      r = r_lo;
+    } else {
+      const float va = ll_asinf(q);
+      const float rowf = (va + p.ang_bottom) / p.ang_res_y;
+      if (!(rowf == rowf)) return false;
+      r = row_class(p, va);
+    }
+  }
   if (r < 0 || r >= p.V) return false;
-  const float ha = ll_atan2f(pt.x, pt.y);
-  // imageProjection.cpp:200, evaluated in double because of M_PI_2 and * 0.5
-  const double cd = -round(((double)ha - LL_PI_2) / (double)p.ang_res_x) + p.H * 0.5;
+  double cd;
+  {
+    const float hf = atan2f(pt.x, pt.y);
+    const double c_lo = col_value(p, step_ulps(hf, FAST_ULPS)), c_hi = col_value(p, step_ulps(hf, -FAST_ULPS));
+    cd = (hf == hf && c_lo == c_hi) ? c_lo : col_value(p, ll_atan2f(pt.x, pt.y));
+  }
   int c = (int)cd;
   if (c >= p.H) c -= p.H;
   if (c < 0 || c >= p.H) return false;
@@ -73,8 +116,15 @@ __device__ __forceinline__ bool ground_pair(const DevParams& p, const float4 low
   const float dX = upper.x - lower.x;
   const float dY = upper.y - lower.y;
   const float dZ = upper.z - lower.z;
-  const float ang = ll_atan2f(dZ, sqrtf(dX * dX + dY * dY + dZ * dZ));
-  return (double)(ang - p.sensor_mount_angle) <= 10.0 * (LL_PI / 180.0);
+  const float nrm = sqrtf(dX * dX + dY * dY + dZ * dZ);
+  const double thr = 10.0 * (LL_PI / 180.0);
+  // the test is monotonic in the angle: decide from the fast atan2f when both ends of its error interval agree
+  const float af = atan2f(dZ, nrm);
+  const bool g_lo = (double)(step_ulps(af, -FAST_ULPS) - p.sensor_mount_angle) <= thr;
+  const bool g_hi = (double)(step_ulps(af, FAST_ULPS) - p.sensor_mount_angle) <= thr;
+  if (af == af && g_lo == g_hi) return g_lo;
+  const float ang = ll_atan2f(dZ, nrm);
+  return (double)(ang - p.sensor_mount_angle) <= thr;
 }
 
 #define GG_ROWS 8
