@@ -281,8 +281,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int ite
   }
 }
 
-__global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st) {
+__device__ __noinline__ void map_solve_body(float* Tm, int* map_iters, double* trace, float* matP, int* map_flags, int iter, const double* tot);
+
+__global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st, int iter) {
   __shared__ double sh_part[MAP_THREADS / 32][MAP_NACC];
+  __shared__ double sh_tot[MAP_NACC];
+  __shared__ int sh_last;
   const DevParams& p = st.p;
   const int s = blockIdx.y;
   double* out = st.map_partials + ((size_t)s * MAP_BLOCKS + blockIdx.x) * MAP_NACC;
@@ -343,28 +347,36 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st) {
     for (int w = 0; w < MAP_THREADS / 32; ++w) v += sh_part[w][threadIdx.x];
     out[threadIdx.x] = v;
   }
-}
-
-// One block per sequence: fixed-order sum of the partials, 6x6 solve (LMOptimization, mapOptmization.cpp:1257-1312),
-// degeneracy projection, pose update and convergence flag.  (Folding this into the last-finishing block of k_map_iter
-// was tried and gave wrong solves; it stays a launch of its own.)
-__global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
-  __shared__ double tot[MAP_NACC];
-  const int s = blockIdx.x;
-  if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
+  // The block that delivers the last partial sums of its sequence finishes the iteration: fixed-order sum of the
+  // partials, then LMOptimization's solve / pose update / convergence flag (no separate launch).
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sh_last = (atomicAdd(st.map_ticket + s, 1) == MAP_BLOCKS - 1) ? 1 : 0;
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence();
   if (threadIdx.x < MAP_NACC) {
     const double* part = st.map_partials + (size_t)s * MAP_BLOCKS * MAP_NACC;
     double v = 0.0;
-    for (int b = 0; b < MAP_BLOCKS; ++b) v += part[b * MAP_NACC + threadIdx.x];
-    tot[threadIdx.x] = v;
+    for (int b = 0; b < MAP_BLOCKS; ++b) v += __ldcg(part + b * MAP_NACC + threadIdx.x);
+    sh_tot[threadIdx.x] = v;
   }
-  __syncwarp();
+  __syncthreads();
   if (threadIdx.x != 0) return;
-  float* Tm = st.transform_tobe_mapped + s * 6;
+  st.map_ticket[s] = 0;
+  double tot[MAP_NACC];
+  for (int i = 0; i < MAP_NACC; ++i) tot[i] = sh_tot[i];
+  map_solve_body(st.transform_tobe_mapped + s * 6, st.map_iters + s * 2, st.map_trace + ((size_t)s * 10 + iter) * 34,
+                 st.map_matP + s * 36, st.map_flags + s * 4, iter, tot);
+}
+
+// LMOptimization after the normal equations are summed (mapOptmization.cpp:1257-1312): 6x6 solve, degeneracy projection,
+// pose update, convergence flag.  One thread.  Kept out of line and fed from a private copy of the totals: nvcc 12.9 -O3
+// miscompiles this code when it is inlined next to code that produces the totals in shared memory (see ll_smallmat.h).
+__device__ __noinline__ void map_solve_body(float* Tm, int* map_iters, double* trace, float* matP, int* map_flags, int iter, const double* tot) {
   const int rows = (int)tot[27];
-  st.map_iters[s * 2 + 0] = iter + 1;
-  st.map_iters[s * 2 + 1] = rows;
-  double* trace = st.map_trace + ((size_t)s * 10 + iter) * 34;
+  map_iters[0] = iter + 1;
+  map_iters[1] = rows;
   for (int i = 0; i < 28; ++i) trace[i] = tot[i];
   for (int i = 28; i < 34; ++i) trace[i] = 0.0;
   if (rows < 50) return;  // LMOptimization returns false: keep iterating (mapOptmization.cpp:1208-1210)
@@ -375,9 +387,8 @@ __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
   for (int r = 0; r < 6; ++r) AtB[r] = (float)tot[21 + r];
   for (int i = 0; i < 36; ++i) A2[i] = AtA[i];
   llm::colpiv_qr_solve<6, 6>(A2, AtB, X);
-  float* matP = st.map_matP + s * 36;
-  if (iter == 0) st.map_flags[s * 4 + 0] = llm::degeneracy_projector<6>(AtA, 100.f, matP) ? 1 : 0;
-  if (st.map_flags[s * 4 + 0]) {
+  if (iter == 0) map_flags[0] = llm::degeneracy_projector<6>(AtA, 100.f, matP) ? 1 : 0;
+  if (map_flags[0]) {
     float X2[6];
     for (int i = 0; i < 6; ++i) X2[i] = X[i];
     for (int r = 0; r < 6; ++r) {
@@ -393,13 +404,14 @@ __global__ void __launch_bounds__(32) k_map_solve(DevState st, int iter) {
   const double t0 = (double)(X[3] * 100), t1 = (double)(X[4] * 100), t2 = (double)(X[5] * 100);
   const float deltaR = (float)sqrt(r0 * r0 + r1 * r1 + r2 * r2);
   const float deltaT = (float)sqrt(t0 * t0 + t1 * t1 + t2 * t2);
-  if ((double)deltaR < 0.05 && (double)deltaT < 0.05) st.map_flags[s * 4 + 1] = 1;
+  if ((double)deltaR < 0.05 && (double)deltaT < 0.05) map_flags[1] = 1;
 }
 
 __global__ void k_map_begin(DevState st) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= st.p.B) return;
   st.map_flags[s * 4 + 1] = 0;
+  st.map_ticket[s] = 0;
   st.map_iters[s * 2 + 0] = 0;
   st.map_iters[s * 2 + 1] = 0;
 }
@@ -488,8 +500,7 @@ void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
   LL_LAUNCH(ctx, "k_map_begin", k_map_begin<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
   for (int iter = 0; iter < 10; ++iter) {
     LL_LAUNCH(ctx, "k_map_knn", k_map_knn<<<dim3(KNN_BLOCKS, p.B), KNN_THREADS, 0, ctx.stream>>>(st, iter));
-    LL_LAUNCH(ctx, "k_map_iter", k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st));
-    LL_LAUNCH(ctx, "k_map_solve", k_map_solve<<<p.B, 32, 0, ctx.stream>>>(st, iter));
+    LL_LAUNCH(ctx, "k_map_iter", k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st, iter));
   }
   LL_LAUNCH(ctx, "k_map_update", k_map_update<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
 }

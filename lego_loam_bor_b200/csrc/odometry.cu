@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
   build_window_tables(sh.win, st, s, surf ? 1 : 0, last_n);  // ends with a barrier
   STAGE_CLOCK(1);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int gl = threadIdx.x & (SG - 1), grp = threadIdx.x / SG;
+  const int gl = threadIdx.x & (SG - 1);
   const unsigned gmask = SG == 32 ? 0xffffffffu : ((1u << (SG & 31)) - 1u) << (lane & ~(SG - 1));
   for (int iter = 0; iter < 25; ++iter) {
     float T[6];
