@@ -412,13 +412,29 @@ def main():
     def upload(f):
         gpu.set_scans_host_ptr(host.data_ptr() + f * frame_bytes, counts[f], stride)
 
+    pose_host = torch.empty((2, 3, B, 6), dtype=torch.float32).pin_memory()  # two steps in flight x (sum, cur, map)
+
     def step_host(f):
-        """Scan f was staged by upload(f).  Enqueue its processing, stage scan f+1 (its H2D copy overlaps the
-        kernels of scan f: the library double-buffers the input), then read the poses back (synchronises)."""
+        """Scan f was staged by upload(f).  Enqueue its processing and the read-back of its poses, stage scan f+1 (its
+        H2D copy overlaps the kernels of scan f: the library double-buffers the input), then collect the poses of scan
+        f-1: a consumer one scan behind, like the reference's stage threads behind their Channels."""
         gpu.process_scans()
+        slot = pose_host[f & 1]
+        gpu.poses_async(slot[0].data_ptr(), slot[1].data_ptr(), slot[2].data_ptr())
+        step_host.in_flight += 1
         if f + 1 < n_frames:
             upload(f + 1)
-        return gpu.poses()
+        if step_host.in_flight == 2:
+            gpu.wait_poses()          # the poses of scan f-1 are on the host now
+            step_host.in_flight -= 1
+        return pose_host[(f - 1) & 1]
+
+    step_host.in_flight = 0
+
+    def drain_poses():
+        while step_host.in_flight:
+            gpu.wait_poses()
+            step_host.in_flight -= 1
 
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
@@ -508,6 +524,7 @@ def main():
     step_host(f); f += 1
     for _ in range(min(args.warmup, 3)):
         step_host(f); f += 1
+    drain_poses()
     e2e_steps = min(args.steps, n_frames - f - 1)
     if world > 1:
         dist.barrier()
@@ -520,6 +537,7 @@ def main():
         for _ in range(e2e_steps):
             h2d += int(counts[f].sum()) * 16 + B * 4
             step_host(f); f += 1
+        drain_poses()
         join()
         e1.record(stream)
     torch.cuda.synchronize(dev)

@@ -201,6 +201,13 @@ int ll_process_scans(ll_handle* h);
 /* Poses of all sequences, f32[batch][6] each, host pointers (any may be NULL).
  * Synchronises the stream. */
 int ll_get_poses(ll_handle* h, float* transform_sum, float* transform_cur, float* transform_tobe_mapped);
+/* The same copies enqueued behind the work already submitted, without waiting: the caller may submit the next scans
+ * first and collect these poses later with ll_wait_poses (a pipelined consumer, like the reference's stage threads
+ * behind their Channels, main.cpp:37-38).  The destination buffers must stay valid until ll_wait_poses returns; use
+ * page-locked memory for the copies to be truly asynchronous.  At most two read-backs may be in flight;
+ * ll_wait_poses waits for the oldest one. */
+int ll_get_poses_async(ll_handle* h, float* transform_sum, float* transform_cur, float* transform_tobe_mapped);
+int ll_wait_poses(ll_handle* h);
 /* Copy one array of one sequence to host.  *n_elems receives the element count
  * (points for "pt" buffers).  dst may be NULL to query the count only.
  * Synchronises the stream. */

@@ -35,7 +35,7 @@ EXPORTS = [
     "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
     "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
     "ll_map_set_initial_guess_async", "ll_map_set_poses", "ll_map_predict_pose",
-    "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_download", "ll_upload", "ll_synchronize",
+    "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_get_poses_async", "ll_wait_poses", "ll_download", "ll_upload", "ll_synchronize",
     "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
     "ll_get_kernel_time_table",
 ]
@@ -77,6 +77,8 @@ def load_library(path=None):
     lib.ll_map_set_scan.argtypes = [vp, ip, vp, ip, vp, ip]
     lib.ll_map_set_initial_guess.argtypes = [vp, vp]
     lib.ll_get_poses.argtypes = [vp, vp, vp, vp]
+    lib.ll_get_poses_async.argtypes = [vp, vp, vp, vp]
+    lib.ll_wait_poses.argtypes = [vp]
     lib.ll_download.argtypes = [vp, ip, ip, vp, sz, C.POINTER(sz)]
     lib.ll_upload.argtypes = [vp, ip, ip, vp, sz]
     lib.ll_enable_stage_timing.argtypes = [vp, ip]
@@ -197,6 +199,13 @@ class LegoLoam:
         self._ck(self.lib.ll_get_poses(self.h, ts.ctypes.data, tc.ctypes.data, tm.ctypes.data), "ll_get_poses")
         return ts, tc, tm
 
+    def poses_async(self, ts_ptr, tc_ptr, tm_ptr):
+        """Enqueue the pose copies into caller-owned (pinned) float32 [batch, 6] buffers given as raw addresses."""
+        self._ck(self.lib.ll_get_poses_async(self.h, ts_ptr, tc_ptr, tm_ptr), "ll_get_poses_async")
+
+    def wait_poses(self):
+        self._ck(self.lib.ll_wait_poses(self.h), "ll_wait_poses")
+
     def download(self, name, seq=0):
         bid, dt, w = BUFFERS[name]
         n = C.c_size_t(0)
@@ -293,6 +302,15 @@ class LegoLoamStreams:
     def synchronize(self):
         for p in self.parts:
             p.synchronize()
+
+    def poses_async(self, ts_ptr, tc_ptr, tm_ptr):
+        for i, p in enumerate(self.parts):
+            o = i * self.sub * 24
+            p.poses_async(ts_ptr + o, tc_ptr + o, tm_ptr + o)
+
+    def wait_poses(self):
+        for p in self.parts:
+            p.wait_poses()
 
     def download(self, name, seq=0):
         p, k = self._loc(seq)

@@ -39,6 +39,8 @@ struct ll_handle {
   int pending = -1;  // buffer waiting to be consumed by ll_image_projection
   bool timing = false;
   cudaEvent_t ev[6];
+  cudaEvent_t pose_ev[2] = {nullptr, nullptr};  // ll_get_poses_async / ll_wait_poses: up to two read-backs in flight
+  int pose_head = 0, pose_pending = 0;
   float stage_ms[5];
   bool ev_valid = false;
 };
@@ -246,6 +248,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.vox_tmp_surf, BN, false)); CK(dev_alloc(h, &st.vox_tmp_out, (size_t)B * st.cap_outlier, false));
   CK(dev_alloc(h, &st.vox_tmp_counts, (size_t)B * 2));
   for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->ev[i]));
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->pose_ev[i], cudaEventDisableTiming));
   CK(cudaStreamSynchronize(h->ctx.stream));
   *out = h;
   return LL_OK;
@@ -261,6 +264,7 @@ int ll_destroy(ll_handle* h) {
   for (int b = 0; b < 2; ++b) { cudaEventDestroy(h->copied[b]); cudaEventDestroy(h->consumed[b]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   for (int i = 0; i < 6; ++i) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i) if (h->pose_ev[i]) cudaEventDestroy(h->pose_ev[i]);
   if (h->ctx.ev_start) {
     for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { cudaEventDestroy(h->ctx.ev_start[i]); cudaEventDestroy(h->ctx.ev_stop[i]); }
     delete[] h->ctx.ev_start;
@@ -507,6 +511,27 @@ int ll_get_poses(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   if (tcur) CK(cudaMemcpyAsync(tcur, h->st.transform_cur, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_get_poses_async(ll_handle* h, float* tsum, float* tcur, float* tmap) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (h->pose_pending >= 2) { h->err = "ll_get_poses_async: two read-backs already in flight, call ll_wait_poses"; return LL_ERR_STATE; }
+  const size_t bytes = (size_t)h->st.p.B * 24;
+  if (tsum) CK(cudaMemcpyAsync(tsum, h->st.transform_sum, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  if (tcur) CK(cudaMemcpyAsync(tcur, h->st.transform_cur, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaEventRecord(h->pose_ev[(h->pose_head + h->pose_pending) & 1], h->ctx.stream));
+  h->pose_pending += 1;
+  return LL_OK;
+}
+
+int ll_wait_poses(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (h->pose_pending == 0) { h->err = "ll_wait_poses: no ll_get_poses_async pending"; return LL_ERR_STATE; }
+  CK(cudaEventSynchronize(h->pose_ev[h->pose_head]));  // the oldest one
+  h->pose_head ^= 1;
+  h->pose_pending -= 1;
   return LL_OK;
 }
 
