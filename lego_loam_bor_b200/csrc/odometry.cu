@@ -187,7 +187,9 @@ __device__ __forceinline__ void build_window_tables(WinTables& w, const DevState
 
 // Warp-wide reduction of Best (all 32 lanes; SG == 32): hardware integer min-reductions on the distance bits
 // (non-negative floats order like unsigned ints) and on the tie-break key, payload from the winning lane.
+template <int G>
 __device__ __forceinline__ void best_group_reduce(unsigned gmask, Best& m) {
+  if (G == 1) return;  // one thread per feature point: nothing to merge
   const unsigned mybits = m.key != BEST_NONE ? __float_as_uint(m.d2) : 0xffffffffu;
   const unsigned minbits = __reduce_min_sync(gmask, mybits);
   if (minbits == 0xffffffffu) {  // no lane has a candidate: only the runner-up distances need merging
@@ -211,7 +213,7 @@ __device__ __forceinline__ void best_group_reduce(unsigned gmask, Best& m) {
 // edge points) do not serialise on one lane.  `want` != 0 restricts the visit to buckets whose ring signature
 // intersects it.  f(point) is called for every stored point of the visited buckets (by some lane of the group);
 // aliasing buckets only add candidates.
-template <typename F>
+template <int G, typename F>
 __device__ __forceinline__ void group_visit_shell(const HashGrid& g, const int* __restrict__ cs, const unsigned* __restrict__ occ,
                                                   const unsigned* __restrict__ sig, unsigned want, const float4* __restrict__ pts,
                                                   int cx, int cy, int cz, int r_lo, int r, int gl, unsigned gmask, float qx, float qy,
@@ -222,7 +224,7 @@ __device__ __forceinline__ void group_visit_shell(const HashGrid& g, const int* 
   const bool tabled = r <= LL_SHELL_TABLE_R;
   const int t_begin = tabled ? k_shell_start[r_lo] : 0;
   const int t_end = tabled ? k_shell_start[r + 1] : side * side * side;
-  for (int t0 = t_begin; t0 < t_end; t0 += SG) {  // uniform over the group
+  for (int t0 = t_begin; t0 < t_end; t0 += G) {  // uniform over the group
     const int t = t0 + gl;
     int b0 = 0, b1 = 0;
     if (t < t_end) {
@@ -252,12 +254,16 @@ __device__ __forceinline__ void group_visit_shell(const HashGrid& g, const int* 
         }
       }
     }
-    unsigned m = __ballot_sync(gmask, b1 > b0) & gmask;
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int sb0 = __shfl_sync(gmask, b0, src), sb1 = __shfl_sync(gmask, b1, src);
-      for (int k = sb0 + gl; k < sb1; k += SG) f(__ldg(pts + k));
+    if (G == 1) {
+      for (int k = b0; k < b1; ++k) f(__ldg(pts + k));
+    } else {
+      unsigned m = __ballot_sync(gmask, b1 > b0) & gmask;
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int sb0 = __shfl_sync(gmask, b0, src), sb1 = __shfl_sync(gmask, b1, src);
+        for (int k = sb0 + gl; k < sb1; k += G) f(__ldg(pts + k));
+      }
     }
   }
 }
@@ -280,7 +286,7 @@ struct CorrS {
 // !fresh: the grid still indexes an OLDER cloud (the reference rebuilds its kd-trees only when both last-frame
 // clouds are large enough, featureAssociation.cpp:1356, while the clouds are always swapped): the 1-NN runs on
 // the stale grid and the window scans run linearly over the current cloud, as in the reference.  Rare.
-template <int STAGE>
+template <int STAGE, int G>
 __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTables& win, int s, const float4 sel, int cur_n, int last_n,
                                               const float4* __restrict__ last, bool fresh, int gl, unsigned gmask, int seed = -1) {
   const DevParams& p = st.p;
@@ -310,11 +316,11 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
     // a seeded search already has a tight bound: its first pass covers the whole 3x3x3 block (one round of dependent loads less)
     const int r_lo = r;
     if (r == 0 && nn.key != BEST_NONE && rmax >= 1 && LL_SHELL_TABLE_R >= 1) r = 1;
-    group_visit_shell(g, cs_tab, occ, sig, 0u, pts, cx, cy, cz, r_lo, r, gl, gmask, sel.x, sel.y, sel.z, hb * hb, [&](const float4 q) {
+    group_visit_shell<G>(g, cs_tab, occ, sig, 0u, pts, cx, cy, cz, r_lo, r, gl, gmask, sel.x, sel.y, sel.z, hb * hb, [&](const float4 q) {
       const int w = __float_as_int(q.w);
       best_update(t, nn_dist2(sel.x, sel.y, sel.z, q), w & 0xffffff, w);
     });
-    best_group_reduce(gmask, t);
+    best_group_reduce<G>(gmask, t);
     // merge the shell into the running result (both are uniform over the group)
     float sec = fminf(nn.second, t.second);
     if (t.key != BEST_NONE && (nn.key == BEST_NONE || t.d2 < nn.d2 || (t.d2 == nn.d2 && t.key < nn.key))) {
@@ -348,7 +354,7 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
     for (int d = -2; d <= 2; ++d) want |= 1u << ((csr + 1 + d) & 31);
     float wb = lim + SLACK_HORIZON;  // pruning horizon: the farther of the two current minima + SLACK_HORIZON
     for (int r = 0; r <= rmax; ++r) {
-      group_visit_shell(g, cs_tab, occ, sig, want, pts, cx, cy, cz, r, r, gl, gmask, sel.x, sel.y, sel.z, wb * wb, [&](const float4 q) {
+      group_visit_shell<G>(g, cs_tab, occ, sig, want, pts, cx, cy, cz, r, r, gl, gmask, sel.x, sel.y, sel.z, wb * wb, [&](const float4 q) {
         const int w = __float_as_int(q.w);
         const int j = w & 0xffffff;
         const int id = (int)((unsigned)w >> 24) - 1;
@@ -361,8 +367,8 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
         if (same) best_update(m2, d2, ord, j); else best_update(m3, d2, ord, j);
       });
       Best t2 = m2, t3 = m3;
-      best_group_reduce(gmask, t2);
-      best_group_reduce(gmask, t3);
+      best_group_reduce<G>(gmask, t2);
+      best_group_reduce<G>(gmask, t3);
       const float reach = (float)r * g.cell;
       wseen2 = reach * reach * 0.9999f;
       wb = sqrtf(fmaxf(t2.d2, t3.d2)) + SLACK_HORIZON;  // d2 is the cap while a minimum is still empty
@@ -380,7 +386,7 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
     // runs next to the closest point can be skipped there: ids below csr + 1 end before up_tab[csr + 1]
     const int up0 = surf ? closest + 1 : max(closest + 1, win.up_tab[min(max(csr + 1, 0), WIN_R - 1)]);
     const int dn0 = surf ? closest - 1 : min(closest - 1, (csr - 1 >= 0) ? win.dn_tab[min(csr - 1, WIN_R - 1)] : -1);
-    for (int j = up0 + gl; j < jend; j += SG) {
+    for (int j = up0 + gl; j < jend; j += G) {
       const float4 q = last[j];
       const int id = (int)q.w;
       const float d2 = sq_dist_ref(q, sel);
@@ -391,7 +397,7 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
         best_update(m2, d2, ord, j);
       }
     }
-    for (int j = dn0 - gl; j > dn_break; j -= SG) {
+    for (int j = dn0 - gl; j > dn_break; j -= G) {
       const float4 q = last[j];
       const int id = (int)q.w;
       const float d2 = sq_dist_ref(q, sel);
@@ -402,8 +408,8 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
         best_update(m2, d2, ord, j);
       }
     }
-    best_group_reduce(gmask, m2);
-    if (surf) best_group_reduce(gmask, m3);
+    best_group_reduce<G>(gmask, m2);
+    if (surf) best_group_reduce<G>(gmask, m3);
   }
   // slack of the window minima: a found one must keep its lead and stay inside the radius, an empty one must stay empty
   if (m2.key != BEST_NONE) {
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) k_odom_search(DevState st) {
     sel.y = __shfl_sync(gmask, mysel.y, q, SG);
     sel.z = __shfl_sync(gmask, mysel.z, q, SG);
     sel.w = 0.f;
-    const CorrS c = group_search<STAGE>(st, win, s, sel, n, last_n, last, fresh, gl, gmask);
+    const CorrS c = group_search<STAGE, SG>(st, win, s, sel, n, last_n, last, fresh, gl, gmask);
     if (gl == 0) {
       float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
       const bool ok = corr_geometry<STAGE>(c, last, &ga, &gb);
@@ -796,7 +802,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
       __syncthreads();
       const int nlist = sh_nlist;
       if (threadIdx.x == 0) clk[5] += nlist;
-      // searches differ a lot in length: warps take the next list entry when they are done with one
+      // a warp per point; searches differ a lot in length, so warps take the next list entry when they are done with one
+      // (one THREAD per point was tried for the seeded re-search: the few points without a nearby seed walk every shell
+      // and hold their whole warp, which made the stage several times slower)
       for (;;) {
         int l = 0;
         if (gl == 0) l = atomicAdd(&sh_next, 1);
@@ -805,7 +813,7 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
         const int i = sh_list[l];
         const float4 sel = sh_s0[i];
         __syncwarp(gmask);  // every lane has read it before lane 0 overwrites it below
-        const CorrS c = group_search<STAGE>(st, sh.win, s, sel, n, last_n, last, fresh, gl, gmask, sh_cl[i]);
+        const CorrS c = group_search<STAGE, SG>(st, sh.win, s, sel, n, last_n, last, fresh, gl, gmask, sh_cl[i]);
         if (gl == 0) {
           float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
           sh_cl[i] = c.closest;
