@@ -241,7 +241,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.map_trace, (size_t)B * 10 * 34));
   st.map_knn_cap = p.cap_less_sharp + N;
   CK(dev_alloc(h, &st.map_knn_rec, (size_t)B * st.map_knn_cap * 11, false));
-  CK(dev_alloc(h, &st.map_knn_sel, (size_t)B * st.map_knn_cap, false)); CK(dev_alloc(h, &st.map_ticket, (size_t)B));
+  CK(dev_alloc(h, &st.map_knn_sel, (size_t)B * st.map_knn_cap, false)); CK(dev_alloc(h, &st.map_fit, (size_t)B * st.map_knn_cap * 2, false)); CK(dev_alloc(h, &st.map_ticket, (size_t)B));
   st.vox_cap = N + st.cap_outlier;
   CK(dev_alloc(h, &st.vox_key0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_key1, (size_t)B * 3 * st.vox_cap, false));
   CK(dev_alloc(h, &st.vox_val0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_val1, (size_t)B * 3 * st.vox_cap, false));

@@ -139,6 +139,7 @@ struct DevState {
   float4* map_knn_rec;                           // [B][map_knn_cap][11] per query: 10 nearest map points (x,y,z,index) + (p0, bound)
   int* map_knn_sel;                              // [B][map_knn_cap] positions of the current 5-NN inside the record (5 x 4 bits), bit 31 valid
   int map_knn_cap;
+  float4* map_fit;                               // [B][map_knn_cap][2] cached neighbour-only part of the line / plane fit
   int* map_ticket;                               // [B] blocks of k_map_iter that have delivered their partial sums
   double* map_partials;                          // [B][max_blocks][28]
   double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)

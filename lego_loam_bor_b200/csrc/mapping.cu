@@ -22,6 +22,7 @@ namespace {
 #define MAP_BLOCKS 96
 #define KNN_BLOCKS 112
 #define MAP_THREADS 128
+#define MAP_USE_FIT_CACHE 1
 #define MAP_NACC 28  // 21 upper-triangle J^T J + 6 J^T r + row count
 
 __device__ __forceinline__ bool map_guard(const DevState& st, int s) {
@@ -51,9 +52,12 @@ __device__ __forceinline__ float4 point_associate_to_map(const MapPose& m, const
   return make_float4(m.cPitch * x2 + m.sPitch * z2 + m.tX, y2 + m.tY, -m.sPitch * x2 + m.cPitch * z2 + m.tZ, pi.w);
 }
 
-// cornerOptimization body for one point; returns false if rejected
-__device__ __forceinline__ bool corner_fit(const float4 sel, const float4* q, float4* coeff) {
-  if (__float_as_int(q[4].w) < 0) return false;  // pointSearchSqDis[4] < 1.0 failed
+// cornerOptimization / surfOptimization are split in two: the part that only depends on the five neighbours (the line
+// through the cluster / the plane fit and its validity) and the part that depends on the transformed query point.
+// Between LM iterations the ordered neighbour set of most points does not change, so the first part is cached.
+
+// cornerOptimization, neighbours only (mapOptmization.cpp:1037-1091): g0 = (x1, y1, z1, valid), g1 = (x2, y2, z2, -)
+__device__ __forceinline__ void corner_geom(const float4* q, float4* g0, float4* g1) {
   float cx = 0, cy = 0, cz = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) { cx += q[j].x; cy += q[j].y; cz += q[j].z; }
@@ -69,15 +73,20 @@ __device__ __forceinline__ bool corner_fit(const float4 sel, const float4* q, fl
   const float matA1[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
   float matD1[3], matV1[9];
   llm::self_adjoint_eigen<3>(matA1, matD1, matV1);
-  if (!(matD1[2] > 3 * matD1[1])) return false;
-  const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+  const bool valid = matD1[2] > 3 * matD1[1];
   // row 0 of the eigenvector matrix (sic), mapOptmization.cpp:1086-1091; 0.1 * v in double
-  const float x1 = (float)((double)cx + 0.1 * (double)matV1[0]);
-  const float y1 = (float)((double)cy + 0.1 * (double)matV1[1]);
-  const float z1 = (float)((double)cz + 0.1 * (double)matV1[2]);
-  const float x2 = (float)((double)cx - 0.1 * (double)matV1[0]);
-  const float y2 = (float)((double)cy - 0.1 * (double)matV1[1]);
-  const float z2 = (float)((double)cz - 0.1 * (double)matV1[2]);
+  *g0 = make_float4((float)((double)cx + 0.1 * (double)matV1[0]), (float)((double)cy + 0.1 * (double)matV1[1]),
+                    (float)((double)cz + 0.1 * (double)matV1[2]), valid ? 1.f : 0.f);
+  *g1 = make_float4((float)((double)cx - 0.1 * (double)matV1[0]), (float)((double)cy - 0.1 * (double)matV1[1]),
+                    (float)((double)cz - 0.1 * (double)matV1[2]), 0.f);
+}
+
+// cornerOptimization, query-dependent part (mapOptmization.cpp:1093-1131); returns false if rejected
+__device__ __forceinline__ bool corner_eval(const float4 sel, const float4 g0, const float4 g1, float4* coeff) {
+  if (g0.w == 0.f) return false;
+  const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+  const float x1 = g0.x, y1 = g0.y, z1 = g0.z;
+  const float x2 = g1.x, y2 = g1.y, z2 = g1.z;
   const float a012 = sqrtf(((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) * ((x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1)) +
                            ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) * ((x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1)) +
                            ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)) * ((y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1)));
@@ -94,9 +103,8 @@ __device__ __forceinline__ bool corner_fit(const float4 sel, const float4* q, fl
   return (double)w > 0.1;
 }
 
-// surfOptimization body for one point
-__device__ __forceinline__ bool surf_fit(const float4 sel, const float4* q, float4* coeff) {
-  if (__float_as_int(q[4].w) < 0) return false;
+// surfOptimization, neighbours only (mapOptmization.cpp:1145-1175): g0 = unit plane (pa, pb, pc, pd), g1.x = planeValid
+__device__ __forceinline__ void surf_geom(const float4* q, float4* g0, float4* g1) {
   float matA0[15], matX0[3];
   const float matB0[5] = {-1, -1, -1, -1, -1};
 #pragma unroll
@@ -110,13 +118,19 @@ __device__ __forceinline__ bool surf_fit(const float4 sel, const float4* q, floa
   for (int j = 0; j < 5; j++) {
     if ((double)fabsf(pa * q[j].x + pb * q[j].y + pc * q[j].z + pd) > 0.2) { planeValid = false; break; }
   }
-  if (!planeValid) return false;
+  *g0 = make_float4(pa, pb, pc, pd);
+  *g1 = make_float4(planeValid ? 1.f : 0.f, 0.f, 0.f, 0.f);
+}
+
+// surfOptimization, query-dependent part (mapOptmization.cpp:1177-1194)
+__device__ __forceinline__ bool surf_eval(const float4 sel, const float4 g0, const float4 g1, float4* coeff) {
+  if (g1.x == 0.f) return false;
+  const float pa = g0.x, pb = g0.y, pc = g0.z, pd = g0.w;
   const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
   const float w = (float)(1 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
   *coeff = make_float4(w * pa, w * pb, w * pc, w * pd2);
   return (double)w > 0.1;
 }
-
 
 // Exact 5-NN of every down-sampled scan point in the local map, one THREAD per query.
 //
@@ -132,7 +146,9 @@ __device__ __forceinline__ bool surf_fit(const float4 sel, const float4* q, floa
 // in registers; consecutive queries are consecutive voxels of the VoxelGrid output, so neighbouring threads walk the
 // same buckets and share them through L1.
 #define KNN_THREADS 128
+#ifndef KNN_K
 #define KNN_K 10
+#endif
 #define KNN_REC (KNN_K + 1)
 
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
@@ -189,8 +205,11 @@ __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int ite
             const float delta = sqrtf(dx * dx + dy * dy + dz * dz);
             if (sqrtf(d5[4]) + delta + 1e-4f < sqrtf(stt.w)) {
               // d5[4] < bound <= 1: all five are inside the acceptance radius
-              st.map_knn_sel[(size_t)s * st.map_knn_cap + q] =
-                  (int)(0x80000000u | (unsigned)p5[0] | ((unsigned)p5[1] << 4) | ((unsigned)p5[2] << 8) | ((unsigned)p5[3] << 12) | ((unsigned)p5[4] << 16));
+              const unsigned neww = 0x80000000u | (unsigned)p5[0] | ((unsigned)p5[1] << 4) | ((unsigned)p5[2] << 8) | ((unsigned)p5[3] << 12) | ((unsigned)p5[4] << 16);
+              int* selp = st.map_knn_sel + (size_t)s * st.map_knn_cap + q;
+              // bit 30: the ordered neighbours are the ones k_map_iter last fitted, its cached line / plane still holds
+              const unsigned oldw = (unsigned)*selp;
+              *selp = (int)(((oldw & 0xbfffffffu) == neww) ? (neww | 0x40000000u) : neww);
               need = false;
             }
           }
@@ -305,15 +324,21 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st, int iter)
     const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
     const float4 sel = point_associate_to_map(mp, ori);
     float4 cf;
-    float4 nb[5];
-    {
+    const unsigned selw = (unsigned)st.map_knn_sel[(size_t)s * st.map_knn_cap + q];
+    if (!(selw >> 31)) continue;  // fewer than five map points within 1 m (pointSearchSqDis[4] < 1.0 fails)
+    float4* fit = st.map_fit + ((size_t)s * st.map_knn_cap + q) * 2;
+    float4 g0, g1;
+    if ((selw & 0x40000000u) && MAP_USE_FIT_CACHE) {
+      g0 = fit[0]; g1 = fit[1];
+    } else {
+      float4 nb[5];
       const float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
-      const unsigned selw = (unsigned)st.map_knn_sel[(size_t)s * st.map_knn_cap + q];
 #pragma unroll
       for (int i = 0; i < 5; ++i) nb[i] = rec[(selw >> (4 * i)) & 15u];
-      if (!(selw >> 31)) nb[4].w = __int_as_float(-1);  // fewer than five map points within 1 m: rejected by the fits
+      if (corner) corner_geom(nb, &g0, &g1); else surf_geom(nb, &g0, &g1);
+      fit[0] = g0; fit[1] = g1;
     }
-    const bool ok = corner ? corner_fit(sel, nb, &cf) : surf_fit(sel, nb, &cf);
+    const bool ok = corner ? corner_eval(sel, g0, g1, &cf) : surf_eval(sel, g0, g1, &cf);
     if (!ok) continue;
     // mapOptmization.cpp:1223-1255
     const float arx = (crx * sry * srz * ori.x + crx * crz * sry * ori.y - srx * sry * ori.z) * cf.x +
