@@ -562,7 +562,14 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         per_launch_s = (k_ms * 1e-3 / k_n) if k_n else float("nan")
-        alg = algorithmic_bytes(dominant, st) * B
+        alg = algorithmic_bytes(dominant, st) * sub   # one launch covers one sub-batch
+        traffic = None
+        try:  # dram bytes per launch from the committed ncu --set full capture (profiles/r1_traffic.json)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if dominant in tr:
+                traffic = tr[dominant]["dram_bytes_per_sequence"] * sub
+        except Exception:
+            pass
         achieved = alg / per_launch_s / 1e9 if k_n else 0.0
         shares = {k: round(v[0] / sum(x[0] for x in table.values()), 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])}
         line = {
@@ -574,7 +581,7 @@ def main():
                     "d2h_bytes_per_step": B * 6 * 4 * 3, "steps": e2e_steps, "ms_per_step": e2e_ms / max(1, e2e_steps)},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "avg_launch_us": per_launch_s * 1e6, "launches_timed": k_n,
                          "kernel_time_share_profiling_pass": shares},
             "kernel_rooflines": kernel_rooflines(alone, st, sub, peak),
