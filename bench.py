@@ -42,6 +42,10 @@ def parse_args():
     ap.add_argument("--config", default="C", help="sensor config: A 16x1800, B 32x1800, C 64x2048")
     ap.add_argument("--unique-seqs", type=int, default=0, help="distinct synthetic sequences per GPU (0 = batch)")
     ap.add_argument("--no-map", action="store_true", help="skip scan-to-map")
+    ap.add_argument("--map", default="synthetic", choices=["synthetic", "live"],
+                    help="synthetic: scan-to-map against a fixed pre-built local map (headline workload); live: the "
+                         "whole MapOptimization::run body -- key frames saved and the local map re-assembled from them "
+                         "on the device every mapping cycle (SURVEY 8 f2)")
     ap.add_argument("--cpu-frames", type=int, default=11, help="frames per sequence of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--time-kernel", default="", help="kernel to report in `roofline` (default: the slowest)")
@@ -162,6 +166,10 @@ def algorithmic_bytes(kernel, st):
         # 5-NN: query + 10-candidate record written (full search) or read (reuse) + the map read once
         "k_map_knn": (qs + qc) * (16 + 176) + (ms + mc) * 16,
         "k_map_iter": (qs + qc) * (16 + 4 + 5 * 16), "k_map_solve": 0,
+        # key frames / local map (--map live): one appended key frame per cycle (point + voxel key in, voxel sums
+        # read-modify-written), every occupied voxel read and one centroid written, the key frame's clouds stored
+        "k_kf_select": 0, "k_kf_decide": 0, "k_kf_accumulate": (qs + qc) * (16 + 8 + 2 * 28),
+        "k_kf_extract": (ms + mc) * (8 + 20 + 16), "k_kf_store": (qs + qc) * (16 + 28),
     }
     return float(table.get(kernel, 0))
 
@@ -170,7 +178,7 @@ def algorithmic_bytes(kernel, st):
 # CPU arm (oracle): the reference's algorithm on the host cores
 
 
-def cpu_pipeline(params, cfg_name, n_threads, n_frames, use_map, frames_data=None):
+def cpu_pipeline(params, cfg_name, n_threads, n_frames, use_map, frames_data=None, live=False):
     """Runs n_threads independent sequences of n_frames frames through the CPU oracle, one thread per
     sequence (the ctypes calls release the GIL).  Returns (scans/s, wall seconds, scans, per-stage seconds)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -178,12 +186,12 @@ def cpu_pipeline(params, cfg_name, n_threads, n_frames, use_map, frames_data=Non
     from oracle import oracle_py
     cfg = synth.make_config(params)
     scans = frames_data or synth.scans(cfg, range(n_threads), range(n_frames), threads=n_threads)
-    maps = {s: local_maps(cfg, s) for s in range(n_threads)} if use_map else {}
+    maps = {s: local_maps(cfg, s) for s in range(n_threads)} if use_map and not live else {}
     oracles = [oracle_py.Oracle(params, libm=True, nanoflann=True) for _ in range(n_threads)]
     for s, o in enumerate(oracles):  # frame 0 only initialises (featureAssociation.cpp:1414-1417)
         o.image_projection(scans[(s, 0)])
         o.feature_association()
-        if use_map:
+        if use_map and not live:
             o.map_set_local(*maps[s])
             x, y, z, roll, pitch, yaw = synth.pose(cfg, s, 0)
             o.map_set_poses(np.array([0, yaw, 0, y, z, x], np.float32), np.zeros(6, np.float32))
@@ -194,10 +202,13 @@ def cpu_pipeline(params, cfg_name, n_threads, n_frames, use_map, frames_data=Non
         for f in range(1, n_frames):
             o.image_projection(scans[(s, f)])
             if o.feature_association() == 1 and use_map:
+                if live:
+                    o.mapping_cycle()
+                    continue
                 o.map_downsample_current_scan()
                 o.map_predict_pose()
                 o.scan_to_map()
-        return o.timers()
+        return np.concatenate([o.timers(), [o.timer_map_assembly()]])
 
     t0 = time.time()
     with ThreadPoolExecutor(n_threads) as ex:
@@ -217,7 +228,8 @@ def run_reference_arm(args, params):
     n_frames = 1 + args.warmup + args.steps
     scans = synth.scans(cfg, range(cores), range(n_frames), threads=cores)
     use_map = not args.no_map
-    maps = {s: local_maps(cfg, s) for s in range(cores)} if use_map else {}
+    live = args.map == "live"
+    maps = {s: local_maps(cfg, s) for s in range(cores)} if use_map and not live else {}
     oracles = [oracle_py.Oracle(params, libm=True, nanoflann=True) for _ in range(cores)]
     from concurrent.futures import ThreadPoolExecutor
 
@@ -225,13 +237,16 @@ def run_reference_arm(args, params):
         o = oracles[s]
         o.image_projection(scans[(s, f)])
         if o.feature_association() == 1 and use_map:
+            if live:
+                o.mapping_cycle()
+                return
             o.map_downsample_current_scan()
             o.map_predict_pose()
             o.scan_to_map()
 
     with ThreadPoolExecutor(cores) as ex:
         for s in range(cores):
-            if use_map:
+            if use_map and not live:
                 oracles[s].map_set_local(*maps[s])
                 x, y, z, roll, pitch, yaw = synth.pose(cfg, s, 0)
                 oracles[s].map_set_poses(np.array([0, yaw, 0, y, z, x], np.float32), np.zeros(6, np.float32))
@@ -258,7 +273,8 @@ def run_reference_arm(args, params):
 def workload_config(args, params, batch, where):
     return {"workload": f"{params.num_vertical_scans}x{params.num_horizontal_scans} synthetic lidar, {batch} independent "
                         f"sequences per {'GPU' if where == 'gpu' else 'host'}, full hot path per scan (projection, ground, "
-                        "segmentation, features, scan-to-scan LM" + ("" if args.no_map else ", scan-to-map every 5th scan vs synthetic local map") + ")",
+                        "segmentation, features, scan-to-scan LM" + ("" if args.no_map else (", scan-to-map every 5th scan vs synthetic local map" if args.map == "synthetic" else ", whole mapping cycle every 5th scan: key frames + local map assembled from them + scan-to-map")) + ")",
+            "map": "none" if args.no_map else args.map,
             "sensor": args.config, "batch_per_gpu": batch, "streams_per_gpu": args.streams, "parallelism": f"replicas x{args.gpus} (independent sequences, no collective)",
             "l2": "every step reads a distinct set of scans (inputs per step ~ L2 size, dataset >> L2); no reuse between steps"}
 
@@ -292,13 +308,17 @@ PSF_KERNELS = ["k_project_scatter", "k_gather_ground", "k_ccl_rows", "k_ccl_merg
                "k_feature_compact"]
 
 
-def single_sequence_latency(params, devdata, counts, stride, n_frames, B, dev, torch, local_map=None, aft0=None):
+def single_sequence_latency(params, devdata, counts, stride, n_frames, B, dev, torch, local_map=None, aft0=None, live=False):
     """p50 / p95 device latency of one scan of ONE sequence (batch 1, one stream; BASELINE.json configs[3]):
     the projection..odometry chain of every scan, scan-to-map on every 5th."""
     from lego_loam_bor_b200.capi import LegoLoam
     stream = torch.cuda.Stream(device=dev)
     one = LegoLoam(params, batch=1, max_points=stride, device=dev.index, stream=stream.cuda_stream)
-    if local_map is not None:
+    if live:
+        N1 = params.num_vertical_scans * params.num_horizontal_scans
+        one.map_enable_keyframes(max_keyframes=min(1024, n_frames // 5 + 8), pool_points=(n_frames // 5 + 8) * (N1 // 8),
+                                 max_map_corner=N1 // 2, max_map_surf=N1)
+    elif local_map is not None:
         one.map_set_local(0, *local_map)
         one.map_set_poses(aft0, np.zeros((1, 6), np.float32))
     frame_bytes = B * stride * 16
@@ -387,13 +407,22 @@ def main():
             for ss in sub_streams:
                 stream.wait_stream(ss)
 
-    if use_map:
+    live = use_map and args.map == "live"
+    if live:
+        kf_cap = min(1024, max(16, n_frames // max(1, params.mapping_frequency_divider) + 8))
+        gpu.map_enable_keyframes(max_keyframes=kf_cap, pool_points=kf_cap * (N // 8), max_map_corner=N // 2, max_map_surf=N)
+    elif use_map:
         for k, s in enumerate(seq_ids):
             cm, sm = local_maps(cfg, s)
             gpu.map_set_local(k, cm, sm)
     frame_bytes = B * stride * 16
 
     def seed_map_poses():
+        if live:
+            return  # the map frame is the odometry frame of the first key frame, like the reference
+        _seed_map_poses()
+
+    def _seed_map_poses():
         """transformAftMapped = pose of frame 0 in the map frame, transformBefMapped = odometry origin; from
         then on the odometry -> map chain (transformAssociateToMap / transformUpdate) stays on the device."""
         aft = np.zeros((B, 6), np.float32)
@@ -513,7 +542,7 @@ def main():
             x, y, z, roll, pitch, yaw = synth.pose(cfg, seq_ids[0], 0)
             aft0 = np.array([[0, yaw, 0, y, z, x]], np.float32)
         latency = single_sequence_latency(params, devdata, counts, stride, n_frames, B, dev, torch,
-                                          local_maps(cfg, seq_ids[0]) if use_map else None, aft0)
+                                          local_maps(cfg, seq_ids[0]) if use_map else None, aft0, live=live)
 
     # ---- end-to-end: same C ABI, pinned host scans, H2D + pose D2H inside the timed region ----
     gpu.reset()
@@ -592,13 +621,13 @@ def main():
         }
         if not args.skip_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, 64))
-            v, wall, n_scans, stage_s, kind = cpu_pipeline(params, args.config, cores, args.cpu_frames, use_map)
+            v, wall, n_scans, stage_s, kind = cpu_pipeline(params, args.config, cores, args.cpu_frames, use_map, live=live)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "knn": kind,
                                     "sample": f"{cores} sequences x {args.cpu_frames - 1} scans of the same workload on "
                                               f"{cores} host threads ({wall:.1f} s wall)",
                                     "stage_seconds_sum": {"image_projection": stage_s[0], "feature_extraction": stage_s[1],
                                                           "scan_to_scan": stage_s[2], "scan_to_map": stage_s[3],
-                                                          "downsample": stage_s[4]}}
+                                                          "downsample": stage_s[4], "map_assembly_keyframes": stage_s[5]}}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -122,6 +122,12 @@ typedef enum ll_buffer {
   LL_BUF_SCAN_OUTLIER_DS = 39, /* pt[..] laserCloudOutlierLastDS */
   LL_BUF_STAGE_CLOCKS = 40,    /* i64[16] profiling aid: nanoseconds the two scan-to-scan LM stages of the last frame spent per phase
                                   (stage*8 + {0 total, 1 prologue, 2 re-search, 3 rows + reduction, 4 solve, 5 re-searched points}) */
+  /* MapOptimization key frames and local map (mapOptimization.h:96-135; needs ll_map_enable_keyframes) */
+  LL_BUF_KEYFRAME_STATE = 41,      /* i32[4] key frames stored (cloudKeyPoses3D->size()), surroundingExistingKeyPosesID.size(),
+                                      1 if the last extractSurroundingKeyFrames erased a key frame, capacity error bits (0 = none:
+                                      1 key-frame slots, 2 point pool, 4 voxel table, 8 local-map output, 16 voxel index range) */
+  LL_BUF_KEY_POSES_6D = 42,        /* f32[K][6] cloudKeyPoses6D as (roll, pitch, yaw, x, y, z) */
+  LL_BUF_SURROUNDING_KEY_IDS = 43, /* i32[..] surroundingExistingKeyPosesID */
   LL_BUF_COUNT_
 } ll_buffer;
 
@@ -191,9 +197,35 @@ int ll_map_predict_pose(ll_handle* h);
  * LMOptimization) (mapOptmization.cpp:1028-1332) for all sequences. */
 int ll_scan_to_map(ll_handle* h);
 
+/* ---- key frames and the local map on the device ----
+ * MapOptimization::saveKeyFramesAndFactor (mapOptmization.cpp:1335-1474, iSAM2 == identity because loop closure is
+ * off), extractSurroundingKeyFrames (:856-996, the enable_loop_closure == false branch) and transformPointCloud
+ * (:443-473) for all sequences, without host round trips.
+ *
+ * ll_map_enable_keyframes allocates the per-sequence stores: max_keyframes key poses (<= 1024), pool_points points
+ * for all key-frame clouds of one sequence (corner + surf + outlier, already down-sampled), and local maps of up to
+ * max_map_corner / max_map_surf points (laserCloudCornerFromMapDS / laserCloudSurfFromMapDS).  A sequence that
+ * outgrows a capacity stops saving key frames / truncates its map and raises a bit in LL_BUF_KEYFRAME_STATE[3].
+ * Fails with LL_ERR_STATE when params.enable_loop_closure is set (the loop-closure branch is not built). */
+int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, int max_map_corner, int max_map_surf);
+/* extractSurroundingKeyFrames: radius search over the key poses around currentRobotPosPoint, 1 m VoxelGrid of those
+ * poses, update of surroundingExistingKeyPosesID, concatenation of the surrounding key-frame clouds and the 0.2 m /
+ * 0.4 m VoxelGrid that gives the local map used by ll_scan_to_map. */
+int ll_map_extract_surrounding_keyframes(ll_handle* h);
+/* saveKeyFramesAndFactor: the 0.3 m rule, key pose, copies of laserCloudCornerLastDS / SurfLastDS / OutlierLastDS
+ * (left on the device by ll_map_downsample_current_scan), stored transformed by the key pose. */
+int ll_map_save_keyframe(ll_handle* h);
+/* One body of MapOptimization::run (:1526-1562): ll_map_predict_pose, ll_map_extract_surrounding_keyframes,
+ * ll_map_downsample_current_scan, ll_scan_to_map, ll_map_save_keyframe. */
+int ll_mapping_cycle(ll_handle* h);
+/* One stored key-frame cloud (which: 0 corner, 1 surf, 2 outlier) of one sequence, transformed by its key pose, in
+ * the point order of the down-sampled scan cloud it was copied from.  Synchronises the stream. */
+int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, void* dst, size_t dst_bytes, size_t* n_elems);
+
 /* One full frame for every sequence: ll_image_projection + ll_feature_association,
  * and every mapping_frequency_divider-th odometry frame also ll_map_downsample_current_scan +
- * ll_map_predict_pose + ll_scan_to_map when a local map is set.  Returns 1 on such frames, else 0. */
+ * ll_map_predict_pose + ll_scan_to_map when a local map is set -- or, after ll_map_enable_keyframes, ll_mapping_cycle.
+ * Returns 1 on such frames, else 0. */
 int ll_process_scans(ll_handle* h);
 
 /* ---- results ------------------------------------------------------------------- */

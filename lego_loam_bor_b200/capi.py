@@ -28,6 +28,7 @@ BUFFERS = {
     "MAP_TRACE": (35, np.float64, 1), "TRANSFORM_BEF_MAPPED": (36, np.float32, 1),
     "TRANSFORM_AFT_MAPPED": (37, np.float32, 1), "SCAN_SURF_DS": (38, np.float32, 4),
     "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
+    "KEYFRAME_STATE": (41, np.int32, 1), "KEY_POSES_6D": (42, np.float32, 6), "SURROUNDING_KEY_IDS": (43, np.int32, 1),
 }
 
 EXPORTS = [
@@ -38,6 +39,8 @@ EXPORTS = [
     "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_get_poses_async", "ll_wait_poses", "ll_download", "ll_upload", "ll_synchronize",
     "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
     "ll_get_kernel_time_table",
+    "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
+    "ll_map_download_keyframe",
 ]
 
 _lib = None
@@ -86,6 +89,10 @@ def load_library(path=None):
     lib.ll_time_kernel.argtypes = [vp, C.c_char_p]
     lib.ll_get_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.ll_get_kernel_time_table.argtypes = [vp, C.c_char_p, sz]
+    lib.ll_map_enable_keyframes.argtypes = [vp, ip, ip, ip, ip]
+    for name in ("ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle"):
+        getattr(lib, name).argtypes = [vp]
+    lib.ll_map_download_keyframe.argtypes = [vp, ip, ip, ip, vp, sz, C.POINTER(sz)]
     if path == LIB_CUDA:
         _lib = lib
     return lib
@@ -189,6 +196,32 @@ class LegoLoam:
     def scan_to_map(self):
         self._ck(self.lib.ll_scan_to_map(self.h), "ll_scan_to_map")
 
+    def map_enable_keyframes(self, max_keyframes=256, pool_points=None, max_map_corner=None, max_map_surf=None):
+        """Key frames and the local map on the device (MapOptimization::saveKeyFramesAndFactor /
+        extractSurroundingKeyFrames); after this, process_scans runs whole mapping cycles."""
+        pool_points = pool_points or max_keyframes * (self.N // 4)
+        max_map_corner = max_map_corner or self.N
+        max_map_surf = max_map_surf or 2 * self.N
+        self._ck(self.lib.ll_map_enable_keyframes(self.h, max_keyframes, pool_points, max_map_corner, max_map_surf),
+                 "ll_map_enable_keyframes")
+
+    def map_extract_surrounding_keyframes(self):
+        return self._ck(self.lib.ll_map_extract_surrounding_keyframes(self.h), "ll_map_extract_surrounding_keyframes")
+
+    def map_save_keyframe(self):
+        return self._ck(self.lib.ll_map_save_keyframe(self.h), "ll_map_save_keyframe")
+
+    def mapping_cycle(self):
+        return self._ck(self.lib.ll_mapping_cycle(self.h), "ll_mapping_cycle")
+
+    def download_keyframe(self, seq, keyframe, which):
+        n = C.c_size_t(0)
+        self._ck(self.lib.ll_map_download_keyframe(self.h, seq, keyframe, which, None, 0, C.byref(n)), "ll_map_download_keyframe")
+        out = np.empty((n.value, 4), np.float32)
+        self._ck(self.lib.ll_map_download_keyframe(self.h, seq, keyframe, which, out.ctypes.data, out.nbytes, C.byref(n)),
+                 "ll_map_download_keyframe")
+        return out
+
     def synchronize(self):
         self._ck(self.lib.ll_synchronize(self.h), "ll_synchronize")
 
@@ -288,6 +321,10 @@ class LegoLoamStreams:
     def map_set_local(self, seq, corner, surf):
         p, k = self._loc(seq)
         p.map_set_local(k, corner, surf)
+
+    def map_enable_keyframes(self, *a, **kw):
+        for p in self.parts:
+            p.map_enable_keyframes(*a, **kw)
 
     def map_set_poses(self, aft, bef):
         aft = np.ascontiguousarray(aft, np.float32).reshape(self.batch, 6)

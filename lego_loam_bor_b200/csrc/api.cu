@@ -112,6 +112,25 @@ int stage_counts(ll_handle* h, const int32_t* n_points, int stride_points, const
   return LL_OK;
 }
 
+// cloudKeyPoses3D/6D, the key-frame clouds and the surrounding cache start empty; PointType() positions are zero
+int reset_keyframes(ll_handle* h) {
+  KeyframeStore& kf = h->st.kf;
+  const int B = h->st.p.B;
+  cudaStream_t sm = h->ctx.stream;
+  CK(cudaMemsetAsync(kf.kf_count, 0, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.pool_used, 0, (size_t)B * 4, sm));
+  CK(cudaMemsetAsync(kf.kf_new, 0xff, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.robot_pos, 0, (size_t)B * 32, sm));
+  CK(cudaMemsetAsync(kf.transform_last, 0, (size_t)B * 24, sm)); CK(cudaMemsetAsync(kf.sur_n, 0, (size_t)B * 4, sm));
+  CK(cudaMemsetAsync(kf.sur_first, 0, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.sur_rebuild, 0, (size_t)B * 4, sm));
+  CK(cudaMemsetAsync(kf.sur_valid, 0, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.err, 0, (size_t)B * 4, sm));
+  for (int m = 0; m < 2; ++m) {
+    const VoxTable& t = kf.tbl[m];
+    CK(cudaMemsetAsync(t.key, 0xff, (size_t)B * t.parts * t.sub_cap * 8, sm));
+    CK(cudaMemsetAsync(t.list_n, 0, (size_t)B * t.parts * 4, sm));
+  }
+  CK(cudaMemsetAsync(h->st.map_counts, 0, (size_t)B * 8, sm));
+  return LL_OK;
+}
+
 int check_stream(ll_handle* h, const char* where) {
   if (h->ctx.first_error != cudaSuccess) {
     h->err = std::string(where) + ": launch of " + (h->ctx.first_error_kernel ? h->ctx.first_error_kernel : "?") +
@@ -306,6 +325,7 @@ int ll_reset(ll_handle* h) {
   h->frames = 0;
   h->odom_cycles = 0;
   h->handed_to_mapping = false;
+  if (st.kf.enabled) { const int rc = reset_keyframes(h); if (rc) return rc; }
   return LL_OK;
 }
 
@@ -476,6 +496,113 @@ int ll_scan_to_map(ll_handle* h) {
   return check_stream(h, "ll_scan_to_map");
 }
 
+int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, int max_map_corner, int max_map_surf) {
+  if (!h || max_keyframes < 1 || max_keyframes > 1024 || pool_points < 1 || max_map_corner < 1 || max_map_surf < 1) return LL_ERR_INVALID_ARG;
+  if (h->prm.enable_loop_closure) { h->err = "ll_map_enable_keyframes: the loop-closure branch of extractSurroundingKeyFrames is not built"; return LL_ERR_STATE; }
+  DevState& st = h->st;
+  KeyframeStore& kf = st.kf;
+  if (kf.enabled) { h->err = "ll_map_enable_keyframes: already enabled"; return LL_ERR_STATE; }
+  const int B = st.p.B;
+  {
+    // at least the requested capacities (ensure_map_capacity adds headroom when it has to grow)
+    const int rc = ensure_map_capacity(h, max_map_corner > st.cap_map_corner ? max_map_corner : st.cap_map_corner,
+                                       max_map_surf > st.cap_map_surf ? max_map_surf : st.cap_map_surf);
+    if (rc) return rc;
+  }
+  kf.kf_cap = max_keyframes;
+  kf.pool_cap = pool_points;
+  const double r = (double)h->prm.surrounding_keyframe_search_radius;
+  kf.radius2 = (float)(r * r);  // nanoflann_pcl.h:163
+  CK(dev_alloc(h, &kf.kf_count, (size_t)B)); CK(dev_alloc(h, &kf.kf_pose, (size_t)B * kf.kf_cap * 6));
+  CK(dev_alloc(h, &kf.kf_off, (size_t)B * kf.kf_cap * 4)); CK(dev_alloc(h, &kf.pool_used, (size_t)B));
+  CK(dev_alloc(h, &kf.pool_pts, (size_t)B * kf.pool_cap, false)); CK(dev_alloc(h, &kf.pool_key, (size_t)B * kf.pool_cap, false));
+  CK(dev_alloc(h, &kf.pool_perm, (size_t)B * kf.pool_cap, false)); CK(dev_alloc(h, &kf.kf_new, (size_t)B));
+  CK(dev_alloc(h, &kf.robot_pos, (size_t)B * 8)); CK(dev_alloc(h, &kf.transform_last, (size_t)B * 6));
+  CK(dev_alloc(h, &kf.sur_ids, (size_t)B * kf.kf_cap)); CK(dev_alloc(h, &kf.sur_n, (size_t)B));
+  CK(dev_alloc(h, &kf.sur_first, (size_t)B)); CK(dev_alloc(h, &kf.sur_rebuild, (size_t)B));
+  CK(dev_alloc(h, &kf.sur_valid, (size_t)B)); CK(dev_alloc(h, &kf.err, (size_t)B));
+  // voxel tables: twice the map capacity in slots (they are filled to at most 3/4)
+  const float leaf[2] = {0.2f, 0.4f};  // downSizeFilterCorner, downSizeFilterSurf (mapOptmization.cpp:71-72)
+  const int parts[2] = {1, 4};
+  const int want[2] = {st.cap_map_corner, st.cap_map_surf};
+  for (int m = 0; m < 2; ++m) {
+    VoxTable& t = kf.tbl[m];
+    t.parts = parts[m];
+    t.sub_cap = next_pow2((2 * want[m] + parts[m] - 1) / parts[m]);
+    if (t.sub_cap < 1024) t.sub_cap = 1024;
+    t.leaf = leaf[m];
+    const size_t slots = (size_t)B * t.parts * t.sub_cap;
+    CK(dev_alloc(h, &t.key, slots, false)); CK(dev_alloc(h, &t.sum, slots, false)); CK(dev_alloc(h, &t.cnt, slots, false));
+    CK(dev_alloc(h, &t.list, slots, false)); CK(dev_alloc(h, &t.list_n, (size_t)B * t.parts));
+  }
+  kf.sort_cap = st.cap_map_corner > st.cap_map_surf ? st.cap_map_corner : st.cap_map_surf;
+  CK(dev_alloc(h, &kf.sk0, (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.sk1, (size_t)B * 2 * kf.sort_cap, false));
+  CK(dev_alloc(h, &kf.sv0, (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.sv1, (size_t)B * 2 * kf.sort_cap, false));
+  kf.enabled = 1;
+  { const int rc = reset_keyframes(h); if (rc) return rc; }
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  h->map_set = true;
+  return LL_OK;
+}
+
+int ll_map_extract_surrounding_keyframes(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!h->st.kf.enabled) { h->err = "ll_map_extract_surrounding_keyframes: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
+  launch_extract_surrounding_keyframes(h->ctx, h->st);
+  return check_stream(h, "ll_map_extract_surrounding_keyframes");
+}
+
+int ll_map_save_keyframe(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!h->st.kf.enabled) { h->err = "ll_map_save_keyframe: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
+  launch_save_keyframe(h->ctx, h->st);
+  return check_stream(h, "ll_map_save_keyframe");
+}
+
+int ll_mapping_cycle(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  if (!h->st.kf.enabled) { h->err = "ll_mapping_cycle: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
+  // MapOptimization::run, mapOptmization.cpp:1545-1560
+  int rc = ll_map_predict_pose(h);
+  if (rc < 0) return rc;
+  rc = ll_map_extract_surrounding_keyframes(h);
+  if (rc < 0) return rc;
+  rc = ll_map_downsample_current_scan(h);
+  if (rc < 0) return rc;
+  rc = ll_scan_to_map(h);
+  if (rc < 0) return rc;
+  return ll_map_save_keyframe(h);
+}
+
+int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, void* dst, size_t dst_bytes, size_t* n_elems) {
+  if (!h || seq < 0 || seq >= h->st.p.B || which < 0 || which > 2) return LL_ERR_INVALID_ARG;
+  KeyframeStore& kf = h->st.kf;
+  if (!kf.enabled) { h->err = "ll_map_download_keyframe: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
+  int count = 0, off[4];
+  CK(cudaMemcpyAsync(&count, kf.kf_count + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  if (keyframe < 0 || keyframe >= count) return LL_ERR_INVALID_ARG;
+  CK(cudaMemcpyAsync(off, kf.kf_off + ((size_t)seq * kf.kf_cap + keyframe) * 4, 16, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  const size_t n = (size_t)(off[which + 1] - off[which]);
+  if (n_elems) *n_elems = n;
+  if (!dst) return LL_OK;
+  if (dst_bytes < n * 16) return LL_ERR_CAPACITY;
+  if (!n) return LL_OK;
+  // the pool holds the cloud sorted by voxel; undo that with the stored permutation
+  std::vector<float> pts(n * 4);
+  std::vector<int> perm(n);
+  CK(cudaMemcpyAsync(pts.data(), kf.pool_pts + (size_t)seq * kf.pool_cap + off[which], n * 16, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaMemcpyAsync(perm.data(), kf.pool_perm + (size_t)seq * kf.pool_cap + off[which], n * 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  float* out = (float*)dst;
+  for (size_t u = 0; u < n; ++u) {
+    if (perm[u] < 0 || (size_t)perm[u] >= n) { h->err = "ll_map_download_keyframe: corrupt permutation"; return LL_ERR_STATE; }
+    memcpy(out + (size_t)perm[u] * 4, pts.data() + u * 4, 16);
+  }
+  return LL_OK;
+}
+
 int ll_process_scans(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   int rc = ll_image_projection(h);
@@ -483,12 +610,17 @@ int ll_process_scans(ll_handle* h) {
   rc = ll_feature_association(h);
   if (rc < 0) return rc;
   if (rc == 1 && h->map_set) {
-    rc = ll_map_downsample_current_scan(h);
-    if (rc < 0) return rc;
-    rc = ll_map_predict_pose(h);
-    if (rc < 0) return rc;
-    rc = ll_scan_to_map(h);
-    if (rc < 0) return rc;
+    if (h->st.kf.enabled) {
+      rc = ll_mapping_cycle(h);
+      if (rc < 0) return rc;
+    } else {
+      rc = ll_map_downsample_current_scan(h);
+      if (rc < 0) return rc;
+      rc = ll_map_predict_pose(h);
+      if (rc < 0) return rc;
+      rc = ll_scan_to_map(h);
+      if (rc < 0) return rc;
+    }
     if (h->timing) cudaEventRecord(h->ev[5], h->ctx.stream);
     h->ev_valid = true;
     return 1;
@@ -672,6 +804,25 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_TRANSFORM_BEF_MAPPED: src = st.transform_bef_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_TRANSFORM_AFT_MAPPED: src = st.transform_aft_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_OUTLIER_LAST: COUNTED(st.outlier_last, 16, (size_t)st.cap_outlier, st.odom_flags + seq * 4 + 3); break;
+    case LL_BUF_KEYFRAME_STATE: {
+      if (!st.kf.enabled) return LL_ERR_STATE;
+      int v[4];
+      CK(cudaMemcpyAsync(&v[0], st.kf.kf_count + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaMemcpyAsync(&v[1], st.kf.sur_n + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaMemcpyAsync(&v[2], st.kf.sur_rebuild + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaMemcpyAsync(&v[3], st.kf.err + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaStreamSynchronize(h->ctx.stream));
+      if (n_elems) *n_elems = 4;
+      if (!dst) return LL_OK;
+      if (dst_bytes < 16) return LL_ERR_CAPACITY;
+      memcpy(dst, v, 16);
+      return LL_OK;
+    }
+    case LL_BUF_KEY_POSES_6D: if (!st.kf.enabled) return LL_ERR_STATE;
+      { const int rc__ = fetch_count(h, st.kf.kf_count + seq, &cnt); if (rc__) return rc__; }
+      src = st.kf.kf_pose + (size_t)seq * st.kf.kf_cap * 6; elem = 24; n = (size_t)cnt; break;
+    case LL_BUF_SURROUNDING_KEY_IDS: if (!st.kf.enabled) return LL_ERR_STATE;
+      COUNTED(st.kf.sur_ids, 4, (size_t)st.kf.kf_cap, st.kf.sur_n + seq); break;
     case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: {
       // gathered from the per-ring counters (stride 8)
       std::vector<int> rc((size_t)p.V * 8);

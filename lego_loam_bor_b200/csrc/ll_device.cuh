@@ -34,6 +34,45 @@ struct HashGrid {
   int cap;           // point capacity per sequence
 };
 
+// Sparse voxel accumulator of one local map (keyframes.cu): open-addressing table keyed by the absolute voxel
+// coordinates, split into `parts` independent sub-tables (a voxel belongs to exactly one, chosen by a hash of its key).
+struct VoxTable {
+  unsigned long long* key;  // [B][parts][sub_cap] packed voxel (iz, iy, ix), all ones = empty
+  float4* sum;              // [B][parts][sub_cap] running sums of x, y, z, intensity in concatenation order
+  int* cnt;                 // [B][parts][sub_cap] points summed
+  unsigned* list;           // [B][parts][sub_cap] slots in use, in insertion order
+  int* list_n;              // [B][parts]
+  int parts, sub_cap;       // sub_cap is a power of two
+  float leaf;               // VoxelGrid leaf size (m)
+};
+
+// MapOptimization's key-frame state for every sequence (mapOptimization.h:96-135), SURVEY.md section 8 f2.
+struct KeyframeStore {
+  int enabled;
+  int kf_cap;                    // key frames per sequence (<= 1024)
+  int pool_cap;                  // points per sequence over all key-frame clouds
+  float radius2;                 // (float)(surrounding_keyframe_search_radius^2), squared in double (nanoflann_pcl.h:163)
+  int* kf_count;                 // [B] cloudKeyPoses3D->size()
+  float* kf_pose;                // [B][kf_cap][6] cloudKeyPoses6D: roll, pitch, yaw, x, y, z
+  int* kf_off;                   // [B][kf_cap][4] pool offsets of the corner, surf, outlier cloud and the end
+  int* pool_used;                // [B]
+  float4* pool_pts;              // [B][pool_cap] key-frame clouds transformed by their key pose; each cloud stable-sorted by voxel
+  unsigned long long* pool_key;  // [B][pool_cap] packed absolute voxel of every stored point (leaf of the map it goes into)
+  int* pool_perm;                // [B][pool_cap] position of every stored point in its down-sampled scan cloud
+  int* kf_new;                   // [B] index of the key frame ll_map_save_keyframe is storing, or -1
+  float* robot_pos;              // [B][8] currentRobotPosPoint xyz, pad, previousRobotPosPoint xyz, pad
+  float* transform_last;         // [B][6]
+  int* sur_ids;                  // [B][kf_cap] surroundingExistingKeyPosesID
+  int* sur_n;                    // [B]
+  int* sur_first;                // [B] first list position whose clouds still have to be summed into the voxel tables
+  int* sur_rebuild;              // [B] 1: a key frame was erased, the tables are rebuilt from list position 0
+  int* sur_valid;                // [B] 0: no key frames yet (extractSurroundingKeyFrames returns early, maps stay empty)
+  int* err;                      // [B] capacity error bits (LL_BUF_KEYFRAME_STATE[3])
+  VoxTable tbl[2];               // 0: corner map (leaf 0.2), 1: surf map (leaf 0.4)
+  unsigned *sk0, *sk1, *sv0, *sv1;  // [B][2][sort_cap] sort scratch of the local-map extraction
+  int sort_cap;
+};
+
 struct DevParams {
   int B, V, H, N, max_pts;
   // ImageProjection derived constants (imageProjection.cpp:64-84), computed on the host with
@@ -145,6 +184,8 @@ struct DevState {
   double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)
   int* map_rows;                                 // [B][max_blocks]
   int map_max_blocks;
+  // ---- MapOptimization key frames / local map ----
+  KeyframeStore kf;
 };
 
 // ---- small device helpers --------------------------------------------------------------

@@ -75,3 +75,6 @@ void launch_grid_build2(LaunchCtx& ctx, int B, HashGrid& g0, const float4* pts0,
 void launch_scan_to_map(LaunchCtx& ctx, DevState& st);
 void launch_map_predict_pose(LaunchCtx& ctx, DevState& st);
 void launch_downsample_current_scan(LaunchCtx& ctx, DevState& st);
+// keyframes.cu: saveKeyFramesAndFactor / extractSurroundingKeyFrames on the device
+void launch_extract_surrounding_keyframes(LaunchCtx& ctx, DevState& st);
+void launch_save_keyframe(LaunchCtx& ctx, DevState& st);

@@ -8,13 +8,13 @@
 // One block per (sequence, cloud).  The voxel indices are sorted with a block-local stable LSD radix
 // sort (8-bit digits, only as many passes as the index range needs) that ping-pongs through global
 // scratch; stability keeps the input order inside a voxel, so the sequential float sums match the CPU.
+#include "block_sort.cuh"
 #include "ll_device.cuh"
 #include "ll_kernels.h"
 
 namespace {
 
-#define VG_THREADS 1024
-#define VG_WARPS (VG_THREADS / 32)
+#define VG_THREADS BS_THREADS
 
 struct VoxJob {
   const float4* a;   // first input cloud [B][stride_a]
@@ -48,10 +48,8 @@ __device__ __forceinline__ float ord2f_vg(int i) { return __int_as_float(i >= 0 
 
 __global__ void __launch_bounds__(VG_THREADS) k_voxel_grid(VoxArgs args) {
   __shared__ int sh_imn[3], sh_imx[3];
-  __shared__ int warp_tot[33];
-  __shared__ unsigned sh_hist[256];
-  __shared__ unsigned sh_base[256];
-  __shared__ unsigned short sh_whist[VG_WARPS][256];
+  __shared__ BlockSortSmem sort_sm;
+  int* const warp_tot = sort_sm.warp_tot;
   const int s = blockIdx.x;
   const int jid = blockIdx.y;
   const VoxJob& job = args.job[jid];
@@ -64,8 +62,8 @@ __global__ void __launch_bounds__(VG_THREADS) k_voxel_grid(VoxArgs args) {
     return;
   }
   const size_t soff = ((size_t)s * 3 + jid) * args.cap;
-  unsigned* key[2] = {args.key0 + soff, args.key1 + soff};
-  unsigned* val[2] = {args.val0 + soff, args.val1 + soff};
+  unsigned* const key[2] = {args.key0 + soff, args.key1 + soff};
+  unsigned* const val[2] = {args.val0 + soff, args.val1 + soff};
   const float inv = 1.0f / job.leaf;
   // ---- bounding box ----
   if (threadIdx.x < 3) { sh_imn[threadIdx.x] = f2ord_vg(FLT_MAX); sh_imx[threadIdx.x] = f2ord_vg(-FLT_MAX); }
@@ -121,64 +119,8 @@ __global__ void __launch_bounds__(VG_THREADS) k_voxel_grid(VoxArgs args) {
     val[0][i] = (unsigned)i;
   }
   __syncthreads();
-  // ---- stable LSD radix sort, 8 bits per pass ----
-  int passes = 1;
-  while (passes < 4 && (max_idx >> (8 * passes)) > 0) ++passes;
-  int cur = 0;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int pass = 0; pass < passes; ++pass) {
-    const int shift = 8 * pass;
-    const unsigned* kin = key[cur];
-    const unsigned* vin = val[cur];
-    unsigned* kout = key[cur ^ 1];
-    unsigned* vout = val[cur ^ 1];
-    if (threadIdx.x < 256) sh_hist[threadIdx.x] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += VG_THREADS) atomicAdd(&sh_hist[(kin[i] >> shift) & 255u], 1u);
-    __syncthreads();
-    {
-      int total;
-      const int v = threadIdx.x < 256 ? (int)sh_hist[threadIdx.x] : 0;
-      const int ex = block_exclusive_scan(v, warp_tot, &total);
-      if (threadIdx.x < 256) sh_base[threadIdx.x] = (unsigned)ex;
-    }
-    __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += VG_THREADS) {
-      const int i = t0 + threadIdx.x;
-      for (int d = lane; d < 256; d += 32) sh_whist[wid][d] = 0;
-      __syncwarp();
-      unsigned k = 0, v = 0, dg = 0, rank = 0;
-      const bool active = i < n;
-      if (active) { k = kin[i]; v = vin[i]; dg = (k >> shift) & 255u; }
-      const unsigned amask = __ballot_sync(0xffffffffu, active);
-      if (active) {
-        const unsigned peers = __match_any_sync(amask, dg);
-        rank = __popc(peers & ((1u << lane) - 1u));
-        if (rank == 0) sh_whist[wid][dg] = (unsigned short)__popc(peers);
-      }
-      __syncthreads();
-      // exclusive scan over warps for every digit, and advance the bin bases
-      if (threadIdx.x < 256) {
-        unsigned run = 0;
-        for (int w = 0; w < VG_WARPS; ++w) {
-          const unsigned c = sh_whist[w][threadIdx.x];
-          sh_whist[w][threadIdx.x] = (unsigned short)run;
-          run += c;
-        }
-        sh_hist[threadIdx.x] = run;  // tile total of this digit
-      }
-      __syncthreads();
-      if (active) {
-        const unsigned pos = sh_base[dg] + sh_whist[wid][dg] + rank;
-        kout[pos] = k;
-        vout[pos] = v;
-      }
-      __syncthreads();
-      if (threadIdx.x < 256) sh_base[threadIdx.x] += sh_hist[threadIdx.x];
-      __syncthreads();
-    }
-    cur ^= 1;
-  }
+  // ---- stable LSD radix sort (block_sort.cuh) ----
+  const int cur = block_radix_sort(key, val, n, max_idx, sort_sm);
   const unsigned* ks = key[cur];
   const unsigned* vs = val[cur];
   // ---- one centroid per run of equal voxel index ----

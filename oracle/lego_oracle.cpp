@@ -203,6 +203,7 @@ struct lo_handle {
     for (int i = 0; i < 340; ++i) map_trace[i] = 0.0;
     lessFlatRawCount.assign(V, 0);
     for (int i = 0; i < 5; ++i) timers[i] = 0;
+    resetKeyFrames();
   }
 
   /* ================= ImageProjection ================= */
@@ -1168,13 +1169,176 @@ struct lo_handle {
   }
 
   void downsampleCurrentScan() { /* mapOptmization.cpp:999-1026 */
-    std::vector<P4> surfDS, outDS, total;
+    std::vector<P4>& surfDS = surfLastDS;
+    std::vector<P4>& outDS = outlierLastDS;
+    std::vector<P4> total;
     voxel_grid(cornerLast, 0.2f, scanCornerDS);
     voxel_grid(surfLast, 0.4f, surfDS);
     voxel_grid(outlierLast, 0.4f, outDS);
     total = surfDS;
     total.insert(total.end(), outDS.begin(), outDS.end());
     voxel_grid(total, 0.4f, scanSurfTotalDS);
+  }
+
+  /* ================= MapOptimization: key frames and the local map, loop closure off =================
+   *   cloudKeyPoses3D/6D, the three key-frame cloud stores, the surrounding-key-frame
+   * cache and the two robot positions are the members of mapOptimization.h; iSAM2 is replaced by the identity
+   * (SURVEY.md sections 8c, 11.5: a pure odometry chain's optimum is its initial values, and the double
+   * RzRyRx -> rpy round trip returns the float it was given away from gimbal lock). */
+  struct Pose6 { float roll, pitch, yaw, x, y, z; };
+  std::vector<P4> surfLastDS, outlierLastDS;    /* laserCloudSurfLastDS, laserCloudOutlierLastDS */
+  std::vector<P4> cloudKeyPoses3D;               /* intensity = key-frame index */
+  std::vector<Pose6> cloudKeyPoses6D;
+  std::vector<std::vector<P4> > cornerCloudKeyFrames, surfCloudKeyFrames, outlierCloudKeyFrames;
+  std::vector<int> surroundingExistingKeyPosesID;
+  std::vector<std::vector<P4> > surroundingCornerCloudKeyFrames, surroundingSurfCloudKeyFrames, surroundingOutlierCloudKeyFrames;
+  std::unique_ptr<oknn::KdTree> kdSurroundingKeyPoses;
+  P4 currentRobotPosPoint, previousRobotPosPoint; /* PointType(): zeros */
+  float transformLast[6];
+  int last_rebuild; /* test aid: 1 when the last extractSurroundingKeyFrames erased a key frame */
+
+  void resetKeyFrames() {
+    surfLastDS.clear(); outlierLastDS.clear();
+    cloudKeyPoses3D.clear(); cloudKeyPoses6D.clear();
+    cornerCloudKeyFrames.clear(); surfCloudKeyFrames.clear(); outlierCloudKeyFrames.clear();
+    surroundingExistingKeyPosesID.clear();
+    surroundingCornerCloudKeyFrames.clear(); surroundingSurfCloudKeyFrames.clear(); surroundingOutlierCloudKeyFrames.clear();
+    kdSurroundingKeyPoses.reset(new oknn::KdTree());
+    currentRobotPosPoint.x = currentRobotPosPoint.y = currentRobotPosPoint.z = currentRobotPosPoint.i = 0.f;
+    previousRobotPosPoint = currentRobotPosPoint;
+    for (int i = 0; i < 6; ++i) transformLast[i] = 0;
+    last_rebuild = 0;
+    timer_map_assembly = 0;
+  }
+
+  /* updateTransformPointCloudSinCos + transformPointCloud (mapOptmization.cpp:428-473) */
+  std::vector<P4> transformPointCloud(const std::vector<P4>& cloudIn, const Pose6& tIn) {
+    const float ctRoll = cos_(tIn.roll), stRoll = sin_(tIn.roll);
+    const float ctPitch = cos_(tIn.pitch), stPitch = sin_(tIn.pitch);
+    const float ctYaw = cos_(tIn.yaw), stYaw = sin_(tIn.yaw);
+    const float tInX = tIn.x, tInY = tIn.y, tInZ = tIn.z;
+    std::vector<P4> cloudOut(cloudIn.size());
+    for (size_t i = 0; i < cloudIn.size(); ++i) {
+      const P4* pointFrom = &cloudIn[i];
+      float x1 = ctYaw * pointFrom->x - stYaw * pointFrom->y;
+      float y1 = stYaw * pointFrom->x + ctYaw * pointFrom->y;
+      float z1 = pointFrom->z;
+      float x2 = x1;
+      float y2 = ctRoll * y1 - stRoll * z1;
+      float z2 = stRoll * y1 + ctRoll * z1;
+      P4 pointTo;
+      pointTo.x = ctPitch * x2 + stPitch * z2 + tInX;
+      pointTo.y = y2 + tInY;
+      pointTo.z = -stPitch * x2 + ctPitch * z2 + tInZ;
+      pointTo.i = pointFrom->i;
+      cloudOut[i] = pointTo;
+    }
+    return cloudOut;
+  }
+
+  void clearCloud() { mapCorner.clear(); mapSurf.clear(); } /* mapOptmization.cpp:1518-1523 */
+
+  void extractSurroundingKeyFrames() { /* mapOptmization.cpp:856-996, the enable_loop_closure == false branch :915-987 */
+    last_rebuild = 0;
+    clearCloud(); /* the reference clears at the end of the previous cycle (:1560) */
+    if (cloudKeyPoses3D.empty()) return;
+    std::vector<P4> surroundingKeyPoses, surroundingKeyPosesDS;
+    std::vector<int> pointSearchInd;
+    std::vector<float> pointSearchSqDis;
+    kdSurroundingKeyPoses->setInputCloud(cloudKeyPoses3D);
+    kdSurroundingKeyPoses->radiusSearch(currentRobotPosPoint, (double)prm.surrounding_keyframe_search_radius, pointSearchInd,
+                                        pointSearchSqDis);
+    for (size_t i = 0; i < pointSearchInd.size(); ++i) surroundingKeyPoses.push_back(cloudKeyPoses3D[pointSearchInd[i]]);
+    voxel_grid(surroundingKeyPoses, 1.0f, surroundingKeyPosesDS); /* downSizeFilterSurroundingKeyPoses, :78 */
+    /* delete key frames that are not in the surrounding region (:935-955) */
+    const int numSurroundingPosesDS = (int)surroundingKeyPosesDS.size();
+    for (int i = 0; i < (int)surroundingExistingKeyPosesID.size(); ++i) {
+      bool existingFlag = false;
+      for (int j = 0; j < numSurroundingPosesDS; ++j) {
+        if (surroundingExistingKeyPosesID[i] == (int)surroundingKeyPosesDS[j].i) { existingFlag = true; break; }
+      }
+      if (existingFlag == false) {
+        surroundingExistingKeyPosesID.erase(surroundingExistingKeyPosesID.begin() + i);
+        surroundingCornerCloudKeyFrames.erase(surroundingCornerCloudKeyFrames.begin() + i);
+        surroundingSurfCloudKeyFrames.erase(surroundingSurfCloudKeyFrames.begin() + i);
+        surroundingOutlierCloudKeyFrames.erase(surroundingOutlierCloudKeyFrames.begin() + i);
+        --i;
+        last_rebuild = 1;
+      }
+    }
+    /* add new key frames (:957-980) */
+    for (int i = 0; i < numSurroundingPosesDS; ++i) {
+      bool existingFlag = false;
+      for (size_t k = 0; k < surroundingExistingKeyPosesID.size(); ++k) {
+        if (surroundingExistingKeyPosesID[k] == (int)surroundingKeyPosesDS[i].i) { existingFlag = true; break; }
+      }
+      if (existingFlag == true) continue;
+      const int thisKeyInd = (int)surroundingKeyPosesDS[i].i;
+      const Pose6 thisTransformation = cloudKeyPoses6D[thisKeyInd];
+      surroundingExistingKeyPosesID.push_back(thisKeyInd);
+      surroundingCornerCloudKeyFrames.push_back(transformPointCloud(cornerCloudKeyFrames[thisKeyInd], thisTransformation));
+      surroundingSurfCloudKeyFrames.push_back(transformPointCloud(surfCloudKeyFrames[thisKeyInd], thisTransformation));
+      surroundingOutlierCloudKeyFrames.push_back(transformPointCloud(outlierCloudKeyFrames[thisKeyInd], thisTransformation));
+    }
+    std::vector<P4> laserCloudCornerFromMap, laserCloudSurfFromMap;
+    for (size_t i = 0; i < surroundingExistingKeyPosesID.size(); ++i) { /* :982-986 */
+      laserCloudCornerFromMap.insert(laserCloudCornerFromMap.end(), surroundingCornerCloudKeyFrames[i].begin(), surroundingCornerCloudKeyFrames[i].end());
+      laserCloudSurfFromMap.insert(laserCloudSurfFromMap.end(), surroundingSurfCloudKeyFrames[i].begin(), surroundingSurfCloudKeyFrames[i].end());
+      laserCloudSurfFromMap.insert(laserCloudSurfFromMap.end(), surroundingOutlierCloudKeyFrames[i].begin(), surroundingOutlierCloudKeyFrames[i].end());
+    }
+    voxel_grid(laserCloudCornerFromMap, 0.2f, mapCorner); /* downSizeFilterCorner :989-991 */
+    voxel_grid(laserCloudSurfFromMap, 0.4f, mapSurf);     /* downSizeFilterSurf :993-995 */
+  }
+
+  void saveKeyFramesAndFactor() { /* mapOptmization.cpp:1335-1474 with iSAM2 == identity */
+    currentRobotPosPoint.x = transformAftMapped[3];
+    currentRobotPosPoint.y = transformAftMapped[4];
+    currentRobotPosPoint.z = transformAftMapped[5];
+    bool saveThisKeyFrame = true;
+    if (om::sqrt_((previousRobotPosPoint.x - currentRobotPosPoint.x) * (previousRobotPosPoint.x - currentRobotPosPoint.x) +
+                  (previousRobotPosPoint.y - currentRobotPosPoint.y) * (previousRobotPosPoint.y - currentRobotPosPoint.y) +
+                  (previousRobotPosPoint.z - currentRobotPosPoint.z) * (previousRobotPosPoint.z - currentRobotPosPoint.z)) < 0.3) {
+      saveThisKeyFrame = false;
+    }
+    if (saveThisKeyFrame == false && !cloudKeyPoses3D.empty()) return;
+    previousRobotPosPoint = currentRobotPosPoint;
+    /* first key frame: PriorFactor on transformTobeMapped (:1362-1376); later: transformAftMapped (:1391-1400).
+     * latestEstimate == the inserted initial value. */
+    const float* est = cloudKeyPoses3D.empty() ? transformTobeMapped : transformAftMapped;
+    if (cloudKeyPoses3D.empty()) for (int i = 0; i < 6; ++i) transformLast[i] = transformTobeMapped[i];
+    P4 thisPose3D;
+    thisPose3D.x = est[3]; thisPose3D.y = est[4]; thisPose3D.z = est[5]; /* translation().y(), .z(), .x() of Point3(T[5],T[3],T[4]) */
+    thisPose3D.i = (float)cloudKeyPoses3D.size();
+    cloudKeyPoses3D.push_back(thisPose3D);
+    Pose6 thisPose6D;
+    thisPose6D.x = thisPose3D.x; thisPose6D.y = thisPose3D.y; thisPose6D.z = thisPose3D.z;
+    thisPose6D.roll = est[0]; thisPose6D.pitch = est[1]; thisPose6D.yaw = est[2]; /* rotation().pitch(), .yaw(), .roll() of RzRyRx(T[2],T[0],T[1]) */
+    cloudKeyPoses6D.push_back(thisPose6D);
+    if (cloudKeyPoses3D.size() > 1) { /* :1440-1452 */
+      for (int i = 0; i < 6; ++i) { transformLast[i] = transformAftMapped[i]; transformTobeMapped[i] = transformAftMapped[i]; }
+    }
+    cornerCloudKeyFrames.push_back(scanCornerDS); /* copies of laserCloudCornerLastDS / SurfLastDS / OutlierLastDS :1461-1470 */
+    surfCloudKeyFrames.push_back(surfLastDS);
+    outlierCloudKeyFrames.push_back(outlierLastDS);
+  }
+
+  /* one body of MapOptimization::run (mapOptmization.cpp:1526-1562); transformSum arrives as FeatureAssociation's */
+  double timer_map_assembly;
+  void mappingCycle() {
+    transformAssociateToMap();
+    double t0 = now_s();
+    extractSurroundingKeyFrames();
+    double t1 = now_s();
+    downsampleCurrentScan();
+    double t2 = now_s();
+    scan2MapOptimization();
+    double t3 = now_s();
+    saveKeyFramesAndFactor();
+    timer_map_assembly += (t1 - t0) + (now_s() - t3);
+    timers[4] += t2 - t1;
+    timers[3] += t3 - t2;
+    /* correctPoses: nothing without a closed loop; clearCloud() is left to the next cycle's extract so that the
+     * local map of this cycle stays downloadable */
   }
 };
 
@@ -1257,6 +1421,19 @@ int lo_scan_to_map(lo_handle* h) {
   return 0;
 }
 
+/* ---- key frames and the local map ---- */
+int lo_map_extract_surrounding_keyframes(lo_handle* h) { h->extractSurroundingKeyFrames(); return 0; }
+int lo_map_save_keyframe(lo_handle* h) { h->saveKeyFramesAndFactor(); return 0; }
+int lo_mapping_cycle(lo_handle* h) { h->mappingCycle(); return 0; }
+double lo_get_timer_map_assembly(lo_handle* h) { return h->timer_map_assembly; }
+/* which: 0 corner, 1 surf, 2 outlier; the key frame's cloud transformed by its own pose (transformPointCloud) */
+int lo_map_download_keyframe(lo_handle* h, int kf, int which, void* dst, size_t dst_bytes, size_t* n) {
+  if (kf < 0 || kf >= (int)h->cloudKeyPoses6D.size() || which < 0 || which > 2) return LL_ERR_INVALID_ARG;
+  const std::vector<P4>& src = which == 0 ? h->cornerCloudKeyFrames[kf] : (which == 1 ? h->surfCloudKeyFrames[kf] : h->outlierCloudKeyFrames[kf]);
+  const std::vector<P4> t = h->transformPointCloud(src, h->cloudKeyPoses6D[kf]);
+  return copy_out(t.data(), t.size(), dst, dst_bytes, n);
+}
+
 int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n) {
   const size_t S = h->segmented_cloud.size();
   switch (buffer) {
@@ -1298,6 +1475,14 @@ int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n
     case LL_BUF_TRANSFORM_AFT_MAPPED: return copy_out(h->transformAftMapped, 6, dst, dst_bytes, n);
     case LL_BUF_OUTLIER_LAST: return copy_out(h->outlierLast.data(), h->outlierLast.size(), dst, dst_bytes, n);
     case LL_BUF_SURF_LESS_FLAT_RAW_COUNT: return copy_out(h->lessFlatRawCount.data(), h->lessFlatRawCount.size(), dst, dst_bytes, n);
+    case LL_BUF_SCAN_SURF_DS: return copy_out(h->surfLastDS.data(), h->surfLastDS.size(), dst, dst_bytes, n);
+    case LL_BUF_SCAN_OUTLIER_DS: return copy_out(h->outlierLastDS.data(), h->outlierLastDS.size(), dst, dst_bytes, n);
+    case LL_BUF_KEYFRAME_STATE: {
+      int v[4] = {(int)h->cloudKeyPoses6D.size(), (int)h->surroundingExistingKeyPosesID.size(), h->last_rebuild, 0};
+      return copy_out(v, 4, dst, dst_bytes, n);
+    }
+    case LL_BUF_KEY_POSES_6D: return copy_out(h->cloudKeyPoses6D.data(), h->cloudKeyPoses6D.size(), dst, dst_bytes, n);
+    case LL_BUF_SURROUNDING_KEY_IDS: return copy_out(h->surroundingExistingKeyPosesID.data(), h->surroundingExistingKeyPosesID.size(), dst, dst_bytes, n);
     default: return LL_ERR_INVALID_ARG;
   }
 }

@@ -40,6 +40,13 @@ int lo_map_set_initial_guess(lo_handle* h, const float* t6);
 int lo_map_set_poses(lo_handle* h, const float* aft6, const float* bef6);
 int lo_map_predict_pose(lo_handle* h);
 int lo_scan_to_map(lo_handle* h);
+/* Key frames and the local map, loop closure off (mapOptmization.cpp:856-996, 1335-1474, 1526-1562). */
+int lo_map_extract_surrounding_keyframes(lo_handle* h);
+int lo_map_save_keyframe(lo_handle* h);
+/* transformAssociateToMap, extractSurroundingKeyFrames, downsampleCurrentScan, scan2MapOptimization, saveKeyFramesAndFactor */
+int lo_mapping_cycle(lo_handle* h);
+int lo_map_download_keyframe(lo_handle* h, int kf, int which, void* dst, size_t dst_bytes, size_t* n_elems);
+double lo_get_timer_map_assembly(lo_handle* h);
 int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n_elems);
 int lo_upload(lo_handle* h, int buffer, const void* src, size_t n_elems);
 

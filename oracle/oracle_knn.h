@@ -207,6 +207,36 @@ class KdTree {
 #endif
     return port_.knn(qq, k, idx, d2);
   }
+  /* radiusSearch of nanoflann_pcl.h:155-175: squared radius computed in double and cast to float, points accepted
+   * while d2 < r2 (strict, nanoflann.hpp:249-253), results sorted ascending by distance (sorted = true is the
+   * wrapper's default, nanoflann_pcl.h:69).  The sort is std::sort on distance only, so the order of equal
+   * distances is unspecified in the reference; the port backend keeps ascending index for them. */
+  int radiusSearch(const P4& q, double radius, std::vector<int>& idx, std::vector<float>& d2) const {
+    idx.clear(); d2.clear();
+    if (!built_ || cloud_.empty()) return 0;
+    const float qq[3] = {q.x, q.y, q.z};
+    const float r2 = static_cast<float>(radius * radius);
+#ifdef ORACLE_WITH_NANOFLANN
+    if (used_nf_) {
+      std::vector<std::pair<int, float> > id;
+      id.reserve(128);
+      nanoflann::RadiusResultSet<float, int> rs(r2, id);
+      nf_.findNeighbors(rs, qq, nanoflann::SearchParams());
+      std::sort(id.begin(), id.end(), nanoflann::IndexDist_Sorter());
+      for (size_t i = 0; i < id.size(); ++i) { idx.push_back(id[i].first); d2.push_back(id[i].second); }
+      return (int)id.size();
+    }
+#endif
+    std::vector<std::pair<float, int> > id;
+    for (size_t i = 0; i < cloud_.size(); ++i) {
+      const float d = dist2(qq, cloud_[i]);
+      if (d < r2) id.push_back(std::make_pair(d, (int)i));
+    }
+    std::stable_sort(id.begin(), id.end(),
+                     [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
+    for (size_t i = 0; i < id.size(); ++i) { idx.push_back(id[i].second); d2.push_back(id[i].first); }
+    return (int)id.size();
+  }
  private:
   std::vector<P4> cloud_;
   bool built_ = false;

@@ -29,7 +29,8 @@ BUFFERS = {
     "OUTLIER_LAST": (33,) + PT[1:], "SURF_LESS_FLAT_RAW_COUNT": (34, np.int32, 1),
     "MAP_TRACE": (35, np.float64, 1), "TRANSFORM_BEF_MAPPED": (36, np.float32, 1),
     "TRANSFORM_AFT_MAPPED": (37, np.float32, 1), "SCAN_SURF_DS": (38, np.float32, 4),
-    "SCAN_OUTLIER_DS": (39, np.float32, 4),
+    "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
+    "KEYFRAME_STATE": (41, np.int32, 1), "KEY_POSES_6D": (42, np.float32, 6), "SURROUNDING_KEY_IDS": (43, np.int32, 1),
 }
 
 
@@ -72,6 +73,11 @@ def load(prefer_ref=True):
         lib.lo_knn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.lo_get_timers.argtypes = [C.c_void_p, C.c_void_p]
         lib.lo_get_timers.restype = None
+        for name in ("lo_map_extract_surrounding_keyframes", "lo_map_save_keyframe", "lo_mapping_cycle"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.lo_map_download_keyframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        lib.lo_get_timer_map_assembly.argtypes = [C.c_void_p]
+        lib.lo_get_timer_map_assembly.restype = C.c_double
         _libs[key] = lib
     return _libs[key]
 
@@ -150,6 +156,30 @@ class Oracle:
     def scan_to_map(self):
         self._select()
         return self.lib.lo_scan_to_map(self.h)
+
+    def map_extract_surrounding_keyframes(self):
+        self._select()
+        return self.lib.lo_map_extract_surrounding_keyframes(self.h)
+
+    def map_save_keyframe(self):
+        self._select()
+        return self.lib.lo_map_save_keyframe(self.h)
+
+    def mapping_cycle(self):
+        self._select()
+        return self.lib.lo_mapping_cycle(self.h)
+
+    def download_keyframe(self, kf, which):
+        n = C.c_size_t(0)
+        rc = self.lib.lo_map_download_keyframe(self.h, kf, which, None, 0, C.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"lo_map_download_keyframe({kf}, {which}) -> {rc}")
+        out = np.empty((n.value, 4), np.float32)
+        self.lib.lo_map_download_keyframe(self.h, kf, which, out.ctypes.data, out.nbytes, C.byref(n))
+        return out
+
+    def timer_map_assembly(self):
+        return self.lib.lo_get_timer_map_assembly(self.h)
 
     def download(self, name):
         bid, dt, w = BUFFERS[name]
