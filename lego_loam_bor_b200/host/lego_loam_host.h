@@ -7,14 +7,14 @@
 //   sensor_msgs::PointCloud2ConstPtr       ->  (const float* xyzi, int n, double stamp)
 //   pcl::PointCloud<PointXYZI>::Ptr        ->  std::vector<PointXYZI> (16-byte points)
 // All heavy work is enqueued on the GPU through include/lego_loam_b200.h; the payloads that travel
-// through the channels carry host copies only where a downstream HOST stage needs them (key-frame
-// storage in MapOptimization).  Device state is shared by the three stages, so the hand-offs are
-// synchronous (blocking channels = the reference's bag mode, main.cpp:37-38) and GPU calls are
-// serialised by one mutex; the stage threads exist for interface parity, not for overlap.
+// through the channels carry host copies only when Device::download_payloads asks for them.  Device
+// state is shared by the three stages, so the hand-offs are synchronous (blocking channels = the
+// reference's bag mode, main.cpp:37-38) and GPU calls are serialised by one mutex; the stage threads
+// exist for interface parity, not for overlap.
 //
-// Host glue kept on the CPU on purpose ("MapOptimization - rest"): key-frame
-// selection and storage, sub-map assembly with pcl::VoxelGrid semantics, iSAM2 replaced by identity
-// (loop closure is off by default, loam_config.yaml:24).
+// MapOptimization's key frames, surrounding-key-frame selection and local-map assembly run on the
+// device too (ll_map_save_keyframe / ll_map_extract_surrounding_keyframes);
+// iSAM2 is the identity because loop closure is off (loam_config.yaml:24).
 #pragma once
 
 #include <atomic>
@@ -147,11 +147,6 @@ class FeatureAssociation {
   std::thread _run_thread;
 };
 
-struct KeyFrame {
-  float pose[6];  // transformAftMapped when saved (roll=pose[0], pitch=pose[1], yaw=pose[2], x,y,z)
-  Cloud corner, surf, outlier;
-};
-
 class MapOptimization {
  public:
   MapOptimization(const LegoLoamParams& params, std::shared_ptr<Device> dev, Channel<AssociationOut>& input_channel);
@@ -162,23 +157,12 @@ class MapOptimization {
   void transformAftMapped(float out6[6]);
 
  private:
-  void extractSurroundingKeyFrames(const float pos[3]);  // mapOptmization.cpp:857-996 (loop closure off)
-  void saveKeyFramesAndFactor(const AssociationOut& in); // mapOptmization.cpp:1335-1478 (iSAM2 = identity)
   std::shared_ptr<Device> _dev;
   Channel<AssociationOut>& _input_channel;
   std::thread _run_thread;
-  float _search_radius;
-  std::vector<KeyFrame> _key_frames;
-  std::vector<int> _surrounding_ids;
-  std::vector<Cloud> _surrounding_corner, _surrounding_surf, _surrounding_outlier;
-  Cloud _corner_from_map_ds, _surf_from_map_ds;
-  float _previous_pos[3] = {0, 0, 0};
   float _aft[6] = {0, 0, 0, 0, 0, 0};
   std::mutex _pose_mtx;
   std::atomic<size_t> _n_key_frames{0}, _cycles{0};
 };
-
-// pcl::VoxelGrid<PointXYZI> semantics on the host (for the sub-map assembly only)
-void voxelGridFilter(const Cloud& in, float leaf, Cloud& out);
 
 }  // namespace lego_loam

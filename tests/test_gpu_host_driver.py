@@ -31,12 +31,16 @@ def test_sequence_driver_matches_c_abi(built, tmp_path):
     rows = np.loadtxt(out)
     assert rows.shape == (n_frames, 15)
     gpu = LegoLoam(p, batch=1)
+    gpu.map_enable_keyframes(max_keyframes=32)
     for i in range(n_frames):
         gpu.set_scans_host([scans[(0, i)]])
-        gpu.image_projection()
-        gpu.feature_association()
+        gpu.process_scans()
         ts = gpu.download("TRANSFORM_SUM")
         assert np.array_equal(rows[i, 1:7].astype(np.float32), ts), f"frame {i}: odometry differs"
+        # the stage classes run the same mapping cycle (key frames + local map on the device) as ll_process_scans
+        am = gpu.download("TRANSFORM_AFT_MAPPED")
+        assert np.array_equal(rows[i, 7:13].astype(np.float32), am), f"frame {i}: transformAftMapped differs"
+        assert rows[i, 13] == gpu.download("KEYFRAME_STATE")[0], f"frame {i}: key-frame count differs"
     # mapping: frames 5, 10, 15 are handed over; the first cycle only stores a key frame (empty map)
     assert rows[-1, 14] == 3 and rows[-1, 13] >= 2
     aft = rows[-1, 7:13]
