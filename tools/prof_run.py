@@ -1,5 +1,5 @@
 """Short run for ncu captures: B sequences of config C, one stream, F frames (default 16 x 8, map on).
-  python tools/prof_run.py [B] [F] [streams]"""
+  python tools/prof_run.py [B] [F] [synthetic|live]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,12 +22,15 @@ for f in range(F):
         a = scans[(s, f)]; hv[f, k, :len(a)] = a; counts[f, k] = len(a)
 devdata = host.to(dev)
 gpu = LegoLoam(params, batch=B, max_points=N, device=0)
-for k in range(B):
-    gpu.map_set_local(k, *bench.local_maps(cfg, seq_ids[k]))
-aft = np.zeros((B, 6), np.float32)
-for k, s in enumerate(seq_ids):
-    x, y, z, r, p, yaw = synth.pose(cfg, s, 0); aft[k] = [0, yaw, 0, y, z, x]
-gpu.map_set_poses(aft, np.zeros((B, 6), np.float32))
+if len(sys.argv) > 3 and sys.argv[3] == "live":
+    gpu.map_enable_keyframes(max_keyframes=F // 5 + 8, pool_points=(F // 5 + 8) * (N // 8), max_map_corner=N // 2, max_map_surf=N)
+else:
+    for k in range(B):
+        gpu.map_set_local(k, *bench.local_maps(cfg, seq_ids[k]))
+    aft = np.zeros((B, 6), np.float32)
+    for k, s in enumerate(seq_ids):
+        x, y, z, r, p, yaw = synth.pose(cfg, s, 0); aft[k] = [0, yaw, 0, y, z, x]
+    gpu.map_set_poses(aft, np.zeros((B, 6), np.float32))
 for f in range(F):
     gpu.set_scans_device(devdata.data_ptr() + f * B * N * 16, counts[f], N)
     gpu.process_scans()
