@@ -84,16 +84,19 @@ def main():
             "scan_to_map_iters_rows": [int(x) for x in iters], "state_after_rebuild": [int(x) for x in st]}
     if with_cpu:
         from oracle.oracle_py import Oracle
-        o = Oracle(params, libm=True, nanoflann=True)
+        o = Oracle(params, libm=False, nanoflann=True)  # portable math: bit-comparable with the device
         for f in range(7):
             o.image_projection(scans[(0, f)])
             if o.feature_association() == 1:
                 o.mapping_cycle()
         k0 = int(o.download("KEYFRAME_STATE")[0])
-        for i in range(K - k0 + 1):
+        for i in range(K - k0):
             o.map_set_poses(grid_pose(i), np.zeros(6, np.float32))
             o.map_save_keyframe()
         t0 = time.time(); o.map_extract_surrounding_keyframes(); t_ext = time.time() - t0
+        o.map_set_poses(grid_pose(K - k0), np.zeros(6, np.float32))
+        o.map_save_keyframe()
+        o.map_extract_surrounding_keyframes()   # same two-step history as the GPU side (the list order matters)
         o.map_set_initial_guess(guess[0])
         t0 = time.time(); o.scan_to_map(); t_s2m = time.time() - t0
         line["cpu_ms_one_core"] = {"extract": 1e3 * t_ext, "scan_to_map": 1e3 * t_s2m,
