@@ -133,3 +133,54 @@ def test_keyframe_erase_and_radius(built):
     assert rebuilds >= 4 and emptied == len(seqs), (rebuilds, emptied)
     for k in range(len(seqs)):
         _compare_keyframes(gpu, oracles[k], k, f"end seq {k}", 0, exact=True)
+
+
+def test_full_size_batch_slot_invariance(built):
+    """BASELINE configs[4] shape: 64 sequences of 64x2048 in one batch (4 sub-batches of 16 on 4 streams, like bench.py),
+    whole pipeline with the live local map.  Size-independent properties: a sequence gives the same bits whatever
+    slot / sub-batch it runs in (4 distinct sequences replicated over the 64 slots), and the four distinct ones agree
+    with the oracle."""
+    import torch
+    from lego_loam_bor_b200.capi import LegoLoamStreams
+    from oracle.oracle_py import Oracle
+    B, U, n_frames = 64, 4, 11
+    p, cfg, scans = make_scans("C", list(range(U)), range(n_frames))
+    N = p.num_vertical_scans * p.num_horizontal_scans
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    gpu = LegoLoamStreams(p, B, 4, max_points=N, device=0, streams=[s.cuda_stream for s in streams])
+    gpu.map_enable_keyframes(max_keyframes=16)
+    oracles = [Oracle(p) for _ in range(U)]
+    stride = max(len(scans[(u, f)]) for u in range(U) for f in range(n_frames))
+    host = torch.zeros((B, stride, 4), dtype=torch.float32).pin_memory()
+    counts = np.zeros(B, np.int32)
+    for f in range(n_frames):
+        gpu.synchronize()
+        for k in range(B):
+            a = scans[(k % U, f)]
+            host.numpy()[k, :len(a)] = a
+            counts[k] = len(a)
+        gpu.set_scans_host_ptr(host.data_ptr(), counts, stride)
+        gpu.process_scans()
+        for u in range(U):
+            oracles[u].image_projection(scans[(u, f)])
+            if oracles[u].feature_association() == 1:
+                oracles[u].mapping_cycle()
+    gpu.synchronize()
+    names = ["TRANSFORM_SUM", "TRANSFORM_AFT_MAPPED", "CORNER_LAST", "SURF_LAST", "LABEL_MAT", "MAP_CORNER", "MAP_SURF",
+             "SURROUNDING_KEY_IDS", "KEY_POSES_6D", "MAP_ITERS"]
+    ref = {(u, n): gpu.download(n, u) for u in range(U) for n in names}
+    for k in range(U, B):
+        for n in names:
+            assert same_bits(gpu.download(n, k), ref[(k % U, n)]), f"slot {k} differs from slot {k % U} in {n}"
+    for u in range(U):
+        o = oracles[u]
+        assert int(gpu.download("KEYFRAME_STATE", u)[3]) == 0
+        assert np.array_equal(gpu.download("LABEL_MAT", u), o.download("LABEL_MAT"))
+        assert np.array_equal(gpu.download("SURROUNDING_KEY_IDS", u), o.download("SURROUNDING_KEY_IDS"))
+        assert np.array_equal(gpu.download("MAP_ITERS", u), o.download("MAP_ITERS"))
+        for name in ("TRANSFORM_SUM", "TRANSFORM_AFT_MAPPED"):
+            a, b = gpu.download(name, u), o.download(name)
+            assert np.all(np.abs(a[:3] - b[:3]) <= POSE_TOL_RAD) and np.all(np.abs(a[3:] - b[3:]) <= POSE_TOL_M), f"{name} {a} vs {b}"
+        for name in ("MAP_CORNER", "MAP_SURF"):
+            a, b = gpu.download(name, u), o.download(name)
+            assert a.shape == b.shape and np.abs(a - b).max() <= 2e-4, f"{name}: {a.shape} vs {b.shape}"
