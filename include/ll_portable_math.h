@@ -139,20 +139,76 @@ LL_HD void ll_sincosd(double x, double* s_out, double* c_out) {
   *c_out = c;
 }
 
+#if defined(__CUDACC__)
+/* out-of-line copy of the full routine for the (rare) device fall-back, so that the short cut below does not drag the
+ * whole reduction + two long polynomials into every call site */
+static __device__ __noinline__ void ll_sincosd_outofline(double x, double* s_out, double* c_out) { ll_sincosd(x, s_out, c_out); }
+#endif
+#if defined(__CUDA_ARCH__)
+/* Device-only certified short cut for |x| < 0.25 (every per-point angle of TransformToStart / TransformToEnd and most
+ * poses): sin and cos from short fused-multiply-add Taylor chains in double.  For such x the reduction above gives k = 0
+ * and r = x exactly, and both this chain and ll_sincosd are within 1.5e-16 relative of the true value (truncation
+ * < 1e-17; the leading term is exact, the correction term is < 0.032 of it), so the two doubles differ by less than
+ * 3e-16 relative.  The float results can only differ if a float rounding boundary lies inside that gap: the value is
+ * accepted only when rounding the double moved by -/+ 1e-15 relative gives the same float, otherwise the caller falls
+ * back to ll_sincosd.  The result is therefore bit-identical to the portable definition by construction. */
+__device__ __forceinline__ bool ll_sincosf_small(float x, float* s, float* c) {
+  if (!(fabsf(x) < 0.25f)) return false;
+  const double r = (double)x, z = r * r;
+  double ps = -1.0 / 39916800.0;
+  ps = fma(z, ps, 1.0 / 362880.0);
+  ps = fma(z, ps, -1.0 / 5040.0);
+  ps = fma(z, ps, 1.0 / 120.0);
+  ps = fma(z, ps, -1.0 / 6.0);
+  const double ds = fma(r * z, ps, r);
+  double pc = 1.0 / 479001600.0;
+  pc = fma(z, pc, -1.0 / 3628800.0);
+  pc = fma(z, pc, 1.0 / 40320.0);
+  pc = fma(z, pc, -1.0 / 720.0);
+  pc = fma(z, pc, 1.0 / 24.0);
+  pc = fma(z, pc, -0.5);
+  const double dc = fma(z, pc, 1.0);
+  const float sf = (float)ds, cf = (float)dc;
+  const double es = fabs(ds) * 1e-15, ec = 1e-15;
+  if ((float)(ds - es) != sf || (float)(ds + es) != sf || (float)(dc - ec) != cf || (float)(dc + ec) != cf) return false;
+  *s = sf;
+  *c = cf;
+  return true;
+}
+#endif
+
 LL_HD void ll_sincosf(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  if (ll_sincosf_small(x, s, c)) return;
+  double sd, cd;
+  ll_sincosd_outofline((double)x, &sd, &cd);
+#else
   double sd, cd;
   ll_sincosd((double)x, &sd, &cd);
+#endif
   *s = (float)sd;
   *c = (float)cd;
 }
 LL_HD float ll_sinf(float x) {
+#if defined(__CUDA_ARCH__)
+  { float sf, cf; if (ll_sincosf_small(x, &sf, &cf)) return sf; }
+  double sd, cd;
+  ll_sincosd_outofline((double)x, &sd, &cd);
+#else
   double sd, cd;
   ll_sincosd((double)x, &sd, &cd);
+#endif
   return (float)sd;
 }
 LL_HD float ll_cosf(float x) {
+#if defined(__CUDA_ARCH__)
+  { float sf, cf; if (ll_sincosf_small(x, &sf, &cf)) return cf; }
+  double sd, cd;
+  ll_sincosd_outofline((double)x, &sd, &cd);
+#else
   double sd, cd;
   ll_sincosd((double)x, &sd, &cd);
+#endif
   return (float)cd;
 }
 LL_HD float ll_tanf(float x) {

@@ -42,6 +42,18 @@ __device__ __forceinline__ MapPose make_map_pose(const float* T) {  // mapOptmiz
   return m;
 }
 
+// updatePointAssociateToMapSinCos once per block: one warp-0 thread evaluates the six values, everybody reads them
+__device__ __forceinline__ MapPose block_map_pose(const float* T_global, MapPose* sh) {
+  if (threadIdx.x == 0) {
+    float T[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) T[k] = T_global[k];
+    *sh = make_map_pose(T);
+  }
+  __syncthreads();
+  return *sh;
+}
+
 __device__ __forceinline__ float4 point_associate_to_map(const MapPose& m, const float4 pi) {  // :412-426
   const float x1 = m.cYaw * pi.x - m.sYaw * pi.y;
   const float y1 = m.sYaw * pi.x + m.cYaw * pi.y;
@@ -162,10 +174,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int ite
   if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
   const int nc = st.scan_ds_counts[s * 2 + 0], ns = st.scan_ds_counts[s * 2 + 1];
   const int nq = nc + ns;
-  float T[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) T[k] = st.transform_tobe_mapped[s * 6 + k];
-  const MapPose mp = make_map_pose(T);
+  __shared__ MapPose sh_pose;
+  const MapPose mp = block_map_pose(st.transform_tobe_mapped + s * 6, &sh_pose);
   for (int qbase = blockIdx.x * KNN_THREADS; qbase < nq; qbase += gridDim.x * KNN_THREADS) {
     if (threadIdx.x == 0) sh_n = 0;
     __syncthreads();
@@ -310,10 +320,8 @@ __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st, int iter)
   const int s = blockIdx.y;
   double* out = st.map_partials + ((size_t)s * MAP_BLOCKS + blockIdx.x) * MAP_NACC;
   if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
-  float T[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) T[k] = st.transform_tobe_mapped[s * 6 + k];
-  const MapPose mp = make_map_pose(T);
+  __shared__ MapPose sh_pose;
+  const MapPose mp = block_map_pose(st.transform_tobe_mapped + s * 6, &sh_pose);
   const float srx = mp.sRoll, crx = mp.cRoll, sry = mp.sPitch, cry = mp.cPitch, srz = mp.sYaw, crz = mp.cYaw;
   const int nc = st.scan_ds_counts[s * 2 + 0], ns = st.scan_ds_counts[s * 2 + 1];
   double acc[MAP_NACC];
