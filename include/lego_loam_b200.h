@@ -10,6 +10,10 @@
  *   ll_feature_association   FeatureAssociation::runFeatureAssociation loop body
  *                                                                    src/featureAssociation.cpp:1386-1450
  *   ll_scan_to_map           MapOptimization::scan2MapOptimization  src/mapOptmization.cpp:1315-1332
+ *   ll_map_save_keyframe / ll_map_extract_surrounding_keyframes / ll_mapping_cycle
+ *                            MapOptimization::saveKeyFramesAndFactor / extractSurroundingKeyFrames / run
+ *                                                                    src/mapOptmization.cpp:1335-1474, 856-996, 1545-1560
+ *   ll_set_scans_pointcloud2_host   pcl::fromROSMsg + removeNaNFromPointCloud  src/imageProjection.cpp:159-161
  *   LegoLoamParams           config/loam_config.yaml:1-35 (same key names)
  *   LL_BUF_SEG_* / ll_cloud_info   cloud_msgs/msg/cloud_info.msg:1-13
  *
@@ -128,6 +132,7 @@ typedef enum ll_buffer {
                                       1 key-frame slots, 2 point pool, 4 voxel table, 8 local-map output, 16 voxel index range) */
   LL_BUF_KEY_POSES_6D = 42,        /* f32[K][6] cloudKeyPoses6D as (roll, pitch, yaw, x, y, z) */
   LL_BUF_SURROUNDING_KEY_IDS = 43, /* i32[..] surroundingExistingKeyPosesID */
+  LL_BUF_INPUT_CLOUD = 44,         /* pt[n] the scan staged by the last ll_set_scans_* call (after NaN removal) */
   LL_BUF_COUNT_
 } ll_buffer;
 
@@ -153,6 +158,14 @@ int64_t ll_kernel_launches(const ll_handle* h);
  * memory is pinned): the next ll_image_projection consumes it, and calling ll_set_scans_host for scan
  * f+1 before reading back the results of scan f overlaps that copy with the kernels of scan f. */
 int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, int stride_points);
+/* sensor_msgs/PointCloud2 ingest: pcl::fromROSMsg + pcl::removeNaNFromPointCloud of
+ * imageProjection.cpp:159-161 on the device.  data: the messages' `data` arrays, [batch][stride_bytes] host bytes;
+ * n_points[batch] = width * height; point_step and the byte offsets of the FLOAT32 fields x, y, z, intensity as listed
+ * in msg.fields (off_intensity < 0: the message has no such field, intensity = 0).  is_dense is the message flag:
+ * when set PCL copies the cloud unchecked, otherwise every point with a non-finite x, y or z is dropped, order kept.
+ * Staged like ll_set_scans_host (copy stream, double buffered); the next ll_image_projection consumes it. */
+int ll_set_scans_pointcloud2_host(ll_handle* h, const uint8_t* data, const int32_t* n_points, size_t stride_bytes, int point_step,
+                                  int off_x, int off_y, int off_z, int off_intensity, int is_dense);
 /* Same, for scans that already live in device memory (no copy is made; the buffer
  * must stay valid until the next ll_image_projection has been enqueued). */
 int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_points, int stride_points);

@@ -29,6 +29,7 @@ BUFFERS = {
     "TRANSFORM_AFT_MAPPED": (37, np.float32, 1), "SCAN_SURF_DS": (38, np.float32, 4),
     "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
     "KEYFRAME_STATE": (41, np.int32, 1), "KEY_POSES_6D": (42, np.float32, 6), "SURROUNDING_KEY_IDS": (43, np.int32, 1),
+    "INPUT_CLOUD": (44, np.float32, 4),
 }
 
 EXPORTS = [
@@ -40,7 +41,7 @@ EXPORTS = [
     "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
     "ll_get_kernel_time_table",
     "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
-    "ll_map_download_keyframe",
+    "ll_map_download_keyframe", "ll_set_scans_pointcloud2_host",
 ]
 
 _lib = None
@@ -93,6 +94,7 @@ def load_library(path=None):
     for name in ("ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle"):
         getattr(lib, name).argtypes = [vp]
     lib.ll_map_download_keyframe.argtypes = [vp, ip, ip, ip, vp, sz, C.POINTER(sz)]
+    lib.ll_set_scans_pointcloud2_host.argtypes = [vp, vp, vp, sz, ip, ip, ip, ip, ip, ip]
     if path == LIB_CUDA:
         _lib = lib
     return lib
@@ -152,6 +154,18 @@ class LegoLoam:
     def set_scans_host_ptr(self, ptr, counts, stride):
         counts = np.ascontiguousarray(counts, np.int32)
         self._ck(self.lib.ll_set_scans_host(self.h, ptr, counts.ctypes.data, stride), "ll_set_scans_host")
+
+    def set_scans_pointcloud2(self, messages, point_step, off_x, off_y, off_z, off_intensity, is_dense=False):
+        """messages: list (len batch) of uint8 arrays, the `data` of one sensor_msgs/PointCloud2 each."""
+        stride = max(1, max(len(m) for m in messages))
+        packed = np.zeros((self.batch, stride), np.uint8)
+        counts = np.zeros(self.batch, np.int32)
+        for i, m in enumerate(messages):
+            packed[i, :len(m)] = m
+            counts[i] = len(m) // point_step
+        self._ck(self.lib.ll_set_scans_pointcloud2_host(self.h, packed.ctypes.data, counts.ctypes.data, stride, point_step,
+                                                        off_x, off_y, off_z, off_intensity, 1 if is_dense else 0),
+                 "ll_set_scans_pointcloud2_host")
 
     def set_scans_device(self, dev_ptr, counts, stride):
         counts = np.ascontiguousarray(counts, np.int32)

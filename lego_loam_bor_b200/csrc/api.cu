@@ -35,6 +35,10 @@ struct ll_handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copied[2], consumed[2];
   bool consumed_valid[2] = {false, false};
+  uint8_t* raw_buf[2] = {nullptr, nullptr};  // ll_set_scans_pointcloud2_host: raw message bytes, [B][raw_stride]
+  size_t raw_stride = 0;
+  int* n_raw_buf[2] = {nullptr, nullptr};
+  int* pc2_tile_cnt = nullptr;
   int wr = 0;        // buffer the next ll_set_scans_host writes
   int pending = -1;  // buffer waiting to be consumed by ll_image_projection
   bool timing = false;
@@ -259,7 +263,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.map_partials, (size_t)B * st.map_max_blocks * 28));
   CK(dev_alloc(h, &st.map_trace, (size_t)B * 10 * 34));
   st.map_knn_cap = p.cap_less_sharp + N;
-  CK(dev_alloc(h, &st.map_knn_rec, (size_t)B * st.map_knn_cap * 11, false));
+  CK(dev_alloc(h, &st.map_knn_rec, (size_t)B * st.map_knn_cap * (LL_KNN_K + 1), false));
   CK(dev_alloc(h, &st.map_knn_sel, (size_t)B * st.map_knn_cap, false)); CK(dev_alloc(h, &st.map_fit, (size_t)B * st.map_knn_cap * 2, false)); CK(dev_alloc(h, &st.map_ticket, (size_t)B));
   st.vox_cap = N + st.cap_outlier;
   CK(dev_alloc(h, &st.vox_key0, (size_t)B * 3 * st.vox_cap, false)); CK(dev_alloc(h, &st.vox_key1, (size_t)B * 3 * st.vox_cap, false));
@@ -348,6 +352,50 @@ int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, 
   h->pending = b;
   h->wr ^= 1;
   return LL_OK;
+}
+
+int ll_set_scans_pointcloud2_host(ll_handle* h, const uint8_t* data, const int32_t* n_points, size_t stride_bytes, int point_step,
+                                  int off_x, int off_y, int off_z, int off_intensity, int is_dense) {
+  if (!h || !data || !n_points || point_step < 12) return LL_ERR_INVALID_ARG;
+  const int offs[4] = {off_x, off_y, off_z, off_intensity};
+  for (int k = 0; k < 4; ++k) {
+    if (k == 3 && offs[k] < 0) continue;  // no intensity field in the message
+    if (offs[k] < 0 || offs[k] + 4 > point_step) { h->err = "ll_set_scans_pointcloud2_host: field offset outside the point record"; return LL_ERR_INVALID_ARG; }
+  }
+  DevState& st = h->st;
+  const int B = st.p.B;
+  for (int s = 0; s < B; ++s) {
+    if (n_points[s] < 0 || (size_t)n_points[s] * point_step > stride_bytes) { h->err = "ll_set_scans_pointcloud2_host: n_points * point_step exceeds stride_bytes"; return LL_ERR_INVALID_ARG; }
+    if (n_points[s] > st.p.max_pts) { h->err = "ll_set_scans_pointcloud2_host: message larger than max_points"; return LL_ERR_CAPACITY; }
+  }
+  const size_t need = (size_t)st.p.max_pts * point_step;
+  if (need > h->raw_stride) {
+    CK(cudaStreamSynchronize(h->copy_stream));
+    for (int b = 0; b < 2; ++b) {
+      CK(dev_alloc(h, &h->raw_buf[b], (size_t)B * need, false));
+      if (!h->n_raw_buf[b]) CK(dev_alloc(h, &h->n_raw_buf[b], B));
+    }
+    if (!h->pc2_tile_cnt) CK(dev_alloc(h, &h->pc2_tile_cnt, (size_t)B * ((st.p.max_pts + pc2_tile_points() - 1) / pc2_tile_points())));
+    h->raw_stride = need;
+  }
+  const int b = h->wr;
+  if (h->consumed_valid[b]) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[b], 0));
+  { const int rc = stage_counts(h, n_points, st.p.max_pts, "ll_set_scans_pointcloud2_host", h->n_raw_buf[b], h->copy_stream); if (rc) return rc; }
+  for (int s = 0; s < B; ++s) {
+    if (n_points[s] == 0) continue;
+    CK(cudaMemcpyAsync(h->raw_buf[b] + (size_t)s * h->raw_stride, data + (size_t)s * stride_bytes, (size_t)n_points[s] * point_step,
+                       cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  Pc2Args a;
+  a.raw = h->raw_buf[b]; a.raw_stride = h->raw_stride; a.n_raw = h->n_raw_buf[b];
+  a.point_step = point_step; a.off_x = off_x; a.off_y = off_y; a.off_z = off_z; a.off_intensity = off_intensity; a.is_dense = is_dense ? 1 : 0;
+  a.out = h->in_buf[b]; a.out_stride = st.p.max_pts; a.n_out = h->n_in_buf[b];
+  a.tile_cnt = h->pc2_tile_cnt; a.ntiles = (st.p.max_pts + pc2_tile_points() - 1) / pc2_tile_points();
+  launch_decode_pointcloud2(h->ctx, h->copy_stream, B, a);
+  CK(cudaEventRecord(h->copied[b], h->copy_stream));
+  h->pending = b;
+  h->wr ^= 1;
+  return check_stream(h, "ll_set_scans_pointcloud2_host");
 }
 
 int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_points, int stride_points) {
@@ -804,6 +852,16 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_TRANSFORM_BEF_MAPPED: src = st.transform_bef_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_TRANSFORM_AFT_MAPPED: src = st.transform_aft_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_OUTLIER_LAST: COUNTED(st.outlier_last, 16, (size_t)st.cap_outlier, st.odom_flags + seq * 4 + 3); break;
+    case LL_BUF_INPUT_CLOUD: {
+      // the scans staged by the last ll_set_scans_* call (or consumed by the last ll_image_projection)
+      const float4* buf = h->pending >= 0 ? h->in_buf[h->pending] : st.in_pts;
+      const int* cntp = h->pending >= 0 ? h->n_in_buf[h->pending] : st.n_in;
+      const int stride = h->pending >= 0 ? st.p.max_pts : st.in_stride;
+      if (!buf) return LL_ERR_STATE;
+      if (h->pending >= 0) CK(cudaStreamSynchronize(h->copy_stream));
+      COUNTED(buf, 16, (size_t)stride, cntp + seq);
+      break;
+    }
     case LL_BUF_KEYFRAME_STATE: {
       if (!st.kf.enabled) return LL_ERR_STATE;
       int v[4];

@@ -15,6 +15,10 @@
 #include "../../include/ll_portable_math.h"
 
 #define LL_MAX_RINGS 128
+// scan-to-map k-NN: map points recorded per query by a full search (mapping.cu, k_map_knn); <= 16 (4-bit positions)
+#ifndef LL_KNN_K
+#define LL_KNN_K 10
+#endif
 #define LL_INVALID_LABEL 999999
 
 // hash grid over a point cloud (replaces nanoflann::KdTreeFLANN, nanoflann_pcl.h:54-152)

@@ -78,3 +78,17 @@ void launch_downsample_current_scan(LaunchCtx& ctx, DevState& st);
 // keyframes.cu: saveKeyFramesAndFactor / extractSurroundingKeyFrames on the device
 void launch_extract_surrounding_keyframes(LaunchCtx& ctx, DevState& st);
 void launch_save_keyframe(LaunchCtx& ctx, DevState& st);
+// ingest.cu: sensor_msgs/PointCloud2 decode + removeNaNFromPointCloud (imageProjection.cpp:159-161)
+struct Pc2Args {
+  const uint8_t* raw;   // [B][raw_stride] message data
+  size_t raw_stride;
+  const int* n_raw;     // [B] width * height
+  int point_step, off_x, off_y, off_z, off_intensity, is_dense;
+  float4* out;          // [B][out_stride]
+  int out_stride;
+  int* n_out;           // [B]
+  int* tile_cnt;        // [B][ntiles]
+  int ntiles;
+};
+void launch_decode_pointcloud2(LaunchCtx& ctx, cudaStream_t stream, int B, const Pc2Args& a);
+int pc2_tile_points();

@@ -158,9 +158,7 @@ __device__ __forceinline__ bool surf_eval(const float4 sel, const float4 g0, con
 // in registers; consecutive queries are consecutive voxels of the VoxelGrid output, so neighbouring threads walk the
 // same buckets and share them through L1.
 #define KNN_THREADS 128
-#ifndef KNN_K
-#define KNN_K 10
-#endif
+#define KNN_K LL_KNN_K
 #define KNN_REC (KNN_K + 1)
 
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }

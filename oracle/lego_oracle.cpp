@@ -1497,6 +1497,27 @@ int lo_upload(lo_handle* h, int buffer, const void* src, size_t n_elems) {
   }
 }
 
+/* pcl::fromROSMsg + pcl::removeNaNFromPointCloud (imageProjection.cpp:159-161) restated: FLOAT32 fields x, y, z,
+ * intensity of every point_step-sized record (absent intensity field: the PointXYZI default 0); a dense cloud is
+ * copied unchecked, otherwise points with a non-finite x, y or z are dropped and the order is kept.  PCL is not
+ * vendored: parity unpinned.  Returns the number of points written to out_xyzi. */
+int lo_decode_pointcloud2(const unsigned char* data, int n_points, int point_step, int off_x, int off_y, int off_z,
+                          int off_intensity, int is_dense, float* out_xyzi) {
+  int m = 0;
+  for (int i = 0; i < n_points; ++i) {
+    const unsigned char* rec = data + (size_t)i * point_step;
+    float x, y, z, in = 0.f;
+    std::memcpy(&x, rec + off_x, 4);
+    std::memcpy(&y, rec + off_y, 4);
+    std::memcpy(&z, rec + off_z, 4);
+    if (off_intensity >= 0) std::memcpy(&in, rec + off_intensity, 4);
+    if (!is_dense && (!std::isfinite(x) || !std::isfinite(y) || !std::isfinite(z))) continue;
+    out_xyzi[4 * m + 0] = x; out_xyzi[4 * m + 1] = y; out_xyzi[4 * m + 2] = z; out_xyzi[4 * m + 3] = in;
+    ++m;
+  }
+  return m;
+}
+
 int lo_voxel_grid(const float* xyzi, int n, float leaf, float* out_xyzi) {
   std::vector<P4> in(n), out;
   if (n) std::memcpy(in.data(), xyzi, sizeof(P4) * (size_t)n);

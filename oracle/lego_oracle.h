@@ -50,6 +50,9 @@ double lo_get_timer_map_assembly(lo_handle* h);
 int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n_elems);
 int lo_upload(lo_handle* h, int buffer, const void* src, size_t n_elems);
 
+/* sensor_msgs/PointCloud2 -> xyzi with NaN removal (imageProjection.cpp:159-161); returns the number of points kept. */
+int lo_decode_pointcloud2(const unsigned char* data, int n_points, int point_step, int off_x, int off_y, int off_z,
+                          int off_intensity, int is_dense, float* out_xyzi);
 /* pcl::VoxelGrid restatement on its own: out must hold n points; returns output count. */
 int lo_voxel_grid(const float* xyzi, int n, float leaf, float* out_xyzi);
 /* k-NN on its own (for kd-tree pin tests): idx[nq*k], d2[nq*k]. */

@@ -78,6 +78,7 @@ def load(prefer_ref=True):
         lib.lo_map_download_keyframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.lo_get_timer_map_assembly.argtypes = [C.c_void_p]
         lib.lo_get_timer_map_assembly.restype = C.c_double
+        lib.lo_decode_pointcloud2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _libs[key] = lib
     return _libs[key]
 
@@ -205,6 +206,16 @@ class Oracle:
 
     def reset_timers(self):
         self.lib.lo_reset_timers(self.h)
+
+
+def decode_pointcloud2(data, n_points, point_step, off_x, off_y, off_z, off_intensity, is_dense, prefer_ref=True):
+    """fromROSMsg + removeNaNFromPointCloud on raw message bytes (uint8 array) -> float32 [m, 4]."""
+    lib = load(prefer_ref)
+    data = np.ascontiguousarray(data, np.uint8)
+    out = np.empty((max(1, n_points), 4), np.float32)
+    m = lib.lo_decode_pointcloud2(data.ctypes.data, n_points, point_step, off_x, off_y, off_z, off_intensity, 1 if is_dense else 0,
+                                  out.ctypes.data)
+    return out[:m].copy()
 
 
 def voxel_grid(xyzi, leaf, prefer_ref=True):
