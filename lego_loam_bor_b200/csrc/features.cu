@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int 
 #define PICK_WARPS 4
 
 __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
-  extern __shared__ unsigned char sh_picked_all[];  // [PICK_WARPS][H + 32] picked bytes, then [PICK_WARPS][H + 32] u16 column indices
+  extern __shared__ unsigned char sh_picked_all[];  // [PICK_WARPS][H + 32] picked bytes, then [PICK_WARPS][H + 32] u16 column indices, then u16 lists
+  __shared__ int sh_stale[PICK_WARPS];
   const DevParams& p = st.p;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ring = blockIdx.x * PICK_WARPS + wid, s = blockIdx.y;
@@ -259,9 +260,24 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
     sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
     sm_col[t] = (unsigned short)st.seg_col[base + span_lo + t];
   }
-  __syncwarp();
   const size_t rs = (size_t)s * p.V + ring;
-  const int* offs = st.sext_off + rs * 16;
+  // the twelve candidate lists of the ring (contiguous, offsets relative to a) as 16-bit positions inside the ring,
+  // and their thirteen offsets in lanes 0..12: nothing inside the pick loops below comes from global memory
+  unsigned short* sm_list = reinterpret_cast<unsigned short*>(sh_picked_all + (size_t)PICK_WARPS * (p.H + 32) * 3) + (size_t)wid * (p.H + 32);
+  const int off_lane = lane < 13 ? st.sext_off[rs * 16 + lane] : 0;
+  bool stale_here = false;
+  {
+    const int l0 = __shfl_sync(0xffffffffu, off_lane, 0), l1 = __shfl_sync(0xffffffffu, off_lane, 12);
+    const unsigned* src = st.scan_list + base + a;
+    for (int t = l0 + lane; t < l1; t += 32) {
+      int d = (int)src[t] - a;
+      // the stale cloudSmoothness entry at position 4 (k_feature_sort) may point anywhere in the cloud: escape code
+      if (d < 0 || d >= 0xffff) { sh_stale[wid] = (int)src[t]; d = 0xffff; }
+      if (d < 4 || (int)src[t] > end) stale_here = true;  // not one of this ring's own candidates [start, end]
+      sm_list[t] = (unsigned short)d;
+    }
+  }
+  __syncwarp();
   int* o_sharp_i = st.st_sharp_ind + rs * 12;
   int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
   int* o_flat_i = st.st_flat_ind + rs * 24;
@@ -291,71 +307,94 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
     if (!skip && lane >= 6 && lane <= 10 && lane < stop_b) set_picked(g);
     __syncwarp();
   };
-  for (int j = 0; j < 6; ++j) {
-    // edge candidates of sextant j in descending-curvature visiting order (featureAssociation.cpp:288-328)
-    {
-      const unsigned* list = st.scan_list + base + a + offs[2 * j];
-      const int len = offs[2 * j + 1] - offs[2 * j];
-      int largest = 0;
-      int pos = 0;
-      while (pos < len && largest < 20) {
-        const int t = pos + lane;
-        bool cand = false;
-        int ind = 0;
-        if (t < len) {
-          ind = (int)list[t];
-          cand = get_picked(ind) == 0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m == 0) { pos += 32; continue; }
-        const int w = __ffs(m) - 1;
-        const int pick = __shfl_sync(0xffffffffu, ind, w);
-        largest++;
-        if (lane == 0) {
-          if (largest <= 2) {
-            st.cloud_label[base + pick] = 2;
-            o_sharp_i[n_sharp] = pick;
-          } else {
-            st.cloud_label[base + pick] = 1;
-          }
-          o_lsharp_i[n_lsharp] = pick;
-        }
-        if (largest <= 2) n_sharp++;
-        n_lsharp++;
-        mark_neighbors(pick);
-        pos = pos + w + 1;
-      }
-    }
-    // flat candidates in ascending-curvature visiting order (featureAssociation.cpp:330-368)
-    {
-      const unsigned* list = st.scan_list + base + a + offs[2 * j + 1];
-      const int len = offs[2 * j + 2] - offs[2 * j + 1];
-      int smallest = 0;
-      int pos = 0;
-      while (pos < len) {
-        const int t = pos + lane;
-        bool cand = false;
-        int ind = 0;
-        if (t < len) {
-          ind = (int)list[t];
-          cand = get_picked(ind) == 0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (m == 0) { pos += 32; continue; }
-        const int w = __ffs(m) - 1;
-        const int pick = __shfl_sync(0xffffffffu, ind, w);
-        smallest++;
-        if (lane == 0) {
-          st.cloud_label[base + pick] = -1;
-          o_flat_i[n_flat] = pick;
-        }
-        n_flat++;
-        if (smallest >= 4) break;  // the 4th pick breaks before the suppression (sic, :339-342)
-        mark_neighbors(pick);
-        pos = pos + w + 1;
-      }
-    }
+  // Fast accessors: every candidate of a ring lies in [start, end], so the pick and its +-5 neighbours are inside the
+  // span held in shared memory and inside [0, colsz): no range checks, no global fall-back.  Only the stale
+  // cloudSmoothness entry of position 4 (ring 0) can point elsewhere; a ring that holds such an entry uses the general
+  // accessors above.
+  auto get_picked_fast = [&](int g) -> int { return (int)sm_picked[g - span_lo]; };
+  auto mark_neighbors_fast = [&](int ind) {
+    const int off = lane <= 5 ? lane : 5 - lane;  // lane 0: the pick; 1..5: ind+1..ind+5; 6..10: ind-1..ind-5
+    const int l = ind - span_lo + off;
+    bool bad = false;
+    // l < 0 only for ind - k < 0 at the very start of the cloud: the reference `continue`s there (:317)
+    if (lane >= 1 && lane <= 10 && l >= 0) bad = abs((int)sm_col[l] - (int)sm_col[l + (lane <= 5 ? -1 : 1)]) > 10;
+    const unsigned bm = __ballot_sync(0xffffffffu, bad);
+    const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
+    const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
+    if (l >= 0 && (lane == 0 || (lane <= 5 && lane < stop_f) || (lane >= 6 && lane <= 10 && lane < stop_b))) sm_picked[l] = 1;
+    __syncwarp();
+  };
+  const bool has_stale = __ballot_sync(0xffffffffu, stale_here) != 0u;
+#define PICK_SEXTANTS(GET_PICKED, MARK_NEIGHBORS) \
+  for (int j = 0; j < 6; ++j) { \
+    { \
+      const int lo = __shfl_sync(0xffffffffu, off_lane, 2 * j); \
+      const unsigned short* list = sm_list + lo; \
+      const int len = __shfl_sync(0xffffffffu, off_lane, 2 * j + 1) - lo; \
+      int largest = 0; \
+      for (int wbase = 0; wbase < len && largest < 20; wbase += 32) { \
+        const int t = wbase + lane; \
+        const bool have = t < len; \
+        const int ind = have ? (list[t] == 0xffff ? sh_stale[wid] : a + (int)list[t]) : 0; \
+        int next = 0; \
+        while (largest < 20) { \
+          const bool cand = have && lane >= next && GET_PICKED(ind) == 0; \
+          const unsigned m = __ballot_sync(0xffffffffu, cand); \
+          if (m == 0) break; \
+          const int w = __ffs(m) - 1; \
+          const int pick = __shfl_sync(0xffffffffu, ind, w); \
+          largest++; \
+          if (lane == 0) { \
+            if (largest <= 2) { \
+              st.cloud_label[base + pick] = 2; \
+              o_sharp_i[n_sharp] = pick; \
+            } else { \
+              st.cloud_label[base + pick] = 1; \
+            } \
+            o_lsharp_i[n_lsharp] = pick; \
+          } \
+          if (largest <= 2) n_sharp++; \
+          n_lsharp++; \
+          MARK_NEIGHBORS(pick); \
+          next = w + 1; \
+        } \
+      } \
+    } \
+    { \
+      const int lo = __shfl_sync(0xffffffffu, off_lane, 2 * j + 1); \
+      const unsigned short* list = sm_list + lo; \
+      const int len = __shfl_sync(0xffffffffu, off_lane, 2 * j + 2) - lo; \
+      int smallest = 0; \
+      for (int wbase = 0; wbase < len && smallest < 4; wbase += 32) { \
+        const int t = wbase + lane; \
+        const bool have = t < len; \
+        const int ind = have ? (list[t] == 0xffff ? sh_stale[wid] : a + (int)list[t]) : 0; \
+        int next = 0; \
+        while (true) { \
+          const bool cand = have && lane >= next && GET_PICKED(ind) == 0; \
+          const unsigned m = __ballot_sync(0xffffffffu, cand); \
+          if (m == 0) break; \
+          const int w = __ffs(m) - 1; \
+          const int pick = __shfl_sync(0xffffffffu, ind, w); \
+          smallest++; \
+          if (lane == 0) { \
+            st.cloud_label[base + pick] = -1; \
+            o_flat_i[n_flat] = pick; \
+          } \
+          n_flat++; \
+          if (smallest >= 4) break; \
+          MARK_NEIGHBORS(pick); \
+          next = w + 1; \
+        } \
+      } \
+    } \
   }
+  if (has_stale) {
+    PICK_SEXTANTS(get_picked, mark_neighbors)
+  } else {
+    PICK_SEXTANTS(get_picked_fast, mark_neighbors_fast)
+  }
+#undef PICK_SEXTANTS
   __syncwarp();
   // persist cloudNeighborPicked for this ring's own range (entries are only ever set to 1 here)
   for (int t = lane; t < L; t += 32) {
@@ -598,7 +637,12 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
     LL_LAUNCH(ctx, "k_feature_sort", k_feature_sort<<<grid_rings, SORT_THREADS, smem, ctx.stream>>>(st, cap2));
   }
   {
-    const size_t smem = (size_t)PICK_WARPS * (p.H + 32) * 3;
+    const size_t smem = (size_t)PICK_WARPS * (p.H + 32) * 5;  // picked bytes + u16 columns + u16 candidate lists
+    static size_t pick_configured = 0;
+    if (smem > 48 * 1024 && smem > pick_configured) {
+      cudaFuncSetAttribute(k_feature_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      pick_configured = smem;
+    }
     LL_LAUNCH(ctx, "k_feature_pick",
               k_feature_pick<<<dim3((p.V + PICK_WARPS - 1) / PICK_WARPS, p.B), PICK_WARPS * 32, smem, ctx.stream>>>(st));
   }
