@@ -104,36 +104,53 @@ __global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
 
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int n /* pow2 */, int total /* multiple of n */) {
-  // sorts every aligned block of n keys ascending (direction-free bitonic network)
+// Direction-free bitonic network, ascending, over every aligned block of n keys of key[0 .. total) in shared memory
+// (n a power of two, total a multiple of n, blockDim.x a multiple of 32).  One compare-exchange per loop trip: pair
+// t owns the elements i (t with a zero bit inserted at the stride) and its partner, so no thread idles on the upper
+// half of a pair.  All strides <= 32 of a merge phase touch one aligned 64-key block per 32 consecutive pairs, i.e.
+// per warp, so they run back to back with warp-level synchronisation only; a block-wide barrier is needed only
+// around strides >= 64.
+template <typename T>
+__device__ __forceinline__ void block_bitonic_sort(T* key, int n, int total) {
+  const int half = total >> 1;
+  const int lane = threadIdx.x & 31;
   for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
-        if (l > i) {
-          const unsigned long long a = key[i], b = key[l];
-          if (a > b) { key[i] = b; key[l] = a; }
-        }
+    int j = k >> 1;
+    for (; j > 32; j >>= 1) {
+      const int jm = j - 1;
+      const bool flip = (j == (k >> 1));
+      for (int t = threadIdx.x; t < half; t += blockDim.x) {
+        const int i = ((t & ~jm) << 1) | (t & jm);
+        const int l = flip ? (i ^ (k - 1)) : (i | j);
+        const T a = key[i], b = key[l];
+        if (a > b) { key[i] = b; key[l] = a; }
       }
       __syncthreads();
     }
+    for (int t0 = threadIdx.x - lane; t0 < half; t0 += blockDim.x) {  // warp-uniform trip count
+      const int t = t0 + lane;
+      for (int jj = j; jj > 0; jj >>= 1) {
+        if (t < half) {
+          const int jm = jj - 1;
+          const int i = ((t & ~jm) << 1) | (t & jm);
+          const int l = (jj == (k >> 1)) ? (i ^ (k - 1)) : (i | jj);
+          const T a = key[i], b = key[l];
+          if (a > b) { key[i] = b; key[l] = a; }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   }
+}
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int n /* pow2 */, int total /* multiple of n */) {
+  block_bitonic_sort<unsigned long long>(key, n, total);
 }
 
 template <typename T>
 __device__ __forceinline__ void bitonic_sort_t(T* key, int n /* pow2 */) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
-        if (l > i) {
-          const T a = key[i], b = key[l];
-          if (a > b) { key[i] = b; key[l] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
+  block_bitonic_sort<T>(key, n, n);
 }
 
 // order-preserving float <-> int map (an involution), for shared-memory atomicMin/Max on floats

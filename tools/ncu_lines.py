@@ -1,33 +1,31 @@
-"""Top source lines of a kernel in an ncu report by instructions executed / stall samples.
-  python tools/ncu_lines.py report.ncu-rep kernel_regex [launch_skip] [top_n]"""
-import csv, subprocess, sys
-rep, rx = sys.argv[1], sys.argv[2]
-skip = sys.argv[3] if len(sys.argv) > 3 else "0"
-top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name",
-                      "regex:" + rx, "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-fname = ""
-data = []
-hdr = None
+"""Per-CUDA-source-line instruction and stall-sample shares from an ncu report captured with --import-source on:
+  ncu -i rep.ncu-rep --page source --print-source cuda,sass --csv > lines.csv ; python tools/ncu_lines.py lines.csv [top]"""
+import collections, csv, os, re, sys
+rows = list(csv.reader(open(sys.argv[1])))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+fn, fpath, hdr, cur = None, None, None, None
+per = collections.OrderedDict()
 for r in rows:
-    if len(r) >= 2 and r[0] in ("File Path", "File Name"):
-        fname = r[1].split("/")[-1]
+    if len(r) == 2 and r[0] == "File Path":
+        fpath = os.path.basename(r[1]); continue
+    if len(r) == 2 and r[0] == "Function Name":
+        fn = re.sub(r"\(.*", "", re.sub(r".*::", "", r[1])); continue
+    if r and r[0] == "Line No":
+        hdr = r; isamp = hdr.index("# Samples"); iex = hdr.index("Instructions Executed"); continue
+    if hdr is None or len(r) != len(hdr):
         continue
-    if len(r) > 8 and r[0] == "Line No":
-        hdr = r
-        ci = hdr.index("Instructions Executed"); si = hdr.index("# Samples"); ti = hdr.index("Thread Instructions Executed")
+    if r[0] != "":
+        cur = (fpath, int(r[0]), r[1].strip()); continue
+    if r[2] in ("...", "") or cur is None:
         continue
-    if hdr and len(r) > ci and r[0] not in ("", "Line No"):
-        try:
-            data.append((int(r[ci]), int(r[si]), int(r[ti]), fname, r[0], r[1].strip()[:100]))
-        except ValueError:
-            pass
-tot = sum(d[0] for d in data); tots = sum(d[1] for d in data)
-print("total warp instructions", tot, "samples", tots)
-print("--- by instructions")
-for d in sorted(data, reverse=True)[:top]:
-    print(f"{d[0]:10d} {100*d[0]/max(tot,1):5.1f}%  smp {100*d[1]/max(tots,1):5.1f}%  thr/inst {d[2]/max(d[0],1):4.1f}  {d[3]}:{d[4]}  {d[5]}")
-print("--- by stall samples")
-for d in sorted(data, key=lambda x: -x[1])[:top // 2]:
-    print(f"{d[0]:10d} {100*d[0]/max(tot,1):5.1f}%  smp {100*d[1]/max(tots,1):5.1f}%  thr/inst {d[2]/max(d[0],1):4.1f}  {d[3]}:{d[4]}  {d[5]}")
+    try:
+        s, e = int(r[isamp]), int(r[iex])
+    except ValueError:
+        continue
+    d = per.setdefault(fn, collections.OrderedDict())
+    a = d.setdefault(cur, [0, 0]); a[0] += s; a[1] += e
+for k, d in per.items():
+    ts, ti = sum(v[0] for v in d.values()), sum(v[1] for v in d.values())
+    print(f"===== {k}: {ts} samples, {ti} warp instructions")
+    for (f, ln, src), (s, e) in sorted(d.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"  {f}:{ln:<4d} inst {100 * e / max(1, ti):5.1f}%  samples {100 * s / max(1, ts):5.1f}%  {src[:96]}")
