@@ -25,6 +25,7 @@ namespace {
 __global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
   __shared__ float sh_r[FP_THREADS + 2 * FP_HALO];
   __shared__ int sh_c[FP_THREADS + 2 * FP_HALO];
+  __shared__ unsigned char sh_f[FP_THREADS + 2 * FP_HALO];
   const DevParams& p = st.p;
   const int s = blockIdx.y;
   const int S = st.seg_count[s];
@@ -36,6 +37,23 @@ __global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
     const bool ok = idx >= 0 && idx < S;
     sh_r[t] = ok ? st.seg_range[base + idx] : 0.f;
     sh_c[t] = ok ? (int)st.seg_col[base + idx] : 0;
+  }
+  __syncthreads();
+  // markOccludedPoints (featureAssociation.cpp:226-262), step 1: the depth test of every neighbouring pair (k, k+1),
+  // evaluated once per pair: 1 = k is the far side (marks k-5 .. k), 2 = k+1 is the far side (marks k+1 .. k+6)
+  for (int t = threadIdx.x; t < FP_THREADS + 2 * FP_HALO - 1; t += FP_THREADS) {
+    const int k = b0 - FP_HALO + t;  // loop index of the reference
+    unsigned char f = 0;
+    if (k >= 5 && k < S - 6) {
+      const float depth1 = sh_r[t], depth2 = sh_r[t + 1];
+      const int cdiff = abs(sh_c[t + 1] - sh_c[t]);
+      if (cdiff < 10) {
+        const bool far_near = (double)(depth1 - depth2) > 0.3;
+        const bool near_far = !far_near && (double)(depth2 - depth1) > 0.3;
+        f = far_near ? 1 : (near_far ? 2 : 0);
+      }
+    }
+    sh_f[t] = f;
   }
   __syncthreads();
   const int i = b0 + threadIdx.x;
@@ -70,21 +88,10 @@ __global__ void __launch_bounds__(FP_THREADS) k_feature_prep(DevState st) {
   const float* r = sh_r + FP_HALO + threadIdx.x;  // r[k] = range of point i + k
   const int* c = sh_c + FP_HALO + threadIdx.x;
   const bool interior = (i >= 5 && i < S - 5);
-  // ---- markOccludedPoints as a gather (featureAssociation.cpp:226-262) ----
-  bool mark = false;
-#pragma unroll
-  for (int d = -6; d <= 5; ++d) {
-    const int k = i + d;  // loop index of the reference that could write picked[i]
-    if (k < 5 || k >= S - 6) continue;
-    const float depth1 = r[d], depth2 = r[d + 1];
-    const int cdiff = abs(c[d + 1] - c[d]);
-    if (cdiff < 10) {
-      const bool far_near = (double)(depth1 - depth2) > 0.3;   // marks k-5 .. k
-      const bool near_far = !far_near && (double)(depth2 - depth1) > 0.3;  // marks k+1 .. k+6
-      if (far_near && d >= 0) mark = true;
-      if (near_far && d <= -1) mark = true;
-    }
-  }
+  // ---- markOccludedPoints, step 2: gather (all its writes are idempotent "= 1") ----
+  // picked[i] is written by the far-side-left test of pairs i .. i+5 and by the far-side-right test of pairs i-6 .. i-1
+  const unsigned char* f = sh_f + FP_HALO + threadIdx.x;
+  bool mark = (((f[0] | f[1] | f[2] | f[3] | f[4] | f[5]) & 1) | ((f[-6] | f[-5] | f[-4] | f[-3] | f[-2] | f[-1]) & 2)) != 0;
   if (i >= 5 && i < S - 6) {
     const float diff1 = fabsf(r[-1] - r[0]);
     const float diff2 = fabsf(r[1] - r[0]);
