@@ -48,7 +48,10 @@ __device__ __noinline__ float4 transform_to_start(const float4 pi, const float* 
   return make_float4(cry * x2 - sry * z2, y2, sry * x2 + cry * z2, pi.w);
 }
 
-__device__ __forceinline__ float4 transform_to_end(const float4 pi, const float* T) {
+// sin / cos of the three whole-sweep angles transformCur[0..2]: the same for every point of a sequence
+struct EndTrig { float srx, crx, sry, cry, srz, crz; };
+
+__device__ __forceinline__ float4 transform_to_end(const float4 pi, const float* T, const EndTrig& e) {
   // featureAssociation.cpp:422-471
   const float s = 10 * (pi.w - (float)(int)pi.w);
   float rx = s * T[0], ry = s * T[1], rz = s * T[2];
@@ -66,11 +69,8 @@ __device__ __forceinline__ float4 transform_to_end(const float4 pi, const float*
   const float x3 = cry * x2 - sry * z2;
   const float y3 = y2;
   const float z3 = sry * x2 + cry * z2;
-  rx = T[0]; ry = T[1]; rz = T[2];
   tx = T[3]; ty = T[4]; tz = T[5];
-  ll_sincosf(rz, &srz, &crz);
-  ll_sincosf(rx, &srx, &crx);
-  ll_sincosf(ry, &sry, &cry);
+  srz = e.srz; crz = e.crz; srx = e.srx; crx = e.crx; sry = e.sry; cry = e.cry;  // of T[2], T[0], T[1] (:452-460)
   const float x4 = cry * x3 + sry * z3;
   const float y4 = y3;
   const float z4 = -sry * x3 + cry * z3;
@@ -608,6 +608,14 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   float T[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) T[k] = st.transform_cur[s * 6 + k];
+  __shared__ EndTrig sh_end;
+  if (threadIdx.x == 0) {
+    ll_sincosf(T[0], &sh_end.srx, &sh_end.crx);
+    ll_sincosf(T[1], &sh_end.sry, &sh_end.cry);
+    ll_sincosf(T[2], &sh_end.srz, &sh_end.crz);
+  }
+  __syncthreads();
+  const EndTrig et = sh_end;
   const int n_corner = st.feat_counts[s * 4 + 1];
   const int n_surf = st.feat_counts[s * 4 + 3];
   // window tables are double buffered by frame parity: this frame fills one half (reset while the previous
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   }
   if (i < n_corner) {
     const float4 q = st.corner_less_sharp[(size_t)s * p.cap_less_sharp + i];
-    st.corner_last[(size_t)s * p.cap_less_sharp + i] = first_frame ? q : transform_to_end(q, T);
+    st.corner_last[(size_t)s * p.cap_less_sharp + i] = first_frame ? q : transform_to_end(q, T, et);
     // ring run boundaries of the new last-frame cloud: id = int(intensity) is the same before and after TransformToEnd
     const float4* src = st.corner_less_sharp + (size_t)s * p.cap_less_sharp;
     const int id = min(max((int)q.w, 0), WIN_R - 1);
@@ -632,7 +640,7 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   }
   if (i < n_surf) {
     const float4 q = st.surf_less_flat[(size_t)s * p.N + i];
-    st.surf_last[(size_t)s * p.N + i] = first_frame ? q : transform_to_end(q, T);
+    st.surf_last[(size_t)s * p.N + i] = first_frame ? q : transform_to_end(q, T, et);
     const float4* src = st.surf_less_flat + (size_t)s * p.N;
     const int id = min(max((int)q.w, 0), WIN_R - 1);
     const int idp = i > 0 ? min(max((int)src[i - 1].w, 0), WIN_R - 1) : -1;
