@@ -259,10 +259,11 @@ __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int ite
       // 2b: candidates of the concatenated buckets, four independent loads per step.  A point is a candidate
       // if it is closer than 1 m (such a point necessarily lies in one of the 27 cells); two of the 27 cells can
       // share a bucket (hash collision), so an index that is already in the list is skipped.
-      float bd[KNN_REC];
-      int bi[KNN_REC];
+      // sorted top-(KNN_K+1) as 64-bit keys (d2 bits << 32 | index): for the non-negative d2 an unsigned compare of
+      // the keys is the lexicographic (d2, index) order of cand_less, and an insertion step is one compare + selects
+      unsigned long long bk[KNN_REC];
 #pragma unroll
-      for (int i = 0; i < KNN_REC; ++i) { bd[i] = 1.0f; bi[i] = 0x7fffffff; }
+      for (int i = 0; i < KNN_REC; ++i) bk[i] = ((unsigned long long)__float_as_uint(1.0f) << 32) | 0x7fffffffull;
       for (int u = 0; u < nb; ++u) {
         const int2 be = sh_bucket[u][threadIdx.x];
         for (int k = be.x; k < be.y; k += 4) {
@@ -272,26 +273,30 @@ __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int ite
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             if (k + v >= be.y) continue;
-            float cd = nn_dist2(sel.x, sel.y, sel.z, cpt[v]);
-            if (cd < bd[KNN_K]) {
-              int ci = __float_as_int(cpt[v].w);
+            const float cd = nn_dist2(sel.x, sel.y, sel.z, cpt[v]);
+            if (cd < __uint_as_float((unsigned)(bk[KNN_K] >> 32))) {
+              const unsigned ci = (unsigned)__float_as_int(cpt[v].w);
               bool dup = false;
 #pragma unroll
-              for (int i = 0; i < KNN_REC; ++i) dup = dup || (bi[i] == ci);
+              for (int i = 0; i < KNN_REC; ++i) dup = dup || ((unsigned)bk[i] == ci);
               if (!dup) {
+                unsigned long long key = ((unsigned long long)__float_as_uint(cd) << 32) | ci;
 #pragma unroll
                 for (int i = 0; i < KNN_REC; ++i) {
-                  if (cand_less(cd, ci, bd[i], bi[i])) {
-                    const float td = bd[i]; const int ti = bi[i];
-                    bd[i] = cd; bi[i] = ci;
-                    cd = td; ci = ti;
-                  }
+                  const unsigned long long b = bk[i];
+                  const bool lt = key < b;
+                  bk[i] = lt ? key : b;
+                  key = lt ? b : key;
                 }
               }
             }
           }
         }
       }
+      float bd[KNN_REC];
+      int bi[KNN_REC];
+#pragma unroll
+      for (int i = 0; i < KNN_REC; ++i) { bd[i] = __uint_as_float((unsigned)(bk[i] >> 32)); bi[i] = (int)(unsigned)bk[i]; }
       const float4* mpts = corner ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
       float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
 #pragma unroll
