@@ -384,6 +384,18 @@ LLM_SOLVER bool degeneracy_projector(const float* AtA, float thr, float* P) {
   return degenerate;
 }
 
+/* Certified skip of the degeneracy test: the largest eigenvalue of a symmetric matrix is at least trace / N, and the
+ * float symmetric-QR eigenvalues are within ~1e-5 relative of the true ones, so trace / N >= 2 * thr proves that
+ * the largest COMPUTED eigenvalue is >= thr, i.e. that degeneracy_projector would return false (its P is then never
+ * read: featureAssociation.cpp:893-899, mapOptmization.cpp:1287-1292 only use matP when isDegenerate).  NaN / Inf
+ * fail the comparison and take the full path. */
+template <int N>
+LLM_HD bool certainly_not_degenerate(const float* AtA, float thr) {
+  float tr = 0.f;
+  for (int i = 0; i < N; ++i) tr += AtA[i * N + i];
+  return tr >= 2.f * thr * (float)N && tr < FLT_MAX;
+}
+
 }  // namespace llm
 
 #endif /* LL_SMALLMAT_H */

@@ -423,7 +423,7 @@ __device__ __noinline__ void map_solve_body(float* Tm, int* map_iters, double* t
   for (int r = 0; r < 6; ++r) AtB[r] = (float)tot[21 + r];
   for (int i = 0; i < 36; ++i) A2[i] = AtA[i];
   llm::colpiv_qr_solve<6, 6>(A2, AtB, X);
-  if (iter == 0) map_flags[0] = llm::degeneracy_projector<6>(AtA, 100.f, matP) ? 1 : 0;
+  if (iter == 0) map_flags[0] = llm::certainly_not_degenerate<6>(AtA, 100.f) ? 0 : (llm::degeneracy_projector<6>(AtA, 100.f, matP) ? 1 : 0);
   if (map_flags[0]) {
     float X2[6];
     for (int i = 0; i < 6; ++i) X2[i] = X[i];

@@ -874,7 +874,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
           for (int k = 0; k < 9; ++k) A2[k] = AtA[k];
           llm::colpiv_qr_solve<3, 3>(A2, AtB, X);
           float* matP = st.odom_matP + s * 9;
-          if (iter == 0) st.odom_flags[s * 4 + 0] = llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0;
+          if (iter == 0)
+            st.odom_flags[s * 4 + 0] = llm::certainly_not_degenerate<3>(AtA, 10.f) ? 0 : (llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0);
           if (st.odom_flags[s * 4 + 0]) {
             const float X2[3] = {X[0], X[1], X[2]};
             for (int r = 0; r < 3; ++r) X[r] = matP[r * 3 + 0] * X2[0] + matP[r * 3 + 1] * X2[1] + matP[r * 3 + 2] * X2[2];
