@@ -153,6 +153,157 @@ LLM_SOLVER void colpiv_qr_solve(float* A, const float* b_in, float* x) {
   for (int i = 0; i < rank; ++i) x[perm[i]] = c[i];
 }
 
+/* colpiv_qr_solve<3, 3> with every array index a compile-time constant (column swaps, the pivot count, the rank and
+ * the final permutation are resolved with explicit comparisons), so that on the device everything stays in registers:
+ * the generic routine above is out of line and indexes its arrays dynamically, which costs the single thread that
+ * solves the 3x3 normal equations of a scan-to-scan LM iteration several microseconds.  Same operations in the same
+ * order as the generic code -- tests/csrc/check_qr3.cpp compares the two bit for bit on random and degenerate systems. */
+#define LLM_SWAPF(a, b) do { const float t__ = (a); (a) = (b); (b) = t__; } while (0)
+LLM_HD void colpiv_qr_solve3(const float* A_in, const float* b_in, float* x) {
+  const float eps = FLT_EPSILON;
+  float a00 = A_in[0], a01 = A_in[1], a02 = A_in[2], a10 = A_in[3], a11 = A_in[4], a12 = A_in[5], a20 = A_in[6], a21 = A_in[7],
+        a22 = A_in[8];
+  float nu0, nu1, nu2, nd0, nd1, nd2;
+  int p0 = 0, p1 = 1, p2 = 2;
+  float maxnorm = 0.f;
+  { float s = 0.f; s += a00 * a00; s += a10 * a10; s += a20 * a20; nd0 = nu0 = sqrt_(s); if (nu0 > maxnorm) maxnorm = nu0; }
+  { float s = 0.f; s += a01 * a01; s += a11 * a11; s += a21 * a21; nd1 = nu1 = sqrt_(s); if (nu1 > maxnorm) maxnorm = nu1; }
+  { float s = 0.f; s += a02 * a02; s += a12 * a12; s += a22 * a22; nd2 = nu2 = sqrt_(s); if (nu2 > maxnorm) maxnorm = nu2; }
+  const float thr_helper = (maxnorm * eps) * (maxnorm * eps) / 3.f;
+  const float downdate_thr = sqrt_(eps);
+  int nonzero_pivots = 3;
+  float maxpivot = 0.f;
+  float h0, h1, h2;
+  /* ---- k = 0 ---- */
+  {
+    int big = 0;
+    float bigv = nu0;
+    if (nu1 > bigv) { bigv = nu1; big = 1; }
+    if (nu2 > bigv) { bigv = nu2; big = 2; }
+    const float big_sq = bigv * bigv;
+    if (nonzero_pivots == 3 && big_sq < thr_helper * 3.f) nonzero_pivots = 0;
+    if (big == 1) {
+      LLM_SWAPF(a00, a01); LLM_SWAPF(a10, a11); LLM_SWAPF(a20, a21); LLM_SWAPF(nu0, nu1); LLM_SWAPF(nd0, nd1);
+      const int t = p0; p0 = p1; p1 = t;
+    } else if (big == 2) {
+      LLM_SWAPF(a00, a02); LLM_SWAPF(a10, a12); LLM_SWAPF(a20, a22); LLM_SWAPF(nu0, nu2); LLM_SWAPF(nd0, nd2);
+      const int t = p0; p0 = p2; p2 = t;
+    }
+    /* make_householder on (a00, a10, a20) */
+    float tail_sq = 0.f;
+    tail_sq += a10 * a10;
+    tail_sq += a20 * a20;
+    const float c0 = a00;
+    float beta;
+    if (tail_sq <= FLT_MIN) {
+      h0 = 0.f; beta = c0; a10 = 0.f; a20 = 0.f;
+    } else {
+      float b = sqrt_(c0 * c0 + tail_sq);
+      if (c0 >= 0.f) b = -b;
+      const float d = c0 - b;
+      a10 = a10 / d; a20 = a20 / d;
+      h0 = (b - c0) / b;
+      beta = b;
+    }
+    a00 = beta;
+    if (fabs_(beta) > maxpivot) maxpivot = fabs_(beta);
+    if (h0 != 0.f) {
+      { float t = 0.f; t += a10 * a11; t += a20 * a21; t += a01; a01 -= h0 * t; a11 -= h0 * a10 * t; a21 -= h0 * a20 * t; }
+      { float t = 0.f; t += a10 * a12; t += a20 * a22; t += a02; a02 -= h0 * t; a12 -= h0 * a10 * t; a22 -= h0 * a20 * t; }
+    }
+    if (nu1 != 0.f) {
+      float t = fabs_(a01) / nu1;
+      t = (1.f + t) * (1.f - t);
+      if (t < 0.f) t = 0.f;
+      const float q = nu1 / nd1;
+      const float t2 = t * (q * q);
+      if (t2 <= downdate_thr) { float s = 0.f; s += a11 * a11; s += a21 * a21; nd1 = sqrt_(s); nu1 = nd1; } else { nu1 *= sqrt_(t); }
+    }
+    if (nu2 != 0.f) {
+      float t = fabs_(a02) / nu2;
+      t = (1.f + t) * (1.f - t);
+      if (t < 0.f) t = 0.f;
+      const float q = nu2 / nd2;
+      const float t2 = t * (q * q);
+      if (t2 <= downdate_thr) { float s = 0.f; s += a12 * a12; s += a22 * a22; nd2 = sqrt_(s); nu2 = nd2; } else { nu2 *= sqrt_(t); }
+    }
+  }
+  /* ---- k = 1 ---- */
+  {
+    int big = 1;
+    float bigv = nu1;
+    if (nu2 > bigv) { bigv = nu2; big = 2; }
+    const float big_sq = bigv * bigv;
+    if (nonzero_pivots == 3 && big_sq < thr_helper * 2.f) nonzero_pivots = 1;
+    if (big == 2) {
+      LLM_SWAPF(a01, a02); LLM_SWAPF(a11, a12); LLM_SWAPF(a21, a22); LLM_SWAPF(nu1, nu2); LLM_SWAPF(nd1, nd2);
+      const int t = p1; p1 = p2; p2 = t;
+    }
+    /* make_householder on (a11, a21) */
+    float tail_sq = 0.f;
+    tail_sq += a21 * a21;
+    const float c0 = a11;
+    float beta;
+    if (tail_sq <= FLT_MIN) {
+      h1 = 0.f; beta = c0; a21 = 0.f;
+    } else {
+      float b = sqrt_(c0 * c0 + tail_sq);
+      if (c0 >= 0.f) b = -b;
+      const float d = c0 - b;
+      a21 = a21 / d;
+      h1 = (b - c0) / b;
+      beta = b;
+    }
+    a11 = beta;
+    if (fabs_(beta) > maxpivot) maxpivot = fabs_(beta);
+    if (h1 != 0.f) {
+      float t = 0.f; t += a21 * a22; t += a12; a12 -= h1 * t; a22 -= h1 * a21 * t;
+    }
+    if (nu2 != 0.f) {
+      float t = fabs_(a12) / nu2;
+      t = (1.f + t) * (1.f - t);
+      if (t < 0.f) t = 0.f;
+      const float q = nu2 / nd2;
+      const float t2 = t * (q * q);
+      if (t2 <= downdate_thr) { float s = 0.f; s += a22 * a22; nd2 = sqrt_(s); nu2 = nd2; } else { nu2 *= sqrt_(t); }
+    }
+  }
+  /* ---- k = 2 ---- */
+  {
+    const float bigv = nu2;
+    const float big_sq = bigv * bigv;
+    if (nonzero_pivots == 3 && big_sq < thr_helper * 1.f) nonzero_pivots = 2;
+    /* make_householder with n == 1 */
+    h2 = 0.f;
+    const float beta = a22;
+    a22 = beta;
+    if (fabs_(beta) > maxpivot) maxpivot = fabs_(beta);
+  }
+  const float premul = fabs_(maxpivot) * (eps * 3.f);
+  int rank = 0;
+  if (0 < nonzero_pivots) rank += (fabs_(a00) > premul) ? 1 : 0;
+  if (1 < nonzero_pivots) rank += (fabs_(a11) > premul) ? 1 : 0;
+  if (2 < nonzero_pivots) rank += (fabs_(a22) > premul) ? 1 : 0;
+  float c0 = b_in[0], c1 = b_in[1], c2 = b_in[2];
+  if (0 < nonzero_pivots && h0 != 0.f) {
+    float t = 0.f; t += a10 * c1; t += a20 * c2; t += c0; c0 -= h0 * t; c1 -= h0 * a10 * t; c2 -= h0 * a20 * t;
+  }
+  if (1 < nonzero_pivots && h1 != 0.f) {
+    float t = 0.f; t += a21 * c2; t += c1; c1 -= h1 * t; c2 -= h1 * a21 * t;
+  }
+  if (2 < nonzero_pivots) c2 *= (1.f - h2);
+  /* back substitution on the leading rank x rank upper triangle */
+  if (rank > 2) { const float s = c2; c2 = s / a22; }
+  if (rank > 1) { float s = c1; if (rank > 2) s -= a12 * c2; c1 = s / a11; }
+  if (rank > 0) { float s = c0; if (rank > 1) s -= a01 * c1; if (rank > 2) s -= a02 * c2; c0 = s / a00; }
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+  if (rank > 0) { if (p0 == 0) x0 = c0; else if (p0 == 1) x1 = c0; else x2 = c0; }
+  if (rank > 1) { if (p1 == 0) x0 = c1; else if (p1 == 1) x1 = c1; else x2 = c1; }
+  if (rank > 2) { if (p2 == 0) x0 = c2; else if (p2 == 1) x1 = c2; else x2 = c2; }
+  x[0] = x0; x[1] = x1; x[2] = x2;
+}
+#undef LLM_SWAPF
+
 LLM_HD void make_givens(float p, float q, float* c, float* s) {
   if (q == 0.f) {
     *c = p < 0.f ? -1.f : 1.f;

@@ -870,9 +870,8 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
           float AtA[9] = {(float)tot[0], (float)tot[1], (float)tot[2], (float)tot[1], (float)tot[3],
                           (float)tot[4], (float)tot[2], (float)tot[4], (float)tot[5]};
           float AtB[3] = {(float)tot[6], (float)tot[7], (float)tot[8]};
-          float A2[9], X[3];
-          for (int k = 0; k < 9; ++k) A2[k] = AtA[k];
-          llm::colpiv_qr_solve<3, 3>(A2, AtB, X);
+          float X[3];
+          llm::colpiv_qr_solve3(AtA, AtB, X);  // == colpiv_qr_solve<3, 3>, bit for bit (tests/csrc/check_qr3.cpp)
           float* matP = st.odom_matP + s * 9;
           if (iter == 0)
             st.odom_flags[s * 4 + 0] = llm::certainly_not_degenerate<3>(AtA, 10.f) ? 0 : (llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0);
