@@ -141,11 +141,14 @@ __global__ void __launch_bounds__(256) k_ccl_merge(DevState st) {
     // parents, at whatever time they were read, imply equal components) and are vertically connected
     // themselves: that column, or one further left, does the union.
     const bool skip = pl >= 0 && plu >= 0 && pl == pc && plu == pu && seg_edge(rl, rlu, p.sin_ay, p.cos_ay, p.seg_tan_theta);
-    if (!skip) uf_union(parent, cell, up);
+    // the finds start from the parents already loaded (the run heads written by k_ccl_rows, or better): any node of a
+    // component stands for it, and this saves the two dependent loads of starting at the cells themselves
+    if (!skip) uf_union(parent, pc, pu);
   }
   if (col == p.H - 1 && p.H > 1) {
     const int w = cell - col;  // column 0 of the same row (imageProjection.cpp:446-451)
-    if (__ldcg(parent + w) >= 0 && seg_edge(r, range[w], p.sin_ax, p.cos_ax, p.seg_tan_theta)) uf_union(parent, cell, w);
+    const int pw = __ldcg(parent + w);
+    if (pw >= 0 && seg_edge(r, range[w], p.sin_ax, p.cos_ax, p.seg_tan_theta)) uf_union(parent, pc, pw);
   }
 }
 
