@@ -605,6 +605,11 @@ __global__ void __launch_bounds__(256) k_publish_clouds_last(DevState st, int fi
   const DevParams& p = st.p;
   const int s = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  {
+    // the grid covers the capacity (N points); blocks past the longest of the three clouds have nothing to do
+    const int longest = max(max(st.feat_counts[s * 4 + 1], st.feat_counts[s * 4 + 3]), max(first_frame ? 0 : st.outlier_count[s], 2 * WIN_R));
+    if ((int)(blockIdx.x * blockDim.x) >= longest) return;
+  }
   float T[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) T[k] = st.transform_cur[s * 6 + k];
