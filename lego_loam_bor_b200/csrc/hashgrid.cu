@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(256) k_grid_count(BuildArgs a) {
   if (!seq_enabled(a, s)) return;
   const BuildJob& j = a.job[blockIdx.z];
   const int n = min(j.counts[s * j.count_stride + j.count_off], j.g.cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 q = j.pts[(size_t)s * j.stride + i];
-  const uint32_t h = grid_hash(grid_cell(q.x, j.g.inv_cell), grid_cell(q.y, j.g.inv_cell), grid_cell(q.z, j.g.inv_cell), j.g.tbl);
-  atomicAdd(j.g.cnt + (size_t)s * j.g.tbl + h, 1);
+  // grid-stride: the launch is sized for a typical cloud, not for the capacity (most capacity-sized blocks would be empty)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q = j.pts[(size_t)s * j.stride + i];
+    const uint32_t h = grid_hash(grid_cell(q.x, j.g.inv_cell), grid_cell(q.y, j.g.inv_cell), grid_cell(q.z, j.g.inv_cell), j.g.tbl);
+    atomicAdd(j.g.cnt + (size_t)s * j.g.tbl + h, 1);
+  }
 }
 
 // per-tile totals of the bucket counters
@@ -109,18 +110,18 @@ __global__ void __launch_bounds__(256) k_grid_fill(BuildArgs a) {
   if (!seq_enabled(a, s)) return;
   const BuildJob& j = a.job[blockIdx.z];
   const int n = min(j.counts[s * j.count_stride + j.count_off], j.g.cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 q = j.pts[(size_t)s * j.stride + i];
-  const uint32_t h = grid_hash(grid_cell(q.x, j.g.inv_cell), grid_cell(q.y, j.g.inv_cell), grid_cell(q.z, j.g.inv_cell), j.g.tbl);
-  const int pos = atomicAdd(j.g.cursor + (size_t)s * j.g.tbl + h, 1);
-  int w = i;
-  if (a.pack_ring) {
-    const int idp = min(max((int)q.w + 1, 0), 255);  // ring id = int(intensity), -1..254
-    w |= idp << 24;
-    if (j.g.sig) atomicOr(j.g.sig + (size_t)s * j.g.tbl + h, 1u << (idp & 31));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 q = j.pts[(size_t)s * j.stride + i];
+    const uint32_t h = grid_hash(grid_cell(q.x, j.g.inv_cell), grid_cell(q.y, j.g.inv_cell), grid_cell(q.z, j.g.inv_cell), j.g.tbl);
+    const int pos = atomicAdd(j.g.cursor + (size_t)s * j.g.tbl + h, 1);
+    int w = i;
+    if (a.pack_ring) {
+      const int idp = min(max((int)q.w + 1, 0), 255);  // ring id = int(intensity), -1..254
+      w |= idp << 24;
+      if (j.g.sig) atomicOr(j.g.sig + (size_t)s * j.g.tbl + h, 1u << (idp & 31));
+    }
+    j.g.sorted[(size_t)s * j.g.cap + pos] = make_float4(q.x, q.y, q.z, __int_as_float(w));
   }
-  j.g.sorted[(size_t)s * j.g.cap + pos] = make_float4(q.x, q.y, q.z, __int_as_float(w));
 }
 
 }  // namespace
@@ -136,8 +137,10 @@ void launch_grid_build2(LaunchCtx& ctx, int B, HashGrid& g0, const float4* pts0,
   a.pack_ring = pack_ring ? 1 : 0;
   const int cap = g0.cap > g1.cap ? g0.cap : g1.cap;
   const int ntiles = g0.ntiles > g1.ntiles ? g0.ntiles : g1.ntiles;
-  LL_LAUNCH(ctx, "k_grid_count", k_grid_count<<<dim3((cap + 255) / 256, B, 2), 256, 0, ctx.stream>>>(a));
+  // enough blocks to fill the GPU at small batches, few enough that large batches do not launch thousands of idle ones
+  const int pblocks = (cap + 255) / 256 < 64 ? (cap + 255) / 256 : 64;
+  LL_LAUNCH(ctx, "k_grid_count", k_grid_count<<<dim3(pblocks, B, 2), 256, 0, ctx.stream>>>(a));
   LL_LAUNCH(ctx, "k_grid_tile_sums", k_grid_tile_sums<<<dim3(ntiles, B, 2), GS_THREADS, 0, ctx.stream>>>(a));
   LL_LAUNCH(ctx, "k_grid_scan", k_grid_scan<<<dim3(ntiles, B, 2), GS_THREADS, 0, ctx.stream>>>(a));
-  LL_LAUNCH(ctx, "k_grid_fill", k_grid_fill<<<dim3((cap + 255) / 256, B, 2), 256, 0, ctx.stream>>>(a));
+  LL_LAUNCH(ctx, "k_grid_fill", k_grid_fill<<<dim3(pblocks, B, 2), 256, 0, ctx.stream>>>(a));
 }
