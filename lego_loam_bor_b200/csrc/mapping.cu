@@ -202,7 +202,7 @@ __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) 
 __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int iter) {
   __shared__ int sh_need[KNN_THREADS];
   __shared__ int sh_n;
-  __shared__ int2 sh_bucket[27][KNN_THREADS];  // per thread: its non-empty buckets (start, end), column-major: no bank conflicts
+  __shared__ int2 sh_bucket[9][KNN_THREADS];  // per thread: the non-empty buckets (start, end) of the current batch of nine cells, column-major: no bank conflicts
   const DevParams& p = st.p;
   const int s = blockIdx.y;
   if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
@@ -274,57 +274,66 @@ __global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int ite
       const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
       const float4* pts = g.sorted + (size_t)s * g.cap;
       const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
-      // 2a: the non-empty buckets among the 27 cells, nine at a time so that the bitmap loads (and then the
-      // cell_start loads of the occupied ones) are independent and in flight together: this kernel is bound by
-      // memory latency, not by bandwidth or issue rate.
-      int nb = 0;
-#pragma unroll
-      for (int z = 0; z < 3; ++z) {
-        uint32_t hh[9];
-        unsigned occw[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          int dx, dy, dz;
-          knn_cell_offset(z * 9 + t, &dx, &dy, &dz);
-          hh[t] = grid_hash(cx + dx, cy + dy, cz + dz, g.tbl);
-          occw[t] = occ[hh[t] >> 5];
-        }
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          if ((occw[t] >> (hh[t] & 31)) & 1u) sh_bucket[nb++][threadIdx.x] = make_int2(cs[hh[t]], cs[hh[t] + 1]);
-        }
-      }
-      // 2b: candidates of the concatenated buckets, four independent loads per step.  A point is a candidate
-      // if it is closer than 1 m (such a point necessarily lies in one of the 27 cells); two of the 27 cells can
-      // share a bucket (hash collision), so an index that is already in the list is skipped.
       // sorted top-(KNN_K+1) as 64-bit keys (d2 bits << 32 | index): for the non-negative d2 an unsigned compare of
       // the keys is the lexicographic (d2, index) order of cand_less, and an insertion step is one compare + selects
       unsigned long long bk[KNN_REC];
 #pragma unroll
       for (int i = 0; i < KNN_REC; ++i) bk[i] = ((unsigned long long)__float_as_uint(1.0f) << 32) | 0x7fffffffull;
-      for (int u = 0; u < nb; ++u) {
-        const int2 be = sh_bucket[u][threadIdx.x];
-        for (int k = be.x; k < be.y; k += 4) {
-          float4 cpt[4];
+      // position of the query inside its cell: the gap to a neighbouring cell along an axis is f or cell - f
+      const float fx = sel.x - (float)cx * g.cell, fy = sel.y - (float)cy * g.cell, fz = sel.z - (float)cz * g.cell;
+      // Three batches of nine cells, nearest first.  2a: the non-empty buckets of the batch; the bitmap loads (and then the
+      // cell_start loads of the occupied ones) are independent and in flight together: this kernel is bound by memory
+      // latency.  From the second batch on, a cell whose nearest corner is farther than the current (KNN_K+1)-th best
+      // cannot contribute (the threshold only drops), so it is skipped without touching the bitmap.
 #pragma unroll
-          for (int v = 0; v < 4; ++v) cpt[v] = pts[min(k + v, be.y - 1)];
+      for (int z = 0; z < 3; ++z) {
+        int nb = 0;
+        uint32_t hh[9];
+        unsigned occw[9];
+        const float thr = __uint_as_float((unsigned)(bk[KNN_K] >> 32));
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            if (k + v >= be.y) continue;
-            const float cd = nn_dist2(sel.x, sel.y, sel.z, cpt[v]);
-            if (cd < __uint_as_float((unsigned)(bk[KNN_K] >> 32))) {
-              const unsigned ci = (unsigned)__float_as_int(cpt[v].w);
-              bool dup = false;
+        for (int t = 0; t < 9; ++t) {
+          int dx, dy, dz;
+          knn_cell_offset(z * 9 + t, &dx, &dy, &dz);
+          const float gx = dx < 0 ? fx : (dx > 0 ? g.cell - fx : 0.f);
+          const float gy = dy < 0 ? fy : (dy > 0 ? g.cell - fy : 0.f);
+          const float gz = dz < 0 ? fz : (dz > 0 ? g.cell - fz : 0.f);
+          // 0.999: the gaps and the candidate distances are rounded differently; never skip a cell on a rounding error
+          const bool reach = z == 0 || (gx * gx + gy * gy + gz * gz) * 0.999f <= thr;
+          hh[t] = grid_hash(cx + dx, cy + dy, cz + dz, g.tbl);
+          occw[t] = reach ? occ[hh[t] >> 5] : 0u;
+        }
 #pragma unroll
-              for (int i = 0; i < KNN_REC; ++i) dup = dup || ((unsigned)bk[i] == ci);
-              if (!dup) {
-                unsigned long long key = ((unsigned long long)__float_as_uint(cd) << 32) | ci;
+        for (int t = 0; t < 9; ++t) {
+          if ((occw[t] >> (hh[t] & 31)) & 1u) sh_bucket[nb++][threadIdx.x] = make_int2(cs[hh[t]], cs[hh[t] + 1]);
+        }
+        // 2b: candidates of the batch's buckets, four independent loads per step.  A point is a candidate if it is
+        // closer than 1 m (such a point necessarily lies in one of the 27 cells); two of the 27 cells can share a
+        // bucket (hash collision), so an index that is already in the list is skipped.
+        for (int u = 0; u < nb; ++u) {
+          const int2 be = sh_bucket[u][threadIdx.x];
+          for (int k = be.x; k < be.y; k += 4) {
+            float4 cpt[4];
 #pragma unroll
-                for (int i = 0; i < KNN_REC; ++i) {
-                  const unsigned long long b = bk[i];
-                  const bool lt = key < b;
-                  bk[i] = lt ? key : b;
-                  key = lt ? b : key;
+            for (int v = 0; v < 4; ++v) cpt[v] = pts[min(k + v, be.y - 1)];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              if (k + v >= be.y) continue;
+              const float cd = nn_dist2(sel.x, sel.y, sel.z, cpt[v]);
+              if (cd < __uint_as_float((unsigned)(bk[KNN_K] >> 32))) {
+                const unsigned ci = (unsigned)__float_as_int(cpt[v].w);
+                bool dup = false;
+#pragma unroll
+                for (int i = 0; i < KNN_REC; ++i) dup = dup || ((unsigned)bk[i] == ci);
+                if (!dup) {
+                  unsigned long long key = ((unsigned long long)__float_as_uint(cd) << 32) | ci;
+#pragma unroll
+                  for (int i = 0; i < KNN_REC; ++i) {
+                    const unsigned long long b = bk[i];
+                    const bool lt = key < b;
+                    bk[i] = lt ? key : b;
+                    key = lt ? b : key;
+                  }
                 }
               }
             }
