@@ -199,7 +199,7 @@ __device__ __forceinline__ void knn_cell_offset(int n, int* dx, int* dy, int* dz
 
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
-__global__ void __launch_bounds__(KNN_THREADS, 6) k_map_knn(DevState st, int iter) {
+__global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int iter) {
   __shared__ int sh_need[KNN_THREADS];
   __shared__ int sh_n;
   __shared__ int2 sh_bucket[9][KNN_THREADS];  // per thread: the non-empty buckets (start, end) of the current batch of nine cells, column-major: no bank conflicts
