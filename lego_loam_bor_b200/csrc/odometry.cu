@@ -120,7 +120,7 @@ __device__ __forceinline__ bool odom_guard(const DevState& st, int s) {
   return !(st.last_counts[s * 2 + 0] < 10 || st.last_counts[s * 2 + 1] < 100);
 }
 
-#define LM_THREADS 512
+#define LM_THREADS 768
 #define LM_WARPS (LM_THREADS / 32)
 #define WIN_R (LL_MAX_RINGS + 8)
 
@@ -787,6 +787,9 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int gl = threadIdx.x & (SG - 1);
   const unsigned gmask = SG == 32 ? 0xffffffffu : ((1u << (SG & 31)) - 1u) << (lane & ~(SG - 1));
+  // isDegenerate (a member shared by both stages, featureAssociation.h:115): read once, kept in a register by the
+  // thread that solves; iteration 0 overwrites it when it has enough rows
+  int degenerate = st.odom_flags[s * 4 + 0];
   for (int iter = 0; iter < 25; ++iter) {
     float T[6];
 #pragma unroll
@@ -878,9 +881,11 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
           float X[3];
           llm::colpiv_qr_solve3(AtA, AtB, X);  // == colpiv_qr_solve<3, 3>, bit for bit (tests/csrc/check_qr3.cpp)
           float* matP = st.odom_matP + s * 9;
-          if (iter == 0)
-            st.odom_flags[s * 4 + 0] = llm::certainly_not_degenerate<3>(AtA, 10.f) ? 0 : (llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0);
-          if (st.odom_flags[s * 4 + 0]) {
+          if (iter == 0) {
+            degenerate = llm::certainly_not_degenerate<3>(AtA, 10.f) ? 0 : (llm::degeneracy_projector<3>(AtA, 10.f, matP) ? 1 : 0);
+            st.odom_flags[s * 4 + 0] = degenerate;
+          }
+          if (degenerate) {
             const float X2[3] = {X[0], X[1], X[2]};
             for (int r = 0; r < 3; ++r) X[r] = matP[r * 3 + 0] * X2[0] + matP[r * 3 + 1] * X2[1] + matP[r * 3 + 2] * X2[2];
           }
