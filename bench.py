@@ -13,7 +13,9 @@ independent batches (weak scaling, no data-path collective).
 
 One JSON line is printed by rank 0 (keys: see the task contract).  `value` is timed with inputs already
 resident in HBM; `e2e` goes through the same C ABI with pinned HOST scans (H2D inside the timed
-region, pose D2H every step).
+region, pose D2H every step).  `--e2e-input xyz` (default) hands the scans over as packed 12-byte points
+(ll_set_scans_xyz_host: the path never reads the intensity a sensor reports, imageProjection.cpp:216), `xyzi`
+as 16-byte points (ll_set_scans_host); the other form is measured too and reported as `e2e_alt`.
 """
 import argparse
 import json
@@ -49,6 +51,9 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=11, help="frames per sequence of the cpu_baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--time-kernel", default="", help="kernel to report in `roofline` (default: the slowest)")
+    ap.add_argument("--e2e-input", default="xyz", choices=["xyz", "xyzi"],
+                    help="host point format of the `e2e` leg: packed 12-byte xyz (ll_set_scans_xyz_host; the path never reads "
+                         "the sensor's intensity) or 16-byte xyzi (ll_set_scans_host); the other one is reported as e2e_alt")
     ap.add_argument("--streams", type=int, default=4, help="split the batch over this many handles / CUDA streams")
     return ap.parse_args()
 
@@ -438,8 +443,14 @@ def main():
         gpu.set_scans_device(devdata.data_ptr() + f * frame_bytes, counts[f], stride)
         gpu.process_scans()
 
+    host_xyz = host[..., :3].contiguous().pin_memory()   # the same scans as packed 12-byte points
+    e2e_kind = [args.e2e_input]
+
     def upload(f):
-        gpu.set_scans_host_ptr(host.data_ptr() + f * frame_bytes, counts[f], stride)
+        if e2e_kind[0] == "xyz":
+            gpu.set_scans_xyz_host_ptr(host_xyz.data_ptr() + f * (frame_bytes // 4 * 3), counts[f], stride)
+        else:
+            gpu.set_scans_host_ptr(host.data_ptr() + f * frame_bytes, counts[f], stride)
 
     pose_host = torch.empty((2, 3, B, 6), dtype=torch.float32).pin_memory()  # two steps in flight x (sum, cur, map)
 
@@ -545,42 +556,49 @@ def main():
                                           local_maps(cfg, seq_ids[0]) if use_map else None, aft0, live=live)
 
     # ---- end-to-end: same C ABI, pinned host scans, H2D + pose D2H inside the timed region ----
-    gpu.reset()
-    if use_map:
-        seed_map_poses()
-    f = 0
-    upload(f)
-    step_host(f); f += 1
-    for _ in range(min(args.warmup, 3)):
+    def run_e2e(kind):
+        e2e_kind[0] = kind
+        gpu.reset()
+        if use_map:
+            seed_map_poses()
+        f = 0
+        upload(f)
         step_host(f); f += 1
-    drain_poses()
-    e2e_steps = min(args.steps, n_frames - f - 1)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h2d = 0
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        fork(e0)
-        for _ in range(e2e_steps):
-            h2d += int(counts[f].sum()) * 16 + B * 4
+        for _ in range(min(args.warmup, 3)):
             step_host(f); f += 1
         drain_poses()
-        join()
-        e1.record(stream)
-    torch.cuda.synchronize(dev)
-    e2e_ms = e0.elapsed_time(e1)
+        steps = min(args.steps, n_frames - f - 1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d = 0
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            fork(e0)
+            for _ in range(steps):
+                h2d += int(counts[f].sum()) * (12 if kind == "xyz" else 16) + B * 4
+                step_host(f); f += 1
+            drain_poses()
+            join()
+            e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), steps, h2d
+
+    alt_kind = "xyzi" if args.e2e_input == "xyz" else "xyz"
+    alt_ms, alt_steps, alt_h2d = run_e2e(alt_kind)
+    e2e_ms, e2e_steps, h2d = run_e2e(args.e2e_input)
     clocks = sampler.stop(t_begin, t_end)
     if clocks.get("samples", 0) == 0:
         clocks = sampler.stop()  # timed region shorter than one sample: report the whole run
 
     # ---- max over ranks ----
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_ms, alt_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     value, dev_ms = aggregate_throughput(world, B, args.steps, float(times[0]))
     e2e_value, e2e_ms = aggregate_throughput(world, B, e2e_steps, float(times[1]))
+    alt_value, alt_ms = aggregate_throughput(world, B, alt_steps, float(times[2]))
 
     if rank == 0:
         peaks = {}
@@ -607,7 +625,11 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, params, B, "gpu"),
             "p50_scan_latency_ms": latency["p50_ms"] if latency else None, "latency_single_sequence": latency,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, e2e_steps),
-                    "d2h_bytes_per_step": B * 6 * 4 * 3, "steps": e2e_steps, "ms_per_step": e2e_ms / max(1, e2e_steps)},
+                    "d2h_bytes_per_step": B * 6 * 4 * 3, "steps": e2e_steps, "ms_per_step": e2e_ms / max(1, e2e_steps),
+                    "host_points": args.e2e_input},
+            "e2e_alt": {"value": alt_value, "unit": UNIT, "h2d_bytes_per_step": alt_h2d // max(1, alt_steps),
+                        "d2h_bytes_per_step": B * 6 * 4 * 3, "steps": alt_steps, "ms_per_step": alt_ms / max(1, alt_steps),
+                        "host_points": alt_kind},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,

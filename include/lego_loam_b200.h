@@ -158,6 +158,11 @@ int64_t ll_kernel_launches(const ll_handle* h);
  * memory is pinned): the next ll_image_projection consumes it, and calling ll_set_scans_host for scan
  * f+1 before reading back the results of scan f overlaps that copy with the kernels of scan f. */
 int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, int stride_points);
+/* Same with packed 12-byte points, xyz[batch][stride_points][3] floats: three quarters of the host->device bytes.
+ * The path never reads the intensity a sensor reports -- projectPointCloud overwrites it with row + col / 10000
+ * (imageProjection.cpp:216) before anything uses it -- so every output is identical to ll_set_scans_host's.
+ * LL_BUF_INPUT_CLOUD then returns 3 floats per point. */
+int ll_set_scans_xyz_host(ll_handle* h, const float* xyz, const int32_t* n_points, int stride_points);
 /* sensor_msgs/PointCloud2 ingest: pcl::fromROSMsg + pcl::removeNaNFromPointCloud of
  * imageProjection.cpp:159-161 on the device.  data: the messages' `data` arrays, [batch][stride_bytes] host bytes;
  * n_points[batch] = width * height; point_step and the byte offsets of the FLOAT32 fields x, y, z, intensity as listed

@@ -41,7 +41,7 @@ EXPORTS = [
     "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
     "ll_get_kernel_time_table",
     "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
-    "ll_map_download_keyframe", "ll_set_scans_pointcloud2_host",
+    "ll_map_download_keyframe", "ll_set_scans_pointcloud2_host", "ll_set_scans_xyz_host",
 ]
 
 _lib = None
@@ -71,6 +71,7 @@ def load_library(path=None):
     lib.ll_kernel_launches.argtypes = [vp]
     lib.ll_kernel_launches.restype = C.c_int64
     lib.ll_set_scans_host.argtypes = [vp, vp, vp, ip]
+    lib.ll_set_scans_xyz_host.argtypes = [vp, vp, vp, ip]
     lib.ll_set_scans_device.argtypes = [vp, vp, vp, ip]
     lib.ll_map_set_initial_guess_async.argtypes = [vp, vp]
     lib.ll_map_set_poses.argtypes = [vp, vp, vp]
@@ -148,12 +149,37 @@ class LegoLoam:
                 counts[i] = len(s)
         counts = np.ascontiguousarray(counts, np.int32)
         self._keep = (packed, counts)
+        self._in_width = 4
         self._ck(self.lib.ll_set_scans_host(self.h, packed.ctypes.data, counts.ctypes.data, packed.shape[1]),
                  "ll_set_scans_host")
 
     def set_scans_host_ptr(self, ptr, counts, stride):
         counts = np.ascontiguousarray(counts, np.int32)
+        self._in_width = 4
         self._ck(self.lib.ll_set_scans_host(self.h, ptr, counts.ctypes.data, stride), "ll_set_scans_host")
+
+    def set_scans_xyz_host(self, scans):
+        """Packed 12-byte points: list (len batch) of float32 [n_i, 3] arrays, or (packed [batch, stride, 3], counts)."""
+        if isinstance(scans, tuple):
+            packed, counts = scans
+        else:
+            stride = max(1, max(len(s) for s in scans))
+            packed = np.zeros((self.batch, stride, 3), np.float32)
+            counts = np.zeros(self.batch, np.int32)
+            for i, s in enumerate(scans):
+                packed[i, :len(s)] = np.asarray(s, np.float32)[:, :3]
+                counts[i] = len(s)
+        packed = np.ascontiguousarray(packed, np.float32)
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._keep = (packed, counts)
+        self._in_width = 3
+        self._ck(self.lib.ll_set_scans_xyz_host(self.h, packed.ctypes.data, counts.ctypes.data, packed.shape[1]),
+                 "ll_set_scans_xyz_host")
+
+    def set_scans_xyz_host_ptr(self, ptr, counts, stride):
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._in_width = 3
+        self._ck(self.lib.ll_set_scans_xyz_host(self.h, ptr, counts.ctypes.data, stride), "ll_set_scans_xyz_host")
 
     def set_scans_pointcloud2(self, messages, point_step, off_x, off_y, off_z, off_intensity, is_dense=False):
         """messages: list (len batch) of uint8 arrays, the `data` of one sensor_msgs/PointCloud2 each."""
@@ -255,6 +281,8 @@ class LegoLoam:
 
     def download(self, name, seq=0):
         bid, dt, w = BUFFERS[name]
+        if name == "INPUT_CLOUD":
+            w = getattr(self, "_in_width", 4)   # packed xyz scans come back as they went in
         n = C.c_size_t(0)
         self._ck(self.lib.ll_download(self.h, seq, bid, None, 0, C.byref(n)), f"ll_download({name})")
         out = np.empty((n.value, w) if w > 1 else (n.value,), dt)
@@ -328,6 +356,10 @@ class LegoLoamStreams:
     def set_scans_host_ptr(self, ptr, counts, stride):
         for i, p in enumerate(self.parts):
             p.set_scans_host_ptr(ptr + i * self.sub * stride * 16, counts[i * self.sub:(i + 1) * self.sub], stride)
+
+    def set_scans_xyz_host_ptr(self, ptr, counts, stride):
+        for i, p in enumerate(self.parts):
+            p.set_scans_xyz_host_ptr(ptr + i * self.sub * stride * 12, counts[i * self.sub:(i + 1) * self.sub], stride)
 
     def process_scans(self):
         return [p.process_scans() for p in self.parts][0]

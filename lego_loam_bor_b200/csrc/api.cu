@@ -39,6 +39,7 @@ struct ll_handle {
   size_t raw_stride = 0;
   int* n_raw_buf[2] = {nullptr, nullptr};
   int* pc2_tile_cnt = nullptr;
+  bool buf_xyz3[2] = {false, false};  // the staged scans are packed 12-byte points (ll_set_scans_xyz_host)
   int wr = 0;        // buffer the next ll_set_scans_host writes
   int pending = -1;  // buffer waiting to be consumed by ll_image_projection
   bool timing = false;
@@ -349,6 +350,29 @@ int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, 
                        (size_t)n_points[s] * 16, cudaMemcpyHostToDevice, h->copy_stream));
   }
   CK(cudaEventRecord(h->copied[b], h->copy_stream));
+  h->buf_xyz3[b] = false;
+  h->pending = b;
+  h->wr ^= 1;
+  return LL_OK;
+}
+
+int ll_set_scans_xyz_host(ll_handle* h, const float* xyz, const int32_t* n_points, int stride_points) {
+  if (!h || !xyz || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  const int B = st.p.B;
+  if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_xyz_host: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
+  const int b = h->wr;
+  if (h->consumed_valid[b]) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[b], 0));
+  { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_xyz_host", h->n_in_buf[b], h->copy_stream); if (rc) return rc; }
+  // the same input buffer, packed: sequence s starts at float 3 * s * max_pts
+  float* dst = reinterpret_cast<float*>(h->in_buf[b]);
+  for (int s = 0; s < B; ++s) {
+    if (n_points[s] == 0) continue;
+    CK(cudaMemcpyAsync(dst + (size_t)s * st.p.max_pts * 3, xyz + (size_t)s * stride_points * 3,
+                       (size_t)n_points[s] * 12, cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  CK(cudaEventRecord(h->copied[b], h->copy_stream));
+  h->buf_xyz3[b] = true;
   h->pending = b;
   h->wr ^= 1;
   return LL_OK;
@@ -393,6 +417,7 @@ int ll_set_scans_pointcloud2_host(ll_handle* h, const uint8_t* data, const int32
   a.tile_cnt = h->pc2_tile_cnt; a.ntiles = (st.p.max_pts + pc2_tile_points() - 1) / pc2_tile_points();
   launch_decode_pointcloud2(h->ctx, h->copy_stream, B, a);
   CK(cudaEventRecord(h->copied[b], h->copy_stream));
+  h->buf_xyz3[b] = false;
   h->pending = b;
   h->wr ^= 1;
   return check_stream(h, "ll_set_scans_pointcloud2_host");
@@ -406,6 +431,7 @@ int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_po
   st.n_in = h->n_in_default;
   st.in_pts = (const float4*)xyzi_dev;
   st.in_stride = stride_points;
+  st.in_xyz3 = 0;
   h->pending = -1;
   return LL_OK;
 }
@@ -419,6 +445,7 @@ int ll_image_projection(ll_handle* h) {
     h->st.in_pts = h->in_buf[pb];
     h->st.n_in = h->n_in_buf[pb];
     h->st.in_stride = h->st.p.max_pts;
+    h->st.in_xyz3 = h->buf_xyz3[pb] ? 1 : 0;
     h->pending = -1;
   }
   if (!h->st.in_pts) { h->err = "ll_image_projection: no scans set"; return LL_ERR_STATE; }
@@ -859,7 +886,10 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       const int stride = h->pending >= 0 ? st.p.max_pts : st.in_stride;
       if (!buf) return LL_ERR_STATE;
       if (h->pending >= 0) CK(cudaStreamSynchronize(h->copy_stream));
-      COUNTED(buf, 16, (size_t)stride, cntp + seq);
+      // packed scans (ll_set_scans_xyz_host) come back as they went in: 3 floats per point
+      const bool xyz3 = h->pending >= 0 ? h->buf_xyz3[h->pending] : st.in_xyz3 != 0;
+      if (xyz3) COUNTED(buf, 12, (size_t)stride, cntp + seq);
+      else COUNTED(buf, 16, (size_t)stride, cntp + seq);
       break;
     }
     case LL_BUF_KEYFRAME_STATE: {

@@ -93,8 +93,9 @@ struct DevParams {
 struct DevState {
   DevParams p;
   // ---- input ----
-  const float4* in_pts;  // [B][in_stride]
+  const float4* in_pts;  // [B][in_stride] (x, y, z, intensity), or packed (x, y, z) floats when in_xyz3 is set
   int in_stride;
+  int in_xyz3;           // ll_set_scans_xyz_host: 12-byte points (the path never reads the input intensity)
   int* n_in;             // [B]
   uint32_t frame_tag;    // increases every frame; makes `winner` self-clearing
   // ---- ImageProjection ----

@@ -78,11 +78,20 @@ __device__ __forceinline__ bool project_cell(const DevParams& p, const float4 pt
   return true;
 }
 
+// input point i of sequence s; the intensity the sensor reported is never read (imageProjection.cpp:216 overwrites it)
+__device__ __forceinline__ float4 ld_in(const DevState& st, int s, uint32_t i) {
+  if (st.in_xyz3) {
+    const float* q = reinterpret_cast<const float*>(st.in_pts) + ((size_t)s * st.in_stride + i) * 3;
+    return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+  }
+  return ld_pt(st.in_pts + (size_t)s * st.in_stride + i);
+}
+
 __global__ void __launch_bounds__(256) k_project_scatter(DevState st) {
   const int s = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st.n_in[s]) return;
-  const float4 pt = ld_pt(st.in_pts + (size_t)s * st.in_stride + i);
+  const float4 pt = ld_in(st, s, (uint32_t)i);
   int row, col;
   float range;
   if (!project_cell(st.p, pt, &row, &col, &range)) return;
@@ -99,7 +108,7 @@ __device__ __forceinline__ CellVal load_cell(const DevState& st, int s, int row,
   CellVal c;
   const unsigned long long w = st.winner[(size_t)s * st.p.N + row * st.p.H + col];
   if ((uint32_t)(w >> 32) == st.frame_tag) {
-    const float4 q = ld_pt(st.in_pts + (size_t)s * st.in_stride + (uint32_t)w);
+    const float4 q = ld_in(st, s, (uint32_t)w);
     c.range = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
     // intensity = (float)row + (float)col / 10000.0 in double (imageProjection.cpp:216)
     c.pt = make_float4(q.x, q.y, q.z, (float)((double)(float)row + (double)(float)col / 10000.0));
@@ -139,8 +148,8 @@ __global__ void __launch_bounds__(128) k_gather_ground(DevState st) {
     const int n = st.n_in[s];
     float so = 0.f, eo = 0.f, diff = 0.f;
     if (n > 0) {
-      const float4 a = ld_pt(st.in_pts + (size_t)s * st.in_stride);
-      const float4 b = ld_pt(st.in_pts + (size_t)s * st.in_stride + (n - 1));
+      const float4 a = ld_in(st, s, 0u);
+      const float4 b = ld_in(st, s, (uint32_t)(n - 1));
       so = -ll_atan2f(a.y, a.x);
       eo = (float)((double)(-ll_atan2f(b.y, b.x)) + 2.0 * LL_PI);
       if ((double)(eo - so) > 3.0 * LL_PI) {

@@ -73,3 +73,37 @@ def test_device_decode_and_projection(built):
     # without the intensity field
     gpu.set_scans_pointcloud2(msgs, 22, 0, 4, 8, -1)
     assert np.all(gpu.download("INPUT_CLOUD", 0)[:, 3] == 0)
+
+
+@pytest.mark.gpu
+def test_packed_xyz_scans_match_xyzi(built):
+    """ll_set_scans_xyz_host (12-byte points) against the oracle fed with the same scans as x, y, z, intensity: the
+    reported intensity is overwritten by projectPointCloud (imageProjection.cpp:216) before anything reads it, so every
+    output of the path is identical.  Ragged batch incl. an empty and a one-point scan, two frames (the input is double
+    buffered), then the whole path through ll_process_scans."""
+    from lego_loam_bor_b200.capi import LegoLoam
+    from oracle.oracle_py import Oracle
+    from parity_utils import make_scans, same_bits
+    p, cfg, scans = make_scans("A", [0, 1], [0, 1, 2])
+    seqs = [lambda f: scans[(0, f)], lambda f: scans[(1, f)][:9001], lambda f: scans[(0, f)][:0], lambda f: scans[(1, f)][:1]]
+    gpu = LegoLoam(p, batch=len(seqs))
+    oracles = [Oracle(p) for _ in seqs]
+    for f in range(3):
+        batch = [np.ascontiguousarray(s(f)) for s in seqs]
+        gpu.set_scans_xyz_host([b[:, :3] for b in batch])
+        for k, b in enumerate(batch):
+            got = gpu.download("INPUT_CLOUD", k)
+            assert got.shape == (len(b), 3) and same_bits(got, np.ascontiguousarray(b[:, :3]))
+        gpu.process_scans()
+        for k, b in enumerate(batch):
+            o = oracles[k]
+            noisy = b.copy()
+            noisy[:, 3] = 255.0 * ((np.arange(len(b)) * 37) % 101) / 100.0   # whatever the sensor reported
+            o.image_projection(noisy)
+            o.feature_association()
+            for name in ("RANGE_MAT", "FULL_CLOUD", "GROUND_MAT", "LABEL_MAT", "SEG_CLOUD", "SEG_COL_IND", "SURF_LAST", "CORNER_LAST"):
+                assert same_bits(gpu.download(name, k), o.download(name)), f"frame {f} seq {k}: {name}"
+            assert same_bits(gpu.download("TRANSFORM_SUM", k), o.download("TRANSFORM_SUM")), f"frame {f} seq {k}: pose"
+    # switching back to 16-byte points on the same handle
+    gpu.set_scans_host([np.ascontiguousarray(s(2)) for s in seqs])
+    assert gpu.download("INPUT_CLOUD", 0).shape == (len(seqs[0](2)), 4)
