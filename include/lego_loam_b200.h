@@ -258,6 +258,19 @@ int ll_get_poses(ll_handle* h, float* transform_sum, float* transform_cur, float
  * ll_wait_poses waits for the oldest one. */
 int ll_get_poses_async(ll_handle* h, float* transform_sum, float* transform_cur, float* transform_tobe_mapped);
 int ll_wait_poses(ll_handle* h);
+/* nav_msgs/Odometry form of a pose.  pose7 = position x, y, z, orientation x, y, z, w as
+ * FeatureAssociation::publishOdometry (featureAssociation.cpp:1286-1298) and MapOptimization::publishTF
+ * (mapOptmization.cpp:510-522) fill them: tf::createQuaternionMsgFromRollPitchYaw(t[2], -t[0], -t[1]) in double, then
+ * (x, y, z, w) = (-q.y, -q.z, q.x, q.w).  ll_odometry_to_transform is the consumer's side, OdometryToTransform of
+ * utility.h:96-110 (tf::Matrix3x3(tf::Quaternion(z, -x, -y, w)).getRPY).  Pure host functions, no handle needed.
+ * tf is not vendored in the reference tree: setRPY / getRPY are restated from its published LinearMath sources. */
+void ll_transform_to_odometry(const float* transform6, double* pose7);
+void ll_odometry_to_transform(const double* pose7, float* transform6);
+/* The two odometry messages of the path for every sequence (either pointer may be NULL): laser_odometry f64[batch][7]
+ * from transformSum (/laser_odom_to_init), odom_aft_mapped f64[batch][13] = pose7 of transformAftMapped followed by
+ * twist.angular = transformBefMapped[0..2], twist.linear = transformBefMapped[3..5] (mapOptmization.cpp:524-529).
+ * Synchronises the stream. */
+int ll_get_odometry(ll_handle* h, double* laser_odometry, double* odom_aft_mapped);
 /* Copy one array of one sequence to host.  *n_elems receives the element count
  * (points for "pt" buffers).  dst may be NULL to query the count only.
  * Synchronises the stream. */

@@ -42,6 +42,7 @@ EXPORTS = [
     "ll_get_kernel_time_table",
     "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
     "ll_map_download_keyframe", "ll_set_scans_pointcloud2_host", "ll_set_scans_xyz_host",
+    "ll_transform_to_odometry", "ll_odometry_to_transform", "ll_get_odometry",
 ]
 
 _lib = None
@@ -49,6 +50,22 @@ _lib = None
 
 class LegoLoamError(RuntimeError):
     pass
+
+
+def transform_to_odometry(t6):
+    """ll_transform_to_odometry: pose 6-vector -> position + orientation quaternion (host function, no GPU needed)."""
+    t = np.ascontiguousarray(t6, np.float32)
+    o = np.zeros(7, np.float64)
+    load_library().ll_transform_to_odometry(t.ctypes.data, o.ctypes.data)
+    return o
+
+
+def odometry_to_transform(o7):
+    """ll_odometry_to_transform: OdometryToTransform of utility.h:96-110."""
+    o = np.ascontiguousarray(o7, np.float64)
+    t = np.zeros(6, np.float32)
+    load_library().ll_odometry_to_transform(o.ctypes.data, t.ctypes.data)
+    return t
 
 
 def load_library(path=None):
@@ -72,6 +89,11 @@ def load_library(path=None):
     lib.ll_kernel_launches.restype = C.c_int64
     lib.ll_set_scans_host.argtypes = [vp, vp, vp, ip]
     lib.ll_set_scans_xyz_host.argtypes = [vp, vp, vp, ip]
+    lib.ll_transform_to_odometry.argtypes = [vp, vp]
+    lib.ll_transform_to_odometry.restype = None
+    lib.ll_odometry_to_transform.argtypes = [vp, vp]
+    lib.ll_odometry_to_transform.restype = None
+    lib.ll_get_odometry.argtypes = [vp, vp, vp]
     lib.ll_set_scans_device.argtypes = [vp, vp, vp, ip]
     lib.ll_map_set_initial_guess_async.argtypes = [vp, vp]
     lib.ll_map_set_poses.argtypes = [vp, vp, vp]
@@ -272,6 +294,13 @@ class LegoLoam:
         self._ck(self.lib.ll_get_poses(self.h, ts.ctypes.data, tc.ctypes.data, tm.ctypes.data), "ll_get_poses")
         return ts, tc, tm
 
+    def odometry(self):
+        """(laser_odometry f64[batch, 7], odom_aft_mapped f64[batch, 13]): the nav_msgs/Odometry fields of the path."""
+        lo = np.zeros((self.batch, 7), np.float64)
+        am = np.zeros((self.batch, 13), np.float64)
+        self._ck(self.lib.ll_get_odometry(self.h, lo.ctypes.data, am.ctypes.data), "ll_get_odometry")
+        return lo, am
+
     def poses_async(self, ts_ptr, tc_ptr, tm_ptr):
         """Enqueue the pose copies into caller-owned (pinned) float32 [batch, 6] buffers given as raw addresses."""
         self._ck(self.lib.ll_get_poses_async(self.h, ts_ptr, tc_ptr, tm_ptr), "ll_get_poses_async")
@@ -385,6 +414,13 @@ class LegoLoamStreams:
     def synchronize(self):
         for p in self.parts:
             p.synchronize()
+
+    def odometry(self):
+        """(laser_odometry f64[batch, 7], odom_aft_mapped f64[batch, 13]): the nav_msgs/Odometry fields of the path."""
+        lo = np.zeros((self.batch, 7), np.float64)
+        am = np.zeros((self.batch, 13), np.float64)
+        self._ck(self.lib.ll_get_odometry(self.h, lo.ctypes.data, am.ctypes.data), "ll_get_odometry")
+        return lo, am
 
     def poses_async(self, ts_ptr, tc_ptr, tm_ptr):
         for i, p in enumerate(self.parts):

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of include/lego_loam_b200.h: handle lifetime, device memory, stage sequencing.
 // No CPU fallback anywhere: without a usable CUDA device ll_create fails with LL_ERR_NO_DEVICE.
 #include <math.h>
+#include <cmath>
 #include <stdio.h>
 #include <string.h>
 
@@ -718,6 +719,67 @@ int ll_get_poses(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   if (tcur) CK(cudaMemcpyAsync(tcur, h->st.transform_cur, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+// tf::Quaternion::setRPY (tf/LinearMath/Quaternion.h) on (roll, pitch, yaw) = (t[2], -t[0], -t[1]), then the axis
+// shuffle of featureAssociation.cpp:1290-1296 / mapOptmization.cpp:516-522
+void ll_transform_to_odometry(const float* t, double* o) {
+  const double roll = (double)t[2], pitch = (double)(-t[0]), yaw = (double)(-t[1]);
+  const double hy = yaw * 0.5, hp = pitch * 0.5, hr = roll * 0.5;
+  const double cy = std::cos(hy), sy = std::sin(hy), cp = std::cos(hp), sp = std::sin(hp), cr = std::cos(hr), sr = std::sin(hr);
+  const double qx = sr * cp * cy - cr * sp * sy;
+  const double qy = cr * sp * cy + sr * cp * sy;
+  const double qz = cr * cp * sy - sr * sp * cy;
+  const double qw = cr * cp * cy + sr * sp * sy;
+  o[0] = t[3]; o[1] = t[4]; o[2] = t[5];
+  o[3] = -qy; o[4] = -qz; o[5] = qx; o[6] = qw;
+}
+
+// utility.h:96-110: tf::Matrix3x3(tf::Quaternion(o.z, -o.x, -o.y, o.w)).getRPY(roll, pitch, yaw) (Matrix3x3::setRotation
+// + getEulerYPR, solution 1), transform = (-pitch, -yaw, roll, position)
+void ll_odometry_to_transform(const double* o, float* t) {
+  const double x = o[5], y = -o[3], z = -o[4], w = o[6];
+  const double d = x * x + y * y + z * z + w * w;
+  const double s = 2.0 / d;
+  const double xs = x * s, ys = y * s, zs = z * s;
+  const double wx = w * xs, wy = w * ys, wz = w * zs;
+  const double xx = x * xs, xy = x * ys, xz = x * zs;
+  const double yy = y * ys, yz = y * zs, zz = z * zs;
+  const double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+  const double m01 = xy - wz, m02 = xz + wy;
+  double roll, pitch, yaw;
+  if (std::fabs(m20) >= 1.0) {  // gimbal lock branch of getEulerYPR
+    yaw = 0.0;
+    const double delta = std::atan2(m21, m22);
+    if (m20 < 0.0) { pitch = 3.14159265358979323846 / 2.0; roll = delta; }
+    else { pitch = -3.14159265358979323846 / 2.0; roll = delta; }
+    (void)m01; (void)m02;
+  } else {
+    pitch = -std::asin(m20);
+    roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+    yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+  }
+  t[0] = (float)(-pitch); t[1] = (float)(-yaw); t[2] = (float)roll;
+  t[3] = (float)o[0]; t[4] = (float)o[1]; t[5] = (float)o[2];
+}
+
+int ll_get_odometry(ll_handle* h, double* laser_odometry, double* odom_aft_mapped) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  const int B = h->st.p.B;
+  std::vector<float> ts((size_t)B * 6), ta((size_t)B * 6), tb((size_t)B * 6);
+  CK(cudaMemcpyAsync(ts.data(), h->st.transform_sum, (size_t)B * 24, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaMemcpyAsync(ta.data(), h->st.transform_aft_mapped, (size_t)B * 24, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaMemcpyAsync(tb.data(), h->st.transform_bef_mapped, (size_t)B * 24, cudaMemcpyDeviceToHost, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  for (int s = 0; s < B; ++s) {
+    if (laser_odometry) ll_transform_to_odometry(&ts[(size_t)s * 6], laser_odometry + (size_t)s * 7);
+    if (odom_aft_mapped) {
+      double* o = odom_aft_mapped + (size_t)s * 13;
+      ll_transform_to_odometry(&ta[(size_t)s * 6], o);
+      for (int k = 0; k < 6; ++k) o[7 + k] = (double)tb[(size_t)s * 6 + k];
+    }
+  }
   return LL_OK;
 }
 

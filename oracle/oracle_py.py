@@ -235,3 +235,38 @@ def knn(cloud, query, k, nanoflann=True, prefer_ref=True):
     d2 = np.empty((len(query), k), np.float32)
     lib.lo_knn(cloud.ctypes.data, len(cloud), query.ctypes.data, len(query), k, idx.ctypes.data, d2.ctypes.data)
     return idx, d2
+
+
+# ---- nav_msgs/Odometry form of a pose; tf is not vendored: parity unpinned ----
+def _quat_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], np.float64)
+
+
+def transform_to_odometry(t6):
+    """featureAssociation.cpp:1286-1298 / mapOptmization.cpp:510-522: position x, y, z + orientation x, y, z, w.
+    tf::createQuaternionMsgFromRollPitchYaw(t[2], -t[0], -t[1]) written as the product Rz(yaw) Ry(pitch) Rx(roll)."""
+    t = np.asarray(t6, np.float32)
+    roll, pitch, yaw = np.float64(t[2]), np.float64(-t[0]), np.float64(-t[1])
+    qx = np.array([np.sin(roll / 2), 0, 0, np.cos(roll / 2)])
+    qy = np.array([0, np.sin(pitch / 2), 0, np.cos(pitch / 2)])
+    qz = np.array([0, 0, np.sin(yaw / 2), np.cos(yaw / 2)])
+    q = _quat_mul(_quat_mul(qz, qy), qx)
+    return np.array([t[3], t[4], t[5], -q[1], -q[2], q[0], q[3]], np.float64)
+
+
+def odometry_to_transform(o7):
+    """utility.h:96-110: tf::Matrix3x3(tf::Quaternion(o.z, -o.x, -o.y, o.w)).getRPY, transform = (-pitch, -yaw, roll, pos)."""
+    o = np.asarray(o7, np.float64)
+    x, y, z, w = o[5], -o[3], -o[4], o[6]
+    n = x * x + y * y + z * z + w * w
+    x, y, z, w = np.array([x, y, z, w]) / np.sqrt(n)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    pitch = -np.arcsin(R[2, 0])
+    roll = np.arctan2(R[2, 1], R[2, 2])
+    yaw = np.arctan2(R[1, 0], R[0, 0])
+    return np.array([-pitch, -yaw, roll, o[0], o[1], o[2]]).astype(np.float32)
