@@ -41,10 +41,22 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
   return x;
 }
 
+// both roots at once: the two chains of dependent loads are walked in lock step, so a union waits for the longer chain
+// instead of the sum of the two (this kernel is bound by the latency of these loads)
+__device__ __forceinline__ void uf_find2(int* parent, int& a, int& b) {
+  int pa = __ldcg(parent + a), pb = __ldcg(parent + b);
+  while (pa != a || pb != b) {
+    const int ga = __ldcg(parent + pa), gb = __ldcg(parent + pb);
+    if (pa != a && ga != pa) parent[a] = ga;  // path halving; any ancestor is a valid parent
+    if (pb != b && gb != pb) parent[b] = gb;
+    a = pa; pa = ga;
+    b = pb; pb = gb;
+  }
+}
+
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
+    uf_find2(parent, a, b);
     if (a == b) return;
     if (a > b) { const int t = a; a = b; b = t; }
     const int old = atomicMin(parent + b, a);  // link the larger root under the smaller
