@@ -46,7 +46,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(CSRC, "build", os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", src, "-o", obj]
+        # LEGO_LOAM_B200_NVCC_EXTRA: extra flags (e.g. -DSEG_TRIPS=8) for A/B builds
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("LEGO_LOAM_B200_NVCC_EXTRA", "").split() + ["-I", INCLUDE, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, pr in procs:

@@ -248,9 +248,50 @@ __global__ void __launch_bounds__(256) k_seg_count(DevState st) {
   if (threadIdx.x < 3) st.tile_counts[((size_t)s * p.V + row) * 4 + threadIdx.x] = sh_cnt[threadIdx.x];
 }
 
+#ifndef SEG_TRIPS
+#define SEG_TRIPS 4
+#endif
+
+// SEG_TRIPS block-wide exclusive scans at once (256 threads): one pair of barriers for all of them
+__device__ __forceinline__ void block_exclusive_scan_trips(const int (&v)[SEG_TRIPS], int (&ex)[SEG_TRIPS], int (&total)[SEG_TRIPS],
+                                                           int (*sh)[SEG_TRIPS]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc[SEG_TRIPS];
+#pragma unroll
+  for (int t = 0; t < SEG_TRIPS; ++t) {
+    inc[t] = v[t];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, inc[t], o);
+      if (lane >= o) inc[t] += x;
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int t = 0; t < SEG_TRIPS; ++t) sh[wid][t] = inc[t];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < SEG_TRIPS; ++t) {
+    int pre = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+      const int x = sh[w][t];
+      if (w < wid) pre += x;
+      tot += x;
+    }
+    ex[t] = pre + inc[t] - v[t];
+    total[t] = tot;
+  }
+  __syncthreads();
+}
+
+// One block per (sequence, row).  The row is handled SEG_TRIPS x 256 columns at a time: the classification of all those
+// cells (a chain of dependent loads each: parent -> component size -> row mask), then the points of the kept cells and
+// their orientation, are in flight together, and one multi-scan orders them; the kernel is a single wave of blocks, so its
+// duration is the latency of one block.
 __global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
   __shared__ int sh_pre[3];
-  __shared__ int warp_tot[33];
+  __shared__ int sh_scan[8][SEG_TRIPS];
   const DevParams& p = st.p;
   const int row = blockIdx.x, s = blockIdx.y;
   const size_t base = (size_t)s * p.N;
@@ -266,40 +307,67 @@ __global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
   int run_root = sh_pre[0], run_keep = sh_pre[1], run_out = sh_pre[2];
   const int keep_before_row = run_keep;
   const float start_ori = st.orientation[s * 4 + 0];
-  for (int c0 = 0; c0 < p.H; c0 += blockDim.x) {
-    const int col = c0 + threadIdx.x;
-    const int f = col < p.H ? classify_cell(st, base, row, col) : 0;
-    // one packed scan for the three flags (each partial sum <= 256 < 2^10)
-    const int packed = (f & 1) | (((f >> 1) & 1) << 10) | (((f >> 2) & 1) << 20);
-    int total;
-    const int ex = block_exclusive_scan(packed, warp_tot, &total);
-    const int cell = row * p.H + col;
-    if (f & 1) st.label_mat[base + cell] = run_root + (ex & 1023) + 1;
-    if (f & 2) {
-      const int pos = run_keep + ((ex >> 10) & 1023);
-      const float4 pt = st.full_cloud[base + cell];
-      st.seg_cloud[base + pos] = pt;
-      st.seg_range[base + pos] = st.range_mat[base + cell];
-      st.seg_col[base + pos] = (uint32_t)col;
-      st.seg_ground[base + pos] = st.ground_mat[base + cell] == 1 ? 1 : 0;
-      // adjustDistortion's sequential halfPassed flag (featureAssociation.cpp:162,173-187): the flag
-      // flips at the FIRST segmented point whose branch-1 orientation is more than pi past the start;
-      // record candidates here, k_feature_prep reads the minimum.
-      float ori = -ll_atan2f(pt.y, pt.x);  // point.x = seg.y, point.z = seg.x after the axis swap
-      st.seg_ori[base + pos] = ori;        // adjustDistortion's raw orientation, reused by k_feature_prep
-      if ((double)ori < (double)start_ori - LL_PI / 2)
-        ori = (float)((double)ori + 2 * LL_PI);
-      else if ((double)ori > (double)start_ori + LL_PI * 3 / 2)
-        ori = (float)((double)ori - 2 * LL_PI);
-      if ((double)(ori - start_ori) > LL_PI) atomicMin(st.half_idx + s, pos);
+  for (int c0 = 0; c0 < p.H; c0 += 256 * SEG_TRIPS) {
+    int f[SEG_TRIPS], packed[SEG_TRIPS];
+#pragma unroll
+    for (int t = 0; t < SEG_TRIPS; ++t) {
+      const int col = c0 + t * 256 + threadIdx.x;
+      f[t] = col < p.H ? classify_cell(st, base, row, col) : 0;
+      // one packed scan for the three flags (each partial sum <= 256 < 2^10)
+      packed[t] = (f[t] & 1) | (((f[t] >> 1) & 1) << 10) | (((f[t] >> 2) & 1) << 20);
     }
-    if (f & 4) {
-      const int pos = run_out + ((ex >> 20) & 1023);
-      if (pos < st.cap_outlier) st.outlier_cloud[(size_t)s * st.cap_outlier + pos] = st.full_cloud[base + cell];
+    float4 pt[SEG_TRIPS];
+    float rng[SEG_TRIPS], ori_raw[SEG_TRIPS];
+    bool gnd[SEG_TRIPS];
+#pragma unroll
+    for (int t = 0; t < SEG_TRIPS; ++t) {
+      const int cell = row * p.H + c0 + t * 256 + threadIdx.x;
+      pt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rng[t] = 0.f;
+      gnd[t] = false;
+      if (f[t] & 6) pt[t] = st.full_cloud[base + cell];
+      if (f[t] & 2) {
+        rng[t] = st.range_mat[base + cell];
+        gnd[t] = st.ground_mat[base + cell] == 1;
+      }
     }
-    run_root += total & 1023;
-    run_keep += (total >> 10) & 1023;
-    run_out += (total >> 20) & 1023;
+#pragma unroll
+    for (int t = 0; t < SEG_TRIPS; ++t) {
+      ori_raw[t] = 0.f;
+      if (f[t] & 2) ori_raw[t] = -ll_atan2f(pt[t].y, pt[t].x);  // point.x = seg.y, point.z = seg.x after the axis swap
+    }
+    int ex[SEG_TRIPS], total[SEG_TRIPS];
+    block_exclusive_scan_trips(packed, ex, total, sh_scan);
+#pragma unroll
+    for (int t = 0; t < SEG_TRIPS; ++t) {
+      const int col = c0 + t * 256 + threadIdx.x;
+      const int cell = row * p.H + col;
+      if (f[t] & 1) st.label_mat[base + cell] = run_root + (ex[t] & 1023) + 1;
+      if (f[t] & 2) {
+        const int pos = run_keep + ((ex[t] >> 10) & 1023);
+        st.seg_cloud[base + pos] = pt[t];
+        st.seg_range[base + pos] = rng[t];
+        st.seg_col[base + pos] = (uint32_t)col;
+        st.seg_ground[base + pos] = gnd[t] ? 1 : 0;
+        // adjustDistortion's sequential halfPassed flag (featureAssociation.cpp:162,173-187): the flag
+        // flips at the FIRST segmented point whose branch-1 orientation is more than pi past the start;
+        // record candidates here, k_feature_prep reads the minimum.
+        float ori = ori_raw[t];
+        st.seg_ori[base + pos] = ori;        // adjustDistortion's raw orientation, reused by k_feature_prep
+        if ((double)ori < (double)start_ori - LL_PI / 2)
+          ori = (float)((double)ori + 2 * LL_PI);
+        else if ((double)ori > (double)start_ori + LL_PI * 3 / 2)
+          ori = (float)((double)ori - 2 * LL_PI);
+        if ((double)(ori - start_ori) > LL_PI) atomicMin(st.half_idx + s, pos);
+      }
+      if (f[t] & 4) {
+        const int pos = run_out + ((ex[t] >> 20) & 1023);
+        if (pos < st.cap_outlier) st.outlier_cloud[(size_t)s * st.cap_outlier + pos] = pt[t];
+      }
+      run_root += total[t] & 1023;
+      run_keep += (total[t] >> 10) & 1023;
+      run_out += (total[t] >> 20) & 1023;
+    }
   }
   if (threadIdx.x == 0) {
     st.start_ring[s * p.V + row] = keep_before_row - 1 + 5;  // imageProjection.cpp:361
