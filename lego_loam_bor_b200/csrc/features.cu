@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
 #define LF_THREADS 256
 
 __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
-  extern __shared__ unsigned long long lf_keys[];  // [pow2(H)] then int lfpos[H]
+  extern __shared__ unsigned long long lf_keys[];  // [pow2(H)], then u16 lfpos[H] (positions relative to the ring's first), then int vox[H]
   __shared__ int warp_tot[33];
   __shared__ int sh_sp[6], sh_ep[6];
   __shared__ int sh_imn[3], sh_imx[3];
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
   int hp2 = 1;
   while (hp2 < p.H) hp2 <<= 1;
   unsigned long long* keys = lf_keys;
-  int* sm_lfpos = (int*)(lf_keys + hp2);
+  unsigned short* sm_lfpos = (unsigned short*)(lf_keys + hp2);
   const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
   const size_t rs = (size_t)s * p.V + ring;
   float4* o_lflat = st.st_less_flat + rs * p.H;
@@ -460,8 +460,9 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
   __syncthreads();
   // less-flat collection (featureAssociation.cpp:370-374): by POSITION k over the active sextants
   int n_raw = 0;
+  const int k_lo = sh_sp[0];
   {
-    const int k_lo = sh_sp[0], k_hi = sh_ep[5];
+    const int k_hi = sh_ep[5];
     int run = 0;
     for (int k0 = k_lo; k0 <= k_hi; k0 += LF_THREADS) {
       const int k = k0 + threadIdx.x;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
       }
       int total;
       const int ex = block_exclusive_scan(f, warp_tot, &total);
-      if (f) sm_lfpos[run + ex] = k;
+      if (f) sm_lfpos[run + ex] = (unsigned short)(k - k_lo);
       run += total;
     }
     n_raw = run;
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
     __syncthreads();
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) {
-      const float4 q = st.seg_cloud[base + sm_lfpos[t]];
+      const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[t]];
       mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
       mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
       mn[2] = fminf(mn[2], q.z); mx[2] = fmaxf(mx[2], q.z);
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
     const long long dz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
     if (dx * dy * dz > 2147483647LL) {
       // PCL refuses to filter (index overflow) and returns the input unchanged
-      for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) o_lflat[t] = st.seg_cloud[base + sm_lfpos[t]];
+      for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) o_lflat[t] = st.seg_cloud[base + k_lo + sm_lfpos[t]];
       n_ds = n_raw;
     } else {
       const int minb0 = (int)floorf(bmn[0] * inv), minb1 = (int)floorf(bmn[1] * inv), minb2 = (int)floorf(bmn[2] * inv);
@@ -526,10 +527,11 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
       // same voxel end up adjacent and in input order, so each voxel's float sums keep the input order.
       int pos_bits = 0;
       while ((1 << pos_bits) < n_raw) ++pos_bits;
-      int* sm_vox = sm_lfpos + p.H;              // [H] voxel index of every collected point
-      int* sm_runend = sm_vox + p.H;             // [H] end position (exclusive) of the run starting at position t
+      int* sm_vox = (int*)(sm_lfpos + ((p.H + 1) & ~1));  // [H] voxel index of every collected point
+      int* sm_runend = sm_vox;  // [H] end position (exclusive) of the run starting at position t; written only after the
+                                // last read of sm_vox (barrier after the run keys), so the two share their space
       for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) {
-        const float4 q = st.seg_cloud[base + sm_lfpos[t]];
+        const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[t]];
         const int i0 = (int)floorf(q.x * inv) - minb0;
         const int i1 = (int)floorf(q.y * inv) - minb1;
         const int i2 = (int)floorf(q.z * inv) - minb2;
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
           for (int u = t; u < n_runs && (unsigned)(keys[u] >> pos_bits) == vox; ++u) {
             const int ps = (int)((unsigned)keys[u] & pos_mask), pe = sm_runend[ps];
             for (int v = ps; v < pe; ++v) {
-              const float4 q = st.seg_cloud[base + sm_lfpos[v]];
+              const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[v]];
               cx += q.x; cy += q.y; cz += q.z; ci += q.w;
               ++cnt;
             }
@@ -671,10 +673,12 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
               k_feature_pick<<<dim3((p.V + PICK_WARPS - 1) / PICK_WARPS, p.B), PICK_WARPS * 32, smem, ctx.stream>>>(st));
   }
   {
-    const size_t smem = (size_t)next_pow2(p.H) * 8 + (size_t)p.H * 4 * 3;
+    // 28 KB at H = 2048: seven blocks per SM, so the 1024 blocks of 16 sequences x 64 rings are resident in one wave
+    const size_t smem = (size_t)next_pow2(p.H) * 8 + (size_t)((p.H + 1) & ~1) * 2 + (size_t)p.H * 4;
     static size_t configured = 0;
     if (smem > configured) {
       cudaFuncSetAttribute(k_feature_lessflat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_feature_lessflat, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       configured = smem;
     }
     LL_LAUNCH(ctx, "k_feature_lessflat", k_feature_lessflat<<<grid_rings, LF_THREADS, smem, ctx.stream>>>(st));
