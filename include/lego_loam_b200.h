@@ -296,6 +296,32 @@ int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches);
  * "name total_ms launches\n", into buf (NUL-terminated). */
 int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap);
 
+/* ---- rosbag ingest (replaces rosbag::Bag / rosbag::View of main.cpp:26-35,60-76) ---------- */
+
+/* ROS-less reader of rosbag v2.0 files: the sensor_msgs/PointCloud2 messages of one topic in record-time order, as
+ * rosbag::View hands them to ImageProjection::cloudHandler.  Uncompressed chunks only (bz2 / lz4: LL_ERR_INVALID_ARG,
+ * see ll_bag_last_error).  Pure host code; the bag format and the message layout are restated from their published
+ * specifications (ROS is not vendored in the reference tree: parity unpinned). */
+typedef struct ll_bag ll_bag;
+typedef struct {
+  uint64_t bag_time_ns;            /* record time (what rosbag::View sorts by) */
+  uint32_t stamp_sec, stamp_nsec;  /* header.stamp */
+  uint32_t height, width, point_step, row_step;
+  int32_t is_bigendian, is_dense;
+  int32_t off_x, off_y, off_z, off_intensity; /* byte offsets of the FLOAT32 fields of that name, -1 if absent */
+  const uint8_t* data;             /* points into the bag's buffer: valid until ll_bag_close */
+  uint64_t data_len;
+} ll_pointcloud2_view;
+/* topic NULL or "": the first sensor_msgs/PointCloud2 topic found in the bag (ll_bag_topic tells which). */
+int ll_bag_open(const char* path, const char* topic, ll_bag** out);
+int ll_bag_num_messages(const ll_bag* bag);
+const char* ll_bag_topic(const ll_bag* bag);
+/* Message `index` (0 .. ll_bag_num_messages-1) ready for ll_set_scans_pointcloud2_host:
+ * n_points = width * height, stride_bytes = data_len, point_step and the offsets as given. */
+int ll_bag_get_pointcloud2(const ll_bag* bag, int index, ll_pointcloud2_view* view);
+void ll_bag_close(ll_bag* bag);
+const char* ll_bag_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ EXPORTS = [
     "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
     "ll_map_download_keyframe", "ll_set_scans_pointcloud2_host", "ll_set_scans_xyz_host",
     "ll_transform_to_odometry", "ll_odometry_to_transform", "ll_get_odometry",
+    "ll_bag_open", "ll_bag_num_messages", "ll_bag_topic", "ll_bag_get_pointcloud2", "ll_bag_close", "ll_bag_last_error",
 ]
 
 _lib = None
@@ -50,6 +51,53 @@ _lib = None
 
 class LegoLoamError(RuntimeError):
     pass
+
+
+class PointCloud2View(C.Structure):
+    """ll_pointcloud2_view of include/lego_loam_b200.h"""
+    _fields_ = [("bag_time_ns", C.c_uint64), ("stamp_sec", C.c_uint32), ("stamp_nsec", C.c_uint32),
+                ("height", C.c_uint32), ("width", C.c_uint32), ("point_step", C.c_uint32), ("row_step", C.c_uint32),
+                ("is_bigendian", C.c_int32), ("is_dense", C.c_int32),
+                ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32), ("off_intensity", C.c_int32),
+                ("data", C.c_void_p), ("data_len", C.c_uint64)]
+
+
+class RosBag:
+    """ll_bag_*: the sensor_msgs/PointCloud2 messages of one topic of a rosbag v2.0 file, in time order (host code only)."""
+
+    def __init__(self, path, topic=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.ll_bag_open(os.fsencode(path), topic.encode() if topic else None, C.byref(h))
+        if rc != 0:
+            raise LegoLoamError(f"ll_bag_open({path}): {self.lib.ll_bag_last_error().decode()}")
+        self.h = h
+
+    def __len__(self):
+        return int(self.lib.ll_bag_num_messages(self.h))
+
+    @property
+    def topic(self):
+        return self.lib.ll_bag_topic(self.h).decode()
+
+    def message(self, i):
+        """(view, data): the PointCloud2 header fields and a uint8 copy of its `data` array"""
+        v = PointCloud2View()
+        if self.lib.ll_bag_get_pointcloud2(self.h, i, C.byref(v)) != 0:
+            raise LegoLoamError(f"ll_bag_get_pointcloud2({i}): {self.lib.ll_bag_last_error().decode()}")
+        data = np.ctypeslib.as_array(C.cast(v.data, C.POINTER(C.c_uint8)), shape=(int(v.data_len),)).copy() if v.data_len else np.zeros(0, np.uint8)
+        return v, data
+
+    def close(self):
+        if self.h:
+            self.lib.ll_bag_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def transform_to_odometry(t6):
@@ -94,6 +142,15 @@ def load_library(path=None):
     lib.ll_odometry_to_transform.argtypes = [vp, vp]
     lib.ll_odometry_to_transform.restype = None
     lib.ll_get_odometry.argtypes = [vp, vp, vp]
+    lib.ll_bag_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    lib.ll_bag_num_messages.argtypes = [vp]
+    lib.ll_bag_topic.argtypes = [vp]
+    lib.ll_bag_topic.restype = C.c_char_p
+    lib.ll_bag_get_pointcloud2.argtypes = [vp, ip, vp]
+    lib.ll_bag_close.argtypes = [vp]
+    lib.ll_bag_close.restype = None
+    lib.ll_bag_last_error.argtypes = []
+    lib.ll_bag_last_error.restype = C.c_char_p
     lib.ll_set_scans_device.argtypes = [vp, vp, vp, ip]
     lib.ll_map_set_initial_guess_async.argtypes = [vp, vp]
     lib.ll_map_set_poses.argtypes = [vp, vp, vp]

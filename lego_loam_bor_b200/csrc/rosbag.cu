@@ -1,0 +1,236 @@
+// rosbag.cu -- ROS-less reader of rosbag v2.0 files for the bag mode of the reference's main loop
+// (LeGO-LOAM/src/main.cpp:26-35 bag.open, :60-76 rosbag::View over the lidar topic + instantiate<sensor_msgs::PointCloud2>
+// + IP.cloudHandler).  SURVEY.md section 8 f4.  Host code only (it lives in a .cu file so that the one library build picks
+// it up).  The bag format and the ROS message serialisation are restated from their published specifications (rosbag
+// "Bag format 2.0", sensor_msgs/PointCloud2.msg); ROS is not vendored in the reference tree: parity unpinned.
+//
+// A bag is "#ROSBAG V2.0\n" followed by records; a record is <u32 header_len><header><u32 data_len><data>, a header is a
+// list of <u32 field_len><name>=<value> fields, and the `op` field tells the record type: 0x03 bag header, 0x05 chunk (its
+// data is a run of records again), 0x07 connection (topic + a second header in the data with type / md5sum /
+// message_definition), 0x02 message data (conn, time; data = the serialised message), 0x04 index data, 0x06 chunk info.
+// Only uncompressed chunks are read (compression=none, what `rosbag record` writes by default); bz2 / lz4 chunks are
+// reported as LL_ERR_INVALID_ARG with a message, because neither library may be assumed here.
+// Messages come back in record-time order (stable), like rosbag::View iterates them.
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lego_loam_b200.h"
+
+namespace {
+
+struct Span {
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+};
+
+struct Msg {
+  uint64_t time_ns;
+  size_t order;
+  Span data;
+};
+
+thread_local std::string g_bag_error;
+
+uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// header fields -> name -> value bytes; false on a malformed header
+bool parse_header(Span h, std::map<std::string, Span>* out) {
+  size_t pos = 0;
+  while (pos < h.n) {
+    if (pos + 4 > h.n) return false;
+    const uint32_t len = rd32(h.p + pos);
+    pos += 4;
+    if (len == 0 || pos + len > h.n) return false;
+    const uint8_t* f = h.p + pos;
+    const uint8_t* eq = (const uint8_t*)memchr(f, '=', len);
+    if (!eq) return false;
+    Span v;
+    v.p = eq + 1;
+    v.n = len - (size_t)(eq + 1 - f);
+    (*out)[std::string((const char*)f, (size_t)(eq - f))] = v;
+    pos += len;
+  }
+  return true;
+}
+
+bool next_record(Span buf, size_t* pos, Span* header, Span* data) {
+  if (*pos + 4 > buf.n) return false;
+  const uint32_t hl = rd32(buf.p + *pos);
+  if (*pos + 4 + (size_t)hl + 4 > buf.n) return false;
+  header->p = buf.p + *pos + 4;
+  header->n = hl;
+  const uint32_t dl = rd32(buf.p + *pos + 4 + hl);
+  if (*pos + 8 + (size_t)hl + (size_t)dl > buf.n) return false;
+  data->p = buf.p + *pos + 8 + hl;
+  data->n = dl;
+  *pos += 8 + (size_t)hl + (size_t)dl;
+  return true;
+}
+
+std::string str_of(Span s) { return std::string((const char*)s.p, s.n); }
+
+}  // namespace
+
+struct ll_bag {
+  std::vector<uint8_t> file;
+  std::string topic;
+  std::map<uint32_t, std::pair<std::string, std::string>> conns;  // conn id -> (topic, type)
+  std::vector<Msg> msgs;
+};
+
+namespace {
+
+// records of one level (the file body or the data of a chunk)
+int scan_records(ll_bag* bag, Span buf, bool top_level, const std::string& want_topic) {
+  size_t pos = 0;
+  while (pos < buf.n) {
+    Span h, d;
+    if (!next_record(buf, &pos, &h, &d)) { g_bag_error = "truncated record"; return LL_ERR_INVALID_ARG; }
+    std::map<std::string, Span> f;
+    if (!parse_header(h, &f) || !f.count("op") || f["op"].n != 1) { g_bag_error = "malformed record header"; return LL_ERR_INVALID_ARG; }
+    const uint8_t op = f["op"].p[0];
+    if (op == 0x05) {  // chunk
+      if (!top_level) { g_bag_error = "chunk inside a chunk"; return LL_ERR_INVALID_ARG; }
+      const std::string comp = f.count("compression") ? str_of(f["compression"]) : "none";
+      if (comp != "none") { g_bag_error = "chunk compression '" + comp + "' is not supported (re-record or `rosbag decompress` the bag)"; return LL_ERR_INVALID_ARG; }
+      const int rc = scan_records(bag, d, false, want_topic);
+      if (rc) return rc;
+    } else if (op == 0x07) {  // connection: header has conn + topic, data is a header with type, md5sum, message_definition
+      if (!f.count("conn") || f["conn"].n != 4) { g_bag_error = "connection record without conn"; return LL_ERR_INVALID_ARG; }
+      std::map<std::string, Span> cf;
+      if (!parse_header(d, &cf)) { g_bag_error = "malformed connection data"; return LL_ERR_INVALID_ARG; }
+      const std::string topic = f.count("topic") ? str_of(f["topic"]) : (cf.count("topic") ? str_of(cf["topic"]) : "");
+      bag->conns[rd32(f["conn"].p)] = std::make_pair(topic, cf.count("type") ? str_of(cf["type"]) : "");
+    } else if (op == 0x02) {  // message data
+      if (!f.count("conn") || f["conn"].n != 4 || !f.count("time") || f["time"].n != 8) { g_bag_error = "message record without conn / time"; return LL_ERR_INVALID_ARG; }
+      const auto it = bag->conns.find(rd32(f["conn"].p));
+      if (it == bag->conns.end()) continue;  // the connection record always precedes its messages inside a chunk
+      if (it->second.second != "sensor_msgs/PointCloud2") continue;
+      if (!want_topic.empty() && it->second.first != want_topic) continue;
+      if (want_topic.empty()) {
+        if (bag->topic.empty()) bag->topic = it->second.first;  // first PointCloud2 topic of the bag
+        if (it->second.first != bag->topic) continue;
+      }
+      Msg m;
+      m.time_ns = (uint64_t)rd32(f["time"].p) * 1000000000ull + rd32(f["time"].p + 4);
+      m.order = bag->msgs.size();
+      m.data = d;
+      bag->msgs.push_back(m);
+    }
+    // 0x03 bag header, 0x04 index data, 0x06 chunk info: not needed for a sequential read
+  }
+  return LL_OK;
+}
+
+struct Cursor {
+  const uint8_t* p;
+  size_t n, pos;
+  bool ok;
+  uint32_t u32() {
+    if (pos + 4 > n) { ok = false; return 0; }
+    const uint32_t v = rd32(p + pos);
+    pos += 4;
+    return v;
+  }
+  uint8_t u8() {
+    if (pos + 1 > n) { ok = false; return 0; }
+    return p[pos++];
+  }
+  Span bytes(size_t len) {
+    Span s;
+    if (pos + len > n) { ok = false; return s; }
+    s.p = p + pos;
+    s.n = len;
+    pos += len;
+    return s;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* ll_bag_last_error(void) { return g_bag_error.c_str(); }
+
+int ll_bag_open(const char* path, const char* topic, ll_bag** out) {
+  if (!path || !out) return LL_ERR_INVALID_ARG;
+  *out = nullptr;
+  FILE* fp = fopen(path, "rb");
+  if (!fp) { g_bag_error = std::string("cannot open ") + path; return LL_ERR_INVALID_ARG; }  // main.cpp:31-34: ROS_FATAL + return 1
+  ll_bag* bag = new ll_bag();
+  fseek(fp, 0, SEEK_END);
+  const long sz = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  bag->file.resize(sz > 0 ? (size_t)sz : 0);
+  const size_t got = bag->file.empty() ? 0 : fread(bag->file.data(), 1, bag->file.size(), fp);
+  fclose(fp);
+  static const char magic[] = "#ROSBAG V2.0\n";
+  if (got != bag->file.size() || got < 13 || memcmp(bag->file.data(), magic, 13) != 0) {
+    g_bag_error = "not a rosbag v2.0 file";
+    delete bag;
+    return LL_ERR_INVALID_ARG;
+  }
+  bag->topic = topic ? topic : "";
+  Span body;
+  body.p = bag->file.data() + 13;
+  body.n = bag->file.size() - 13;
+  const int rc = scan_records(bag, body, true, bag->topic);
+  if (rc) { delete bag; return rc; }
+  std::stable_sort(bag->msgs.begin(), bag->msgs.end(), [](const Msg& a, const Msg& b) { return a.time_ns < b.time_ns; });
+  *out = bag;
+  return LL_OK;
+}
+
+int ll_bag_num_messages(const ll_bag* bag) { return bag ? (int)bag->msgs.size() : 0; }
+
+const char* ll_bag_topic(const ll_bag* bag) { return bag ? bag->topic.c_str() : ""; }
+
+// sensor_msgs/PointCloud2: Header header (uint32 seq, time stamp, string frame_id), uint32 height, uint32 width,
+// PointField[] fields (string name, uint32 offset, uint8 datatype, uint32 count), bool is_bigendian, uint32 point_step,
+// uint32 row_step, uint8[] data, bool is_dense; strings and arrays carry a uint32 length, everything little-endian
+int ll_bag_get_pointcloud2(const ll_bag* bag, int index, ll_pointcloud2_view* v) {
+  if (!bag || !v || index < 0 || index >= (int)bag->msgs.size()) return LL_ERR_INVALID_ARG;
+  const Msg& m = bag->msgs[(size_t)index];
+  Cursor c{m.data.p, m.data.n, 0, true};
+  memset(v, 0, sizeof(*v));
+  v->bag_time_ns = m.time_ns;
+  c.u32();  // header.seq
+  v->stamp_sec = c.u32();
+  v->stamp_nsec = c.u32();
+  c.bytes(c.u32());  // frame_id
+  v->height = c.u32();
+  v->width = c.u32();
+  v->off_x = v->off_y = v->off_z = v->off_intensity = -1;
+  const uint32_t nfields = c.u32();
+  for (uint32_t i = 0; i < nfields && c.ok; ++i) {
+    const Span name = c.bytes(c.u32());
+    const uint32_t offset = c.u32();
+    const uint8_t datatype = c.u8();
+    c.u32();  // count
+    if (!c.ok || datatype != 7) continue;  // FLOAT32
+    const std::string nm = str_of(name);
+    if (nm == "x") v->off_x = (int32_t)offset;
+    else if (nm == "y") v->off_y = (int32_t)offset;
+    else if (nm == "z") v->off_z = (int32_t)offset;
+    else if (nm == "intensity") v->off_intensity = (int32_t)offset;
+  }
+  v->is_bigendian = c.u8();
+  v->point_step = c.u32();
+  v->row_step = c.u32();
+  const Span data = c.bytes(c.u32());
+  v->is_dense = c.u8();
+  if (!c.ok) { g_bag_error = "truncated sensor_msgs/PointCloud2 message"; return LL_ERR_INVALID_ARG; }
+  v->data = data.p;
+  v->data_len = data.n;
+  return LL_OK;
+}
+
+void ll_bag_close(ll_bag* bag) { delete bag; }
+
+}  // extern "C"

@@ -65,6 +65,24 @@ ImageProjection::ImageProjection(const LegoLoamParams&, std::shared_ptr<Device> 
     : _dev(dev), _output_channel(output_channel) {}
 
 void ImageProjection::cloudHandler(const float* xyzi, int n_points, double stamp) {
+  handle(stamp, [&]() {
+    const int32_t n = n_points;
+    _dev->check(ll_set_scans_host(_dev->h(), xyzi, &n, std::max(1, n_points)), "ll_set_scans_host");
+  });
+}
+
+void ImageProjection::cloudHandler(const ll_pointcloud2_view& msg) {
+  handle((double)msg.stamp_sec + 1e-9 * (double)msg.stamp_nsec, [&]() {
+    const int32_t n = (int32_t)(msg.width * msg.height);
+    static const uint8_t none = 0;
+    _dev->check(ll_set_scans_pointcloud2_host(_dev->h(), msg.data ? msg.data : &none, &n, (size_t)msg.data_len, (int)msg.point_step, msg.off_x,
+                                              msg.off_y, msg.off_z, msg.off_intensity, msg.is_dense),
+                "ll_set_scans_pointcloud2_host");
+  });
+}
+
+template <class SetScans>
+void ImageProjection::handle(double stamp, SetScans set_scans) {
   Handshake& k = hs(_dev.get());
   {
     // device state is shared: wait until FeatureAssociation has consumed the previous projection
@@ -76,8 +94,7 @@ void ImageProjection::cloudHandler(const float* xyzi, int n_points, double stamp
   out.seg_msg.stamp = stamp;
   {
     std::lock_guard<std::mutex> lk(_dev->mutex());
-    const int32_t n = n_points;
-    _dev->check(ll_set_scans_host(_dev->h(), xyzi, &n, std::max(1, n_points)), "ll_set_scans_host");
+    set_scans();
     _dev->check(ll_image_projection(_dev->h()), "ll_image_projection");
     if (_dev->download_payloads) {
       out.segmented_cloud = _dev->download_cloud(LL_BUF_SEG_CLOUD);

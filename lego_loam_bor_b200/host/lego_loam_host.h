@@ -125,8 +125,13 @@ class ImageProjection {
   ~ImageProjection() = default;
   // imageProjection.cpp:153-174; NaN points must already be removed by the caller
   void cloudHandler(const float* xyzi, int n_points, double stamp);
+  // the same from a sensor_msgs/PointCloud2 (e.g. ll_bag_get_pointcloud2): pcl::fromROSMsg + removeNaNFromPointCloud
+  // (imageProjection.cpp:159-161) run on the device from the message bytes
+  void cloudHandler(const ll_pointcloud2_view& msg);
 
  private:
+  template <class SetScans>
+  void handle(double stamp, SetScans set_scans);
   std::shared_ptr<Device> _dev;
   Channel<ProjectionOut>& _output_channel;
   uint64_t _frame = 0;

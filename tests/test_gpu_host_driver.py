@@ -47,3 +47,32 @@ def test_sequence_driver_matches_c_abi(built, tmp_path):
     assert np.all(np.isfinite(aft)) and np.abs(aft).max() > 0
     # scan-to-map against a map built from the sequence's own key frames stays close to the odometry pose
     assert np.abs(aft[3:] - rows[15, 4:7]).max() < 0.3 and np.abs(aft[:3] - rows[15, 1:4]).max() < 0.1
+
+
+def test_sequence_driver_bag_mode(built, tmp_path):
+    """The same sequence recorded as a rosbag (the reference's bag mode, main.cpp:60-76): the driver reads the
+    PointCloud2 messages of the lidar topic and hands the raw message bytes to ImageProjection::cloudHandler; every pose
+    line must equal the one of the scans.bin run."""
+    from lego_loam_bor_b200._paths import PKG
+    from test_rosbag import make_bag
+    n_frames = 12
+    p, cfg, scans = make_scans("T", [0], range(n_frames))
+    clouds = [scans[(0, i)] for i in range(n_frames)]
+    bin_path, bag_path = tmp_path / "scans.bin", tmp_path / "scans.bag"
+    with open(bin_path, "wb") as f:
+        f.write(np.int32(n_frames).tobytes())
+        for a in clouds:
+            f.write(np.int32(len(a)).tobytes())
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+    make_bag(str(bag_path), clouds, np.random.default_rng(9))
+    exe = os.path.join(PKG, "host", "sequence_driver")
+    outs = []
+    for src in (str(bin_path), str(bag_path) + ":/velodyne_points"):
+        out = tmp_path / ("poses_%d.txt" % len(outs))
+        r = subprocess.run([exe, "T", src, str(out)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(np.loadtxt(out))
+    assert outs[0].shape == outs[1].shape == (n_frames, 15)
+    assert np.array_equal(outs[0], outs[1])
+    r = subprocess.run([exe, "T", str(tmp_path / "missing.bag"), str(tmp_path / "x.txt")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Unable to open rosbag" in r.stderr

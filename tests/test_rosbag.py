@@ -1,0 +1,169 @@
+"""rosbag v2.0 ingest: the bag mode of the reference's main loop (main.cpp:26-35,60-76) without
+ROS.  The reference ships no bag, so the fixtures are written here by a minimal bag writer that follows the published
+"Bag format 2.0" record layout (bag header padded to 4096 bytes, chunks with connection + message records, index data,
+chunk info) and the sensor_msgs/PointCloud2 serialisation; the reader (ll_bag_*) must return exactly the messages of
+one topic, in record-time order, with the header fields ll_set_scans_pointcloud2_host needs."""
+import struct
+
+import numpy as np
+import pytest
+
+
+def _field(name, value):
+    b = name.encode() + b"=" + value
+    return struct.pack("<I", len(b)) + b
+
+
+def _record(fields, data):
+    h = b"".join(_field(n, v) for n, v in fields)
+    return struct.pack("<I", len(h)) + h + struct.pack("<I", len(data)) + data
+
+
+def _string(s):
+    b = s.encode() if isinstance(s, str) else s
+    return struct.pack("<I", len(b)) + b
+
+
+def pointcloud2_message(seq, stamp, frame_id, fields, point_step, data, n_points, is_dense):
+    """fields: list of (name, offset, datatype, count)"""
+    out = struct.pack("<III", seq, stamp[0], stamp[1]) + _string(frame_id)
+    out += struct.pack("<II", 1, n_points)  # height, width
+    out += struct.pack("<I", len(fields))
+    for name, off, dt, cnt in fields:
+        out += _string(name) + struct.pack("<IBI", off, dt, cnt)
+    out += struct.pack("<BII", 0, point_step, point_step * n_points)
+    out += _string(bytes(data)) + struct.pack("<B", 1 if is_dense else 0)
+    return out
+
+
+def write_bag(path, connections, chunks, compression=b"none"):
+    """connections: {conn: (topic, type)}; chunks: list of lists of (conn, (sec, nsec), payload)"""
+    def conn_record(c):
+        topic, typ = connections[c]
+        data = _field("topic", topic.encode()) + _field("type", typ.encode()) + _field("md5sum", b"0" * 32) + \
+            _field("message_definition", b"# not needed by the reader\n")
+        return _record([("op", b"\x07"), ("conn", struct.pack("<I", c)), ("topic", topic.encode())], data)
+
+    body = b""
+    chunk_infos = []
+    for msgs in chunks:
+        inner, seen, index = b"", set(), {}
+        for c, (sec, nsec), payload in msgs:
+            if c not in seen:
+                inner += conn_record(c)
+                seen.add(c)
+            index.setdefault(c, []).append((sec, nsec, len(inner)))
+            inner += _record([("op", b"\x02"), ("conn", struct.pack("<I", c)), ("time", struct.pack("<II", sec, nsec))], payload)
+        chunk_pos = 13 + 4096 + len(body)
+        body += _record([("op", b"\x05"), ("compression", compression), ("size", struct.pack("<I", len(inner)))], inner)
+        for c, entries in index.items():
+            body += _record([("op", b"\x04"), ("ver", struct.pack("<I", 1)), ("conn", struct.pack("<I", c)), ("count", struct.pack("<I", len(entries)))],
+                            b"".join(struct.pack("<III", s, n, o) for s, n, o in entries))
+        times = [t for _, t, _ in msgs]
+        chunk_infos.append((chunk_pos, min(times), max(times), {c: len(e) for c, e in index.items()}))
+    index_pos = 13 + 4096 + len(body)
+    tail = b"".join(conn_record(c) for c in connections)
+    for pos, t0, t1, counts in chunk_infos:
+        tail += _record([("op", b"\x06"), ("ver", struct.pack("<I", 1)), ("chunk_pos", struct.pack("<Q", pos)),
+                         ("start_time", struct.pack("<II", *t0)), ("end_time", struct.pack("<II", *t1)), ("count", struct.pack("<I", len(counts)))],
+                        b"".join(struct.pack("<II", c, n) for c, n in counts.items()))
+    hdr_fields = [("op", b"\x03"), ("index_pos", struct.pack("<Q", index_pos)), ("conn_count", struct.pack("<I", len(connections))),
+                  ("chunk_count", struct.pack("<I", len(chunks)))]
+    h = b"".join(_field(n, v) for n, v in hdr_fields)
+    pad = 4096 - 4 - len(h) - 4
+    bag_header = struct.pack("<I", len(h)) + h + struct.pack("<I", pad) + b" " * pad
+    assert len(bag_header) == 4096
+    with open(path, "wb") as f:
+        f.write(b"#ROSBAG V2.0\n" + bag_header + body + tail)
+
+
+VELO_FIELDS = [("x", 0, 7, 1), ("y", 4, 7, 1), ("z", 8, 7, 1), ("intensity", 12, 7, 1), ("ring", 16, 4, 1), ("time", 18, 7, 1)]
+
+
+def velodyne_bytes(xyzi, rng):
+    rec = np.zeros(len(xyzi), np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"], "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"],
+                                        "offsets": [0, 4, 8, 12, 16, 18], "itemsize": 22}))
+    rec["x"], rec["y"], rec["z"], rec["intensity"] = xyzi[:, 0], xyzi[:, 1], xyzi[:, 2], xyzi[:, 3]
+    rec["ring"] = rng.integers(0, 16, len(xyzi))
+    return np.frombuffer(rec.tobytes(), np.uint8)
+
+
+def make_bag(path, clouds, rng, **kw):
+    """three topics; the lidar messages are spread over two chunks and stored out of time order"""
+    conns = {0: ("/imu/data", "sensor_msgs/Imu"), 1: ("/velodyne_points", "sensor_msgs/PointCloud2"), 2: ("/other_cloud", "sensor_msgs/PointCloud2")}
+    datas = [velodyne_bytes(c, rng) for c in clouds]
+    lidar = [(1, (100 + i // 2, 500000000 * (i % 2)), pointcloud2_message(i, (100 + i // 2, 500000000 * (i % 2) + 7), "velodyne", VELO_FIELDS, 22, d, len(c), i % 2 == 0))
+             for i, (c, d) in enumerate(zip(clouds, datas))]
+    imu = [(0, (100 + i, 1), bytes(rng.integers(0, 255, 40, dtype=np.uint8))) for i in range(3)]
+    other = [(2, (100, 3), pointcloud2_message(0, (100, 3), "x", VELO_FIELDS[:3], 12, np.zeros(24, np.uint8), 2, True))]
+    chunk0 = [imu[0]] + other + [lidar[2], lidar[0]] + [imu[1]]
+    chunk1 = [lidar[3], imu[2], lidar[1]] + lidar[4:]
+    write_bag(path, conns, [chunk0, chunk1], **kw)
+    return datas
+
+
+def test_reader_returns_topic_in_time_order(built, tmp_path):
+    from lego_loam_bor_b200.capi import RosBag
+    rng = np.random.default_rng(2)
+    clouds = [rng.normal(0, 10, (n, 4)).astype(np.float32) for n in (50, 1, 0, 333, 17)]
+    path = str(tmp_path / "t.bag")
+    datas = make_bag(path, clouds, rng)
+    bag = RosBag(path, "/velodyne_points")
+    assert len(bag) == len(clouds) and bag.topic == "/velodyne_points"
+    for i, (c, d) in enumerate(zip(clouds, datas)):
+        v, data = bag.message(i)
+        assert (v.width, v.height, v.point_step, v.row_step) == (len(c), 1, 22, 22 * len(c))
+        assert (v.off_x, v.off_y, v.off_z, v.off_intensity) == (0, 4, 8, 12)
+        assert (v.stamp_sec, v.stamp_nsec) == (100 + i // 2, 500000000 * (i % 2) + 7)
+        assert v.bag_time_ns == (100 + i // 2) * 10**9 + 500000000 * (i % 2)
+        assert v.is_dense == (1 if i % 2 == 0 else 0) and v.is_bigendian == 0
+        assert np.array_equal(data, d)
+    # no topic given: the first PointCloud2 topic of the file
+    first = RosBag(path)
+    assert first.topic == "/other_cloud" and len(first) == 1
+    v, data = first.message(0)
+    assert (v.off_x, v.off_y, v.off_z, v.off_intensity, v.point_step, v.width) == (0, 4, 8, -1, 12, 2)
+    assert len(RosBag(path, "/no_such_topic")) == 0
+
+
+def test_reader_errors(built, tmp_path):
+    from lego_loam_bor_b200.capi import LegoLoamError, RosBag
+    rng = np.random.default_rng(3)
+    clouds = [rng.normal(0, 10, (n, 4)).astype(np.float32) for n in (5, 6, 7, 8, 9)]
+    with pytest.raises(LegoLoamError, match="cannot open"):
+        RosBag(str(tmp_path / "missing.bag"))
+    p = tmp_path / "junk.bag"
+    p.write_bytes(b"#ROSBAG V1.2\n" + b"\0" * 100)
+    with pytest.raises(LegoLoamError, match="not a rosbag v2.0"):
+        RosBag(str(p))
+    make_bag(str(tmp_path / "bz2.bag"), clouds, rng, compression=b"bz2")
+    with pytest.raises(LegoLoamError, match="compression 'bz2' is not supported"):
+        RosBag(str(tmp_path / "bz2.bag"))
+    make_bag(str(tmp_path / "ok.bag"), clouds, rng)
+    whole = (tmp_path / "ok.bag").read_bytes()
+    (tmp_path / "cut.bag").write_bytes(whole[:13 + 4096 + 300])
+    with pytest.raises(LegoLoamError, match="truncated"):
+        RosBag(str(tmp_path / "cut.bag"))
+
+
+@pytest.mark.gpu
+def test_bag_to_device(built, tmp_path):
+    """bag -> ll_set_scans_pointcloud2_host -> projection, against the oracle fed with the same clouds"""
+    from lego_loam_bor_b200.capi import LegoLoam, RosBag
+    from oracle.oracle_py import Oracle
+    from parity_utils import make_scans, same_bits
+    rng = np.random.default_rng(4)
+    p, cfg, scans = make_scans("A", [0], range(5))
+    clouds = [scans[(0, f)] for f in range(5)]
+    path = str(tmp_path / "seq.bag")
+    make_bag(path, clouds, rng)
+    bag = RosBag(path, "/velodyne_points")
+    gpu, o = LegoLoam(p, batch=1), Oracle(p)
+    for i in range(len(bag)):
+        v, data = bag.message(i)
+        gpu.set_scans_pointcloud2([data], v.point_step, v.off_x, v.off_y, v.off_z, v.off_intensity, is_dense=bool(v.is_dense))
+        gpu.process_scans()
+        o.image_projection(clouds[i])
+        o.feature_association()
+        for name in ("RANGE_MAT", "LABEL_MAT", "SEG_COL_IND", "SURF_LAST", "TRANSFORM_SUM"):
+            assert same_bits(gpu.download(name, 0), o.download(name)), f"message {i}: {name}"
