@@ -199,8 +199,121 @@ __device__ __forceinline__ void knn_cell_offset(int n, int* dx, int* dy, int* dz
 
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
+// Full search of ONE query by a whole warp, for the launches in which only a few queries of a block fail the reuse test
+// (LM iterations >= 2): a single thread walks its 27 cells as a chain of dependent loads (tens of microseconds) while the
+// rest of its block waits at the barrier; here lanes 0..26 take one cell each (occupancy word, then bucket bounds), the
+// points of all non-empty buckets are spread over the lanes, and every lane keeps the same sorted top-(KNN_K+1) in
+// registers: a candidate below the current threshold is broadcast and inserted by all lanes alike.  Same candidates
+// (points of the 27 cells closer than 1 m), same (d2, index) order, so the record is the one the thread search writes
+// (up to the choice among exactly equal distances at the last recorded position, which either way keeps the record valid).
+#ifndef KNN_COOP_MAX
+#define KNN_COOP_MAX 24
+#endif
+
+__device__ __forceinline__ void knn_search_warp(const DevState& st, int s, int q, int nc, const MapPose& mp, int* sh /* [3][32] */) {
+  const DevParams& p = st.p;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool corner = q < nc;
+  const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
+  const float4 sel = point_associate_to_map(mp, ori);
+  const HashGrid& g = corner ? st.grid_map_corner : st.grid_map_surf;
+  const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+  const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
+  const float4* pts = g.sorted + (size_t)s * g.cap;
+  const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
+  const float fx = sel.x - (float)cx * g.cell, fy = sel.y - (float)cy * g.cell, fz = sel.z - (float)cz * g.cell;
+  // one cell per lane
+  uint32_t hh = 0x80000000u | (uint32_t)lane;  // lanes without a bucket keep distinct values for the match below
+  bool occd = false;
+  if (lane < 27) {
+    const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+    const float gx = dx < 0 ? fx : (dx > 0 ? g.cell - fx : 0.f);
+    const float gy = dy < 0 ? fy : (dy > 0 ? g.cell - fy : 0.f);
+    const float gz = dz < 0 ? fz : (dz > 0 ? g.cell - fz : 0.f);
+    // a cell whose nearest corner is not closer than 1 m holds no candidate (0.999: never skip on a rounding error)
+    if ((dx == 0 && dy == 0 && dz == 0) || (gx * gx + gy * gy + gz * gz) * 0.999f <= 1.0f) {
+      const uint32_t h = grid_hash(cx + dx, cy + dy, cz + dz, g.tbl);
+      if ((occ[h >> 5] >> (h & 31)) & 1u) { occd = true; hh = h; }
+    }
+  }
+  // two of the 27 cells can share a bucket (hash collision): the lowest lane keeps it
+  const unsigned same = __match_any_sync(full, hh);
+  if (occd && (__ffs(same) - 1) != lane) occd = false;
+  int b0 = 0, cnt = 0;
+  if (occd) { b0 = cs[hh]; cnt = cs[hh + 1] - b0; }
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(full, inc, o);
+    if (lane >= o) inc += x;
+  }
+  const int total = __shfl_sync(full, inc, 31);
+  __syncwarp();
+  sh[lane] = inc - cnt;  // first flat position of this lane's bucket
+  sh[32 + lane] = inc;   // one past its last
+  sh[64 + lane] = b0;
+  __syncwarp();
+  unsigned long long bk[KNN_REC];
+#pragma unroll
+  for (int i = 0; i < KNN_REC; ++i) bk[i] = ((unsigned long long)__float_as_uint(1.0f) << 32) | 0x7fffffffull;
+  // flat position j -> point: the bucket whose [first, last) holds j
+  auto fetch = [&](int j, float4* out) -> bool {
+    if (j >= total) return false;
+    int L = 0;
+    while (sh[32 + L] <= j) ++L;
+    *out = pts[sh[64 + L] + (j - sh[L])];
+    return true;
+  };
+  float4 nxt;
+  bool have_nxt = fetch(lane, &nxt);
+  for (int r0 = 0; r0 < total; r0 += 32) {
+    const float4 cur = nxt;
+    const bool have = have_nxt;
+    have_nxt = fetch(r0 + 32 + lane, &nxt);  // in flight while this round is merged
+    unsigned long long key = ~0ull;
+    bool cand = false;
+    if (have) {
+      const float cd = nn_dist2(sel.x, sel.y, sel.z, cur);
+      key = ((unsigned long long)__float_as_uint(cd) << 32) | (unsigned)__float_as_int(cur.w);
+      cand = cd < 1.0f && key < bk[KNN_K];
+    }
+    unsigned bal = __ballot_sync(full, cand);
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      unsigned long long k2 = __shfl_sync(full, key, src);
+      if (k2 < bk[KNN_K]) {
+#pragma unroll
+        for (int i = 0; i < KNN_REC; ++i) {
+          const unsigned long long b = bk[i];
+          const bool lt = k2 < b;
+          bk[i] = lt ? k2 : b;
+          k2 = lt ? b : k2;
+        }
+      }
+    }
+  }
+  // record: lane i writes candidate i, lane KNN_K the query position + the (KNN_K+1)-th distance
+  const float4* mpts = corner ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
+  float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
+  unsigned long long mine = 0ull;
+#pragma unroll
+  for (int i = 0; i < KNN_REC; ++i) mine = (lane == i) ? bk[i] : mine;
+  if (lane < KNN_K) {
+    const int bi = (int)(unsigned)mine;
+    float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (bi != 0x7fffffff) { c = mpts[bi]; c.w = __int_as_float(bi); }
+    rec[lane] = c;
+  } else if (lane == KNN_K) {
+    rec[KNN_K] = make_float4(sel.x, sel.y, sel.z, __uint_as_float((unsigned)(mine >> 32)));
+    st.map_knn_sel[(size_t)s * st.map_knn_cap + q] = (int)(((int)(unsigned)bk[4] != 0x7fffffff ? 0x80000000u : 0u) | 0x43210u);
+  }
+}
+
 __global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int iter) {
   __shared__ int sh_need[KNN_THREADS];
+  __shared__ int sh_coop[KNN_THREADS / 32][96];
   __shared__ int sh_n;
   __shared__ int2 sh_bucket[9][KNN_THREADS];  // per thread: the non-empty buckets (start, end) of the current batch of nine cells, column-major: no bank conflicts
   const DevParams& p = st.p;
@@ -264,6 +377,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int ite
     __syncthreads();
     // ---- phase 2: full search of the remaining queries, packed onto consecutive threads ----
     const int n_need = sh_n;
+    if (n_need <= KNN_COOP_MAX) {
+      // few stragglers: a warp per query
+      for (int w = threadIdx.x >> 5; w < n_need; w += KNN_THREADS / 32) knn_search_warp(st, s, sh_need[w], nc, mp, sh_coop[threadIdx.x >> 5]);
+    } else
     for (int w = threadIdx.x; w < n_need; w += KNN_THREADS) {
       const int q = sh_need[w];
       const bool corner = q < nc;
