@@ -11,9 +11,13 @@
 // Only uncompressed chunks are read (compression=none, what `rosbag record` writes by default); bz2 / lz4 chunks are
 // reported as LL_ERR_INVALID_ARG with a message, because neither library may be assumed here.
 // Messages come back in record-time order (stable), like rosbag::View iterates them.
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <map>
@@ -78,7 +82,8 @@ std::string str_of(Span s) { return std::string((const char*)s.p, s.n); }
 }  // namespace
 
 struct ll_bag {
-  std::vector<uint8_t> file;
+  const uint8_t* file = nullptr;  // the whole bag, mapped read-only (recordings are gigabytes: no copy is made)
+  size_t file_size = 0;
   std::string topic;
   std::map<uint32_t, std::pair<std::string, std::string>> conns;  // conn id -> (topic, type)
   std::vector<Msg> msgs;
@@ -161,27 +166,38 @@ const char* ll_bag_last_error(void) { return g_bag_error.c_str(); }
 int ll_bag_open(const char* path, const char* topic, ll_bag** out) {
   if (!path || !out) return LL_ERR_INVALID_ARG;
   *out = nullptr;
-  FILE* fp = fopen(path, "rb");
-  if (!fp) { g_bag_error = std::string("cannot open ") + path; return LL_ERR_INVALID_ARG; }  // main.cpp:31-34: ROS_FATAL + return 1
+  const int fd = open(path, O_RDONLY);
+  struct stat sb;
+  if (fd < 0 || fstat(fd, &sb) != 0) {  // main.cpp:31-34: ROS_FATAL + return 1
+    if (fd >= 0) close(fd);
+    g_bag_error = std::string("cannot open ") + path;
+    return LL_ERR_INVALID_ARG;
+  }
   ll_bag* bag = new ll_bag();
-  fseek(fp, 0, SEEK_END);
-  const long sz = ftell(fp);
-  fseek(fp, 0, SEEK_SET);
-  bag->file.resize(sz > 0 ? (size_t)sz : 0);
-  const size_t got = bag->file.empty() ? 0 : fread(bag->file.data(), 1, bag->file.size(), fp);
-  fclose(fp);
+  bag->file_size = (size_t)sb.st_size;
+  if (bag->file_size > 0) {
+    void* m = mmap(nullptr, bag->file_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) {
+      close(fd);
+      delete bag;
+      g_bag_error = std::string("cannot map ") + path;
+      return LL_ERR_INVALID_ARG;
+    }
+    bag->file = (const uint8_t*)m;
+  }
+  close(fd);
   static const char magic[] = "#ROSBAG V2.0\n";
-  if (got != bag->file.size() || got < 13 || memcmp(bag->file.data(), magic, 13) != 0) {
+  if (bag->file_size < 13 || memcmp(bag->file, magic, 13) != 0) {
     g_bag_error = "not a rosbag v2.0 file";
-    delete bag;
+    ll_bag_close(bag);
     return LL_ERR_INVALID_ARG;
   }
   bag->topic = topic ? topic : "";
   Span body;
-  body.p = bag->file.data() + 13;
-  body.n = bag->file.size() - 13;
+  body.p = bag->file + 13;
+  body.n = bag->file_size - 13;
   const int rc = scan_records(bag, body, true, bag->topic);
-  if (rc) { delete bag; return rc; }
+  if (rc) { ll_bag_close(bag); return rc; }
   std::stable_sort(bag->msgs.begin(), bag->msgs.end(), [](const Msg& a, const Msg& b) { return a.time_ns < b.time_ns; });
   *out = bag;
   return LL_OK;
@@ -231,6 +247,10 @@ int ll_bag_get_pointcloud2(const ll_bag* bag, int index, ll_pointcloud2_view* v)
   return LL_OK;
 }
 
-void ll_bag_close(ll_bag* bag) { delete bag; }
+void ll_bag_close(ll_bag* bag) {
+  if (!bag) return;
+  if (bag->file) munmap((void*)bag->file, bag->file_size);
+  delete bag;
+}
 
 }  // extern "C"
