@@ -107,3 +107,23 @@ def test_packed_xyz_scans_match_xyzi(built):
     # switching back to 16-byte points on the same handle
     gpu.set_scans_host([np.ascontiguousarray(s(2)) for s in seqs])
     assert gpu.download("INPUT_CLOUD", 0).shape == (len(seqs[0](2)), 4)
+
+
+def test_oracle_never_reads_the_input_intensity(built):
+    """What ll_set_scans_xyz_host relies on, at the level of the reference's algorithm: projectPointCloud overwrites the
+    intensity of every point it keeps (imageProjection.cpp:216) and nothing reads it before, so two scans that differ only
+    in the sensor's intensity give identical outputs through projection, segmentation, features and odometry."""
+    from oracle.oracle_py import Oracle
+    from parity_utils import make_scans, same_bits
+    p, cfg, scans = make_scans("T", [0], range(4))
+    a, b = Oracle(p), Oracle(p)
+    rng = np.random.default_rng(1)
+    for f in range(4):
+        s0 = np.ascontiguousarray(scans[(0, f)])
+        s1 = s0.copy()
+        s1[:, 3] = rng.uniform(0, 255, len(s1)).astype(np.float32)
+        a.image_projection(s0)
+        b.image_projection(s1)
+        assert a.feature_association() == b.feature_association()
+        for name in ("RANGE_MAT", "FULL_CLOUD", "LABEL_MAT", "SEG_CLOUD", "CORNER_SHARP", "SURF_FLAT", "CORNER_LAST", "SURF_LAST", "OUTLIER_CLOUD", "TRANSFORM_SUM"):
+            assert same_bits(a.download(name), b.download(name)), f"frame {f}: {name}"
