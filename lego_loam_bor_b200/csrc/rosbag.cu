@@ -8,8 +8,9 @@
 // list of <u32 field_len><name>=<value> fields, and the `op` field tells the record type: 0x03 bag header, 0x05 chunk (its
 // data is a run of records again), 0x07 connection (topic + a second header in the data with type / md5sum /
 // message_definition), 0x02 message data (conn, time; data = the serialised message), 0x04 index data, 0x06 chunk info.
-// Only uncompressed chunks are read (compression=none, what `rosbag record` writes by default); bz2 / lz4 chunks are
-// reported as LL_ERR_INVALID_ARG with a message, because neither library may be assumed here.
+// Chunks may be uncompressed (compression=none, what `rosbag record` writes by default) or lz4 (`rosbag record --lz4`:
+// an LZ4 frame, magic 0x184D2204, decoded here by a restatement of the published LZ4 frame / block formats -- checksums are
+// not verified); bz2 chunks are reported as LL_ERR_INVALID_ARG with a message, because no bzip2 library may be assumed here.
 // Messages come back in record-time order (stable), like rosbag::View iterates them.
 #include <fcntl.h>
 #include <stdint.h>
@@ -79,9 +80,79 @@ bool next_record(Span buf, size_t* pos, Span* header, Span* data) {
 
 std::string str_of(Span s) { return std::string((const char*)s.p, s.n); }
 
+// ---- LZ4 (published "LZ4 Frame Format" 1.6 / "LZ4 Block Format") -----------------------------------------------------
+// One block: sequences of <token><literal length ext><literals><u16 offset><match length ext>; the last sequence ends
+// after its literals.  Output goes to dst[*op ...]; matches may reach back into earlier blocks (dependent blocks).
+bool lz4_block(const uint8_t* ip, size_t n, uint8_t* dst, size_t cap, size_t* op) {
+  const uint8_t* const iend = ip + n;
+  while (ip < iend) {
+    const unsigned token = *ip++;
+    size_t lit = token >> 4;
+    if (lit == 15) {
+      unsigned b;
+      do {
+        if (ip >= iend) return false;
+        b = *ip++;
+        lit += b;
+      } while (b == 255);
+    }
+    if ((size_t)(iend - ip) < lit || cap - *op < lit) return false;
+    memcpy(dst + *op, ip, lit);
+    ip += lit;
+    *op += lit;
+    if (ip >= iend) return true;  // last sequence: literals only
+    if (iend - ip < 2) return false;
+    const size_t offset = (size_t)ip[0] | ((size_t)ip[1] << 8);
+    ip += 2;
+    if (offset == 0 || offset > *op) return false;
+    size_t mlen = token & 15u;
+    if (mlen == 15) {
+      unsigned b;
+      do {
+        if (ip >= iend) return false;
+        b = *ip++;
+        mlen += b;
+      } while (b == 255);
+    }
+    mlen += 4;
+    if (cap - *op < mlen) return false;
+    for (size_t i = 0; i < mlen; ++i, ++*op) dst[*op] = dst[*op - offset];  // byte by byte: the match may overlap itself
+  }
+  return true;
+}
+
+// A whole frame into exactly `size` bytes (the chunk header's uncompressed size).
+bool lz4_frame(const uint8_t* ip, size_t n, std::vector<uint8_t>* out, size_t size) {
+  if (n < 7 || rd32(ip) != 0x184D2204u) return false;
+  const unsigned flg = ip[4];
+  if ((flg >> 6) != 1) return false;  // version 01
+  const bool block_checksum = (flg >> 4) & 1, content_size = (flg >> 3) & 1, dict_id = flg & 1;
+  size_t pos = 6 + (content_size ? 8 : 0) + (dict_id ? 4 : 0) + 1;  // FLG, BD, optional fields, header checksum
+  out->resize(size);
+  size_t op = 0;
+  while (true) {
+    if (pos + 4 > n) return false;
+    const uint32_t bs = rd32(ip + pos);
+    pos += 4;
+    if (bs == 0) break;  // EndMark (a content checksum may follow)
+    const size_t len = bs & 0x7fffffffu;
+    if (pos + len > n) return false;
+    if (bs & 0x80000000u) {  // stored block
+      if (size - op < len) return false;
+      memcpy(out->data() + op, ip + pos, len);
+      op += len;
+    } else if (!lz4_block(ip + pos, len, out->data(), size, &op)) {
+      return false;
+    }
+    pos += len + (block_checksum ? 4 : 0);
+  }
+  return op == size;
+}
+
 }  // namespace
 
 struct ll_bag {
+  std::vector<std::vector<uint8_t>> inflated;  // decompressed chunks that hold messages of the topic
   const uint8_t* file = nullptr;  // the whole bag, mapped read-only (recordings are gigabytes: no copy is made)
   size_t file_size = 0;
   std::string topic;
@@ -103,6 +174,19 @@ int scan_records(ll_bag* bag, Span buf, bool top_level, const std::string& want_
     if (op == 0x05) {  // chunk
       if (!top_level) { g_bag_error = "chunk inside a chunk"; return LL_ERR_INVALID_ARG; }
       const std::string comp = f.count("compression") ? str_of(f["compression"]) : "none";
+      if (comp == "lz4") {
+        if (!f.count("size") || f["size"].n != 4) { g_bag_error = "chunk record without size"; return LL_ERR_INVALID_ARG; }
+        bag->inflated.emplace_back();
+        if (!lz4_frame(d.p, d.n, &bag->inflated.back(), rd32(f["size"].p))) { g_bag_error = "corrupt lz4 chunk"; return LL_ERR_INVALID_ARG; }
+        Span u;
+        u.p = bag->inflated.back().data();
+        u.n = bag->inflated.back().size();
+        const size_t before = bag->msgs.size();
+        const int rc = scan_records(bag, u, false, want_topic);
+        if (rc) return rc;
+        if (bag->msgs.size() == before) bag->inflated.pop_back();  // nothing of the topic in this chunk: drop the copy
+        continue;
+      }
       if (comp != "none") { g_bag_error = "chunk compression '" + comp + "' is not supported (re-record or `rosbag decompress` the bag)"; return LL_ERR_INVALID_ARG; }
       const int rc = scan_records(bag, d, false, want_topic);
       if (rc) return rc;

@@ -24,6 +24,67 @@ def _string(s):
     return struct.pack("<I", len(b)) + b
 
 
+def lz4_block_compress(src):
+    """Greedy LZ4 block encoder (published block format: last 5 bytes literal, no match starting in the last 12)."""
+    n, out, anchor, i, table = len(src), bytearray(), 0, 0, {}
+
+    def lengths(v):
+        b = bytearray()
+        while v >= 255:
+            b.append(255)
+            v -= 255
+        b.append(v)
+        return b
+
+    def emit(lit, offset=None, mlen=0):
+        token = (min(len(lit), 15) << 4) | (min(mlen - 4, 15) if offset else 0)
+        out.append(token)
+        if len(lit) >= 15:
+            out.extend(lengths(len(lit) - 15))
+        out.extend(lit)
+        if offset:
+            out.extend(struct.pack("<H", offset))
+            if mlen - 4 >= 15:
+                out.extend(lengths(mlen - 4 - 15))
+
+    while n >= 13 and i <= n - 12:
+        key = bytes(src[i:i + 4])
+        cand = table.get(key)
+        table[key] = i
+        if cand is not None and i - cand <= 65535:
+            m = 4
+            while i + m < n - 5 and src[cand + m] == src[i + m]:
+                m += 1
+            emit(src[anchor:i], i - cand, m)
+            i += m
+            anchor = i
+        else:
+            i += 1
+    emit(src[anchor:])
+    return bytes(out)
+
+
+def lz4_frame_liblz4(src):
+    """The same frame written by the real liblz4 (through pyarrow's codec), an encoder independent of this repo."""
+    import pyarrow as pa
+    return pa.compress(bytes(src), codec="lz4", asbytes=True)
+
+
+def lz4_frame(src, block=3000):
+    """LZ4 frame (magic 0x184D2204) as roslz4 writes bag chunks: independent blocks, content checksum present (its value is
+    not checked by the reader, nor is the header checksum); every third block is stored uncompressed."""
+    out = bytearray(struct.pack("<I", 0x184D2204) + bytes([0x64, 0x70, 0x00]))
+    for k, a in enumerate(range(0, len(src), block)):
+        part = bytes(src[a:a + block])
+        if k % 3 == 2:
+            out += struct.pack("<I", 0x80000000 | len(part)) + part
+        else:
+            c = lz4_block_compress(part)
+            out += struct.pack("<I", len(c)) + c
+    out += struct.pack("<I", 0) + b"\xde\xad\xbe\xef"
+    return bytes(out)
+
+
 def pointcloud2_message(seq, stamp, frame_id, fields, point_step, data, n_points, is_dense):
     """fields: list of (name, offset, datatype, count)"""
     out = struct.pack("<III", seq, stamp[0], stamp[1]) + _string(frame_id)
@@ -55,7 +116,9 @@ def write_bag(path, connections, chunks, compression=b"none"):
             index.setdefault(c, []).append((sec, nsec, len(inner)))
             inner += _record([("op", b"\x02"), ("conn", struct.pack("<I", c)), ("time", struct.pack("<II", sec, nsec))], payload)
         chunk_pos = 13 + 4096 + len(body)
-        body += _record([("op", b"\x05"), ("compression", compression), ("size", struct.pack("<I", len(inner)))], inner)
+        stored = lz4_frame(inner) if compression == b"lz4" else (lz4_frame_liblz4(inner) if compression == b"liblz4" else inner)
+        body += _record([("op", b"\x05"), ("compression", b"lz4" if compression == b"liblz4" else compression),
+                         ("size", struct.pack("<I", len(inner)))], stored)
         for c, entries in index.items():
             body += _record([("op", b"\x04"), ("ver", struct.pack("<I", 1)), ("conn", struct.pack("<I", c)), ("count", struct.pack("<I", len(entries)))],
                             b"".join(struct.pack("<III", s, n, o) for s, n, o in entries))
@@ -124,6 +187,39 @@ def test_reader_returns_topic_in_time_order(built, tmp_path):
     v, data = first.message(0)
     assert (v.off_x, v.off_y, v.off_z, v.off_intensity, v.point_step, v.width) == (0, 4, 8, -1, 12, 2)
     assert len(RosBag(path, "/no_such_topic")) == 0
+
+
+def test_lz4_chunks(built, tmp_path):
+    """`rosbag record --lz4`: the same messages from LZ4-framed chunks (compressed, stored and self-overlapping matches)."""
+    from lego_loam_bor_b200.capi import LegoLoamError, RosBag
+    rng = np.random.default_rng(6)
+    clouds = [rng.normal(0, 10, (n, 4)).astype(np.float32) for n in (400, 1, 0, 900, 17)]
+    clouds[3][100:600] = 0  # long runs of equal bytes: matches that overlap their own output
+    sizes = {}
+    codecs = [b"none", b"lz4"]
+    try:
+        import pyarrow as pa
+        if pa.Codec.is_available("lz4"):
+            codecs.append(b"liblz4")  # chunks compressed by the real library: pins the decoder, not just its round trip
+    except ImportError:
+        pass
+    for comp in codecs:
+        path = tmp_path / (comp.decode() + ".bag")
+        datas = make_bag(str(path), clouds, np.random.default_rng(7), compression=comp)
+        sizes[comp] = path.stat().st_size
+        bag = RosBag(str(path), "/velodyne_points")
+        assert len(bag) == len(clouds)
+        for i, d in enumerate(datas):
+            v, data = bag.message(i)
+            assert v.width == len(clouds[i]) and np.array_equal(data, d), f"{comp} message {i}"
+    assert sizes[b"lz4"] < sizes[b"none"]
+    # a damaged frame is reported, not read past
+    whole = bytearray((tmp_path / "lz4.bag").read_bytes())
+    at = whole.index(struct.pack("<I", 0x184D2204))
+    whole[at + 4] = 0x24  # frame version 00
+    (tmp_path / "bad.bag").write_bytes(bytes(whole))
+    with pytest.raises(LegoLoamError, match="corrupt lz4 chunk"):
+        RosBag(str(tmp_path / "bad.bag"))
 
 
 def test_reader_errors(built, tmp_path):
