@@ -135,3 +135,16 @@ def test_shard_sequences_replication():
     assert bench.shard_sequences(0, 4) == [0, 1, 2, 3]
     assert bench.shard_sequences(3, 4) == [12, 13, 14, 15]
     assert bench.shard_sequences(1, 8, unique=2) == [8, 9, 8, 9, 8, 9, 8, 9]
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/lego_loam_b200.h must compile as strict C99 (no C++ types in the
+    signatures)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "lego_loam_b200.h"\n'
+                   "int main(void) { LegoLoamParams p; ll_pointcloud2_view v; double o[7]; float t[6] = {0};\n"
+                   "  (void)v; ll_default_params(&p); ll_transform_to_odometry(t, o); return o[6] == 1.0 ? 0 : 1; }\n")
+    obj = tmp_path / "abi.o"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(obj)])
