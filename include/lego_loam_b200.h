@@ -299,8 +299,8 @@ int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap);
 /* ---- rosbag ingest (replaces rosbag::Bag / rosbag::View of main.cpp:26-35,60-76) ---------- */
 
 /* ROS-less reader of rosbag v2.0 files: the sensor_msgs/PointCloud2 messages of one topic in record-time order, as
- * rosbag::View hands them to ImageProjection::cloudHandler.  Uncompressed and lz4 chunks (bz2: LL_ERR_INVALID_ARG,
- * see ll_bag_last_error).  Pure host code; the bag format and the message layout are restated from their published
+ * rosbag::View hands them to ImageProjection::cloudHandler.  Uncompressed, lz4 and bz2 chunks (anything else, or a
+ * damaged chunk: LL_ERR_INVALID_ARG, see ll_bag_last_error).  Pure host code; the bag format and the message layout are restated from their published
  * specifications (ROS is not vendored in the reference tree: parity unpinned). */
 typedef struct ll_bag ll_bag;
 typedef struct {

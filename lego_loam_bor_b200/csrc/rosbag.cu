@@ -8,9 +8,10 @@
 // list of <u32 field_len><name>=<value> fields, and the `op` field tells the record type: 0x03 bag header, 0x05 chunk (its
 // data is a run of records again), 0x07 connection (topic + a second header in the data with type / md5sum /
 // message_definition), 0x02 message data (conn, time; data = the serialised message), 0x04 index data, 0x06 chunk info.
-// Chunks may be uncompressed (compression=none, what `rosbag record` writes by default) or lz4 (`rosbag record --lz4`:
-// an LZ4 frame, magic 0x184D2204, decoded here by a restatement of the published LZ4 frame / block formats -- checksums are
-// not verified); bz2 chunks are reported as LL_ERR_INVALID_ARG with a message, because no bzip2 library may be assumed here.
+// Chunks may be uncompressed (compression=none, what `rosbag record` writes by default), lz4 (`rosbag record --lz4`: an
+// LZ4 frame, magic 0x184D2204) or bz2 (`rosbag record -j`: one bzip2 stream); both are decoded here by restatements of
+// the published formats, because neither library may be assumed on the target -- checksums are not verified.
+// tests/test_rosbag.py checks the decoders against chunks written by liblz4 and libbz2.
 // Messages come back in record-time order (stable), like rosbag::View iterates them.
 #include <fcntl.h>
 #include <stdint.h>
@@ -149,6 +150,187 @@ bool lz4_frame(const uint8_t* ip, size_t n, std::vector<uint8_t>* out, size_t si
   return op == size;
 }
 
+// ---- bzip2 (restated from the published format description of bzip2 1.0.x: Huffman-coded MTF/RLE2 of a BWT block) ----
+// Block and stream CRCs are not verified; the obsolete "randomised" block flag is refused.
+struct BitReader {
+  const uint8_t* p;
+  size_t n, pos;  // pos in bits
+  bool ok;
+  uint32_t bits(int k) {  // MSB first, k <= 24
+    uint32_t v = 0;
+    for (int i = 0; i < k; ++i) {
+      if ((pos >> 3) >= n) { ok = false; return 0; }
+      v = (v << 1) | ((p[pos >> 3] >> (7 - (pos & 7))) & 1u);
+      ++pos;
+    }
+    return v;
+  }
+};
+
+bool bz2_stream(const uint8_t* ip, size_t n, std::vector<uint8_t>* out, size_t size) {
+  if (n < 4 || ip[0] != 'B' || ip[1] != 'Z' || ip[2] != 'h' || ip[3] < '1' || ip[3] > '9') return false;
+  const size_t block_max = (size_t)(ip[3] - '0') * 100000;
+  BitReader br{ip, n, 32, true};
+  out->clear();
+  out->reserve(size);
+  std::vector<uint32_t> tt(block_max);
+  while (true) {
+    const uint32_t m1 = br.bits(24), m2 = br.bits(24);
+    if (!br.ok) return false;
+    if (m1 == 0x177245u && m2 == 0x385090u) break;  // end of stream (combined CRC follows)
+    if (m1 != 0x314159u || m2 != 0x265359u) return false;
+    br.bits(16); br.bits(16);  // block CRC
+    if (br.bits(1)) return false;  // randomised blocks: bzip2 < 0.9.5 only
+    const uint32_t orig_ptr = br.bits(24);
+    // symbols in use
+    uint8_t seq_to_unseq[256];
+    int n_in_use = 0;
+    {
+      const uint32_t ranges = br.bits(16);
+      for (int i = 0; i < 16; ++i) {
+        if (!((ranges >> (15 - i)) & 1u)) continue;
+        const uint32_t used = br.bits(16);
+        for (int j = 0; j < 16; ++j)
+          if ((used >> (15 - j)) & 1u) seq_to_unseq[n_in_use++] = (uint8_t)(i * 16 + j);
+      }
+    }
+    if (n_in_use == 0) return false;
+    const int alpha = n_in_use + 2;
+    const int n_groups = (int)br.bits(3);
+    const int n_sel = (int)br.bits(15);
+    if (n_groups < 2 || n_groups > 6 || n_sel < 1 || !br.ok) return false;
+    std::vector<uint8_t> selector((size_t)n_sel);
+    {
+      uint8_t pos[6] = {0, 1, 2, 3, 4, 5};
+      for (int i = 0; i < n_sel; ++i) {
+        int j = 0;
+        while (br.bits(1)) {
+          if (++j >= n_groups) return false;
+        }
+        const uint8_t v = pos[j];
+        for (; j > 0; --j) pos[j] = pos[j - 1];
+        pos[0] = v;
+        selector[(size_t)i] = v;
+      }
+    }
+    // coding tables: delta-coded code lengths, then canonical Huffman decode tables
+    int limit[6][24], base[6][24], perm[6][258], min_len[6];
+    for (int t = 0; t < n_groups; ++t) {
+      uint8_t len[258];
+      int curr = (int)br.bits(5);
+      for (int i = 0; i < alpha; ++i) {
+        while (true) {
+          if (curr < 1 || curr > 20 || !br.ok) return false;
+          if (!br.bits(1)) break;
+          curr += br.bits(1) ? -1 : 1;
+        }
+        len[i] = (uint8_t)curr;
+      }
+      int mn = 32, mx = 0;
+      for (int i = 0; i < alpha; ++i) { mn = len[i] < mn ? len[i] : mn; mx = len[i] > mx ? len[i] : mx; }
+      min_len[t] = mn;
+      int pp = 0;
+      for (int l = mn; l <= mx; ++l)
+        for (int i = 0; i < alpha; ++i)
+          if (len[i] == l) perm[t][pp++] = i;
+      for (int i = 0; i < 24; ++i) { base[t][i] = 0; limit[t][i] = 0; }
+      for (int i = 0; i < alpha; ++i) base[t][len[i] + 1]++;
+      for (int i = 1; i < 24; ++i) base[t][i] += base[t][i - 1];
+      int vec = 0;
+      for (int l = mn; l <= mx; ++l) {
+        vec += base[t][l + 1] - base[t][l];
+        limit[t][l] = vec - 1;
+        vec <<= 1;
+      }
+      for (int l = mn + 1; l <= mx; ++l) base[t][l] = ((limit[t][l - 1] + 1) << 1) - base[t][l];
+      for (int l = mx + 1; l < 24; ++l) limit[t][l] = 0x7fffffff;  // a longer code cannot exist: stop the length walk
+    }
+    // MTF / RLE2 symbols -> tt
+    const int eob = n_in_use + 1;
+    uint8_t yy[256];
+    for (int i = 0; i < 256; ++i) yy[i] = (uint8_t)i;
+    uint32_t unzftab[256] = {0};
+    size_t nblock = 0;
+    int group_no = -1, group_pos = 0, t = 0;
+    auto next_sym = [&]() -> int {
+      if (group_pos == 0) {
+        if (++group_no >= n_sel) { br.ok = false; return eob; }
+        group_pos = 50;
+        t = selector[(size_t)group_no];
+      }
+      --group_pos;
+      int zn = min_len[t];
+      int zvec = (int)br.bits(zn);
+      while (zvec > limit[t][zn]) {
+        if (++zn > 20 || !br.ok) { br.ok = false; return eob; }
+        zvec = (zvec << 1) | (int)br.bits(1);
+      }
+      const int idx = zvec - base[t][zn];
+      if (idx < 0 || idx >= alpha) { br.ok = false; return eob; }
+      return perm[t][idx];
+    };
+    int sym = next_sym();
+    while (br.ok && sym != eob) {
+      if (sym <= 1) {  // RUNA / RUNB: a run length in bijective base 2
+        size_t es = 0, weight = 1;
+        do {
+          es += weight << sym;  // RUNA adds weight, RUNB 2 * weight
+          weight <<= 1;
+          if (weight > (1u << 21)) return false;
+          sym = next_sym();
+        } while (br.ok && sym <= 1);
+        const uint8_t uc = seq_to_unseq[yy[0]];
+        if (nblock + es > block_max) return false;
+        unzftab[uc] += (uint32_t)es;
+        for (size_t i = 0; i < es; ++i) tt[nblock++] = uc;
+        continue;
+      }
+      const int nn = sym - 1;
+      const uint8_t v = yy[nn];
+      for (int j = nn; j > 0; --j) yy[j] = yy[j - 1];
+      yy[0] = v;
+      const uint8_t uc = seq_to_unseq[v];
+      if (nblock >= block_max) return false;
+      unzftab[uc]++;
+      tt[nblock++] = uc;
+      sym = next_sym();
+    }
+    if (!br.ok || orig_ptr >= nblock) return false;
+    // inverse BWT
+    uint32_t cftab[257];
+    cftab[0] = 0;
+    for (int i = 0; i < 256; ++i) cftab[i + 1] = cftab[i] + unzftab[i];
+    for (size_t i = 0; i < nblock; ++i) {
+      const uint8_t uc = (uint8_t)(tt[i] & 0xffu);
+      tt[cftab[uc]] |= (uint32_t)i << 8;
+      cftab[uc]++;
+    }
+    uint32_t tpos = tt[orig_ptr] >> 8;
+    // undo the initial run-length coding: four equal bytes are followed by a repeat count
+    int run = 0, prev = -1;
+    for (size_t i = 0; i < nblock; ++i) {
+      tpos = tt[tpos];
+      const uint8_t ch = (uint8_t)(tpos & 0xffu);
+      tpos >>= 8;
+      if (run == 4) {
+        out->insert(out->end(), (size_t)ch, (uint8_t)prev);
+        run = 0;
+        prev = -1;
+        continue;
+      }
+      out->push_back(ch);
+      if ((int)ch == prev) {
+        ++run;
+      } else {
+        run = 1;
+        prev = ch;
+      }
+      if (out->size() > size) return false;
+    }
+  }
+  return out->size() == size;
+}
+
 }  // namespace
 
 struct ll_bag {
@@ -174,10 +356,12 @@ int scan_records(ll_bag* bag, Span buf, bool top_level, const std::string& want_
     if (op == 0x05) {  // chunk
       if (!top_level) { g_bag_error = "chunk inside a chunk"; return LL_ERR_INVALID_ARG; }
       const std::string comp = f.count("compression") ? str_of(f["compression"]) : "none";
-      if (comp == "lz4") {
+      if (comp == "lz4" || comp == "bz2") {
         if (!f.count("size") || f["size"].n != 4) { g_bag_error = "chunk record without size"; return LL_ERR_INVALID_ARG; }
         bag->inflated.emplace_back();
-        if (!lz4_frame(d.p, d.n, &bag->inflated.back(), rd32(f["size"].p))) { g_bag_error = "corrupt lz4 chunk"; return LL_ERR_INVALID_ARG; }
+        const bool good = comp == "lz4" ? lz4_frame(d.p, d.n, &bag->inflated.back(), rd32(f["size"].p))
+                                        : bz2_stream(d.p, d.n, &bag->inflated.back(), rd32(f["size"].p));
+        if (!good) { g_bag_error = "corrupt " + comp + " chunk"; return LL_ERR_INVALID_ARG; }
         Span u;
         u.p = bag->inflated.back().data();
         u.n = bag->inflated.back().size();

@@ -116,7 +116,11 @@ def write_bag(path, connections, chunks, compression=b"none"):
             index.setdefault(c, []).append((sec, nsec, len(inner)))
             inner += _record([("op", b"\x02"), ("conn", struct.pack("<I", c)), ("time", struct.pack("<II", sec, nsec))], payload)
         chunk_pos = 13 + 4096 + len(body)
-        stored = lz4_frame(inner) if compression == b"lz4" else (lz4_frame_liblz4(inner) if compression == b"liblz4" else inner)
+        if compression == b"bz2":
+            import bz2
+            stored = bz2.compress(inner, 1 if len(body) % 2 else 9)
+        else:
+            stored = lz4_frame(inner) if compression == b"lz4" else (lz4_frame_liblz4(inner) if compression == b"liblz4" else inner)
         body += _record([("op", b"\x05"), ("compression", b"lz4" if compression == b"liblz4" else compression),
                          ("size", struct.pack("<I", len(inner)))], stored)
         for c, entries in index.items():
@@ -189,14 +193,15 @@ def test_reader_returns_topic_in_time_order(built, tmp_path):
     assert len(RosBag(path, "/no_such_topic")) == 0
 
 
-def test_lz4_chunks(built, tmp_path):
-    """`rosbag record --lz4`: the same messages from LZ4-framed chunks (compressed, stored and self-overlapping matches)."""
+def test_compressed_chunks(built, tmp_path):
+    """`rosbag record --lz4` / `-j`: the same messages from LZ4-framed chunks (compressed, stored and self-overlapping
+    matches; written by the test's encoder and by liblz4) and from bzip2 chunks (written by libbz2)."""
     from lego_loam_bor_b200.capi import LegoLoamError, RosBag
     rng = np.random.default_rng(6)
     clouds = [rng.normal(0, 10, (n, 4)).astype(np.float32) for n in (400, 1, 0, 900, 17)]
     clouds[3][100:600] = 0  # long runs of equal bytes: matches that overlap their own output
     sizes = {}
-    codecs = [b"none", b"lz4"]
+    codecs = [b"none", b"lz4", b"bz2"]  # bz2 chunks are written by libbz2 (Python's bz2 module)
     try:
         import pyarrow as pa
         if pa.Codec.is_available("lz4"):
@@ -222,6 +227,32 @@ def test_lz4_chunks(built, tmp_path):
         RosBag(str(tmp_path / "bad.bag"))
 
 
+def test_compressed_chunks_large(built, tmp_path):
+    """Chunks larger than a bzip2 block (100 kB at level 1) and than an LZ4 frame block of the test encoder; long runs of
+    equal bytes (bzip2's initial run-length stage: four equal bytes + a count) and incompressible noise."""
+    from lego_loam_bor_b200.capi import RosBag
+    rng = np.random.default_rng(8)
+    big = rng.normal(0, 30, (14000, 4)).astype(np.float32)
+    big[2000:9000] = 0
+    big[9000:9300, 0] = 1.5
+    clouds = [big, rng.normal(0, 1, (3000, 4)).astype(np.float32), np.zeros((5000, 4), np.float32), big[::-1].copy()]
+    codecs = [b"bz2", b"lz4"]
+    try:
+        import pyarrow as pa
+        if pa.Codec.is_available("lz4"):
+            codecs.append(b"liblz4")
+    except ImportError:
+        pass
+    for comp in codecs:
+        path = tmp_path / (comp.decode() + "_big.bag")
+        datas = make_bag(str(path), clouds, np.random.default_rng(9), compression=comp)
+        bag = RosBag(str(path), "/velodyne_points")
+        assert len(bag) == len(clouds)
+        for i, d in enumerate(datas):
+            v, data = bag.message(i)
+            assert np.array_equal(data, d), f"{comp} message {i}"
+
+
 def test_reader_errors(built, tmp_path):
     from lego_loam_bor_b200.capi import LegoLoamError, RosBag
     rng = np.random.default_rng(3)
@@ -232,9 +263,16 @@ def test_reader_errors(built, tmp_path):
     p.write_bytes(b"#ROSBAG V1.2\n" + b"\0" * 100)
     with pytest.raises(LegoLoamError, match="not a rosbag v2.0"):
         RosBag(str(p))
+    make_bag(str(tmp_path / "xz.bag"), clouds, rng, compression=b"xz")
+    with pytest.raises(LegoLoamError, match="compression 'xz' is not supported"):
+        RosBag(str(tmp_path / "xz.bag"))
     make_bag(str(tmp_path / "bz2.bag"), clouds, rng, compression=b"bz2")
-    with pytest.raises(LegoLoamError, match="compression 'bz2' is not supported"):
-        RosBag(str(tmp_path / "bz2.bag"))
+    whole = bytearray((tmp_path / "bz2.bag").read_bytes())
+    at = whole.index(b"BZh")
+    whole[at + 4] ^= 0xff  # block magic
+    (tmp_path / "bad_bz2.bag").write_bytes(bytes(whole))
+    with pytest.raises(LegoLoamError, match="corrupt bz2 chunk"):
+        RosBag(str(tmp_path / "bad_bz2.bag"))
     make_bag(str(tmp_path / "ok.bag"), clouds, rng)
     whole = (tmp_path / "ok.bag").read_bytes()
     (tmp_path / "cut.bag").write_bytes(whole[:13 + 4096 + 300])
