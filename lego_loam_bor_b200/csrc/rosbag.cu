@@ -358,6 +358,7 @@ int scan_records(ll_bag* bag, Span buf, bool top_level, const std::string& want_
       const std::string comp = f.count("compression") ? str_of(f["compression"]) : "none";
       if (comp == "lz4" || comp == "bz2") {
         if (!f.count("size") || f["size"].n != 4) { g_bag_error = "chunk record without size"; return LL_ERR_INVALID_ARG; }
+        if (rd32(f["size"].p) > (1u << 30)) { g_bag_error = "chunk larger than 1 GiB"; return LL_ERR_INVALID_ARG; }  // rosbag's default is 768 kB
         bag->inflated.emplace_back();
         const bool good = comp == "lz4" ? lz4_frame(d.p, d.n, &bag->inflated.back(), rd32(f["size"].p))
                                         : bz2_stream(d.p, d.n, &bag->inflated.back(), rd32(f["size"].p));

@@ -301,3 +301,50 @@ def test_bag_to_device(built, tmp_path):
         o.feature_association()
         for name in ("RANGE_MAT", "LABEL_MAT", "SEG_COL_IND", "SURF_LAST", "TRANSFORM_SUM"):
             assert same_bits(gpu.download(name, 0), o.download(name)), f"message {i}: {name}"
+
+
+def test_reader_survives_corruption(built, tmp_path):
+    """A bag is an untrusted file: truncated or bit-flipped bags (all three chunk codecs) must end in LegoLoamError or in
+    a readable bag, never in a crash.  The loop runs in a child process so that a crash would show as its exit code."""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(12)
+    clouds = [rng.normal(0, 10, (n, 4)).astype(np.float32) for n in (300, 40, 0, 700, 9)]
+    clouds[3][100:500] = 0
+    for comp in (b"none", b"lz4", b"bz2"):
+        make_bag(str(tmp_path / (comp.decode() + ".bag")), clouds, np.random.default_rng(13), compression=comp)
+    child = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from lego_loam_bor_b200.capi import LegoLoamError, RosBag
+rng = np.random.default_rng(14)
+ok = bad = 0
+for comp in ("none", "lz4", "bz2"):
+    whole = open(sys.argv[2] + "/" + comp + ".bag", "rb").read()
+    for trial in range(150):
+        b = bytearray(whole)
+        if trial % 3 == 0:
+            b = b[:int(rng.integers(0, len(b)))]
+        else:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(13 + 4096, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        path = sys.argv[2] + "/fuzz.bag"
+        open(path, "wb").write(bytes(b))
+        try:
+            bag = RosBag(path, "/velodyne_points")
+            for i in range(len(bag)):
+                try:
+                    bag.message(i)
+                except LegoLoamError:
+                    bad += 1
+            bag.close()
+            ok += 1
+        except LegoLoamError:
+            bad += 1
+print(ok, bad)
+"""
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", child, root, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    ok, bad = map(int, r.stdout.split())
+    assert ok + bad >= 450 and bad > 0
