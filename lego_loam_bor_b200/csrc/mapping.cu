@@ -209,6 +209,9 @@ __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) 
 #ifndef KNN_COOP_MAX
 #define KNN_COOP_MAX 24
 #endif
+#ifndef KNN_SEED_PREV
+#define KNN_SEED_PREV 0
+#endif
 
 __device__ __forceinline__ void knn_search_warp(const DevState& st, int s, int q, int nc, const MapPose& mp, int* sh /* [3][32] */) {
   const DevParams& p = st.p;
@@ -396,6 +399,31 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int ite
       unsigned long long bk[KNN_REC];
 #pragma unroll
       for (int i = 0; i < KNN_REC; ++i) bk[i] = ((unsigned long long)__float_as_uint(1.0f) << 32) | 0x7fffffffull;
+#if KNN_SEED_PREV
+      // Experiment for the next round (off by default, not yet measured on the GPU): a repeated search starts from the
+      // previous record's candidates.  They are map points closer than 1 m if their new distance says so, hence inside the
+      // 27 cells and found again below (skipped there by the duplicate test): the result is the same, but the threshold is
+      // tight from the first cell on, so far fewer candidates pay for a sorted insertion and more cells are pruned.
+      if (iter > 0) {
+        const float4* prev = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
+#pragma unroll
+        for (int c = 0; c < KNN_K; ++c) {
+          const float4 cp = prev[c];
+          const int ci0 = __float_as_int(cp.w);
+          const float cd = nn_dist2(sel.x, sel.y, sel.z, cp);
+          if (ci0 >= 0 && cd < 1.0f) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(cd) << 32) | (unsigned)ci0;
+#pragma unroll
+            for (int i = 0; i < KNN_REC; ++i) {
+              const unsigned long long b = bk[i];
+              const bool lt = key < b;
+              bk[i] = lt ? key : b;
+              key = lt ? b : key;
+            }
+          }
+        }
+      }
+#endif
       // position of the query inside its cell: the gap to a neighbouring cell along an axis is f or cell - f
       const float fx = sel.x - (float)cx * g.cell, fy = sel.y - (float)cy * g.cell, fz = sel.z - (float)cz * g.cell;
       // Three batches of nine cells, nearest first.  2a: the non-empty buckets of the batch; the bitmap loads (and then the
