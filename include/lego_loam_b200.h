@@ -146,6 +146,10 @@ int ll_create(const LegoLoamParams* params, int batch, int max_points, int devic
 int ll_destroy(ll_handle* h);
 /* Forget all per-sequence history (first-frame state, transformCur/Sum, last clouds). */
 int ll_reset(ll_handle* h);
+/* Only the FeatureAssociation side, as if that object had just been constructed (featureAssociation.cpp:96-157): the
+ * next scan is a first frame again.  MapOptimization state (poses, key frames, local map) is kept.  Used to store
+ * key frames from scans that are not consecutive in time (the 500-key-frame map). */
+int ll_reset_feature_association(ll_handle* h);
 const char* ll_last_error(const ll_handle* h);
 /* Number of kernels this handle has launched since creation (bench "gpu_launches"). */
 int64_t ll_kernel_launches(const ll_handle* h);
@@ -220,10 +224,11 @@ int ll_scan_to_map(ll_handle* h);
  * off), extractSurroundingKeyFrames (:856-996, the enable_loop_closure == false branch) and transformPointCloud
  * (:443-473) for all sequences, without host round trips.
  *
- * ll_map_enable_keyframes allocates the per-sequence stores: max_keyframes key poses (<= 1024), pool_points points
+ * ll_map_enable_keyframes allocates the per-sequence stores: max_keyframes key poses (<= 32768), pool_points points
  * for all key-frame clouds of one sequence (corner + surf + outlier, already down-sampled), and local maps of up to
  * max_map_corner / max_map_surf points (laserCloudCornerFromMapDS / laserCloudSurfFromMapDS).  A sequence that
- * outgrows a capacity stops saving key frames / truncates its map and raises a bit in LL_BUF_KEYFRAME_STATE[3].
+ * outgrows a capacity stops saving key frames / truncates its map and raises a bit in LL_BUF_KEYFRAME_STATE[3]; the
+ * next ll_mapping_cycle then returns LL_ERR_CAPACITY (the bits are read back one cycle late, no call waits for the device).
  * Fails with LL_ERR_STATE when params.enable_loop_closure is set (the loop-closure branch is not built). */
 int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, int max_map_corner, int max_map_surf);
 /* extractSurroundingKeyFrames: radius search over the key poses around currentRobotPosPoint, 1 m VoxelGrid of those

@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
         from ._paths import PKG
         if not os.path.exists(os.path.join(PKG, "host", "sequence_driver")):
             build_host()
+        from . import synth
+        synth.build_cuda()
         return LIB_CUDA
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -64,6 +66,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed; see " + log_path)
     subprocess.check_call([nvcc, "-shared", "-o", LIB_CUDA] + objs + ["-lcudart"])
     build_host()
+    from . import synth
+    synth.build_cuda()   # the device version of the synthetic-scan generator (bench / test data, a library of its own)
     return LIB_CUDA
 
 

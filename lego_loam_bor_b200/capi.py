@@ -33,7 +33,7 @@ BUFFERS = {
 }
 
 EXPORTS = [
-    "ll_default_params", "ll_create", "ll_destroy", "ll_reset", "ll_last_error", "ll_kernel_launches",
+    "ll_default_params", "ll_create", "ll_destroy", "ll_reset", "ll_reset_feature_association", "ll_last_error", "ll_kernel_launches",
     "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
     "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
     "ll_map_set_initial_guess_async", "ll_map_set_poses", "ll_map_predict_pose",
@@ -131,6 +131,7 @@ def load_library(path=None):
     lib.ll_create.argtypes = [vp, ip, ip, ip, vp, C.POINTER(vp)]
     lib.ll_destroy.argtypes = [vp]
     lib.ll_reset.argtypes = [vp]
+    lib.ll_reset_feature_association.argtypes = [vp]
     lib.ll_last_error.argtypes = [vp]
     lib.ll_last_error.restype = C.c_char_p
     lib.ll_kernel_launches.argtypes = [vp]
@@ -215,6 +216,9 @@ class LegoLoam:
     def reset(self):
         self._ck(self.lib.ll_reset(self.h), "ll_reset")
 
+    def reset_feature_association(self):
+        self._ck(self.lib.ll_reset_feature_association(self.h), "ll_reset_feature_association")
+
     def set_scans_host(self, scans):
         """scans: list (len batch) of float32 [n_i, 4] arrays, or (packed [batch, stride, 4], counts)."""
         if isinstance(scans, tuple):
@@ -269,6 +273,14 @@ class LegoLoam:
             packed[i, :len(m)] = m
             counts[i] = len(m) // point_step
         self._ck(self.lib.ll_set_scans_pointcloud2_host(self.h, packed.ctypes.data, counts.ctypes.data, stride, point_step,
+                                                        off_x, off_y, off_z, off_intensity, 1 if is_dense else 0),
+                 "ll_set_scans_pointcloud2_host")
+
+    def set_scans_pointcloud2_ptr(self, ptr, counts, stride_bytes, point_step, off_x, off_y, off_z, off_intensity, is_dense=False):
+        """Raw address of host bytes [batch][stride_bytes]: the `data` arrays of one PointCloud2 message per sequence."""
+        counts = np.ascontiguousarray(counts, np.int32)
+        self._in_width = 4
+        self._ck(self.lib.ll_set_scans_pointcloud2_host(self.h, ptr, counts.ctypes.data, stride_bytes, point_step,
                                                         off_x, off_y, off_z, off_intensity, 1 if is_dense else 0),
                  "ll_set_scans_pointcloud2_host")
 
@@ -435,6 +447,30 @@ class LegoLoamStreams:
         for p in self.parts:
             p.reset()
 
+    def reset_feature_association(self):
+        for p in self.parts:
+            p.reset_feature_association()
+
+    def map_set_initial_guess(self, t):
+        t = np.ascontiguousarray(t, np.float32).reshape(self.batch, 6)
+        for i, p in enumerate(self.parts):
+            p.map_set_initial_guess(t[i * self.sub:(i + 1) * self.sub])
+
+    def map_save_keyframe(self):
+        for p in self.parts:
+            p.map_save_keyframe()
+
+    def map_downsample_current_scan(self):
+        for p in self.parts:
+            p.map_downsample_current_scan()
+
+    def image_projection(self):
+        for p in self.parts:
+            p.image_projection()
+
+    def feature_association(self):
+        return [p.feature_association() for p in self.parts][0]
+
     def set_scans_device(self, dev_ptr, counts, stride):
         for i, p in enumerate(self.parts):
             p.set_scans_device(dev_ptr + i * self.sub * stride * 16, counts[i * self.sub:(i + 1) * self.sub], stride)
@@ -442,6 +478,10 @@ class LegoLoamStreams:
     def set_scans_host_ptr(self, ptr, counts, stride):
         for i, p in enumerate(self.parts):
             p.set_scans_host_ptr(ptr + i * self.sub * stride * 16, counts[i * self.sub:(i + 1) * self.sub], stride)
+
+    def set_scans_pointcloud2_ptr(self, ptr, counts, stride_bytes, *fmt):
+        for i, p in enumerate(self.parts):
+            p.set_scans_pointcloud2_ptr(ptr + i * self.sub * stride_bytes, counts[i * self.sub:(i + 1) * self.sub], stride_bytes, *fmt)
 
     def set_scans_xyz_host_ptr(self, ptr, counts, stride):
         for i, p in enumerate(self.parts):

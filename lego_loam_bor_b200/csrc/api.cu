@@ -49,6 +49,10 @@ struct ll_handle {
   int pose_head = 0, pose_pending = 0;
   float stage_ms[5];
   bool ev_valid = false;
+  // capacity error bits of the key-frame store, read back one mapping cycle late without waiting (ll_mapping_cycle)
+  int32_t* h_kf_err = nullptr;
+  cudaEvent_t kf_err_ev = nullptr;
+  bool kf_err_pending = false;
 };
 
 namespace {
@@ -128,12 +132,17 @@ int reset_keyframes(ll_handle* h) {
   CK(cudaMemsetAsync(kf.transform_last, 0, (size_t)B * 24, sm)); CK(cudaMemsetAsync(kf.sur_n, 0, (size_t)B * 4, sm));
   CK(cudaMemsetAsync(kf.sur_first, 0, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.sur_rebuild, 0, (size_t)B * 4, sm));
   CK(cudaMemsetAsync(kf.sur_valid, 0, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.err, 0, (size_t)B * 4, sm));
+  CK(cudaMemsetAsync(kf.sur_n_erased, 0, (size_t)B * 4, sm)); CK(cudaMemsetAsync(kf.sur_last_erased, 0, (size_t)B * 4, sm));
   for (int m = 0; m < 2; ++m) {
     const VoxTable& t = kf.tbl[m];
     CK(cudaMemsetAsync(t.key, 0xff, (size_t)B * t.parts * t.sub_cap * 8, sm));
     CK(cudaMemsetAsync(t.list_n, 0, (size_t)B * t.parts * 4, sm));
+    CK(cudaMemsetAsync(t.list_done, 0, (size_t)B * t.parts * 4, sm));
   }
+  CK(cudaMemsetAsync(kf.xs_cur, 0, (size_t)B * 2 * 4, sm)); CK(cudaMemsetAsync(kf.xs_n, 0, (size_t)B * 2 * 4, sm));
+  CK(cudaMemsetAsync(kf.xs_merge, 0, (size_t)B * 2 * 16, sm)); CK(cudaMemsetAsync(kf.xs_bbox, 0, (size_t)B * 2 * 32, sm));
   CK(cudaMemsetAsync(h->st.map_counts, 0, (size_t)B * 8, sm));
+  h->kf_err_pending = false;
   return LL_OK;
 }
 
@@ -285,6 +294,8 @@ int ll_destroy(ll_handle* h) {
   cudaStreamSynchronize(h->ctx.stream);
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_n_in) cudaFreeHost(h->h_n_in);
+  if (h->h_kf_err) cudaFreeHost(h->h_kf_err);
+  if (h->kf_err_ev) cudaEventDestroy(h->kf_err_ev);
   for (int i = 0; i < 16; ++i) cudaEventDestroy(h->slot_ev[i]);
   for (int b = 0; b < 2; ++b) { cudaEventDestroy(h->copied[b]); cudaEventDestroy(h->consumed[b]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -304,7 +315,7 @@ int ll_destroy(ll_handle* h) {
 const char* ll_last_error(const ll_handle* h) { return h ? h->err.c_str() : "null handle"; }
 int64_t ll_kernel_launches(const ll_handle* h) { return h ? h->ctx.launches : 0; }
 
-int ll_reset(ll_handle* h) {
+int ll_reset_feature_association(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   DevState& st = h->st;
   const DevParams& p = st.p;
@@ -314,12 +325,8 @@ int ll_reset(ll_handle* h) {
   CK(cudaMemsetAsync(st.curvature, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.picked, 0, BN * 4, sm));
   CK(cudaMemsetAsync(st.cloud_label, 0, BN * 4, sm)); CK(cudaMemsetAsync(st.slot4, 0, (size_t)p.B * 8, sm));
   CK(cudaMemsetAsync(st.transform_cur, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_sum, 0, (size_t)p.B * 24, sm));
-  CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm));
-  CK(cudaMemsetAsync(st.transform_bef_mapped, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_aft_mapped, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.last_counts, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_flags, 0, (size_t)p.B * 16, sm));
   CK(cudaMemsetAsync(st.odom_iters, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_matP, 0, (size_t)p.B * 36, sm));
-  CK(cudaMemsetAsync(st.map_flags, 0, (size_t)p.B * 16, sm)); CK(cudaMemsetAsync(st.map_matP, 0, (size_t)p.B * 144, sm));
-  CK(cudaMemsetAsync(st.map_iters, 0, (size_t)p.B * 8, sm));
   CK(cudaMemsetAsync(st.grid_corner_last.cell_start, 0, (size_t)p.B * (st.grid_corner_last.tbl + 1) * 4, sm));
   CK(cudaMemsetAsync(st.grid_corner_last.occ, 0, (size_t)p.B * (st.grid_corner_last.tbl / 32) * 4, sm));
   CK(cudaMemsetAsync(st.grid_surf_last.occ, 0, (size_t)p.B * (st.grid_surf_last.tbl / 32) * 4, sm));
@@ -331,6 +338,19 @@ int ll_reset(ll_handle* h) {
   h->frames = 0;
   h->odom_cycles = 0;
   h->handed_to_mapping = false;
+  return LL_OK;
+}
+
+int ll_reset(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  { const int rc = ll_reset_feature_association(h); if (rc) return rc; }
+  DevState& st = h->st;
+  const DevParams& p = st.p;
+  cudaStream_t sm = h->ctx.stream;
+  CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm));
+  CK(cudaMemsetAsync(st.transform_bef_mapped, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_aft_mapped, 0, (size_t)p.B * 24, sm));
+  CK(cudaMemsetAsync(st.map_flags, 0, (size_t)p.B * 16, sm)); CK(cudaMemsetAsync(st.map_matP, 0, (size_t)p.B * 144, sm));
+  CK(cudaMemsetAsync(st.map_iters, 0, (size_t)p.B * 8, sm));
   if (st.kf.enabled) { const int rc = reset_keyframes(h); if (rc) return rc; }
   return LL_OK;
 }
@@ -573,7 +593,7 @@ int ll_scan_to_map(ll_handle* h) {
 }
 
 int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, int max_map_corner, int max_map_surf) {
-  if (!h || max_keyframes < 1 || max_keyframes > 1024 || pool_points < 1 || max_map_corner < 1 || max_map_surf < 1) return LL_ERR_INVALID_ARG;
+  if (!h || max_keyframes < 1 || max_keyframes > 32768 || pool_points < 1 || max_map_corner < 1 || max_map_surf < 1) return LL_ERR_INVALID_ARG;
   if (h->prm.enable_loop_closure) { h->err = "ll_map_enable_keyframes: the loop-closure branch of extractSurroundingKeyFrames is not built"; return LL_ERR_STATE; }
   DevState& st = h->st;
   KeyframeStore& kf = st.kf;
@@ -593,6 +613,13 @@ int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, in
   CK(dev_alloc(h, &kf.kf_off, (size_t)B * kf.kf_cap * 4)); CK(dev_alloc(h, &kf.pool_used, (size_t)B));
   CK(dev_alloc(h, &kf.pool_pts, (size_t)B * kf.pool_cap, false)); CK(dev_alloc(h, &kf.pool_key, (size_t)B * kf.pool_cap, false));
   CK(dev_alloc(h, &kf.pool_perm, (size_t)B * kf.pool_cap, false)); CK(dev_alloc(h, &kf.kf_new, (size_t)B));
+  CK(dev_alloc(h, &kf.pool_link, (size_t)B * kf.pool_cap, false));
+  CK(dev_alloc(h, &kf.sur_erased, (size_t)B * kf.kf_cap)); CK(dev_alloc(h, &kf.sur_n_erased, (size_t)B));
+  CK(dev_alloc(h, &kf.sur_last_erased, (size_t)B));
+  CK(dev_alloc(h, &kf.sel_k0, (size_t)B * kf.kf_cap, false)); CK(dev_alloc(h, &kf.sel_k1, (size_t)B * kf.kf_cap, false));
+  CK(dev_alloc(h, &kf.sel_v0, (size_t)B * kf.kf_cap, false)); CK(dev_alloc(h, &kf.sel_v1, (size_t)B * kf.kf_cap, false));
+  CK(dev_alloc(h, &kf.sel_rank_idx, (size_t)B * kf.kf_cap, false)); CK(dev_alloc(h, &kf.sel_ds_ids, (size_t)B * kf.kf_cap, false));
+  CK(dev_alloc(h, &kf.sel_first_pos, (size_t)B * kf.kf_cap, false));
   CK(dev_alloc(h, &kf.robot_pos, (size_t)B * 8)); CK(dev_alloc(h, &kf.transform_last, (size_t)B * 6));
   CK(dev_alloc(h, &kf.sur_ids, (size_t)B * kf.kf_cap)); CK(dev_alloc(h, &kf.sur_n, (size_t)B));
   CK(dev_alloc(h, &kf.sur_first, (size_t)B)); CK(dev_alloc(h, &kf.sur_rebuild, (size_t)B));
@@ -610,10 +637,22 @@ int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, in
     const size_t slots = (size_t)B * t.parts * t.sub_cap;
     CK(dev_alloc(h, &t.key, slots, false)); CK(dev_alloc(h, &t.sum, slots, false)); CK(dev_alloc(h, &t.cnt, slots, false));
     CK(dev_alloc(h, &t.list, slots, false)); CK(dev_alloc(h, &t.list_n, (size_t)B * t.parts));
+    CK(dev_alloc(h, &t.head, slots, false)); CK(dev_alloc(h, &t.tail, slots, false)); CK(dev_alloc(h, &t.list_done, (size_t)B * t.parts));
   }
   kf.sort_cap = st.cap_map_corner > st.cap_map_surf ? st.cap_map_corner : st.cap_map_surf;
   CK(dev_alloc(h, &kf.sk0, (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.sk1, (size_t)B * 2 * kf.sort_cap, false));
   CK(dev_alloc(h, &kf.sv0, (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.sv1, (size_t)B * 2 * kf.sort_cap, false));
+  for (int b = 0; b < 2; ++b) {
+    CK(dev_alloc(h, &kf.xs_key[b], (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.xs_slot[b], (size_t)B * 2 * kf.sort_cap, false));
+  }
+  CK(dev_alloc(h, &kf.xn_key, (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.xn_slot, (size_t)B * 2 * kf.sort_cap, false));
+  CK(dev_alloc(h, &kf.xs_cur, (size_t)B * 2)); CK(dev_alloc(h, &kf.xs_n, (size_t)B * 2)); CK(dev_alloc(h, &kf.xs_merge, (size_t)B * 2 * 4));
+  CK(dev_alloc(h, &kf.xs_tile, (size_t)B * 2 * (kf.sort_cap / 1024 + 1))); CK(dev_alloc(h, &kf.xs_bbox, (size_t)B * 2 * 8));
+  if (!h->h_kf_err) {
+    CK(cudaMallocHost((void**)&h->h_kf_err, sizeof(int32_t) * B));
+    memset(h->h_kf_err, 0, sizeof(int32_t) * B);
+    CK(cudaEventCreateWithFlags(&h->kf_err_ev, cudaEventDisableTiming));
+  }
   kf.enabled = 1;
   { const int rc = reset_keyframes(h); if (rc) return rc; }
   CK(cudaStreamSynchronize(h->ctx.stream));
@@ -638,6 +677,18 @@ int ll_map_save_keyframe(ll_handle* h) {
 int ll_mapping_cycle(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (!h->st.kf.enabled) { h->err = "ll_mapping_cycle: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
+  // capacity errors of the previous cycle (a sequence that outgrew the key-frame slots, the point pool, a voxel table or
+  // the local-map capacity) are reported here, one cycle late, so that no call ever waits for the device
+  if (h->kf_err_pending && cudaEventQuery(h->kf_err_ev) == cudaSuccess) {
+    h->kf_err_pending = false;
+    for (int s = 0; s < h->st.p.B; ++s)
+      if (h->h_kf_err[s]) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "ll_mapping_cycle: key-frame store of sequence %d out of capacity (LL_BUF_KEYFRAME_STATE bits %d)", s, h->h_kf_err[s]);
+        h->err = msg;
+        return LL_ERR_CAPACITY;
+      }
+  }
   // MapOptimization::run, mapOptmization.cpp:1545-1560
   int rc = ll_map_predict_pose(h);
   if (rc < 0) return rc;
@@ -647,7 +698,14 @@ int ll_mapping_cycle(ll_handle* h) {
   if (rc < 0) return rc;
   rc = ll_scan_to_map(h);
   if (rc < 0) return rc;
-  return ll_map_save_keyframe(h);
+  rc = ll_map_save_keyframe(h);
+  if (rc < 0) return rc;
+  if (!h->kf_err_pending) {
+    CK(cudaMemcpyAsync(h->h_kf_err, h->st.kf.err, sizeof(int32_t) * h->st.p.B, cudaMemcpyDeviceToHost, h->ctx.stream));
+    CK(cudaEventRecord(h->kf_err_ev, h->ctx.stream));
+    h->kf_err_pending = true;
+  }
+  return LL_OK;
 }
 
 int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, void* dst, size_t dst_bytes, size_t* n_elems) {
@@ -959,7 +1017,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       int v[4];
       CK(cudaMemcpyAsync(&v[0], st.kf.kf_count + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
       CK(cudaMemcpyAsync(&v[1], st.kf.sur_n + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
-      CK(cudaMemcpyAsync(&v[2], st.kf.sur_rebuild + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaMemcpyAsync(&v[2], st.kf.sur_last_erased + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
       CK(cudaMemcpyAsync(&v[3], st.kf.err + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
       CK(cudaStreamSynchronize(h->ctx.stream));
       if (n_elems) *n_elems = 4;

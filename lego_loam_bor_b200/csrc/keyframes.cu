@@ -4,24 +4,33 @@
 // iSAM2 (GTSAM, not vendored) is the identity here: without loop closures the graph is an odometry chain whose
 // optimum is the inserted initial values (SURVEY.md sections 8c, 11.5).
 //
-// The reference concatenates the transformed clouds of all surrounding key frames (hundreds of thousands of points)
-// and runs pcl::VoxelGrid over them every mapping cycle.  A VoxelGrid centroid is a left-to-right float sum over the
-// voxel's points in concatenation order, so it can be kept as a running sum: appending a key frame adds its points to
-// the sums of the voxels it touches, in order.  What is stored per key frame is therefore its three clouds already
-// transformed by the (never changing) key pose and stable-sorted by voxel, so that "the points of this key frame in
-// that voxel, in order" is a contiguous run:
+// The reference concatenates the transformed clouds of all surrounding key frames (10.7 M points for the 500-key-frame
+// map of BASELINE.json configs[3]) and runs pcl::VoxelGrid over them every mapping cycle.  A VoxelGrid centroid is a
+// left-to-right float sum over the voxel's points in concatenation order, so it is kept as a running sum per voxel, and
+// the cycle only touches what changed:
 //
 //   k_kf_decide   thread / sequence : the 0.3 m rule, key pose, pool allocation
-//   k_kf_store    block / (sequence, cloud): transform, voxel keys, stable radix sort, write to the pool
+//   k_kf_store    block / (sequence, cloud): transform by the (never changing) key pose, voxel keys, stable radix sort,
+//                                     write to the pool: "the points of this key frame in that voxel, in order" is a
+//                                     contiguous run
 //   k_kf_select   block / sequence  : radius search over the key poses, 1 m VoxelGrid of the poses (its centroid
 //                                     intensity, cast to int, is the key-frame id -- sic), update of
-//                                     surroundingExistingKeyPosesID (erase + append, order preserved)
-//   k_kf_accumulate block / (sequence, table partition): for every pending key frame in list order, thread per run:
-//                                     find-or-insert the voxel, add the run's points to its sums.  Only appended key
-//                                     frames are pending unless one was erased; then the tables are rebuilt.
-//                                     A voxel belongs to one partition, so no two threads ever touch the same sums.
-//   k_kf_extract  block / (sequence, map): occupied voxels sorted by PCL's voxel index -> centroids -> the local map
-//                                     (laserCloudCornerFromMapDS / laserCloudSurfFromMapDS) ll_scan_to_map reads.
+//                                     surroundingExistingKeyPosesID (erase + append, order preserved); any number of
+//                                     key frames (block radix sorts through global scratch)
+//   k_kf_accumulate block / (sequence, table partition), thread / run:
+//                     append  a key frame that joined the list adds its runs to the sums of their voxels and links
+//                             them at the tail of the voxels' run chains (= concatenation order);
+//                     erase   a key frame that left the list is unlinked from the chains of the voxels it touches and
+//                             those voxels are re-summed from their remaining runs, in chain order -- bit-identical
+//                             to re-summing the whole concatenation, at the cost of the touched voxels only;
+//                     rebuild everything from list position 0 (only under table pressure).
+//                   A voxel belongs to one partition and a key frame has one run per voxel and cloud, so no two threads
+//                   ever touch the same voxel.
+//   k_kfx_sort_new / k_kfx_merge / k_kfx_alive / k_kfx_output
+//                   the voxels in ascending PCL voxel index (= lexicographic (iz, iy, ix)) are kept as a sorted array
+//                   across cycles: the few voxels a cycle creates are sorted by one block and merged in by binary
+//                   search (thread / element, all tiles in parallel); the centroids of the voxels that still have
+//                   points are written in that order -> laserCloudCornerFromMapDS / laserCloudSurfFromMapDS.
 #include "block_sort.cuh"
 #include "ll_device.cuh"
 #include "ll_kernels.h"
@@ -29,7 +38,9 @@
 namespace {
 
 #define KF_THREADS BS_THREADS
-#define KF_MAX 1024
+#define KF_MAX_CAP 32768   // key frames per sequence the select kernel's bitmaps cover
+#define KF_NONE 0xFFFFFFFFu
+#define XS_TILE 1024
 #define KF_BIAS (1 << 20)
 #define KF_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define KF_INVALID 0xFFFFFFFFFFFFFFFEull
@@ -70,11 +81,11 @@ __global__ void k_kf_decide(DevState st) {
   const int n = kf.kf_count[s];
   kf.kf_new[s] = -1;
   if (!save && n > 0) return;
-  rp[4] = cx; rp[5] = cy; rp[6] = cz;  // previousRobotPosPoint = currentRobotPosPoint
   const int nc = st.scan_ds_counts[s * 2 + 0], ns = st.vox_tmp_counts[s * 2 + 0], no = st.vox_tmp_counts[s * 2 + 1];
   if (n >= kf.kf_cap) { kf.err[s] |= KF_ERR_SLOTS; return; }
   const int used = kf.pool_used[s];
   if (used + nc + ns + no > kf.pool_cap) { kf.err[s] |= KF_ERR_POOL; return; }
+  rp[4] = cx; rp[5] = cy; rp[6] = cz;  // previousRobotPosPoint = currentRobotPosPoint
   // first key frame: prior on transformTobeMapped (:1362-1376); later ones: transformAftMapped (:1391-1400)
   const float* est = n == 0 ? tobe : aft;
   float* pose = kf.kf_pose + ((size_t)s * kf.kf_cap + n) * 6;
@@ -201,145 +212,181 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_store(DevState st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// bitonic sort of KF_MAX 64-bit keys in shared memory, ascending; all KF_THREADS threads
-__device__ __forceinline__ void kf_bitonic(unsigned long long* a) {
-  const int i = threadIdx.x;
-  for (int k = 2; k <= KF_MAX; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const int x = i ^ j;
-      if (x > i) {
-        const unsigned long long u = a[i], v = a[x];
-        const bool asc = (i & k) == 0;
-        if ((u > v) == asc) { a[i] = v; a[x] = u; }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 __device__ __forceinline__ bool kf_bit(const unsigned* bm, int i) { return (bm[i >> 5] >> (i & 31)) & 1u; }
 
 // extractSurroundingKeyFrames, the key-pose part (mapOptmization.cpp:915-980)
 __global__ void __launch_bounds__(KF_THREADS) k_kf_select(DevState st) {
-  __shared__ unsigned long long a[KF_MAX];
-  __shared__ int idx_by_rank[KF_MAX];
-  __shared__ int ds_ids[KF_MAX];
-  __shared__ int first_pos[KF_MAX];
-  __shared__ int sur_sm[KF_MAX];
-  __shared__ unsigned in_ds[KF_MAX / 32], in_sur[KF_MAX / 32];
-  __shared__ int warp_tot[33];
+  __shared__ BlockSortSmem sort_sm;
+  __shared__ unsigned in_ds[KF_MAX_CAP / 32], in_sur[KF_MAX_CAP / 32];
   __shared__ int sh_mn[3], sh_mx[3];
+  __shared__ int sh_cnt;
   KeyframeStore& kf = st.kf;
   const int s = blockIdx.x, tid = threadIdx.x;
   const int n = kf.kf_count[s];
   if (n == 0) {  // :857 -- nothing to extract yet, the maps stay empty
-    if (tid == 0) { kf.sur_valid[s] = 0; kf.sur_rebuild[s] = 0; kf.sur_first[s] = kf.sur_n[s]; }
+    if (tid == 0) {
+      kf.sur_valid[s] = 0; kf.sur_rebuild[s] = 0; kf.sur_first[s] = kf.sur_n[s];
+      kf.sur_n_erased[s] = 0; kf.sur_last_erased[s] = 0;
+    }
     return;
   }
+  const size_t sbase = (size_t)s * kf.kf_cap;
+  unsigned* const key[2] = {kf.sel_k0 + sbase, kf.sel_k1 + sbase};
+  unsigned* const val[2] = {kf.sel_v0 + sbase, kf.sel_v1 + sbase};
+  int* rank_idx = kf.sel_rank_idx + sbase;
+  int* ds_ids = kf.sel_ds_ids + sbase;
+  int* first_pos = kf.sel_first_pos + sbase;
+  const float* poses = kf.kf_pose + sbase * 6;
   const float* rp = kf.robot_pos + s * 8;
   const float qx = rp[0], qy = rp[1], qz = rp[2];
-  // radiusSearch (nanoflann_pcl.h:155-175): d2 < r2, ascending by distance (ties: ascending index)
-  float px = 0.f, py = 0.f, pz = 0.f;
-  unsigned long long e = KF_EMPTY;
-  if (tid < n) {
-    const float* pose = kf.kf_pose + ((size_t)s * kf.kf_cap + tid) * 6;
-    px = pose[3]; py = pose[4]; pz = pose[5];
-    float d2 = 0.f, df;
-    df = qx - px; d2 += df * df;
-    df = qy - py; d2 += df * df;
-    df = qz - pz; d2 += df * df;
-    if (d2 < kf.radius2) e = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)tid;
-  }
-  a[tid] = e;
+  if (tid == 0) sh_cnt = 0;
   if (tid < 3) { sh_mn[tid] = INT_MAX; sh_mx[tid] = INT_MIN; }
-  if (tid < KF_MAX / 32) { in_ds[tid] = 0u; in_sur[tid] = 0u; }
-  first_pos[tid] = INT_MAX;
   __syncthreads();
-  const int n_sel = __syncthreads_count(e != KF_EMPTY);
-  kf_bitonic(a);
+  // radiusSearch (nanoflann_pcl.h:155-175): d2 < r2, ascending by distance (ties: ascending index)
+  {
+    int local = 0;
+    for (int i = tid; i < n; i += KF_THREADS) {
+      const float* pose = poses + (size_t)i * 6;
+      float d2 = 0.f, df;
+      df = qx - pose[3]; d2 += df * df;
+      df = qy - pose[4]; d2 += df * df;
+      df = qz - pose[5]; d2 += df * df;
+      const bool in = d2 < kf.radius2;
+      key[0][i] = in ? __float_as_uint(d2) : 0xffffffffu;
+      val[0][i] = (unsigned)i;
+      local += in ? 1 : 0;
+    }
+    local = warp_sum_i(local);
+    if ((tid & 31) == 0 && local) atomicAdd(&sh_cnt, local);
+  }
+  __syncthreads();
+  const int n_sel = sh_cnt;
+  {
+    const int cur = block_radix_sort(key, val, n, 0x100000000LL, sort_sm);
+    for (int t = tid; t < n_sel; t += KF_THREADS) rank_idx[t] = (int)val[cur][t];
+  }
+  __syncthreads();
   // downSizeFilterSurroundingKeyPoses (leaf 1.0, :78): voxel of every selected pose
-  int v0 = 0, v1 = 0, v2 = 0, idx = 0;
-  if (tid < n_sel) {
-    idx = (int)(a[tid] & 0xffffffffu);
-    idx_by_rank[tid] = idx;
-    const float* pose = kf.kf_pose + ((size_t)s * kf.kf_cap + idx) * 6;
-    const float inv = 1.0f / 1.0f;
-    v0 = (int)floorf(pose[3] * inv); v1 = (int)floorf(pose[4] * inv); v2 = (int)floorf(pose[5] * inv);
-    atomicMin(&sh_mn[0], v0); atomicMax(&sh_mx[0], v0);
-    atomicMin(&sh_mn[1], v1); atomicMax(&sh_mx[1], v1);
-    atomicMin(&sh_mn[2], v2); atomicMax(&sh_mx[2], v2);
-  }
-  __syncthreads();
-  e = KF_EMPTY;
-  if (tid < n_sel) {
-    // all selected poses lie within 2 * 50 m of each other, so the index fits 32 bits (no PCL overflow branch)
-    const int div0 = sh_mx[0] - sh_mn[0] + 1, div1 = sh_mx[1] - sh_mn[1] + 1;
-    const unsigned vox = (unsigned)((v0 - sh_mn[0]) + (v1 - sh_mn[1]) * div0 + (v2 - sh_mn[2]) * div0 * div1);
-    e = ((unsigned long long)vox << 32) | (unsigned)tid;  // (voxel, rank in distance order): stable
-  }
-  __syncthreads();
-  a[tid] = e;
-  __syncthreads();
-  kf_bitonic(a);
-  // one output pose per voxel; its id is (int)(mean intensity) = (int)(mean key-frame index) (:940, :962, :968)
-  int head = 0, idv = 0;
-  if (tid < n_sel) {
-    const unsigned vox = (unsigned)(a[tid] >> 32);
-    head = tid == 0 || (unsigned)(a[tid - 1] >> 32) != vox;
-    if (head) {
-      float sum = 0.f;
-      int cnt = 0;
-      for (int u = tid; u < n_sel && (unsigned)(a[u] >> 32) == vox; ++u) {
-        sum += (float)idx_by_rank[(int)(a[u] & 0xffffffffu)];
-        ++cnt;
+  {
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (int t = tid; t < n_sel; t += KF_THREADS) {
+      const float* pose = poses + (size_t)rank_idx[t] * 6;
+      const int v[3] = {(int)floorf(pose[3]), (int)floorf(pose[4]), (int)floorf(pose[5])};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], v[d]); mx[d] = max(mx[d], v[d]); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+        mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
       }
-      idv = (int)(sum / (float)cnt);
+      if ((tid & 31) == 0) { atomicMin(&sh_mn[d], mn[d]); atomicMax(&sh_mx[d], mx[d]); }
     }
   }
-  int n_ds;
-  {
-    const int ex = block_exclusive_scan(head, warp_tot, &n_ds);
-    if (head) ds_ids[ex] = idv;
-  }
   __syncthreads();
-  if (tid < n_ds) {
-    const int id = ds_ids[tid];
+  // all selected poses lie within 2 * radius of each other, so the index fits 32 bits (no PCL overflow branch)
+  const int mn0 = sh_mn[0], mn1 = sh_mn[1], mn2 = sh_mn[2];
+  const int div0 = n_sel ? sh_mx[0] - mn0 + 1 : 1, div1 = n_sel ? sh_mx[1] - mn1 + 1 : 1, div2 = n_sel ? sh_mx[2] - mn2 + 1 : 1;
+  for (int t = tid; t < n_sel; t += KF_THREADS) {
+    const float* pose = poses + (size_t)rank_idx[t] * 6;
+    const int v0 = (int)floorf(pose[3]), v1 = (int)floorf(pose[4]), v2 = (int)floorf(pose[5]);
+    key[0][t] = (unsigned)((v0 - mn0) + (v1 - mn1) * div0 + (v2 - mn2) * div0 * div1);
+    val[0][t] = (unsigned)t;  // rank in distance order: the stable sort keeps it inside a voxel
+  }
+  const int cur2 = block_radix_sort(key, val, n_sel, (long long)div0 * div1 * div2, sort_sm);
+  const unsigned* ks = key[cur2];
+  const unsigned* vs = val[cur2];
+  // one output pose per voxel; its id is (int)(mean intensity) = (int)(mean key-frame index) (:940, :962, :968)
+  int n_ds = 0;
+  for (int t0 = 0; t0 < n_sel; t0 += KF_THREADS) {
+    const int t = t0 + tid;
+    int head = 0, idv = 0;
+    if (t < n_sel) {
+      const unsigned vox = ks[t];
+      head = t == 0 || ks[t - 1] != vox;
+      if (head) {
+        float sum = 0.f;
+        int cnt = 0;
+        for (int u = t; u < n_sel && ks[u] == vox; ++u) { sum += (float)rank_idx[vs[u]]; ++cnt; }
+        idv = (int)(sum / (float)cnt);
+      }
+    }
+    int total;
+    const int ex = block_exclusive_scan(head, sort_sm.warp_tot, &total);
+    if (head) ds_ids[n_ds + ex] = idv;
+    n_ds += total;
+  }
+  for (int w = tid; w < (n + 31) / 32; w += KF_THREADS) { in_ds[w] = 0u; in_sur[w] = 0u; }
+  for (int i = tid; i < n; i += KF_THREADS) first_pos[i] = INT_MAX;
+  __syncthreads();
+  for (int j = tid; j < n_ds; j += KF_THREADS) {
+    const int id = ds_ids[j];
     atomicOr(&in_ds[id >> 5], 1u << (id & 31));
-    atomicMin(&first_pos[id], tid);
+    atomicMin(&first_pos[id], j);
   }
   __syncthreads();
   // erase the key frames that left the surrounding set, keeping the order of the others (:935-955)
   const int m = kf.sur_n[s];
-  int* sur = kf.sur_ids + (size_t)s * kf.kf_cap;
-  int keep = 0, sid = 0;
-  if (tid < m) { sid = sur[tid]; keep = kf_bit(in_ds, sid) ? 1 : 0; }
-  int n_keep;
-  {
-    const int ex = block_exclusive_scan(keep, warp_tot, &n_keep);
-    if (keep) { sur_sm[ex] = sid; atomicOr(&in_sur[sid >> 5], 1u << (sid & 31)); }
+  int* sur = kf.sur_ids + sbase;
+  int* erased = kf.sur_erased + sbase;
+  int n_keep = 0, n_erased = 0;
+  for (int t0 = 0; t0 < m; t0 += KF_THREADS) {
+    const int t = t0 + tid;
+    int keep = 0, gone = 0, sid = 0;
+    if (t < m) { sid = sur[t]; keep = kf_bit(in_ds, sid) ? 1 : 0; gone = 1 - keep; }
+    int tk, tg;
+    const int exk = block_exclusive_scan(keep, sort_sm.warp_tot, &tk);
+    const int exg = block_exclusive_scan(gone, sort_sm.warp_tot, &tg);
+    if (keep) { sur[n_keep + exk] = sid; atomicOr(&in_sur[sid >> 5], 1u << (sid & 31)); }  // in place: n_keep + exk <= t
+    if (gone) erased[n_erased + exg] = sid;
+    n_keep += tk;
+    n_erased += tg;
+    __syncthreads();
   }
-  __syncthreads();
   // append the ids that are not in the list yet, in the order of the down-sampled poses (:957-980)
-  int add = 0, aid = 0;
-  if (tid < n_ds) { aid = ds_ids[tid]; add = (!kf_bit(in_sur, aid) && first_pos[aid] == tid) ? 1 : 0; }
-  int n_add;
-  {
-    const int ex = block_exclusive_scan(add, warp_tot, &n_add);
-    if (add) sur_sm[n_keep + ex] = aid;
+  int n_add = 0;
+  for (int j0 = 0; j0 < n_ds; j0 += KF_THREADS) {
+    const int j = j0 + tid;
+    int add = 0, aid = 0;
+    if (j < n_ds) { aid = ds_ids[j]; add = (!kf_bit(in_sur, aid) && first_pos[aid] == j) ? 1 : 0; }
+    int total;
+    const int ex = block_exclusive_scan(add, sort_sm.warp_tot, &total);
+    if (add && n_keep + n_add + ex < kf.kf_cap) sur[n_keep + n_add + ex] = aid;
+    n_add += total;
   }
-  __syncthreads();
-  const int m_new = n_keep + n_add;
-  if (tid < m_new) sur[tid] = sur_sm[tid];
   if (tid == 0) {
+    const int m_new = min(n_keep + n_add, kf.kf_cap);
+    // erased key frames leave dead voxels behind; when a table runs full, rebuild it from the list instead
+    bool pressure = false;
+    for (int mp = 0; mp < 2; ++mp)
+      for (int part = 0; part < kf.tbl[mp].parts; ++part)
+        pressure |= kf.tbl[mp].list_n[s * kf.tbl[mp].parts + part] > (kf.tbl[mp].sub_cap >> 1);
+    const int rebuild = (n_erased > 0 && pressure) ? 1 : 0;
     kf.sur_n[s] = m_new;
-    kf.sur_rebuild[s] = n_keep != m;
-    kf.sur_first[s] = n_keep != m ? 0 : n_keep;
+    kf.sur_n_erased[s] = n_erased;
+    kf.sur_last_erased[s] = n_erased > 0;
+    kf.sur_rebuild[s] = rebuild;
+    kf.sur_first[s] = rebuild ? 0 : n_keep;
     kf.sur_valid[s] = 1;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // the concatenation of the surrounding clouds (:982-986) + the per-voxel sums of pcl::VoxelGrid, as running sums
+
+__device__ __forceinline__ int kf_find(const unsigned long long* keys, unsigned mask, int sub_cap, unsigned long long k,
+                                       unsigned long long hsh) {
+  unsigned h = (unsigned)hsh & mask;
+  for (int probe = 0; probe < sub_cap; ++probe) {
+    const unsigned long long cur = keys[h];
+    if (cur == k) return (int)h;
+    if (cur == KF_EMPTY) return -1;
+    h = (h + 1u) & mask;
+  }
+  return -1;
+}
+
 __global__ void __launch_bounds__(KF_THREADS) k_kf_accumulate(DevState st) {
   KeyframeStore& kf = st.kf;
   const int s = blockIdx.x;
@@ -351,22 +398,72 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_accumulate(DevState st) {
   unsigned long long* keys = tb.key + tbase;
   float4* sums = tb.sum + tbase;
   int* cnts = tb.cnt + tbase;
+  int* heads = tb.head + tbase;
+  int* tails = tb.tail + tbase;
   unsigned* list = tb.list + tbase;
   int* list_n = tb.list_n + s * tb.parts + part;
   const unsigned mask = (unsigned)tb.sub_cap - 1u;
   const int max_fill = tb.sub_cap - (tb.sub_cap >> 2);
+  const int* sur = kf.sur_ids + (size_t)s * kf.kf_cap;
+  const float4* pts = kf.pool_pts + (size_t)s * kf.pool_cap;
+  const unsigned long long* pkey = kf.pool_key + (size_t)s * kf.pool_cap;
+  unsigned long long* link = kf.pool_link + (size_t)s * kf.pool_cap;
+  const int c_first = map == 0 ? 0 : 1, c_last = map == 0 ? 1 : 3;  // corner | surf then outlier (:983-985)
   if (kf.sur_rebuild[s]) {
     const int ln = min(*list_n, tb.sub_cap);
     for (int i = threadIdx.x; i < ln; i += KF_THREADS) keys[list[i]] = KF_EMPTY;
     __syncthreads();
-    if (threadIdx.x == 0) *list_n = 0;
+    if (threadIdx.x == 0) {
+      *list_n = 0;
+      tb.list_done[s * tb.parts + part] = 0;
+      if (part == 0) kf.xs_n[s * 2 + map] = 0;
+    }
     __syncthreads();
+  } else {
+    // ---- erase: unlink the runs of every key frame that left the list and re-sum the voxels they were in ----
+    const int n_erased = kf.sur_n_erased[s];
+    const int* erased = kf.sur_erased + (size_t)s * kf.kf_cap;
+    for (int e = 0; e < n_erased; ++e) {
+      const int* off = kf.kf_off + ((size_t)s * kf.kf_cap + erased[e]) * 4;
+      for (int c = c_first; c < c_last; ++c) {
+        const int lo = off[c], hi = off[c + 1];
+        for (int i = lo + threadIdx.x; i < hi; i += KF_THREADS) {
+          const unsigned long long k = pkey[i];
+          if (k == KF_INVALID || (i > lo && pkey[i - 1] == k)) continue;  // not the head of a run
+          const unsigned long long hsh = kf_mix(k);
+          if (tb.parts > 1 && (int)((hsh >> 40) % (unsigned)tb.parts) != part) continue;
+          const int slot = kf_find(keys, mask, tb.sub_cap, k, hsh);
+          if (slot < 0) { atomicOr(&kf.err[s], KF_ERR_TABLE); continue; }
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          int cnt = 0;
+          unsigned cur = (unsigned)heads[slot], prev = KF_NONE;
+          while (cur != KF_NONE) {
+            const unsigned long long lk = link[cur];
+            const unsigned nxt = (unsigned)(lk >> 32);
+            const int len = (int)(lk & 0xffffffffu);
+            if (cur == (unsigned)i) {
+              if (prev == KF_NONE) heads[slot] = (int)nxt;
+              else link[prev] = ((unsigned long long)nxt << 32) | (link[prev] & 0xffffffffull);
+              if (nxt == KF_NONE) tails[slot] = (int)prev;
+            } else {
+              for (int u = 0; u < len; ++u) {
+                const float4 q = pts[cur + u];
+                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+              }
+              cnt += len;
+              prev = cur;
+            }
+            cur = nxt;
+          }
+          sums[slot] = acc;
+          cnts[slot] = cnt;
+        }
+        __syncthreads();  // the outlier cloud of the key frame may have a run in the same voxel as its surf cloud
+      }
+    }
   }
+  // ---- append: the key frames from list position sur_first on, in list order ----
   const int first = kf.sur_first[s], last = kf.sur_n[s];
-  const int* sur = kf.sur_ids + (size_t)s * kf.kf_cap;
-  const float4* pts = kf.pool_pts + (size_t)s * kf.pool_cap;
-  const unsigned long long* pkey = kf.pool_key + (size_t)s * kf.pool_cap;
-  const int c_first = map == 0 ? 0 : 1, c_last = map == 0 ? 1 : 3;  // corner | surf then outlier (:983-985)
   for (int r = first; r < last; ++r) {
     const int* off = kf.kf_off + ((size_t)s * kf.kf_cap + sur[r]) * 4;
     for (int c = c_first; c < c_last; ++c) {
@@ -398,47 +495,64 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_accumulate(DevState st) {
         if (slot < 0) { atomicOr(&kf.err[s], KF_ERR_TABLE); continue; }
         float4 acc = fresh ? make_float4(0.f, 0.f, 0.f, 0.f) : sums[slot];
         int cnt = fresh ? 0 : cnts[slot];
+        int len = 0;
         for (int u = i; u < hi && pkey[u] == k; ++u) {
           const float4 q = pts[u];
           acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-          ++cnt;
+          ++len;
         }
         sums[slot] = acc;
-        cnts[slot] = cnt;
+        cnts[slot] = cnt + len;
+        // the run goes to the tail of the voxel's chain
+        link[i] = ((unsigned long long)KF_NONE << 32) | (unsigned)len;
+        const int tl = (fresh || cnt == 0) ? -1 : tails[slot];
+        if (tl < 0) heads[slot] = i;
+        else link[tl] = ((unsigned long long)(unsigned)i << 32) | (link[tl] & 0xffffffffull);
+        tails[slot] = i;
       }
       __syncthreads();  // the next cloud may continue the sums of this one
     }
   }
 }
 
-// downSizeFilterCorner / downSizeFilterSurf output (:989-995): one centroid per voxel, ascending voxel index
-__global__ void __launch_bounds__(KF_THREADS) k_kf_extract(DevState st) {
+// ---------------------------------------------------------------------------------------------------------------
+// downSizeFilterCorner / downSizeFilterSurf output (:989-995): one centroid per voxel, ascending voxel index.
+
+// lower bound: entries of a[0..n) smaller than k
+__device__ __forceinline__ int kfx_lower_bound(const unsigned long long* a, int n, unsigned long long k) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// block / (sequence, map): the voxels created since the last cycle, sorted; sets up this cycle's merge
+__global__ void __launch_bounds__(KF_THREADS) k_kfx_sort_new(DevState st) {
   __shared__ BlockSortSmem sort_sm;
   __shared__ int sh_mn[3], sh_mx[3];
   KeyframeStore& kf = st.kf;
   const int s = blockIdx.x, map = blockIdx.y;
-  int* out_n = st.map_counts + s * 2 + map;
-  if (!kf.sur_valid[s]) {
-    if (threadIdx.x == 0) *out_n = 0;
-    return;
-  }
+  if (!kf.sur_valid[s]) return;
   const VoxTable& tb = kf.tbl[map];
-  float4* out = map == 0 ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
-  const int cap_out = min(map == 0 ? st.cap_map_corner : st.cap_map_surf, kf.sort_cap);
   const size_t soff = ((size_t)s * 2 + map) * kf.sort_cap;
   unsigned* const key[2] = {kf.sk0 + soff, kf.sk1 + soff};
   unsigned* const val[2] = {kf.sv0 + soff, kf.sv1 + soff};
   const size_t tbase = (size_t)s * tb.parts * tb.sub_cap;
+  int* merge = kf.xs_merge + (s * 2 + map) * 4;
+  const int n_old = kf.xs_n[s * 2 + map];
   if (threadIdx.x < 3) { sh_mn[threadIdx.x] = INT_MAX; sh_mx[threadIdx.x] = INT_MIN; }
   __syncthreads();
-  // gather the occupied slots of all partitions (val = slot over the whole table) and their voxel bounding box
   int n = 0;
+  bool overflow = false;
   {
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
     for (int part = 0; part < tb.parts; ++part) {
+      const int done = tb.list_done[s * tb.parts + part];
       const int ln = min(tb.list_n[s * tb.parts + part], tb.sub_cap);
-      const int take = min(ln, kf.sort_cap - n);
-      const unsigned* list = tb.list + tbase + (size_t)part * tb.sub_cap;
+      const int take = max(0, min(ln - done, kf.sort_cap - n_old - n));
+      const unsigned* list = tb.list + tbase + (size_t)part * tb.sub_cap + done;
       for (int i = threadIdx.x; i < take; i += KF_THREADS) {
         const unsigned g = (unsigned)(part * tb.sub_cap) + list[i];
         val[0][n + i] = g;
@@ -447,7 +561,7 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_extract(DevState st) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], v[d]); mx[d] = max(mx[d], v[d]); }
       }
-      if (take < ln && threadIdx.x == 0) atomicOr(&kf.err[s], KF_ERR_MAP);
+      if (take < ln - done) overflow = true;
       n += take;
     }
 #pragma unroll
@@ -460,35 +574,146 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_extract(DevState st) {
     }
   }
   __syncthreads();
+  if (overflow && threadIdx.x == 0) atomicOr(&kf.err[s], KF_ERR_MAP);
   if (n == 0) {
-    if (threadIdx.x == 0) *out_n = 0;
+    if (threadIdx.x == 0) merge[2] = 0;
     return;
   }
   const int mn0 = sh_mn[0], mn1 = sh_mn[1], mn2 = sh_mn[2];
   const int div0 = sh_mx[0] - mn0 + 1, div1 = sh_mx[1] - mn1 + 1, div2 = sh_mx[2] - mn2 + 1;
-  const long long max_idx = (long long)div0 * div1 * div2;
-  if (max_idx > 2147483647LL) {
-    // PCL would warn "leaf size is too small" and return the undecimated cloud; that cloud is not materialised here
-    if (threadIdx.x == 0) { *out_n = 0; atomicOr(&kf.err[s], KF_ERR_RANGE); }
-    return;
-  }
+  const long long max_idx = (long long)div0 * div1 * div2;   // of the new voxels only: their order is what is needed
+  const bool range_ok = max_idx < 0xffffffffLL;
+  if (!range_ok && threadIdx.x == 0) atomicOr(&kf.err[s], KF_ERR_RANGE);
   for (int i = threadIdx.x; i < n; i += KF_THREADS) {
     int v0, v1, v2;
     kf_unpack(tb.key[tbase + val[0][i]], &v0, &v1, &v2);
-    key[0][i] = (unsigned)((v0 - mn0) + (v1 - mn1) * div0 + (v2 - mn2) * div0 * div1);
+    key[0][i] = range_ok ? (unsigned)((v0 - mn0) + (v1 - mn1) * div0 + (v2 - mn2) * div0 * div1) : 0u;
   }
-  const int cur = block_radix_sort(key, val, n, max_idx, sort_sm);
+  const int cur = block_radix_sort(key, val, n, range_ok ? max_idx : 1, sort_sm);
   const unsigned* vs = val[cur];
-  const int n_out = min(n, cap_out);
-  for (int i = threadIdx.x; i < n_out; i += KF_THREADS) {
+  unsigned long long* nk = kf.xn_key + soff;
+  unsigned* ns = kf.xn_slot + soff;
+  for (int i = threadIdx.x; i < n; i += KF_THREADS) {
     const unsigned g = vs[i];
-    const float4 sum = tb.sum[tbase + g];
-    const float fc = (float)tb.cnt[tbase + g];
-    out[i] = make_float4(sum.x / fc, sum.y / fc, sum.z / fc, sum.w / fc);
+    nk[i] = tb.key[tbase + g];
+    ns[i] = g;
   }
   if (threadIdx.x == 0) {
-    *out_n = n_out;
-    if (n_out < n) atomicOr(&kf.err[s], KF_ERR_MAP);
+    for (int part = 0; part < tb.parts; ++part) tb.list_done[s * tb.parts + part] = min(tb.list_n[s * tb.parts + part], tb.sub_cap);
+    const int src = kf.xs_cur[s * 2 + map];
+    merge[0] = src; merge[1] = n_old; merge[2] = n;
+    kf.xs_cur[s * 2 + map] = src ^ 1;
+    kf.xs_n[s * 2 + map] = n_old + n;
+    // running voxel bounding box of the map, for PCL's index overflow test (never shrinks: conservative after erases)
+    int* bb = kf.xs_bbox + (s * 2 + map) * 8;
+    if (n_old == 0) { bb[0] = mn0; bb[1] = mn1; bb[2] = mn2; bb[3] = sh_mx[0]; bb[4] = sh_mx[1]; bb[5] = sh_mx[2]; }
+    else {
+      bb[0] = min(bb[0], mn0); bb[1] = min(bb[1], mn1); bb[2] = min(bb[2], mn2);
+      bb[3] = max(bb[3], sh_mx[0]); bb[4] = max(bb[4], sh_mx[1]); bb[5] = max(bb[5], sh_mx[2]);
+    }
+  }
+}
+
+// thread / element of the old sorted order or of the new voxels: its place in the merged order
+__global__ void __launch_bounds__(XS_TILE) k_kfx_merge(DevState st) {
+  KeyframeStore& kf = st.kf;
+  const int s = blockIdx.y, map = blockIdx.z;
+  if (!kf.sur_valid[s]) return;
+  const int* merge = kf.xs_merge + (s * 2 + map) * 4;
+  const int n_new = merge[2];
+  if (n_new == 0) return;
+  const int src = merge[0], n_old = merge[1];
+  const int j = blockIdx.x * XS_TILE + threadIdx.x;
+  if (j >= n_old + n_new) return;
+  const size_t soff = ((size_t)s * 2 + map) * kf.sort_cap;
+  const unsigned long long* ok = kf.xs_key[src] + soff;
+  const unsigned* os = kf.xs_slot[src] + soff;
+  const unsigned long long* nk = kf.xn_key + soff;
+  const unsigned* ns = kf.xn_slot + soff;
+  unsigned long long* dk = kf.xs_key[src ^ 1] + soff;
+  unsigned* dsl = kf.xs_slot[src ^ 1] + soff;
+  if (j < n_old) {
+    const unsigned long long k = ok[j];
+    const int pos = j + kfx_lower_bound(nk, n_new, k);
+    dk[pos] = k; dsl[pos] = os[j];
+  } else {
+    const int i = j - n_old;
+    const unsigned long long k = nk[i];
+    const int pos = i + kfx_lower_bound(ok, n_old, k);
+    dk[pos] = k; dsl[pos] = ns[i];
+  }
+}
+
+// voxels that still hold points, per tile of the sorted order
+__global__ void __launch_bounds__(XS_TILE) k_kfx_alive(DevState st) {
+  KeyframeStore& kf = st.kf;
+  const int s = blockIdx.y, map = blockIdx.z;
+  if (!kf.sur_valid[s]) return;
+  const int n = kf.xs_n[s * 2 + map];
+  const int j = blockIdx.x * XS_TILE + threadIdx.x;
+  if (blockIdx.x * XS_TILE >= n) return;
+  const VoxTable& tb = kf.tbl[map];
+  const size_t soff = ((size_t)s * 2 + map) * kf.sort_cap;
+  const size_t tbase = (size_t)s * tb.parts * tb.sub_cap;
+  const int cur = kf.xs_cur[s * 2 + map];
+  int alive = 0;
+  if (j < n) alive = tb.cnt[tbase + kf.xs_slot[cur][soff + j]] > 0 ? 1 : 0;
+  const int c = __syncthreads_count(alive);
+  if (threadIdx.x == 0) kf.xs_tile[(size_t)(s * 2 + map) * (kf.sort_cap / XS_TILE + 1) + blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(XS_TILE) k_kfx_output(DevState st) {
+  __shared__ int warp_tot[33];
+  __shared__ int sh_pre;
+  KeyframeStore& kf = st.kf;
+  const int s = blockIdx.y, map = blockIdx.z;
+  int* out_n = st.map_counts + s * 2 + map;
+  if (!kf.sur_valid[s]) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
+    return;
+  }
+  const int n = kf.xs_n[s * 2 + map];
+  if (n == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = 0;
+    return;
+  }
+  if (blockIdx.x * XS_TILE >= n) return;
+  const int* bb = kf.xs_bbox + (s * 2 + map) * 8;
+  const long long max_idx = (long long)(bb[3] - bb[0] + 1) * (bb[4] - bb[1] + 1) * (bb[5] - bb[2] + 1);
+  if (max_idx > 2147483647LL) {
+    // PCL would warn "leaf size is too small" and return the undecimated cloud; that cloud is not materialised here
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *out_n = 0; atomicOr(&kf.err[s], KF_ERR_RANGE); }
+    return;
+  }
+  const VoxTable& tb = kf.tbl[map];
+  const size_t soff = ((size_t)s * 2 + map) * kf.sort_cap;
+  const size_t tbase = (size_t)s * tb.parts * tb.sub_cap;
+  const int cur = kf.xs_cur[s * 2 + map];
+  const int* tiles = kf.xs_tile + (size_t)(s * 2 + map) * (kf.sort_cap / XS_TILE + 1);
+  if (threadIdx.x < 32) {
+    int t = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += 32) t += tiles[k];
+    t = warp_sum_i(t);
+    if (threadIdx.x == 0) sh_pre = t;
+  }
+  const int j = blockIdx.x * XS_TILE + threadIdx.x;
+  unsigned g = 0;
+  int cnt = 0;
+  if (j < n) { g = kf.xs_slot[cur][soff + j]; cnt = tb.cnt[tbase + g]; }
+  int total;
+  const int ex = block_exclusive_scan(cnt > 0 ? 1 : 0, warp_tot, &total);  // syncs: sh_pre is visible after it
+  float4* out = map == 0 ? st.map_corner + (size_t)s * st.cap_map_corner : st.map_surf + (size_t)s * st.cap_map_surf;
+  const int cap_out = map == 0 ? st.cap_map_corner : st.cap_map_surf;
+  const int pos = sh_pre + ex;
+  if (cnt > 0 && pos < cap_out) {
+    const float4 sum = tb.sum[tbase + g];
+    const float fc = (float)cnt;
+    out[pos] = make_float4(sum.x / fc, sum.y / fc, sum.z / fc, sum.w / fc);
+  }
+  if ((blockIdx.x + 1) * XS_TILE >= n && threadIdx.x == 0) {  // the last tile knows the total
+    const int n_out = sh_pre + total;
+    *out_n = min(n_out, cap_out);
+    if (n_out > cap_out) atomicOr(&kf.err[s], KF_ERR_MAP);
   }
 }
 
@@ -496,9 +721,13 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_extract(DevState st) {
 
 void launch_extract_surrounding_keyframes(LaunchCtx& ctx, DevState& st) {
   const int B = st.p.B;
+  const int tiles = (st.kf.sort_cap + XS_TILE - 1) / XS_TILE;
   LL_LAUNCH(ctx, "k_kf_select", k_kf_select<<<B, KF_THREADS, 0, ctx.stream>>>(st));
   LL_LAUNCH(ctx, "k_kf_accumulate", k_kf_accumulate<<<dim3(B, 1 + st.kf.tbl[1].parts), KF_THREADS, 0, ctx.stream>>>(st));
-  LL_LAUNCH(ctx, "k_kf_extract", k_kf_extract<<<dim3(B, 2), KF_THREADS, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_kfx_sort_new", k_kfx_sort_new<<<dim3(B, 2), KF_THREADS, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_kfx_merge", k_kfx_merge<<<dim3(tiles, B, 2), XS_TILE, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_kfx_alive", k_kfx_alive<<<dim3(tiles, B, 2), XS_TILE, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_kfx_output", k_kfx_output<<<dim3(tiles, B, 2), XS_TILE, 0, ctx.stream>>>(st));
 }
 
 void launch_save_keyframe(LaunchCtx& ctx, DevState& st) {

@@ -40,12 +40,17 @@ struct HashGrid {
 
 // Sparse voxel accumulator of one local map (keyframes.cu): open-addressing table keyed by the absolute voxel
 // coordinates, split into `parts` independent sub-tables (a voxel belongs to exactly one, chosen by a hash of its key).
+// Every voxel also heads a chain of the key-frame runs summed into it, in concatenation order (KeyframeStore::pool_link),
+// so that a key frame that leaves the surrounding set is taken out by re-summing only the voxels it touches.
 struct VoxTable {
   unsigned long long* key;  // [B][parts][sub_cap] packed voxel (iz, iy, ix), all ones = empty
   float4* sum;              // [B][parts][sub_cap] running sums of x, y, z, intensity in concatenation order
-  int* cnt;                 // [B][parts][sub_cap] points summed
+  int* cnt;                 // [B][parts][sub_cap] points summed (0: a voxel all of whose key frames have left)
+  int* head;                // [B][parts][sub_cap] pool index of the first run of the chain, -1 = none
+  int* tail;                // [B][parts][sub_cap] pool index of the last run
   unsigned* list;           // [B][parts][sub_cap] slots in use, in insertion order
   int* list_n;              // [B][parts]
+  int* list_done;           // [B][parts] entries of `list` already merged into the sorted order (xs_*)
   int parts, sub_cap;       // sub_cap is a power of two
   float leaf;               // VoxelGrid leaf size (m)
 };
@@ -53,7 +58,7 @@ struct VoxTable {
 // MapOptimization's key-frame state for every sequence (mapOptimization.h:96-135), SURVEY.md section 8 f2.
 struct KeyframeStore {
   int enabled;
-  int kf_cap;                    // key frames per sequence (<= 1024)
+  int kf_cap;                    // key frames per sequence
   int pool_cap;                  // points per sequence over all key-frame clouds
   float radius2;                 // (float)(surrounding_keyframe_search_radius^2), squared in double (nanoflann_pcl.h:163)
   int* kf_count;                 // [B] cloudKeyPoses3D->size()
@@ -63,17 +68,36 @@ struct KeyframeStore {
   float4* pool_pts;              // [B][pool_cap] key-frame clouds transformed by their key pose; each cloud stable-sorted by voxel
   unsigned long long* pool_key;  // [B][pool_cap] packed absolute voxel of every stored point (leaf of the map it goes into)
   int* pool_perm;                // [B][pool_cap] position of every stored point in its down-sampled scan cloud
+  unsigned long long* pool_link; // [B][pool_cap] at the first point of a run that is summed into a voxel: (next run of that voxel's chain << 32) | run length
   int* kf_new;                   // [B] index of the key frame ll_map_save_keyframe is storing, or -1
   float* robot_pos;              // [B][8] currentRobotPosPoint xyz, pad, previousRobotPosPoint xyz, pad
   float* transform_last;         // [B][6]
   int* sur_ids;                  // [B][kf_cap] surroundingExistingKeyPosesID
   int* sur_n;                    // [B]
   int* sur_first;                // [B] first list position whose clouds still have to be summed into the voxel tables
-  int* sur_rebuild;              // [B] 1: a key frame was erased, the tables are rebuilt from list position 0
+  int* sur_rebuild;              // [B] 1: the tables are rebuilt from list position 0 (table pressure after erases)
   int* sur_valid;                // [B] 0: no key frames yet (extractSurroundingKeyFrames returns early, maps stay empty)
+  int* sur_erased;               // [B][kf_cap] key frames the last extractSurroundingKeyFrames erased from the list
+  int* sur_n_erased;             // [B]
+  int* sur_last_erased;          // [B] 1 if the last extractSurroundingKeyFrames erased a key frame (LL_BUF_KEYFRAME_STATE[2])
   int* err;                      // [B] capacity error bits (LL_BUF_KEYFRAME_STATE[3])
   VoxTable tbl[2];               // 0: corner map (leaf 0.2), 1: surf map (leaf 0.4)
-  unsigned *sk0, *sk1, *sv0, *sv1;  // [B][2][sort_cap] sort scratch of the local-map extraction
+  // k_kf_select scratch
+  unsigned *sel_k0, *sel_k1, *sel_v0, *sel_v1;  // [B][kf_cap] radix sort ping-pong
+  int* sel_rank_idx;             // [B][kf_cap] key-frame index of the r-th nearest selected pose
+  int* sel_ds_ids;               // [B][kf_cap] ids of the down-sampled surrounding poses, in voxel order
+  int* sel_first_pos;            // [B][kf_cap] first position of an id in sel_ds_ids
+  // sorted order of the voxels of a map (ascending PCL voxel index = lexicographic (iz, iy, ix)), kept across cycles
+  unsigned long long* xs_key[2]; // ping-pong: [B][2 maps][sort_cap]
+  unsigned* xs_slot[2];          // slot over the whole table (part * sub_cap + slot)
+  int* xs_cur;                   // [B][2] which ping-pong buffer is current
+  int* xs_n;                     // [B][2] voxels in the sorted order (alive or not)
+  int* xs_merge;                 // [B][2][4] merge job of this cycle: source buffer, old count, new count, pad
+  unsigned long long* xn_key;    // [B][2][sort_cap] new voxels of this cycle, sorted
+  unsigned* xn_slot;             // [B][2][sort_cap]
+  int* xs_tile;                  // [B][2][sort_cap / 4096 + 1] alive voxels per tile of the sorted order
+  int* xs_bbox;                  // [B][2][8] running voxel bounding box of a map: min xyz, max xyz
+  unsigned *sk0, *sk1, *sv0, *sv1;  // [B][2][sort_cap] radix sort scratch for the new voxels
   int sort_cap;
 };
 

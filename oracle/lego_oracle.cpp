@@ -182,26 +182,31 @@ struct lo_handle {
     reset();
   }
 
-  void reset() {
-    /* featureAssociation.cpp:96-157 initializationValue */
+  /* a freshly constructed FeatureAssociation (featureAssociation.cpp:96-157 initializationValue); MapOptimization untouched */
+  void resetFeatureAssociation() {
     cloudSmoothness.assign(N, smoothness_t{0.f, 0});
     cloudCurvature.assign(N, 0.f); cloudNeighborPicked.assign(N, 0); cloudLabel.assign(N, 0);
     searchCornerInd1.assign(N, 0.f); searchCornerInd2.assign(N, 0.f);
     searchSurfInd1.assign(N, 0.f); searchSurfInd2.assign(N, 0.f); searchSurfInd3.assign(N, 0.f);
-    for (int i = 0; i < 6; ++i) {
-      transformCur[i] = 0; transformSum[i] = 0; transformTobeMapped[i] = 0;
-      transformBefMapped[i] = 0; transformAftMapped[i] = 0; transformIncre[i] = 0;
-    }
+    for (int i = 0; i < 6; ++i) { transformCur[i] = 0; transformSum[i] = 0; }
     systemInitedLM = false; isDegenerate = false; cycle_count = 0;
     cornerLast.clear(); surfLast.clear(); outlierLast.clear(); cornerLastNum = surfLastNum = 0;
     kdCornerLast.reset(new oknn::KdTree()); kdSurfLast.reset(new oknn::KdTree());
-    kdCornerMap.reset(new oknn::KdTree()); kdSurfMap.reset(new oknn::KdTree());
     for (int i = 0; i < 9; ++i) matP3[i] = 0.f;
+    odom_iters[0] = odom_iters[1] = 0;
+    lessFlatRawCount.assign(V, 0);
+  }
+
+  void reset() {
+    resetFeatureAssociation();
+    for (int i = 0; i < 6; ++i) {
+      transformTobeMapped[i] = 0; transformBefMapped[i] = 0; transformAftMapped[i] = 0; transformIncre[i] = 0;
+    }
+    kdCornerMap.reset(new oknn::KdTree()); kdSurfMap.reset(new oknn::KdTree());
     for (int i = 0; i < 36; ++i) matP6[i] = 0.f; /* mapOptmization.cpp:223 matP.setZero() */
     mapDegenerate = false;
-    odom_iters[0] = odom_iters[1] = 0; map_iters[0] = map_iters[1] = 0;
+    map_iters[0] = map_iters[1] = 0;
     for (int i = 0; i < 340; ++i) map_trace[i] = 0.0;
-    lessFlatRawCount.assign(V, 0);
     for (int i = 0; i < 5; ++i) timers[i] = 0;
     resetKeyFrames();
   }
@@ -1378,6 +1383,7 @@ lo_handle* lo_create(const LegoLoamParams* p) {
 }
 void lo_destroy(lo_handle* h) { delete h; }
 void lo_reset(lo_handle* h) { h->reset(); }
+void lo_reset_feature_association(lo_handle* h) { h->resetFeatureAssociation(); }
 
 int lo_image_projection(lo_handle* h, const float* xyzi, int n) {
   double t0 = now_s();

@@ -28,6 +28,8 @@ int lo_has_nanoflann(void);
 lo_handle* lo_create(const LegoLoamParams* p);
 void lo_destroy(lo_handle* h);
 void lo_reset(lo_handle* h);
+/* a freshly constructed FeatureAssociation (first-frame state, transformCur/Sum, last clouds); MapOptimization state is kept */
+void lo_reset_feature_association(lo_handle* h);
 
 int lo_image_projection(lo_handle* h, const float* xyzi, int n_points);
 /* returns 1 when this frame would be handed to MapOptimization (featureAssociation.cpp:1432), else 0 */

@@ -55,7 +55,7 @@ def load(prefer_ref=True):
         lib = C.CDLL(path)
         lib.lo_create.restype = C.c_void_p
         lib.lo_create.argtypes = [C.c_void_p]
-        for name in ("lo_destroy", "lo_reset", "lo_reset_timers"):
+        for name in ("lo_destroy", "lo_reset", "lo_reset_timers", "lo_reset_feature_association"):
             getattr(lib, name).argtypes = [C.c_void_p]
             getattr(lib, name).restype = None
         lib.lo_image_projection.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -118,6 +118,9 @@ class Oracle:
 
     def reset(self):
         self.lib.lo_reset(self.h)
+
+    def reset_feature_association(self):
+        self.lib.lo_reset_feature_association(self.h)
 
     def image_projection(self, xyzi):
         self._select()
