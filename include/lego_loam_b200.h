@@ -133,6 +133,14 @@ typedef enum ll_buffer {
   LL_BUF_KEY_POSES_6D = 42,        /* f32[K][6] cloudKeyPoses6D as (roll, pitch, yaw, x, y, z) */
   LL_BUF_SURROUNDING_KEY_IDS = 43, /* i32[..] surroundingExistingKeyPosesID */
   LL_BUF_INPUT_CLOUD = 44,         /* pt[n] the scan staged by the last ll_set_scans_* call (after NaN removal) */
+  /* index-level parity aids, filled only after ll_enable_index_trace(h, 1) */
+  LL_BUF_MAP_KNN_IDX = 45,         /* i32[10][Q][5] the 5 nearest map points (indices into MAP_CORNER for the Qc corner queries, which come
+                                      first, into MAP_SURF for the Qs surf queries; ascending distance) of every query in every
+                                      scan-to-map LM iteration of the last ll_scan_to_map; -1 x 5: fifth neighbour not closer than 1 m
+                                      (mapOptmization.cpp:1036,1144) or iteration not run.  Q = Qc + Qs */
+  LL_BUF_ODOM_SEARCH_IDX = 46,     /* i32[2][5][24V][3] scan-to-scan correspondences (pointSearchSurfInd1/2/3, pointSearchCornerInd1/2,
+                                      featureAssociation.h:87-93) of stage 0 surf / 1 corner in search round r (LM iteration 5r) for every
+                                      feature point of the last frame: closest, ind2, ind3 (-1: none / round not run) */
   LL_BUF_COUNT_
 } ll_buffer;
 
@@ -215,6 +223,12 @@ int ll_map_set_initial_guess_async(ll_handle* h, const float* transform_tobe_map
  * the current odometry pose; ll_scan_to_map ends with transformUpdate. */
 int ll_map_set_poses(ll_handle* h, const float* transform_aft_mapped, const float* transform_bef_mapped);
 int ll_map_predict_pose(ll_handle* h);
+/* MapOptimization's copy of the odometry pose (transformSum of mapOptmization.cpp:1539, filled there from
+ * AssociationOut::laser_odometry), f32[batch][6] host.  ll_map_downsample_current_scan -- the hand-over of a scan to
+ * MapOptimization -- already takes this copy on the device, so a FeatureAssociation thread may integrate further scans
+ * before ll_map_predict_pose / ll_scan_to_map run; call this only to override it (a caller that carries the payload
+ * through its own channel). */
+int ll_map_set_odometry(ll_handle* h, const float* transform_sum);
 /* kd-tree replacement build + <=10 x (cornerOptimization, surfOptimization,
  * LMOptimization) (mapOptmization.cpp:1028-1332) for all sequences. */
 int ll_scan_to_map(ll_handle* h);
@@ -238,8 +252,9 @@ int ll_map_extract_surrounding_keyframes(ll_handle* h);
 /* saveKeyFramesAndFactor: the 0.3 m rule, key pose, copies of laserCloudCornerLastDS / SurfLastDS / OutlierLastDS
  * (left on the device by ll_map_downsample_current_scan), stored transformed by the key pose. */
 int ll_map_save_keyframe(ll_handle* h);
-/* One body of MapOptimization::run (:1526-1562): ll_map_predict_pose, ll_map_extract_surrounding_keyframes,
- * ll_map_downsample_current_scan, ll_scan_to_map, ll_map_save_keyframe. */
+/* One body of MapOptimization::run (:1526-1562): ll_map_downsample_current_scan (the hand-over), ll_map_predict_pose,
+ * ll_map_extract_surrounding_keyframes, ll_scan_to_map, ll_map_save_keyframe.  Returns LL_ERR_CAPACITY when a
+ * sequence outgrew a capacity of the key-frame store in the previous cycle. */
 int ll_mapping_cycle(ll_handle* h);
 /* One stored key-frame cloud (which: 0 corner, 1 surf, 2 outlier) of one sequence, transformed by its key pose, in
  * the point order of the down-sampled scan cloud it was copied from.  Synchronises the stream. */
@@ -281,9 +296,14 @@ int ll_get_odometry(ll_handle* h, double* laser_odometry, double* odom_aft_mappe
  * Synchronises the stream. */
 int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, size_t* n_elems);
 /* Overwrite persistent state of one sequence (teacher-forced parity runs):
- * LL_BUF_TRANSFORM_CUR, LL_BUF_TRANSFORM_SUM, LL_BUF_TRANSFORM_TOBE_MAPPED. */
+ * LL_BUF_TRANSFORM_CUR, LL_BUF_TRANSFORM_SUM, LL_BUF_TRANSFORM_TOBE_MAPPED, LL_BUF_TRANSFORM_BEF_MAPPED,
+ * LL_BUF_TRANSFORM_AFT_MAPPED. */
 int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems);
 int ll_synchronize(ll_handle* h);
+
+/* Index-level parity aid: when enabled, ll_scan_to_map records LL_BUF_MAP_KNN_IDX and ll_feature_association records
+ * LL_BUF_ODOM_SEARCH_IDX (extra kernels / stores; off by default). */
+int ll_enable_index_trace(ll_handle* h, int enable);
 
 /* Per-stage device time of the last ll_process_scans call, in milliseconds:
  * [0] projection+ground, [1] segmentation, [2] feature extraction,

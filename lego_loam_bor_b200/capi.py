@@ -29,16 +29,16 @@ BUFFERS = {
     "TRANSFORM_AFT_MAPPED": (37, np.float32, 1), "SCAN_SURF_DS": (38, np.float32, 4),
     "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
     "KEYFRAME_STATE": (41, np.int32, 1), "KEY_POSES_6D": (42, np.float32, 6), "SURROUNDING_KEY_IDS": (43, np.int32, 1),
-    "INPUT_CLOUD": (44, np.float32, 4),
+    "INPUT_CLOUD": (44, np.float32, 4), "MAP_KNN_IDX": (45, np.int32, 5), "ODOM_SEARCH_IDX": (46, np.int32, 3),
 }
 
 EXPORTS = [
     "ll_default_params", "ll_create", "ll_destroy", "ll_reset", "ll_reset_feature_association", "ll_last_error", "ll_kernel_launches",
     "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
     "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
-    "ll_map_set_initial_guess_async", "ll_map_set_poses", "ll_map_predict_pose",
+    "ll_map_set_initial_guess_async", "ll_map_set_poses", "ll_map_set_odometry", "ll_map_predict_pose",
     "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_get_poses_async", "ll_wait_poses", "ll_download", "ll_upload", "ll_synchronize",
-    "ll_enable_stage_timing", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
+    "ll_enable_stage_timing", "ll_enable_index_trace", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
     "ll_get_kernel_time_table",
     "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
     "ll_map_download_keyframe", "ll_set_scans_pointcloud2_host", "ll_set_scans_xyz_host",
@@ -155,6 +155,7 @@ def load_library(path=None):
     lib.ll_set_scans_device.argtypes = [vp, vp, vp, ip]
     lib.ll_map_set_initial_guess_async.argtypes = [vp, vp]
     lib.ll_map_set_poses.argtypes = [vp, vp, vp]
+    lib.ll_map_set_odometry.argtypes = [vp, vp]
     for name in ("ll_image_projection", "ll_feature_association", "ll_map_downsample_current_scan",
                  "ll_scan_to_map", "ll_process_scans", "ll_synchronize", "ll_map_predict_pose"):
         getattr(lib, name).argtypes = [vp]
@@ -167,6 +168,7 @@ def load_library(path=None):
     lib.ll_download.argtypes = [vp, ip, ip, vp, sz, C.POINTER(sz)]
     lib.ll_upload.argtypes = [vp, ip, ip, vp, sz]
     lib.ll_enable_stage_timing.argtypes = [vp, ip]
+    lib.ll_enable_index_trace.argtypes = [vp, ip]
     lib.ll_get_stage_times_ms.argtypes = [vp, vp]
     lib.ll_time_kernel.argtypes = [vp, C.c_char_p]
     lib.ll_get_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -324,6 +326,10 @@ class LegoLoam:
     def map_predict_pose(self):
         self._ck(self.lib.ll_map_predict_pose(self.h), "ll_map_predict_pose")
 
+    def map_set_odometry(self, transform_sum):
+        t = np.ascontiguousarray(transform_sum, np.float32).reshape(self.batch, 6)
+        self._ck(self.lib.ll_map_set_odometry(self.h, t.ctypes.data), "ll_map_set_odometry")
+
     def scan_to_map(self):
         self._ck(self.lib.ll_scan_to_map(self.h), "ll_scan_to_map")
 
@@ -395,6 +401,9 @@ class LegoLoam:
 
     def kernel_launches(self):
         return int(self.lib.ll_kernel_launches(self.h))
+
+    def enable_index_trace(self, on=True):
+        self._ck(self.lib.ll_enable_index_trace(self.h, 1 if on else 0), "ll_enable_index_trace")
 
     def enable_stage_timing(self, on=True):
         self._ck(self.lib.ll_enable_stage_timing(self.h, 1 if on else 0), "ll_enable_stage_timing")

@@ -49,6 +49,8 @@ struct ll_handle {
   int pose_head = 0, pose_pending = 0;
   float stage_ms[5];
   bool ev_valid = false;
+  int* trace_knn = nullptr;   // ll_enable_index_trace
+  int* trace_odom = nullptr;
   // capacity error bits of the key-frame store, read back one mapping cycle late without waiting (ll_mapping_cycle)
   int32_t* h_kf_err = nullptr;
   cudaEvent_t kf_err_ev = nullptr;
@@ -267,7 +269,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.map_counts, (size_t)B * 2));
   CK(dev_alloc(h, &st.scan_corner_ds, (size_t)B * p.cap_less_sharp)); CK(dev_alloc(h, &st.scan_surf_ds, BN));
   CK(dev_alloc(h, &st.scan_ds_counts, (size_t)B * 2));
-  CK(dev_alloc(h, &st.transform_tobe_mapped, (size_t)B * 6));
+  CK(dev_alloc(h, &st.transform_tobe_mapped, (size_t)B * 6)); CK(dev_alloc(h, &st.map_odom, (size_t)B * 6));
   CK(dev_alloc(h, &st.transform_bef_mapped, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_aft_mapped, (size_t)B * 6));
   CK(dev_alloc(h, &st.map_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.map_flags, (size_t)B * 4));
   CK(dev_alloc(h, &st.map_matP, (size_t)B * 36));
@@ -347,7 +349,7 @@ int ll_reset(ll_handle* h) {
   DevState& st = h->st;
   const DevParams& p = st.p;
   cudaStream_t sm = h->ctx.stream;
-  CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm));
+  CK(cudaMemsetAsync(st.transform_tobe_mapped, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.map_odom, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.transform_bef_mapped, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_aft_mapped, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.map_flags, 0, (size_t)p.B * 16, sm)); CK(cudaMemsetAsync(st.map_matP, 0, (size_t)p.B * 144, sm));
   CK(cudaMemsetAsync(st.map_iters, 0, (size_t)p.B * 8, sm));
@@ -553,6 +555,10 @@ int ll_map_set_scan(ll_handle* h, int seq, const float* corner, int nc, const fl
 
 int ll_map_downsample_current_scan(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  // the hand-over to MapOptimization: the scan's clouds are down-sampled into buffers of their own and the odometry
+  // pose that belongs to this scan is kept with them (AssociationOut::laser_odometry, mapOptmization.cpp:1539), so that
+  // FeatureAssociation may integrate further frames before the mapping cycle runs
+  CK(cudaMemcpyAsync(h->st.map_odom, h->st.transform_sum, (size_t)h->st.p.B * 24, cudaMemcpyDeviceToDevice, h->ctx.stream));
   launch_downsample_current_scan(h->ctx, h->st);
   return check_stream(h, "ll_map_downsample_current_scan");
 }
@@ -574,6 +580,13 @@ int ll_map_set_poses(ll_handle* h, const float* aft, const float* bef) {
   if (!h || !aft || !bef) return LL_ERR_INVALID_ARG;
   CK(cudaMemcpyAsync(h->st.transform_aft_mapped, aft, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
   CK(cudaMemcpyAsync(h->st.transform_bef_mapped, bef, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  return LL_OK;
+}
+
+int ll_map_set_odometry(ll_handle* h, const float* transform_sum) {
+  if (!h || !transform_sum) return LL_ERR_INVALID_ARG;
+  CK(cudaMemcpyAsync(h->st.map_odom, transform_sum, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
   CK(cudaStreamSynchronize(h->ctx.stream));
   return LL_OK;
 }
@@ -637,7 +650,7 @@ int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, in
     const size_t slots = (size_t)B * t.parts * t.sub_cap;
     CK(dev_alloc(h, &t.key, slots, false)); CK(dev_alloc(h, &t.sum, slots, false)); CK(dev_alloc(h, &t.cnt, slots, false));
     CK(dev_alloc(h, &t.list, slots, false)); CK(dev_alloc(h, &t.list_n, (size_t)B * t.parts));
-    CK(dev_alloc(h, &t.head, slots, false)); CK(dev_alloc(h, &t.tail, slots, false)); CK(dev_alloc(h, &t.list_done, (size_t)B * t.parts));
+    CK(dev_alloc(h, &t.head, slots, false)); CK(dev_alloc(h, &t.tail, slots, false)); CK(dev_alloc(h, &t.claim, slots)); CK(dev_alloc(h, &t.list_done, (size_t)B * t.parts));
   }
   kf.sort_cap = st.cap_map_corner > st.cap_map_surf ? st.cap_map_corner : st.cap_map_surf;
   CK(dev_alloc(h, &kf.sk0, (size_t)B * 2 * kf.sort_cap, false)); CK(dev_alloc(h, &kf.sk1, (size_t)B * 2 * kf.sort_cap, false));
@@ -689,12 +702,13 @@ int ll_mapping_cycle(ll_handle* h) {
         return LL_ERR_CAPACITY;
       }
   }
-  // MapOptimization::run, mapOptmization.cpp:1545-1560
-  int rc = ll_map_predict_pose(h);
+  // MapOptimization::run, mapOptmization.cpp:1545-1560 (downsampleCurrentScan first: it is the hand-over that fixes which
+  // odometry pose the cycle works with, and it does not depend on the two steps the reference runs before it)
+  int rc = ll_map_downsample_current_scan(h);
+  if (rc < 0) return rc;
+  rc = ll_map_predict_pose(h);
   if (rc < 0) return rc;
   rc = ll_map_extract_surrounding_keyframes(h);
-  if (rc < 0) return rc;
-  rc = ll_map_downsample_current_scan(h);
   if (rc < 0) return rc;
   rc = ll_scan_to_map(h);
   if (rc < 0) return rc;
@@ -920,6 +934,26 @@ int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap) {
   return LL_OK;
 }
 
+int ll_enable_index_trace(ll_handle* h, int enable) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  DevState& st = h->st;
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  if (enable) {
+    if (!h->trace_knn) {
+      CK(dev_alloc(h, &h->trace_knn, (size_t)st.p.B * 10 * st.map_knn_cap * 5, false));
+      CK(dev_alloc(h, &h->trace_odom, (size_t)st.p.B * 2 * 5 * st.p.cap_flat * 3, false));
+      CK(cudaMemsetAsync(h->trace_knn, 0xff, (size_t)st.p.B * 10 * st.map_knn_cap * 5 * 4, h->ctx.stream));
+      CK(cudaMemsetAsync(h->trace_odom, 0xff, (size_t)st.p.B * 2 * 5 * st.p.cap_flat * 3 * 4, h->ctx.stream));
+    }
+    st.map_knn_trace = h->trace_knn;
+    st.odom_trace = h->trace_odom;
+  } else {
+    st.map_knn_trace = nullptr;
+    st.odom_trace = nullptr;
+  }
+  return LL_OK;
+}
+
 int ll_enable_stage_timing(ll_handle* h, int enable) {
   if (!h) return LL_ERR_INVALID_ARG;
   h->timing = enable != 0;
@@ -1012,6 +1046,24 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       else COUNTED(buf, 16, (size_t)stride, cntp + seq);
       break;
     }
+    case LL_BUF_ODOM_SEARCH_IDX:
+      if (!st.odom_trace) { h->err = "ll_download: call ll_enable_index_trace first"; return LL_ERR_STATE; }
+      src = st.odom_trace + (size_t)seq * 2 * 5 * p.cap_flat * 3; elem = 12; n = (size_t)2 * 5 * p.cap_flat; break;
+    case LL_BUF_MAP_KNN_IDX: {
+      if (!st.map_knn_trace) { h->err = "ll_download: call ll_enable_index_trace first"; return LL_ERR_STATE; }
+      int qn[2];
+      CK(cudaMemcpyAsync(qn, st.scan_ds_counts + seq * 2, 8, cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaStreamSynchronize(h->ctx.stream));
+      const size_t Q = (size_t)qn[0] + (size_t)qn[1];
+      if (n_elems) *n_elems = 10 * Q;
+      if (!dst) return LL_OK;
+      if (dst_bytes < 10 * Q * 20) return LL_ERR_CAPACITY;
+      for (int it = 0; it < 10 && Q; ++it)
+        CK(cudaMemcpyAsync((char*)dst + (size_t)it * Q * 20, st.map_knn_trace + (((size_t)seq * 10 + it) * st.map_knn_cap) * 5, Q * 20,
+                           cudaMemcpyDeviceToHost, h->ctx.stream));
+      CK(cudaStreamSynchronize(h->ctx.stream));
+      return LL_OK;
+    }
     case LL_BUF_KEYFRAME_STATE: {
       if (!st.kf.enabled) return LL_ERR_STATE;
       int v[4];
@@ -1064,6 +1116,8 @@ int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems
     case LL_BUF_TRANSFORM_CUR: dst = st.transform_cur + seq * 6; break;
     case LL_BUF_TRANSFORM_SUM: dst = st.transform_sum + seq * 6; break;
     case LL_BUF_TRANSFORM_TOBE_MAPPED: dst = st.transform_tobe_mapped + seq * 6; break;
+    case LL_BUF_TRANSFORM_BEF_MAPPED: dst = st.transform_bef_mapped + seq * 6; break;
+    case LL_BUF_TRANSFORM_AFT_MAPPED: dst = st.transform_aft_mapped + seq * 6; break;
     default: return LL_ERR_INVALID_ARG;
   }
   if (n_elems != 6) return LL_ERR_INVALID_ARG;

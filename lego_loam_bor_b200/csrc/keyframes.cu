@@ -387,6 +387,88 @@ __device__ __forceinline__ int kf_find(const unsigned long long* keys, unsigned 
   return -1;
 }
 
+#define KF_DEAD 0x80000000u   // in the run-length half of pool_link: the run belongs to a key frame that left the list
+
+// ---- erase, step 1: thread / stored point of an erased key frame: flag its runs ----
+__global__ void __launch_bounds__(256) k_kf_erase_mark(DevState st) {
+  KeyframeStore& kf = st.kf;
+  const int s = blockIdx.y;
+  if (!kf.sur_valid[s] || kf.sur_rebuild[s]) return;
+  const int n_erased = kf.sur_n_erased[s];
+  const unsigned long long* pkey = kf.pool_key + (size_t)s * kf.pool_cap;
+  unsigned long long* link = kf.pool_link + (size_t)s * kf.pool_cap;
+  for (int e = blockIdx.z; e < n_erased; e += gridDim.z) {
+    const int* off = kf.kf_off + ((size_t)s * kf.kf_cap + kf.sur_erased[(size_t)s * kf.kf_cap + e]) * 4;
+    const int o0 = off[0], o1 = off[1], o2 = off[2], o3 = off[3];
+    for (int i = o0 + blockIdx.x * blockDim.x + threadIdx.x; i < o3; i += gridDim.x * blockDim.x) {
+      const int lo = i < o1 ? o0 : (i < o2 ? o1 : o2);
+      const unsigned long long k = pkey[i];
+      if (k == KF_INVALID || (i > lo && pkey[i - 1] == k)) continue;  // not the head of a run
+      link[i] |= (unsigned long long)KF_DEAD;
+    }
+  }
+}
+
+// ---- erase, step 2: thread / run of an erased key frame.  The first one to claim the run's voxel walks its chain once:
+// flagged runs are unlinked, the others re-summed in chain order (= the concatenation order of the remaining key
+// frames), which is bit-identical to summing the whole concatenation again. ----
+__global__ void __launch_bounds__(256) k_kf_erase_sweep(DevState st, int stamp) {
+  KeyframeStore& kf = st.kf;
+  const int s = blockIdx.y;
+  if (!kf.sur_valid[s] || kf.sur_rebuild[s]) return;
+  const int n_erased = kf.sur_n_erased[s];
+  const float4* pts = kf.pool_pts + (size_t)s * kf.pool_cap;
+  const unsigned long long* pkey = kf.pool_key + (size_t)s * kf.pool_cap;
+  unsigned long long* link = kf.pool_link + (size_t)s * kf.pool_cap;
+  for (int e = blockIdx.z; e < n_erased; e += gridDim.z) {
+    const int* off = kf.kf_off + ((size_t)s * kf.kf_cap + kf.sur_erased[(size_t)s * kf.kf_cap + e]) * 4;
+    const int o0 = off[0], o1 = off[1], o2 = off[2], o3 = off[3];
+    for (int i = o0 + blockIdx.x * blockDim.x + threadIdx.x; i < o3; i += gridDim.x * blockDim.x) {
+      const int lo = i < o1 ? o0 : (i < o2 ? o1 : o2);
+      const unsigned long long k = pkey[i];
+      if (k == KF_INVALID || (i > lo && pkey[i - 1] == k)) continue;  // not the head of a run
+      const VoxTable& tb = kf.tbl[i < o1 ? 0 : 1];
+      const unsigned long long hsh = kf_mix(k);
+      const int part = tb.parts > 1 ? (int)((hsh >> 40) % (unsigned)tb.parts) : 0;
+      const size_t tbase = ((size_t)s * tb.parts + part) * tb.sub_cap;
+      const int slot = kf_find(tb.key + tbase, (unsigned)tb.sub_cap - 1u, tb.sub_cap, k, hsh);
+      if (slot < 0) { atomicOr(&kf.err[s], KF_ERR_TABLE); continue; }
+      if (atomicExch(tb.claim + tbase + slot, stamp) == stamp) continue;  // another run of this voxel got there first
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+      unsigned cur = (unsigned)tb.head[tbase + slot], prev = KF_NONE, first = KF_NONE;
+      unsigned long long prev_lk = 0ull;  // link word of `prev` as it stands in memory
+      while (cur != KF_NONE) {
+        const unsigned long long lk = link[cur];
+        const float4 q0 = pts[cur];  // every run has at least one point: fetched together with its link
+        const unsigned nxt = (unsigned)(lk >> 32);
+        const unsigned lw = (unsigned)(lk & 0xffffffffu);
+        if (lw & KF_DEAD) {
+          link[cur] = lk & ~(unsigned long long)KF_DEAD;
+        } else {
+          const int len = (int)lw;
+          acc.x += q0.x; acc.y += q0.y; acc.z += q0.z; acc.w += q0.w;
+          for (int u = 1; u < len; ++u) {
+            const float4 q = pts[cur + u];
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+          }
+          cnt += len;
+          if (prev == KF_NONE) first = cur;
+          else if ((unsigned)(prev_lk >> 32) != cur) link[prev] = ((unsigned long long)cur << 32) | (prev_lk & 0xffffffffull);
+          prev = cur;
+          prev_lk = lk;
+        }
+        cur = nxt;
+      }
+      if (prev != KF_NONE && (unsigned)(prev_lk >> 32) != KF_NONE) link[prev] = ((unsigned long long)KF_NONE << 32) | (prev_lk & 0xffffffffull);
+      tb.head[tbase + slot] = (int)first;
+      tb.tail[tbase + slot] = (int)prev;
+      tb.sum[tbase + slot] = acc;
+      tb.cnt[tbase + slot] = cnt;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(KF_THREADS) k_kf_accumulate(DevState st) {
   KeyframeStore& kf = st.kf;
   const int s = blockIdx.x;
@@ -419,48 +501,6 @@ __global__ void __launch_bounds__(KF_THREADS) k_kf_accumulate(DevState st) {
       if (part == 0) kf.xs_n[s * 2 + map] = 0;
     }
     __syncthreads();
-  } else {
-    // ---- erase: unlink the runs of every key frame that left the list and re-sum the voxels they were in ----
-    const int n_erased = kf.sur_n_erased[s];
-    const int* erased = kf.sur_erased + (size_t)s * kf.kf_cap;
-    for (int e = 0; e < n_erased; ++e) {
-      const int* off = kf.kf_off + ((size_t)s * kf.kf_cap + erased[e]) * 4;
-      for (int c = c_first; c < c_last; ++c) {
-        const int lo = off[c], hi = off[c + 1];
-        for (int i = lo + threadIdx.x; i < hi; i += KF_THREADS) {
-          const unsigned long long k = pkey[i];
-          if (k == KF_INVALID || (i > lo && pkey[i - 1] == k)) continue;  // not the head of a run
-          const unsigned long long hsh = kf_mix(k);
-          if (tb.parts > 1 && (int)((hsh >> 40) % (unsigned)tb.parts) != part) continue;
-          const int slot = kf_find(keys, mask, tb.sub_cap, k, hsh);
-          if (slot < 0) { atomicOr(&kf.err[s], KF_ERR_TABLE); continue; }
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          int cnt = 0;
-          unsigned cur = (unsigned)heads[slot], prev = KF_NONE;
-          while (cur != KF_NONE) {
-            const unsigned long long lk = link[cur];
-            const unsigned nxt = (unsigned)(lk >> 32);
-            const int len = (int)(lk & 0xffffffffu);
-            if (cur == (unsigned)i) {
-              if (prev == KF_NONE) heads[slot] = (int)nxt;
-              else link[prev] = ((unsigned long long)nxt << 32) | (link[prev] & 0xffffffffull);
-              if (nxt == KF_NONE) tails[slot] = (int)prev;
-            } else {
-              for (int u = 0; u < len; ++u) {
-                const float4 q = pts[cur + u];
-                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-              }
-              cnt += len;
-              prev = cur;
-            }
-            cur = nxt;
-          }
-          sums[slot] = acc;
-          cnts[slot] = cnt;
-        }
-        __syncthreads();  // the outlier cloud of the key frame may have a run in the same voxel as its surf cloud
-      }
-    }
   }
   // ---- append: the key frames from list position sur_first on, in list order ----
   const int first = kf.sur_first[s], last = kf.sur_n[s];
@@ -723,6 +763,10 @@ void launch_extract_surrounding_keyframes(LaunchCtx& ctx, DevState& st) {
   const int B = st.p.B;
   const int tiles = (st.kf.sort_cap + XS_TILE - 1) / XS_TILE;
   LL_LAUNCH(ctx, "k_kf_select", k_kf_select<<<B, KF_THREADS, 0, ctx.stream>>>(st));
+  // (both erase kernels return at once for the sequences that erased nothing, which is most cycles of most sequences)
+  st.kf.stamp += 1;
+  LL_LAUNCH(ctx, "k_kf_erase_mark", k_kf_erase_mark<<<dim3(16, B, 2), 256, 0, ctx.stream>>>(st));
+  LL_LAUNCH(ctx, "k_kf_erase_sweep", k_kf_erase_sweep<<<dim3(64, B, 2), 256, 0, ctx.stream>>>(st, st.kf.stamp));
   LL_LAUNCH(ctx, "k_kf_accumulate", k_kf_accumulate<<<dim3(B, 1 + st.kf.tbl[1].parts), KF_THREADS, 0, ctx.stream>>>(st));
   LL_LAUNCH(ctx, "k_kfx_sort_new", k_kfx_sort_new<<<dim3(B, 2), KF_THREADS, 0, ctx.stream>>>(st));
   LL_LAUNCH(ctx, "k_kfx_merge", k_kfx_merge<<<dim3(tiles, B, 2), XS_TILE, 0, ctx.stream>>>(st));

@@ -48,6 +48,7 @@ struct VoxTable {
   int* cnt;                 // [B][parts][sub_cap] points summed (0: a voxel all of whose key frames have left)
   int* head;                // [B][parts][sub_cap] pool index of the first run of the chain, -1 = none
   int* tail;                // [B][parts][sub_cap] pool index of the last run
+  int* claim;               // [B][parts][sub_cap] stamp of the erase sweep that last re-summed the voxel
   unsigned* list;           // [B][parts][sub_cap] slots in use, in insertion order
   int* list_n;              // [B][parts]
   int* list_done;           // [B][parts] entries of `list` already merged into the sorted order (xs_*)
@@ -99,6 +100,7 @@ struct KeyframeStore {
   int* xs_bbox;                  // [B][2][8] running voxel bounding box of a map: min xyz, max xyz
   unsigned *sk0, *sk1, *sv0, *sv1;  // [B][2][sort_cap] radix sort scratch for the new voxels
   int sort_cap;
+  int stamp;                     // host counter of extractSurroundingKeyFrames calls (erase sweeps claim voxels with it)
 };
 
 struct DevParams {
@@ -193,6 +195,7 @@ struct DevState {
   float4* scan_corner_ds; float4* scan_surf_ds;  // [B][120V], [B][N]
   int* scan_ds_counts;                           // [B][2]
   float* transform_tobe_mapped;                  // [B][6]
+  float* map_odom;                               // [B][6] MapOptimization::transformSum: the odometry pose handed over with the scan (mapOptmization.cpp:1539)
   float* transform_bef_mapped;                   // [B][6]
   float* transform_aft_mapped;                   // [B][6]
   int* map_iters;                                // [B][2]
@@ -213,6 +216,9 @@ struct DevState {
   double* map_trace;                             // [B][10][34] per-iteration normal equations + step (parity/debug)
   int* map_rows;                                 // [B][max_blocks]
   int map_max_blocks;
+  // index-level parity aids (ll_enable_index_trace); null when disabled
+  int* map_knn_trace;                            // [B][10][map_knn_cap][5]
+  int* odom_trace;                               // [B][2 stages][5 rounds][24V][3]
   // ---- MapOptimization key frames / local map ----
   KeyframeStore kf;
 };

@@ -505,6 +505,20 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int ite
   }
 }
 
+// parity aid (ll_enable_index_trace): the ordered 5-NN indices every query has after k_map_knn of this iteration
+__global__ void __launch_bounds__(256) k_map_knn_trace(DevState st, int iter) {
+  const int s = blockIdx.y;
+  if (!map_guard(st, s) || st.map_flags[s * 4 + 1]) return;
+  const int nq = st.scan_ds_counts[s * 2 + 0] + st.scan_ds_counts[s * 2 + 1];
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    const unsigned w = (unsigned)st.map_knn_sel[(size_t)s * st.map_knn_cap + q];
+    const float4* rec = st.map_knn_rec + ((size_t)s * st.map_knn_cap + q) * KNN_REC;
+    int* out = st.map_knn_trace + (((size_t)s * 10 + iter) * st.map_knn_cap + q) * 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) out[j] = (w & 0x80000000u) ? __float_as_int(rec[(w >> (4 * j)) & 15u].w) : -1;
+  }
+}
+
 __device__ __noinline__ void map_solve_body(float* Tm, int* map_iters, double* trace, float* matP, int* map_flags, int iter, const double* tot);
 
 __global__ void __launch_bounds__(MAP_THREADS) k_map_iter(DevState st, int iter) {
@@ -648,7 +662,7 @@ __global__ void k_map_begin(DevState st) {
 __global__ void k_map_associate(DevState st) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= st.p.B) return;
-  const float* tS = st.transform_sum + s * 6;
+  const float* tS = st.map_odom + s * 6;  // the odometry of the handed-over scan, not FeatureAssociation's live pose
   const float* tB = st.transform_bef_mapped + s * 6;
   const float* tA = st.transform_aft_mapped + s * 6;
   float* tT = st.transform_tobe_mapped + s * 6;
@@ -709,7 +723,7 @@ __global__ void k_map_update(DevState st) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= st.p.B || !map_guard(st, s)) return;
   for (int i = 0; i < 6; ++i) {
-    st.transform_bef_mapped[s * 6 + i] = st.transform_sum[s * 6 + i];
+    st.transform_bef_mapped[s * 6 + i] = st.map_odom[s * 6 + i];
     st.transform_aft_mapped[s * 6 + i] = st.transform_tobe_mapped[s * 6 + i];
   }
 }
@@ -726,8 +740,10 @@ void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
   launch_grid_build2(ctx, p.B, st.grid_map_corner, st.map_corner, st.cap_map_corner, st.map_counts, 2, 0,
                      st.grid_map_surf, st.map_surf, st.cap_map_surf, st.map_counts, 2, 1, nullptr, 0);
   LL_LAUNCH(ctx, "k_map_begin", k_map_begin<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
+  if (st.map_knn_trace) cudaMemsetAsync(st.map_knn_trace, 0xff, (size_t)p.B * 10 * st.map_knn_cap * 5 * sizeof(int), ctx.stream);
   for (int iter = 0; iter < 10; ++iter) {
     LL_LAUNCH(ctx, "k_map_knn", k_map_knn<<<dim3(KNN_BLOCKS, p.B), KNN_THREADS, 0, ctx.stream>>>(st, iter));
+    if (st.map_knn_trace) LL_LAUNCH(ctx, "k_map_knn_trace", k_map_knn_trace<<<dim3(32, p.B), 256, 0, ctx.stream>>>(st, iter));
     LL_LAUNCH(ctx, "k_map_iter", k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st, iter));
   }
   LL_LAUNCH(ctx, "k_map_update", k_map_update<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));

@@ -732,6 +732,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS) k_odom_search(DevState st) {
       if (!surf) st.odom_gb[(size_t)s * cap + i] = gb;
       st.odom_s0[(size_t)s * p.cap_flat + i] = make_float4(sel.x, sel.y, sel.z, c.slack);
       st.odom_cl[(size_t)s * p.cap_flat + i] = c.closest;
+      if (st.odom_trace) {  // parity aid: search round 0
+        int* tr = st.odom_trace + ((((size_t)s * 2 + STAGE) * 5 + 0) * p.cap_flat + i) * 3;
+        tr[0] = c.closest; tr[1] = c.ind2; tr[2] = surf ? c.ind3 : -1;
+      }
     }
   }
 }
@@ -804,6 +808,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
       // Correspondences are refreshed every 5th iteration (featureAssociation.cpp:511,649).  A point that has moved by
       // less than its slack since it was searched keeps its correspondences (CorrS::slack); the others are searched again.
       if (threadIdx.x == 0) { sh_nlist = 0; sh_next = 0; }
+      if (st.odom_trace) {  // parity aid: a point that keeps its correspondences keeps the indices of the previous round
+        int* tr = st.odom_trace + (((size_t)s * 2 + STAGE) * 5 + iter / 5) * p.cap_flat * 3;
+        for (int i = threadIdx.x; i < n * 3; i += LM_THREADS) tr[i] = tr[i - p.cap_flat * 3];
+      }
       __syncthreads();
       for (int i = threadIdx.x; i < n; i += LM_THREADS) {
         const float4 sel = transform_to_start(sh_ori[i], T);
@@ -837,6 +845,10 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_odom_stage(DevState st) {
           sh_ga[i] = ga;
           if (!surf) sh_gb[i] = gb;
           sh_s0[i] = make_float4(sel.x, sel.y, sel.z, c.slack);
+          if (st.odom_trace) {
+            int* tr = st.odom_trace + ((((size_t)s * 2 + STAGE) * 5 + iter / 5) * p.cap_flat + i) * 3;
+            tr[0] = c.closest; tr[1] = c.ind2; tr[2] = surf ? c.ind3 : -1;
+          }
         }
       }
       __syncthreads();
@@ -940,6 +952,7 @@ static size_t stage_smem(const DevParams& p, bool surf) {
 void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
   const DevParams& p = st.p;
   if (!first_frame) {
+    if (st.odom_trace) cudaMemsetAsync(st.odom_trace, 0xff, (size_t)p.B * 2 * 5 * p.cap_flat * 3 * sizeof(int), ctx.stream);
     static bool attr_done = false;
     if (!attr_done) {
       cudaFuncSetAttribute(k_odom_stage<STAGE_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -45,6 +45,18 @@ void Device::waitIdle() {
   std::unique_lock<std::mutex> lk(k.m);
   k.cv.wait(lk, [&]() { return k.associated == k.projected && !k.mapping_busy; });
 }
+void Device::fail(const std::string& what) {
+  {
+    std::lock_guard<std::mutex> lk(_err_mtx);
+    if (!_failed.load()) _error = what;
+  }
+  _failed.store(true);
+  fprintf(stderr, "lego_loam: %s\n", what.c_str());
+}
+std::string Device::error() {
+  std::lock_guard<std::mutex> lk(_err_mtx);
+  return _error;
+}
 template <typename T>
 std::vector<T> Device::download(int buffer) {
   size_t n = 0;
@@ -87,6 +99,7 @@ void ImageProjection::cloudHandler(const ll_pointcloud2_view& msg) {
 
 template <class SetScans>
 void ImageProjection::handle(double stamp, SetScans set_scans) {
+  if (_dev->failed()) throw std::runtime_error("ImageProjection::cloudHandler: a stage failed earlier: " + _dev->error());
   Handshake& k = hs(_dev.get());
   {
     // device state is shared: wait until FeatureAssociation has consumed the previous projection
@@ -147,7 +160,7 @@ void FeatureAssociation::runFeatureAssociation() {
     if (projection.shutdown) break;
     AssociationOut out;
     bool hand_over = false;
-    {
+    if (!_dev->failed()) try {
       std::unique_lock<std::mutex> dl(_dev->mutex());
       const int rc = ll_feature_association(_dev->h());
       _dev->check(rc, "ll_feature_association");
@@ -170,6 +183,13 @@ void FeatureAssociation::runFeatureAssociation() {
         out.stamp = projection.seg_msg.stamp;
         out.frame = projection.frame;
       }
+    } catch (const std::exception& e) {
+      _dev->fail(e.what());
+      if (hand_over) {  // the mapping cycle of this scan will not run
+        std::lock_guard<std::mutex> lk(k.m);
+        k.mapping_busy = false;
+        hand_over = false;
+      }
     }
     {
       std::lock_guard<std::mutex> lk(k.m);
@@ -188,7 +208,7 @@ MapOptimization::MapOptimization(const LegoLoamParams& params, std::shared_ptr<D
     // cloudKeyPoses3D/6D, the key-frame clouds and the local maps live on the device (allocateMemory, mapOptmization.cpp:146-245)
     std::lock_guard<std::mutex> dl(_dev->mutex());
     const int n = params.num_vertical_scans * params.num_horizontal_scans;
-    const int max_keyframes = 1024;
+    const int max_keyframes = 4096;  // ~34 minutes of mapping cycles at 2 Hz; outgrowing it stops the mapping cleanly (Device::failed)
     _dev->check(ll_map_enable_keyframes(_dev->h(), max_keyframes, max_keyframes * (n / 8 + 512), n, 2 * n), "ll_map_enable_keyframes");
   }
   _run_thread = std::thread(&MapOptimization::run, this);  // mapOptmization.cpp:122
@@ -212,11 +232,14 @@ void MapOptimization::run() {
     AssociationOut association;
     _input_channel.receive(association);
     if (association.shutdown) break;
-    {
+    if (!_dev->failed()) try {
       // mapOptmization.cpp:1545-1560, every step on the device.  downsampleCurrentScan already ran at the hand-over
       // (FeatureAssociation thread), before the next frame could overwrite the last-frame clouds; it does not
       // depend on extractSurroundingKeyFrames, so the order of the two is immaterial.
       std::lock_guard<std::mutex> dl(_dev->mutex());
+      // OdometryToTransform(association.laser_odometry, transformSum), mapOptmization.cpp:1539: the pose that belongs to
+      // THIS scan -- FeatureAssociation may have integrated further scans since the hand-over
+      _dev->check(ll_map_set_odometry(_dev->h(), association.laser_odometry), "ll_map_set_odometry");
       _dev->check(ll_map_predict_pose(_dev->h()), "ll_map_predict_pose");                            // transformAssociateToMap
       _dev->check(ll_map_extract_surrounding_keyframes(_dev->h()), "ll_map_extract_surrounding_keyframes");
       _dev->check(ll_scan_to_map(_dev->h()), "ll_scan_to_map");                                      // guards + transformUpdate inside
@@ -225,10 +248,12 @@ void MapOptimization::run() {
       int32_t state[4] = {0, 0, 0, 0};
       _dev->check(ll_download(_dev->h(), 0, LL_BUF_TRANSFORM_AFT_MAPPED, aft, sizeof(aft), nullptr), "ll_download");
       _dev->check(ll_download(_dev->h(), 0, LL_BUF_KEYFRAME_STATE, state, sizeof(state), nullptr), "ll_download");
-      if (state[3] != 0) throw std::runtime_error("MapOptimization: key-frame capacity exceeded (bits " + std::to_string(state[3]) + ")");
+      if (state[3] != 0) _dev->fail("MapOptimization: key-frame capacity exceeded (LL_BUF_KEYFRAME_STATE bits " + std::to_string(state[3]) + "); mapping stops");
       _n_key_frames = (size_t)state[0];
       std::lock_guard<std::mutex> pl(_pose_mtx);
       std::memcpy(_aft, aft, sizeof(aft));
+    } catch (const std::exception& e) {
+      _dev->fail(e.what());
     }
     _cycles++;
     {

@@ -18,6 +18,7 @@
 #pragma once
 
 #include <atomic>
+#include <string>
 #include <condition_variable>
 #include <cstdint>
 #include <memory>
@@ -112,11 +113,19 @@ class Device {
   void waitIdle();
   // when true the stages also download their full payloads (segmented cloud, cloud_info arrays) to the host
   bool download_payloads = false;
+  // A stage thread never throws (that would terminate the process): the first failure is recorded here, the stages
+  // stop touching the device and only drain their channels; cloudHandler (the caller's thread) reports it.
+  void fail(const std::string& what);
+  bool failed() const { return _failed.load(); }
+  std::string error();
 
  private:
   LegoLoamParams _params;
   ll_handle* _h = nullptr;
   std::mutex _mtx;
+  std::atomic<bool> _failed{false};
+  std::mutex _err_mtx;
+  std::string _error;
 };
 
 class ImageProjection {

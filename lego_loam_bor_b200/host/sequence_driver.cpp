@@ -3,7 +3,10 @@
 // ImageProjection::cloudHandler, one message at a time, with blocking channels (the reference's
 // deterministic rosbag mode).
 //
-//   sequence_driver <config: A|B|C|T> <scans.bin | recording.bag[:topic]> <poses.out>
+//   sequence_driver <config: A|B|C|T> <scans.bin | recording.bag[:topic]> <poses.out> [--stream]
+//
+// --stream: the scans are pushed without waiting for the stages in between (the three stage threads overlap like in the
+// reference's live mode); only the line of the last frame is written, after everything has drained.
 //
 // scans.bin: int32 n_frames, then per frame: int32 n_points, n_points * 4 float32 (x, y, z, intensity).
 // recording.bag: a rosbag v2.0 file (main.cpp:26-35,60-76); the sensor_msgs/PointCloud2 messages of `topic` (default: the
@@ -32,6 +35,7 @@ static LegoLoamParams config(const char* name) {
 int main(int argc, char** argv) {
   if (argc < 4) { fprintf(stderr, "usage: %s <A|B|C|T> <scans.bin> <poses.out>\n", argv[0]); return 2; }
   const LegoLoamParams params = config(argv[1]);
+  const bool stream_mode = argc > 4 && !strcmp(argv[4], "--stream");
   std::string in_path = argv[2], topic;
   const size_t bag_ext = in_path.find(".bag");
   ll_bag* bag = nullptr;
@@ -93,7 +97,9 @@ int main(int argc, char** argv) {
       scan.resize((size_t)n * 4);
       if (n && fread(scan.data(), 16, n, f) != (size_t)n) break;
       IP.cloudHandler(scan.data(), n, 0.1 * i);
+      if (stream_mode && i + 1 < n_frames) continue;
       dev->waitIdle();
+      if (dev->failed()) { fprintf(stderr, "fatal: %s\n", dev->error().c_str()); return 1; }
       float ts[6], am[6];
       FA.transformSum(ts);
       MO.transformAftMapped(am);

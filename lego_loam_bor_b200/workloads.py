@@ -21,11 +21,12 @@ def drive_transforms(cfg, seq_ids, f):
 
 def keyframe_capacities(params, n_keyframes, extra_keyframes=64):
     """(max_keyframes, pool_points, max_map_corner, max_map_surf) for ll_map_enable_keyframes: a key frame of an
-    NxN-cell scan holds at most ~N/5 down-sampled points in practice; the arena's local map of 500 key frames has
-    ~1.0 N corner and ~1.2 N surf voxels at 64x2048."""
+    NxN-cell scan holds ~0.16 N (64 beams) to ~0.22 N (16 beams) down-sampled points; the arena's local map of 500 key frames has
+    ~1.0 N corner and ~1.2 N surf voxels at 64x2048 (a sparse 16-beam sensor spreads its few points over more voxels per
+    point: the floors)."""
     N = params.num_vertical_scans * params.num_horizontal_scans
     kf = n_keyframes + extra_keyframes
-    return kf, kf * (N // 5), max(4096, 2 * N), max(4096, 2 * N)
+    return kf, kf * (N // 4 + 512), max(16384, 2 * N), max(49152, 2 * N)
 
 
 def prebuild_keyframes(gpu, cfg, seq_ids, n_keyframes, scans_of, sync=None):

@@ -29,6 +29,8 @@
 #include "oracle_math.h"
 
 namespace om { int g_use_libm = 0; }
+static int g_float_accum = 0;
+static int g_stable_sort = 0;
 namespace oknn {
 #ifdef ORACLE_WITH_NANOFLANN
 int g_use_nanoflann = 1;
@@ -158,6 +160,12 @@ struct lo_handle {
   double map_trace[340];
   std::vector<P4> moOri, moCoeff;
   double timers[5];
+  /* index traces for parity tests: scan-to-scan correspondences of every search round (LM iterations 0, 5, 10, 15, 20)
+   * as [stage][round][feature][3] (closest, ind2, ind3; -1 = none / not run), and the 5-NN of every scan-to-map
+   * iteration as [iteration][query][5] (corner queries first; -1 x 5 when the fifth neighbour is not closer than 1 m) */
+  std::vector<int> odomSearchTrace, mapKnnTrace;
+  int stable_sort; /* 1: equal curvatures keep their position order in extractFeatures (see there) */
+  int float_accum; /* 0: exact double accumulation of J^T J (default); 1: float, row by row; 2: float, 8 partial sums (SIMD-like) */
 
   explicit lo_handle(const LegoLoamParams& p) : prm(p) {
     V = p.num_vertical_scans; H = p.num_horizontal_scans; N = V * H;
@@ -179,6 +187,8 @@ struct lo_handle {
     mapping_frequency_div = p.mapping_frequency_divider;
     const float nd = p.nearest_feature_search_distance;
     nearest_feature_dist_sqr = nd * nd;
+    float_accum = g_float_accum;
+    stable_sort = g_stable_sort;
     reset();
   }
 
@@ -456,7 +466,10 @@ struct lo_handle {
         int sp = (start_ring[i] * (6 - j) + end_ring[i] * j) / 6;
         int ep = (start_ring[i] * (5 - j) + end_ring[i] * (j + 1)) / 6 - 1;
         if (sp >= ep) continue;
-        std::sort(cloudSmoothness.begin() + sp, cloudSmoothness.begin() + ep, by_value());
+        /* std::sort leaves the order of equal curvatures unspecified (libstdc++'s introsort decides); stable_sort is one
+         * of the permitted outcomes and the one a (value, position) sort on the device produces */
+        if (stable_sort) std::stable_sort(cloudSmoothness.begin() + sp, cloudSmoothness.begin() + ep, by_value());
+        else std::sort(cloudSmoothness.begin() + sp, cloudSmoothness.begin() + ep, by_value());
         int largestPickedNum = 0;
         for (int k = ep; k >= sp; k--) {
           int ind = cloudSmoothness[k].ind;
@@ -627,6 +640,7 @@ struct lo_handle {
         }
         searchCornerInd1[i] = closestPointInd;
         searchCornerInd2[i] = minPointInd2;
+        traceOdom(1, iterCount / 5, i, closestPointInd, minPointInd2, -1);
       }
       if (searchCornerInd2[i] >= 0) {
         P4 tripod1 = cornerLast[(int)searchCornerInd1[i]];
@@ -689,6 +703,7 @@ struct lo_handle {
           }
         }
         searchSurfInd1[i] = closestPointInd;
+        traceOdom(0, iterCount / 5, i, closestPointInd, minPointInd2, minPointInd3);
         searchSurfInd2[i] = minPointInd2;
         searchSurfInd3[i] = minPointInd3;
       }
@@ -722,7 +737,32 @@ struct lo_handle {
    * float GEMM summation order is not reproducible; restated as exact double products accumulated in
    * double, rounded to float once (closer to the true value than any float order). */
   template <int C>
-  static void normal_equations(const std::vector<float>& A, const std::vector<float>& B, int n, float* AtA, float* AtB) {
+  void normal_equations(const std::vector<float>& A, const std::vector<float>& B, int n, float* AtA, float* AtB) {
+    if (float_accum) {
+      /* what the reference's Eigen float GEMM does up to its (unreproducible) summation order: float products summed in
+       * float -- row by row (1) or as eight interleaved partial sums added pairwise at the end, like a SIMD kernel (2).
+       * tests/test_oracle_pins.py shows that poses stay inside the parity tolerance and no LM exit flips. */
+      const int L = float_accum == 2 ? 8 : 1;
+      float acc[8][C * C], accb[8][C];
+      for (int l = 0; l < L; ++l) { for (int i = 0; i < C * C; ++i) acc[l][i] = 0.f; for (int i = 0; i < C; ++i) accb[l][i] = 0.f; }
+      for (int r = 0; r < n; ++r) {
+        const int l = r % L;
+        for (int a = 0; a < C; ++a) {
+          for (int b = a; b < C; ++b) acc[l][a * C + b] += A[r * C + a] * A[r * C + b];
+          accb[l][a] += A[r * C + a] * B[r];
+        }
+      }
+      for (int step = 1; step < L; step *= 2)
+        for (int l = 0; l + step < L; l += 2 * step) {
+          for (int i = 0; i < C * C; ++i) acc[l][i] += acc[l + step][i];
+          for (int i = 0; i < C; ++i) accb[l][i] += accb[l + step][i];
+        }
+      for (int a = 0; a < C; ++a) {
+        for (int b = a; b < C; ++b) AtA[a * C + b] = AtA[b * C + a] = acc[0][a * C + b];
+        AtB[a] = accb[0][a];
+      }
+      return;
+    }
     double acc[C * C], accb[C];
     for (int i = 0; i < C * C; ++i) acc[i] = 0.0;
     for (int i = 0; i < C; ++i) accb[i] = 0.0;
@@ -736,6 +776,20 @@ struct lo_handle {
       for (int b = a; b < C; ++b) AtA[a * C + b] = AtA[b * C + a] = (float)acc[a * C + b];
       AtB[a] = (float)accb[a];
     }
+  }
+
+  /* parity aid: the correspondences of search round `round` of stage (0 surf, 1 corner) */
+  void traceOdom(int stage, int round, int i, int a, int b, int c) {
+    const int cap = 24 * V;
+    if (round < 0 || round >= 5 || i < 0 || i >= cap) return;
+    int* t = odomSearchTrace.data() + (((size_t)stage * 5 + round) * cap + i) * 3;
+    t[0] = a; t[1] = b; t[2] = c;
+  }
+  void traceKnn(int iter, int q, const int* ind, const float* dis) {
+    const size_t Q = scanCornerDS.size() + scanSurfTotalDS.size();
+    if (mapKnnTrace.size() != 10 * Q * 5) return;
+    int* t = mapKnnTrace.data() + ((size_t)iter * Q + q) * 5;
+    for (int j = 0; j < 5; ++j) t[j] = dis[4] < 1.0 ? ind[j] : -1;
   }
 
   bool calculateTransformationSurf(int iterCount) { /* featureAssociation.cpp:785-921 */
@@ -852,6 +906,7 @@ struct lo_handle {
   }
 
   void updateTransformation() { /* featureAssociation.cpp:1213-1235 */
+    odomSearchTrace.assign((size_t)2 * 5 * 24 * V * 3, -1);
     odom_iters[0] = odom_iters[1] = 0;
     if (cornerLastNum < 10 || surfLastNum < 100) return;
     for (int iterCount1 = 0; iterCount1 < 25; iterCount1++) {
@@ -1020,7 +1075,7 @@ struct lo_handle {
     }
   }
 
-  void cornerOptimization(int) { /* mapOptmization.cpp:1028-1134 */
+  void cornerOptimization(int iterCount) { /* mapOptmization.cpp:1028-1134 */
     updatePointAssociateToMapSinCos();
     const std::vector<P4>& mp = kdCornerMap->cloud();
     for (size_t i = 0; i < scanCornerDS.size(); i++) {
@@ -1028,6 +1083,7 @@ struct lo_handle {
       pointAssociateToMap(&pointOri, &pointSel);
       int ind[5]; float dis[5];
       kdCornerMap->nearestKSearch(pointSel, 5, ind, dis);
+      traceKnn(iterCount, (int)i, ind, dis);
       if (dis[4] < 1.0) {
         float cx = 0, cy = 0, cz = 0;
         for (int j = 0; j < 5; j++) { cx += mp[ind[j]].x; cy += mp[ind[j]].y; cz += mp[ind[j]].z; }
@@ -1073,7 +1129,7 @@ struct lo_handle {
     }
   }
 
-  void surfOptimization(int) { /* mapOptmization.cpp:1136-1197 */
+  void surfOptimization(int iterCount) { /* mapOptmization.cpp:1136-1197 */
     updatePointAssociateToMapSinCos();
     const std::vector<P4>& mp = kdSurfMap->cloud();
     for (size_t i = 0; i < scanSurfTotalDS.size(); i++) {
@@ -1081,6 +1137,7 @@ struct lo_handle {
       pointAssociateToMap(&pointOri, &pointSel);
       int ind[5]; float dis[5];
       kdSurfMap->nearestKSearch(pointSel, 5, ind, dis);
+      traceKnn(iterCount, (int)(scanCornerDS.size() + i), ind, dis);
       if (dis[4] < 1.0) {
         float matA0[15], matB0[5] = {-1, -1, -1, -1, -1}, matX0[3];
         for (int j = 0; j < 5; j++) { matA0[j * 3 + 0] = mp[ind[j]].x; matA0[j * 3 + 1] = mp[ind[j]].y; matA0[j * 3 + 2] = mp[ind[j]].z; }
@@ -1159,6 +1216,7 @@ struct lo_handle {
 
   void scan2MapOptimization() { /* mapOptmization.cpp:1315-1332 (transformUpdate is host glue) */
     map_iters[0] = 0; map_iters[1] = 0;
+    mapKnnTrace.assign((size_t)10 * (scanCornerDS.size() + scanSurfTotalDS.size()) * 5, -1);
     if (mapCorner.size() > 10 && mapSurf.size() > 100) {
       kdCornerMap->setInputCloud(mapCorner);
       kdSurfMap->setInputCloud(mapSurf);
@@ -1361,6 +1419,8 @@ static int copy_out(const T* src, size_t n, void* dst, size_t dst_bytes, size_t*
 extern "C" {
 
 void lo_set_math_backend(int use_libm) { om::g_use_libm = use_libm ? 1 : 0; }
+void lo_set_accum_backend(int float_accum) { g_float_accum = float_accum; }
+void lo_set_sort_backend(int stable) { g_stable_sort = stable ? 1 : 0; }
 void lo_set_knn_backend(int use_nanoflann) {
 #ifdef ORACLE_WITH_NANOFLANN
   oknn::g_use_nanoflann = use_nanoflann ? 1 : 0;
@@ -1489,6 +1549,14 @@ int lo_download(lo_handle* h, int buffer, void* dst, size_t dst_bytes, size_t* n
     }
     case LL_BUF_KEY_POSES_6D: return copy_out(h->cloudKeyPoses6D.data(), h->cloudKeyPoses6D.size(), dst, dst_bytes, n);
     case LL_BUF_SURROUNDING_KEY_IDS: return copy_out(h->surroundingExistingKeyPosesID.data(), h->surroundingExistingKeyPosesID.size(), dst, dst_bytes, n);
+    case LL_BUF_MAP_KNN_IDX: { /* elements are rows of 5 indices */
+      struct R5 { int v[5]; };
+      return copy_out(reinterpret_cast<const R5*>(h->mapKnnTrace.data()), h->mapKnnTrace.size() / 5, dst, dst_bytes, n);
+    }
+    case LL_BUF_ODOM_SEARCH_IDX: { /* rows of 3 indices */
+      struct R3 { int v[3]; };
+      return copy_out(reinterpret_cast<const R3*>(h->odomSearchTrace.data()), h->odomSearchTrace.size() / 3, dst, dst_bytes, n);
+    }
     default: return LL_ERR_INVALID_ARG;
   }
 }
@@ -1499,6 +1567,8 @@ int lo_upload(lo_handle* h, int buffer, const void* src, size_t n_elems) {
     case LL_BUF_TRANSFORM_CUR: if (n_elems != 6) return LL_ERR_INVALID_ARG; for (int i = 0; i < 6; ++i) h->transformCur[i] = f[i]; return 0;
     case LL_BUF_TRANSFORM_SUM: if (n_elems != 6) return LL_ERR_INVALID_ARG; for (int i = 0; i < 6; ++i) h->transformSum[i] = f[i]; return 0;
     case LL_BUF_TRANSFORM_TOBE_MAPPED: if (n_elems != 6) return LL_ERR_INVALID_ARG; for (int i = 0; i < 6; ++i) h->transformTobeMapped[i] = f[i]; return 0;
+    case LL_BUF_TRANSFORM_BEF_MAPPED: if (n_elems != 6) return LL_ERR_INVALID_ARG; for (int i = 0; i < 6; ++i) h->transformBefMapped[i] = f[i]; return 0;
+    case LL_BUF_TRANSFORM_AFT_MAPPED: if (n_elems != 6) return LL_ERR_INVALID_ARG; for (int i = 0; i < 6; ++i) h->transformAftMapped[i] = f[i]; return 0;
     default: return LL_ERR_INVALID_ARG;
   }
 }

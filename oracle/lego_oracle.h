@@ -24,6 +24,14 @@ typedef struct lo_handle lo_handle;
 void lo_set_math_backend(int use_libm);      /* 0 = portable (default), 1 = glibc float libm */
 void lo_set_knn_backend(int use_nanoflann);  /* 1 = reference nanoflann (if compiled in), 0 = port kd-tree */
 int lo_has_nanoflann(void);
+/* J^T J / J^T r accumulation of the three LM solves of objects created afterwards: 0 = exact double products summed in
+ * double (default, what the CUDA kernels do), 1 = float row by row, 2 = float with eight interleaved partial sums; 1 and 2
+ * bracket what the reference's Eigen float GEMM does (featureAssociation.cpp:860-866, mapOptmization.cpp:1258). */
+void lo_set_accum_backend(int float_accum);
+/* extractFeatures' per-sextant sort of objects created afterwards: 0 = std::sort as in the reference (featureAssociation.cpp:285;
+ * the order of EQUAL curvatures is whatever libstdc++'s introsort leaves), 1 = std::stable_sort (equal curvatures in
+ * position order: one of the outcomes the C++ standard permits, and the one a parallel (value, position) sort gives). */
+void lo_set_sort_backend(int stable);
 
 lo_handle* lo_create(const LegoLoamParams* p);
 void lo_destroy(lo_handle* h);

@@ -31,6 +31,7 @@ BUFFERS = {
     "TRANSFORM_AFT_MAPPED": (37, np.float32, 1), "SCAN_SURF_DS": (38, np.float32, 4),
     "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
     "KEYFRAME_STATE": (41, np.int32, 1), "KEY_POSES_6D": (42, np.float32, 6), "SURROUNDING_KEY_IDS": (43, np.int32, 1),
+    "MAP_KNN_IDX": (45, np.int32, 5), "ODOM_SEARCH_IDX": (46, np.int32, 3),
 }
 
 
@@ -91,13 +92,17 @@ def kind(prefer_ref=True):
 class Oracle:
     """One sequence through the CPU restatement."""
 
-    def __init__(self, params, libm=False, nanoflann=True, prefer_ref=True):
+    def __init__(self, params, libm=False, nanoflann=True, prefer_ref=True, float_accum=0, stable_sort=False):
         self.lib = load(prefer_ref)
+        self.lib.lo_set_accum_backend(int(float_accum))
+        self.lib.lo_set_sort_backend(1 if stable_sort else 0)
         self.lib.lo_set_math_backend(1 if libm else 0)
         self.lib.lo_set_knn_backend(1 if nanoflann else 0)
         self._libm, self._nf = libm, nanoflann
         self.params = params
         self.h = self.lib.lo_create(C.addressof(params))
+        self.lib.lo_set_accum_backend(0)
+        self.lib.lo_set_sort_backend(0)
         if not self.h:
             raise RuntimeError("lo_create failed")
 

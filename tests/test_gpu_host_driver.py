@@ -49,6 +49,33 @@ def test_sequence_driver_matches_c_abi(built, tmp_path):
     assert np.abs(aft[3:] - rows[15, 4:7]).max() < 0.3 and np.abs(aft[:3] - rows[15, 1:4]).max() < 0.1
 
 
+def test_stage_threads_overlap_without_changing_the_result(built, tmp_path):
+    """--stream: scans are pushed without waiting for the stages, so FeatureAssociation integrates further frames while
+    MapOptimization still works on an earlier hand-over (the reference's live mode).  The mapping cycle must use the
+    odometry pose that was handed over WITH its scan (AssociationOut::laser_odometry, mapOptmization.cpp:1539), so the
+    final poses and key frames equal those of the run that waits after every frame."""
+    from lego_loam_bor_b200._paths import PKG
+    n_frames = 27
+    p, cfg, scans = make_scans("T", [1], range(n_frames))
+    path = tmp_path / "scans.bin"
+    with open(path, "wb") as f:
+        f.write(np.int32(n_frames).tobytes())
+        for i in range(n_frames):
+            a = scans[(1, i)]
+            f.write(np.int32(len(a)).tobytes())
+            f.write(np.ascontiguousarray(a, np.float32).tobytes())
+    exe = os.path.join(PKG, "host", "sequence_driver")
+    rows = []
+    for extra in ([], ["--stream"]):
+        out = tmp_path / ("poses%d.txt" % len(rows))
+        r = subprocess.run([exe, "T", str(path), str(out)] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        rows.append(np.atleast_2d(np.loadtxt(out)))
+    assert rows[0].shape == (n_frames, 15) and rows[1].shape == (1, 15)
+    assert np.array_equal(rows[0][-1], rows[1][0]), (rows[0][-1], rows[1][0])
+    assert rows[1][0, 14] == 5 and rows[1][0, 13] >= 4
+
+
 def test_sequence_driver_bag_mode(built, tmp_path):
     """The same sequence recorded as a rosbag (the reference's bag mode, main.cpp:60-76): the driver reads the
     PointCloud2 messages of the lidar topic and hands the raw message bytes to ImageProjection::cloudHandler; every pose

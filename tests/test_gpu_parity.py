@@ -15,12 +15,20 @@ POSE_TOL_RAD = 1e-5
 CURV_RTOL = 1e-5
 
 
-def _run_sequence(cfgname, n_frames, batch_seqs, check_every=1):
+# with the oracle on glibc's libm (what the reference calls) stored angles may differ in the last bit; every DISCRETE output
+# (and every value that involves no inverse trigonometry) must still be identical
+LIBM_EXACT_PROJECTION = [n for n in EXACT_PROJECTION if n != "ORIENTATION"]
+LIBM_EXACT_FEATURES = ["CORNER_SHARP_IND", "CORNER_LESS_SHARP_IND", "SURF_FLAT_IND", "NEIGHBOR_PICKED", "CLOUD_LABEL", "SURF_LESS_FLAT_RAW_COUNT"]
+
+
+def _run_sequence(cfgname, n_frames, batch_seqs, check_every=1, libm=False):
     from lego_loam_bor_b200.capi import LegoLoam
     from oracle.oracle_py import Oracle
     p, cfg, scans = make_scans(cfgname, batch_seqs, range(n_frames))
     gpu = LegoLoam(p, batch=len(batch_seqs))
-    oracles = [Oracle(p) for _ in batch_seqs]
+    oracles = [Oracle(p, libm=libm) for _ in batch_seqs]
+    exact_projection = LIBM_EXACT_PROJECTION if libm else EXACT_PROJECTION
+    exact_features = LIBM_EXACT_FEATURES if libm else EXACT_FEATURES
     report = []
     for f in range(n_frames):
         gpu.set_scans_host([scans[(s, f)] for s in batch_seqs])
@@ -29,12 +37,14 @@ def _run_sequence(cfgname, n_frames, batch_seqs, check_every=1):
             oracles[k].image_projection(scans[(s, f)])
         if f % check_every == 0:
             for k in range(len(batch_seqs)):
-                for name in EXACT_PROJECTION:
+                for name in exact_projection:
                     a, b = gpu.download(name, k), oracles[k].download(name)
                     assert same_bits(a, b), f"frame {f} seq {k}: " + describe_mismatch(name, a, b)
                 # segmented cloud before adjustDistortion
                 a, b = gpu.download("SEG_CLOUD", k), oracles[k].download("SEG_CLOUD")
                 assert same_bits(a, b), f"frame {f} seq {k}: " + describe_mismatch("SEG_CLOUD(pre)", a, b)
+                if libm:
+                    np.testing.assert_allclose(gpu.download("ORIENTATION", k), oracles[k].download("ORIENTATION"), rtol=0, atol=1e-6)
         gpu.feature_association()
         for k in range(len(batch_seqs)):
             oracles[k].feature_association()
@@ -47,7 +57,7 @@ def _run_sequence(cfgname, n_frames, batch_seqs, check_every=1):
                 if curvature_ties(o, S):
                     report.append(f"frame {f} seq {k}: curvature tie inside a sextant (std::sort unstable) - features skipped")
                     continue
-                for name in EXACT_FEATURES:
+                for name in exact_features:
                     a, b = gpu.download(name, k), o.download(name)
                     assert same_bits(a, b), f"frame {f} seq {k}: " + describe_mismatch(name, a, b)
                 # less-flat cloud after the per-ring VoxelGrid, and the clouds handed to the next frame
@@ -80,6 +90,44 @@ def test_32_beam(built):
 def test_64_beam_batch(built):
     """64x2048 (config C geometry), three sequences in one batch."""
     _run_sequence("C", 4, [0, 5, 9])
+
+
+@pytest.mark.parametrize("cfgname,n_frames,seqs", [("T", 8, [0, 1]), ("A", 12, [0]), ("B", 6, [3]), ("C", 31, [2])])
+def test_discrete_outputs_against_glibc_libm(built, cfgname, n_frames, seqs):
+    """The same runs against the oracle on glibc's float libm -- the functions the reference itself calls -- instead of
+    the portable math the oracle shares with the kernels: labels, cloud_info and feature indices bit-exact, LM
+    iteration counts equal, poses within tolerance.  31 frames at 64x2048."""
+    _run_sequence(cfgname, n_frames, seqs, libm=True)
+
+
+def test_64_beam_live_map_against_glibc_libm(built):
+    """64x2048, 31 frames free-running with the whole mapping cycle (six cycles: key frames, local map assembled from
+    them, scan-to-map) against the libm oracle: iteration counts, key-frame bookkeeping equal, poses within tolerance."""
+    from lego_loam_bor_b200.capi import LegoLoam
+    from oracle.oracle_py import Oracle
+    p, cfg, scans = make_scans("C", [4], range(31))
+    gpu = LegoLoam(p, batch=1)
+    gpu.map_enable_keyframes(max_keyframes=16)
+    o = Oracle(p, libm=True)
+    cycles = 0
+    for f in range(31):
+        gpu.set_scans_host([scans[(4, f)]])
+        rc = gpu.process_scans()
+        o.image_projection(scans[(4, f)])
+        handed = o.feature_association()
+        assert handed == rc
+        if handed == 1:
+            o.mapping_cycle()
+            cycles += 1
+            assert np.array_equal(gpu.download("MAP_ITERS"), o.download("MAP_ITERS")), f"frame {f}"
+            assert np.array_equal(gpu.download("KEYFRAME_STATE")[:3], o.download("KEYFRAME_STATE")[:3]), f"frame {f}"
+            assert np.array_equal(gpu.download("SURROUNDING_KEY_IDS"), o.download("SURROUNDING_KEY_IDS"))
+            assert len(gpu.download("MAP_SURF")) == len(o.download("MAP_SURF"))
+        assert np.array_equal(gpu.download("ODOM_ITERS"), o.download("ODOM_ITERS")), f"frame {f}"
+        for name in ("TRANSFORM_SUM", "TRANSFORM_AFT_MAPPED"):
+            a, b = gpu.download(name), o.download(name)
+            assert np.all(np.abs(a[:3] - b[:3]) <= POSE_TOL_RAD) and np.all(np.abs(a[3:] - b[3:]) <= POSE_TOL_M), f"frame {f} {name}: {a} vs {b}"
+    assert cycles == 6
 
 
 def test_empty_and_ragged_inputs(built):
