@@ -9,10 +9,11 @@
 //       The persistent arrays (cloudCurvature / cloudNeighborPicked / cloudLabel /
 //       cloudSmoothness) are only rewritten on [5, S-5) like the reference, stale values elsewhere
 //       survive across frames.
-//   k_extract_features one block per (ring, sequence).  Sorts the six sextants of the ring in shared
+//   k_feature_ring     one block per (ring, sequence).  Sorts the six sextants of the ring in shared
 //       memory (bitonic, key = (curvature, index)), runs the two greedy pick scans with one warp
 //       (32 sorted candidates tested per step), collects the less-flat points and applies the
-//       per-ring 0.2 m VoxelGrid (sort by voxel index, sequential centroid per voxel).
+//       per-ring 0.2 m VoxelGrid (sort by voxel index, sequential centroid per voxel) -- all on the
+//       ring's span held in shared memory.
 //   k_feature_compact  one block per (ring, sequence): concatenates the per-ring results in ring order.
 #include "ll_device.cuh"
 #include "ll_kernels.h"
@@ -167,51 +168,90 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-#define SORT_THREADS 256
+#define FR_THREADS 256
 
-// ---- 1. per-ring candidate sort ----------------------------------------------------------------
-// One block per (ring, sequence).  The reference sorts each sextant of cloudSmoothness by curvature
-// (std::sort(begin + sp, begin + ep), featureAssociation.cpp:275-286) and then scans it downwards for
-// edge points and upwards for flat points.  Only elements that can pass the tests of :291-293 /
-// :333-335 (curvature vs threshold, ground flag) can ever be picked, so only those are sorted, all
-// twelve lists of the ring in ONE bitonic network with the composite key
-//   [list = sextant*2 + (0 edge | 1 flat)] [visit order] [index tie-break]
-// where the visit order is ~curvature for edge lists (descending scan), curvature for flat lists,
-// and the unsorted element at position ep (the reference's sort excludes ep but both scans include
-// it) gets the first / last slot.  Output: scan_list[ring range] = picked
-// candidates in visiting order + the 13 list offsets.
-// cloudSmoothness itself is not stored: for k in [5, S-5) its entry is (curvature[k], k) by
-// construction (featureAssociation.cpp:220-221); the one stale entry that can ever be read, position
-// 4, is carried in `slot4` and updated to the minimum of the sorted
-// range that contains it, which is what the reference's in-place sort leaves there.
-__global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int cap2) {
-  extern __shared__ unsigned long long keys[];  // [cap2]
+// ---- per-ring feature extraction: candidate sort, greedy picks, less-flat collection + VoxelGrid, in ONE block ---------
+// One block per (ring, sequence); everything between the loads of the ring's span and its results lives in shared
+// memory (extractFeatures, featureAssociation.cpp:265-383).
+//
+// 1. Candidate sort.  The reference sorts each sextant of cloudSmoothness by curvature (std::sort(begin + sp,
+//    begin + ep), :275-286) and then scans it downwards for edge points and upwards for flat points.  Only elements that
+//    can pass the tests of :291-293 / :333-335 (curvature vs threshold, ground flag) can ever be picked, so only those
+//    are sorted, all twelve lists of the ring in ONE bitonic network with the composite key
+//      [list = sextant*2 + (0 edge | 1 flat)] [visit order] [index tie-break]
+//    where the visit order is ~curvature for edge lists (descending scan), curvature for flat lists, and the unsorted
+//    element at position ep (the reference's sort excludes ep but both scans include it)
+//    gets the first / last slot.  cloudSmoothness itself is not stored: for k in [5, S-5) its entry is
+//    (curvature[k], k) by construction (:220-221); the one stale entry that can ever be read, position 4 (SURVEY.md
+//    section 9 item 7), is carried in `slot4` and updated to the minimum of the sorted range that contains it, which is
+//    what the reference's in-place sort leaves there.
+// 2. Greedy picks by warp 0; the six sextants of a ring must run in order because a pick suppresses up to 5 neighbours on
+//    either side, across sextant boundaries.  Each step tests 32 consecutive candidates of the sorted list at once; the
+//    only mutable state, cloudNeighborPicked and cloudLabel of the ring's span, are bytes in shared memory.  Rings do not
+//    interact: candidates lie in [start, end], their +-5 neighbours inside the ring's own points [start-5, end+5].
+// 3. Less-flat collection by POSITION (:370-374) and the per-ring 0.2 m pcl::VoxelGrid (:101,377-381): consecutive points
+//    of a ring mostly share a voxel, so the sort runs over RUNS of equal voxel index; runs of the same voxel end up
+//    adjacent and in input order, so each voxel's float sums keep the input order.
+__global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int cap2) {
+  extern __shared__ unsigned long long fr_keys[];  // [cap2] u64, then int vox[H], u16 col / lfpos [H+32] each, u8 picked, i8 label [H+32] each
+  __shared__ int warp_tot[33];
   __shared__ int sh_sp[6], sh_ep[6];
-  __shared__ int sh_cnt[12];
-  __shared__ int sh_n;
+  __shared__ int sh_imn[3], sh_imx[3];
+  __shared__ int sh_stale, sh_has_stale;
+  __shared__ int sh_counts[3];
+  __shared__ unsigned short sh_pick[6][24];   // per sextant: up to 20 edge picks, then up to 4 flat picks (positions from the ring's first)
+  __shared__ int sh_ne[6], sh_nf[6], sh_spill_r[6], sh_spill_l[6];
   __shared__ unsigned long long sh_slot_min;
   const DevParams& p = st.p;
   const int ring = blockIdx.x, s = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const size_t base = (size_t)s * p.N;
+  const size_t rs = (size_t)s * p.V + ring;
+  const int HP = p.H + 32;
+  unsigned long long* keys = fr_keys;
+  int* sm_vox = reinterpret_cast<int*>(fr_keys + cap2);
+  unsigned short* sm_col = reinterpret_cast<unsigned short*>(sm_vox + p.H);
+  unsigned short* sm_lfpos = sm_col + HP;
+  unsigned char* sm_picked = reinterpret_cast<unsigned char*>(sm_lfpos + HP);
+  signed char* sm_label = reinterpret_cast<signed char*>(sm_picked + HP);
   const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
-  const int a = start - 4;
-  int* offs = st.sext_off + ((size_t)s * p.V + ring) * 16;
+  const int a = start - 4, b = end + 6;  // this ring's points are [a - 1, b)
+  const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
+  const int L = max(0, span_hi - span_lo);
   if (threadIdx.x < 6) {
     const int j = threadIdx.x;
     sh_sp[j] = (start * (6 - j) + end * j) / 6;
     sh_ep[j] = (start * (5 - j) + end * (j + 1)) / 6 - 1;
   }
-  if (threadIdx.x < 12) sh_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { sh_n = 0; sh_slot_min = ~0ull; }
+  if (threadIdx.x == 0) { sh_slot_min = ~0ull; sh_stale = 0; sh_has_stale = 0; }
+  for (int t = threadIdx.x; t < L; t += FR_THREADS) {
+    sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
+    sm_col[t] = (unsigned short)st.seg_col[base + span_lo + t];
+    sm_label[t] = (signed char)max(-2, min(3, st.cloud_label[base + span_lo + t]));
+  }
   __syncthreads();
+  // ---- 1. one key per position of the ring ----
+  // The reference sorts every sextant by curvature and scans it downwards for edge points (first unpicked candidate,
+  // 20 times) and upwards for flat points (4 times).  "The next unpicked candidate in sorted order" is the arg-max (arg-min)
+  // over the candidates that are still unpicked, so nothing is sorted here: a warp keeps the sextant's candidates spread
+  // over its lanes and selects with two hardware warp reductions per pick.
+  //   ckey[u]  edge list: curvature bits (position ep: 0xffffffff, scanned first); flat list: 0xfffffffe - curvature bits
+  //            (position ep: 1, scanned last); 0: not a candidate.  ctype[u]: 0 edge, 1 flat, 3 neither.
   const unsigned slot_val = st.slot4[s * 2 + 0];
   const int slot_ind = (int)st.slot4[s * 2 + 1];
-  bool slot_in_sorted_range = false;
-  for (int j = 0; j < 6; ++j) {
+  const int k_first = sh_sp[0];
+  unsigned* ckey = reinterpret_cast<unsigned*>(keys);             // [H]
+  unsigned char* ctype = reinterpret_cast<unsigned char*>(ckey + p.H);  // [H]
+  for (int k0 = k_first; k0 <= sh_ep[5]; k0 += FR_THREADS) {
+    const int k = k0 + threadIdx.x;
+    if (k > sh_ep[5]) break;
+    int j = 0;
+#pragma unroll
+    for (int q = 1; q < 6; ++q) j += (k >= sh_sp[q]) ? 1 : 0;   // sextant ranges tile [sp_0, ep_5]: sp_{q+1} = ep_q + 1
     const int sp = sh_sp[j], ep = sh_ep[j];
-    if (sp >= ep) continue;
-    if (sp == 4) slot_in_sorted_range = true;
-    for (int k = sp + threadIdx.x; k <= ep; k += SORT_THREADS) {
+    unsigned key = 0u;
+    unsigned char type = 3;
+    if (sp < ep && k >= 0 && k < p.N) {
       unsigned vb;
       int ind;
       if (k == 4) { vb = slot_val; ind = slot_ind; }
@@ -221,257 +261,309 @@ __global__ void __launch_bounds__(SORT_THREADS) k_feature_sort(DevState st, int 
       const bool ground = st.seg_ground[base + ind] != 0;
       const bool edge_ok = c > p.edge_threshold && !ground;   // featureAssociation.cpp:291-293
       const bool flat_ok = c < p.surf_threshold && ground;    // featureAssociation.cpp:333-335
-      if (!edge_ok && !flat_ok) continue;
-      const int list = j * 2 + (edge_ok ? 0 : 1);
-      unsigned order;
-      if (k == ep) order = edge_ok ? 0u : 0xffffffffu;        // position ep: scanned first (down) / last (up)
-      else order = edge_ok ? ~vb : vb;
-      const unsigned tb = edge_ok ? (0x1fffffu - (unsigned)ind) : (unsigned)ind;
-      const int slot = atomicAdd(&sh_n, 1);
-      atomicAdd(&sh_cnt[list], 1);
-      keys[slot] = ((unsigned long long)list << 53) | ((unsigned long long)order << 21) | tb;
+      if (edge_ok) { type = 0; key = (k == ep) ? 0xffffffffu : vb; }
+      else if (flat_ok) { type = 1; key = (k == ep) ? 1u : 0xfffffffeu - vb; }
+      if (k == 4 && (edge_ok || flat_ok)) { sh_stale = ind; sh_has_stale = 1; }
     }
+    ckey[k - k_first] = key;
+    ctype[k - k_first] = type;
+  }
+  bool slot_in_sorted_range = false;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) slot_in_sorted_range = slot_in_sorted_range || (sh_sp[j] < sh_ep[j] && sh_sp[j] == 4);
+  __syncthreads();
+  if (threadIdx.x == 0 && slot_in_sorted_range && sh_slot_min != ~0ull) {
+    st.slot4[s * 2 + 0] = (unsigned)(sh_slot_min >> 32);
+    st.slot4[s * 2 + 1] = (unsigned)(sh_slot_min & 0xffffffffull);
+  }
+  // ---- 2. greedy picks ----
+  // The six sextants of a ring run in order in the reference because a pick suppresses up to 5 neighbours on either side,
+  // across a sextant boundary.  Only the first five positions of a sextant can be reached from the previous one, so the
+  // sextants are picked SPECULATIVELY in parallel, one warp each, on the picked flags of their own range; marks that fall
+  // outside the own range are kept as two 5-bit spill masks.  Then the boundaries are checked in order: if none of the
+  // positions sextant j-1 (final) marks at the start of sextant j was picked by sextant j's speculative run, that run is
+  // exactly what the sequential scan does (a candidate that was never picked never influenced a decision); otherwise
+  // sextant j is reset and run again with those marks in place.  Ring 0 (the stale cloudSmoothness entry may point
+  // anywhere) and rings with sextants shorter than 6 points take the sequential path below.
+  bool speculative = sh_has_stale == 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) speculative = speculative && (sh_sp[j] >= sh_ep[j] ? false : (sh_ep[j] - sh_sp[j] + 1 >= 6));
+  if (speculative) {
+    // one sextant by one warp; own range [own_lo, own_hi]: marks inside go to sm_picked, marks outside to the spill masks
+    auto run_sextant = [&](int j, unsigned premark) {
+      const int sp = sh_sp[j], ep = sh_ep[j];
+      const int len = ep - sp + 1;
+      const unsigned* kq = ckey + (sp - k_first);
+      const unsigned char* tq = ctype + (sp - k_first);
+      const int items = (len + 31) >> 5;
+      unsigned spill_r = 0u, spill_l = 0u;
+      int n_edge = 0, n_flat = 0;
+      if (lane < 5 && ((premark >> lane) & 1u)) sm_picked[sp + lane - span_lo] = 1;
+      __syncwarp();
+      for (int type = 0; type < 2; ++type) {
+        const int quota = type == 0 ? 20 : 4;
+        unsigned elig = 0u;
+        for (int i = 0; i < items; ++i) {
+          const int u = lane + 32 * i;
+          if (u < len && tq[u] == type && sm_picked[sp + u - span_lo] == 0) elig |= 1u << i;
+        }
+        int done = 0;
+        while (done < quota) {
+          unsigned bkey = 0u;
+          int bu = -1;
+          unsigned e = elig;
+          while (e) {
+            const int i = __ffs(e) - 1;
+            e &= e - 1;
+            const int u = lane + 32 * i;
+            const unsigned kv = kq[u];
+            // equal keys: the edge scan meets the higher index first, the flat scan the lower one
+            if (kv > bkey || (kv == bkey && type == 0)) { bkey = kv; bu = u; }
+          }
+          const unsigned top = __reduce_max_sync(0xffffffffu, bu >= 0 ? bkey : 0u);
+          if (top == 0u) break;
+          const int myind = (bu >= 0 && bkey == top) ? sp + bu : -1;
+          int pick;
+          if (type == 0) pick = (int)__reduce_max_sync(0xffffffffu, (unsigned)(myind + 1)) - 1;
+          else pick = (int)__reduce_min_sync(0xffffffffu, myind >= 0 ? (unsigned)myind : 0xffffffffu);
+          ++done;
+          if (lane == 0) {
+            sh_pick[j][(type == 0 ? 0 : 20) + done - 1] = (unsigned short)(pick - k_first);
+            sm_label[pick - span_lo] = (signed char)(type == 0 ? (done <= 2 ? 2 : 1) : -1);
+          }
+          if (type == 0) n_edge = done; else n_flat = done;
+          if (type == 1 && done >= 4) break;  // featureAssociation.cpp:339-342: the fourth flat pick suppresses nothing
+          // featureAssociation.cpp:306-326 / 344-366: lane 0 the pick, lanes 1..5 ind+1..ind+5, lanes 6..10 ind-1..ind-5
+          const int off = lane <= 5 ? lane : 5 - lane;
+          const int g = pick + off;
+          const int l = g - span_lo;
+          bool bad = false;
+          // l < 0 only for ind - k < 0 at the very start of the cloud: the reference `continue`s there (:317)
+          if (lane >= 1 && lane <= 10 && l >= 0) bad = abs((int)sm_col[l] - (int)sm_col[l + (lane <= 5 ? -1 : 1)]) > 10;
+          const unsigned bm = __ballot_sync(0xffffffffu, bad);
+          const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
+          const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
+          const bool mark = l >= 0 && (lane == 0 || (lane >= 1 && lane <= 5 && lane < stop_f) || (lane >= 6 && lane <= 10 && lane < stop_b));
+          if (mark && g >= sp && g <= ep) sm_picked[l] = 1;
+          spill_r |= __reduce_or_sync(0xffffffffu, (mark && g > ep) ? 1u << (g - ep - 1) : 0u);
+          spill_l |= __reduce_or_sync(0xffffffffu, (mark && g < sp) ? 1u << (sp - 1 - g) : 0u);
+          __syncwarp();
+          // the positions pick-5 .. pick+5 may have been marked: each belongs to exactly one lane
+          const int lo = max(pick - 5, sp), hi = min(pick + 5, ep);
+          const int first = lo + ((lane - (lo - sp)) & 31);
+          if (first <= hi && sm_picked[first - span_lo]) elig &= ~(1u << ((first - sp) >> 5));
+        }
+      }
+      if (lane == 0) { sh_ne[j] = n_edge; sh_nf[j] = n_flat; sh_spill_r[j] = spill_r; sh_spill_l[j] = spill_l; }
+    };
+    if (wid < 6) run_sextant(wid, 0u);
+    __syncthreads();
+    if (wid == 0) {
+      // boundaries in order; a sextant whose speculative run picked a position its predecessor marks is run again
+      for (int j = 1; j < 6; ++j) {
+        const unsigned r = (unsigned)sh_spill_r[j - 1];
+        if (r == 0u) continue;
+        bool hit = false;
+        const int np = sh_ne[j] + sh_nf[j];
+        if (lane < 24) {
+          const bool mine = lane < 20 ? lane < sh_ne[j] : (lane - 20) < sh_nf[j];
+          if (mine) {
+            const int q = k_first + (int)sh_pick[j][lane] - sh_sp[j];
+            hit = q < 5 && ((r >> q) & 1u);
+          }
+        }
+        (void)np;
+        if (__any_sync(0xffffffffu, hit)) {
+          // reset sextant j to the state before any pick (picked flags from global memory, labels 0: its candidates lie
+          // in [5, S-5), where calculateSmoothness has just reset cloudLabel) and run it with the marks in place
+          for (int t = sh_sp[j] + lane; t <= sh_ep[j]; t += 32) sm_picked[t - span_lo] = (unsigned char)(st.picked[base + t] != 0);
+          if (lane < 24) {
+            const bool mine = lane < 20 ? lane < sh_ne[j] : (lane - 20) < sh_nf[j];
+            if (mine) sm_label[k_first + (int)sh_pick[j][lane] - span_lo] = 0;
+          }
+          // marks sextant j itself put into its predecessor's range are dropped with the run; the new run records its own
+          __syncwarp();
+          run_sextant(j, r);
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    // spills into the neighbours' ranges and the ring's margins (cloudNeighborPicked is only ever set), outputs in scan order
+    if (threadIdx.x < 60) {
+      const int j = threadIdx.x / 10, i = threadIdx.x % 10;
+      const int sp = sh_sp[j], ep = sh_ep[j];
+      if (i < 5) { if ((sh_spill_r[j] >> i) & 1) { const int g = ep + 1 + i; if (g >= span_lo && g < span_hi) sm_picked[g - span_lo] = 1; } }
+      else { if ((sh_spill_l[j] >> (i - 5)) & 1) { const int g = sp - 1 - (i - 5); if (g >= span_lo && g < span_hi) sm_picked[g - span_lo] = 1; } }
+    }
+    if (threadIdx.x == 0) {
+      int* o_sharp_i = st.st_sharp_ind + rs * 12;
+      int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
+      int* o_flat_i = st.st_flat_ind + rs * 24;
+      int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+      for (int j = 0; j < 6; ++j) {
+        for (int t = 0; t < sh_ne[j]; ++t) {
+          const int pick = k_first + (int)sh_pick[j][t];
+          if (t < 2) o_sharp_i[n_sharp++] = pick;
+          o_lsharp_i[n_lsharp++] = pick;
+        }
+        for (int t = 0; t < sh_nf[j]; ++t) o_flat_i[n_flat++] = k_first + (int)sh_pick[j][20 + t];
+      }
+      sh_counts[0] = n_sharp; sh_counts[1] = n_lsharp; sh_counts[2] = n_flat;
+    }
+  } else
+  if (wid == 0) {
+    int* o_sharp_i = st.st_sharp_ind + rs * 12;
+    int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
+    int* o_flat_i = st.st_flat_ind + rs * 24;
+    int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+    const int colsz = p.N;  // segInfo.segmentedCloudColInd.size()
+    const int stale_ind = sh_stale;
+    const bool has_stale = sh_has_stale != 0;
+    auto in_span = [&](int g) { return g >= span_lo && g < span_hi; };
+    auto get_picked = [&](int g) -> int { return in_span(g) ? (int)sm_picked[g - span_lo] : st.picked[base + g]; };
+    auto set_picked = [&](int g) { if (in_span(g)) sm_picked[g - span_lo] = 1; else st.picked[base + g] = 1; };
+    auto get_col = [&](int g) -> int { return in_span(g) ? (int)sm_col[g - span_lo] : (int)st.seg_col[base + g]; };
+    // (general path: the stale entry may point outside this ring's own range, so the label goes to global memory at once)
+    auto set_label = [&](int g, int v) { if (in_span(g)) sm_label[g - span_lo] = (signed char)v; st.cloud_label[base + g] = v; };
+    // featureAssociation.cpp:306-326 / 344-366: lanes 1..5 handle ind+1..ind+5, lanes 6..10 handle ind-1..ind-5
+    auto mark_neighbors = [&](int ind) {
+      int g = -1;          // index this lane may mark
+      bool bad = false;    // column gap > 10 right before it (stops the loop)
+      bool skip = true;    // `continue` cases: out of range
+      if (lane >= 1 && lane <= 5) {
+        g = ind + lane;
+        if (g < colsz) { skip = false; bad = abs(get_col(g) - get_col(g - 1)) > 10; }
+      } else if (lane >= 6 && lane <= 10) {
+        g = ind - (lane - 5);
+        if (g >= 0) { skip = false; bad = abs(get_col(g) - get_col(g + 1)) > 10; }
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, bad);
+      const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
+      const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
+      if (lane == 0) set_picked(ind);
+      if (!skip && lane >= 1 && lane <= 5 && lane < stop_f) set_picked(g);
+      if (!skip && lane >= 6 && lane <= 10 && lane < stop_b) set_picked(g);
+      __syncwarp();
+    };
+    // Fast accessors: every candidate of a ring lies in [start, end], so the pick and its +-5 neighbours are inside the
+    // span held in shared memory and inside [0, colsz): no range checks, no global fall-back.  Only the stale
+    // cloudSmoothness entry of position 4 (ring 0) can point elsewhere; a ring that holds such an entry uses the general
+    // accessors above.
+    auto mark_neighbors_fast = [&](int ind) {
+      const int off = lane <= 5 ? lane : 5 - lane;  // lane 0: the pick; 1..5: ind+1..ind+5; 6..10: ind-1..ind-5
+      const int l = ind - span_lo + off;
+      bool bad = false;
+      // l < 0 only for ind - k < 0 at the very start of the cloud: the reference `continue`s there (:317)
+      if (lane >= 1 && lane <= 10 && l >= 0) bad = abs((int)sm_col[l] - (int)sm_col[l + (lane <= 5 ? -1 : 1)]) > 10;
+      const unsigned bm = __ballot_sync(0xffffffffu, bad);
+      const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
+      const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
+      if (l >= 0 && (lane == 0 || (lane <= 5 && lane < stop_f) || (lane >= 6 && lane <= 10 && lane < stop_b))) sm_picked[l] = 1;
+      __syncwarp();
+    };
+    for (int j = 0; j < 6; ++j) {
+      const int sp = sh_sp[j], ep = sh_ep[j];
+      if (sp >= ep) continue;
+      const int len = ep - sp + 1;
+      const unsigned* kq = ckey + (sp - k_first);
+      const unsigned char* tq = ctype + (sp - k_first);
+      const int items = (len + 31) >> 5;   // candidates per lane: positions sp + lane + 32 i
+      for (int type = 0; type < 2; ++type) {  // edge list, then flat list (featureAssociation.cpp:289-330, 331-368)
+        const int quota = type == 0 ? 20 : 4;
+        // eligibility bits of this lane's candidates (fast path): of this list and not picked yet
+        unsigned elig = 0u;
+        if (!has_stale)
+          for (int i = 0; i < items; ++i) {
+            const int u = lane + 32 * i;
+            if (u < len && tq[u] == type && sm_picked[sp + u - span_lo] == 0) elig |= 1u << i;
+          }
+        int done = 0;
+        while (done < quota) {
+          // this lane's best remaining candidate
+          unsigned bkey = 0u;
+          int bu = -1;
+          if (!has_stale) {
+            unsigned e = elig;
+            while (e) {
+              const int i = __ffs(e) - 1;
+              e &= e - 1;
+              const int u = lane + 32 * i;
+              const unsigned kv = kq[u];
+              // equal keys: the edge scan meets the higher index first, the flat scan the lower one
+              if (kv > bkey || (kv == bkey && type == 0)) { bkey = kv; bu = u; }
+            }
+          } else {
+            for (int i = 0; i < items; ++i) {
+              const int u = lane + 32 * i;
+              if (u >= len || tq[u] != type) continue;
+              const int ind = (sp + u == 4) ? stale_ind : sp + u;
+              if (get_picked(ind) != 0) continue;
+              const unsigned kv = kq[u];
+              if (bu < 0 || kv > bkey || (kv == bkey && type == 0)) { bkey = kv; bu = u; }
+            }
+          }
+          const unsigned top = __reduce_max_sync(0xffffffffu, bu >= 0 ? bkey : 0u);
+          if (top == 0u) break;  // no unpicked candidate left in this list
+          // among equal keys: highest index (edge) / lowest index (flat); ties need the candidates' own indices
+          const int myind = (bu >= 0 && bkey == top) ? ((sp + bu == 4 && has_stale) ? stale_ind : sp + bu) : -1;
+          int pick;
+          if (type == 0) pick = (int)__reduce_max_sync(0xffffffffu, (unsigned)(myind + 1)) - 1;
+          else pick = (int)__reduce_min_sync(0xffffffffu, myind >= 0 ? (unsigned)myind : 0xffffffffu);
+          ++done;
+          if (type == 0) {
+            if (lane == 0) {
+              if (done <= 2) o_sharp_i[n_sharp] = pick;
+              o_lsharp_i[n_lsharp] = pick;
+            }
+            if (done <= 2) n_sharp++;
+            n_lsharp++;
+          } else {
+            if (lane == 0) o_flat_i[n_flat] = pick;
+            n_flat++;
+          }
+          const int lab = type == 0 ? (done <= 2 ? 2 : 1) : -1;
+          if (!has_stale) {
+            if (lane == 0) sm_label[pick - span_lo] = (signed char)lab;
+            if (type == 1 && done >= 4) break;  // featureAssociation.cpp:339-342: the fourth flat pick suppresses nothing
+            mark_neighbors_fast(pick);
+            // the positions pick-5 .. pick+5 may have been marked: each belongs to exactly one lane
+            const int lo = max(pick - 5, sp), hi = min(pick + 5, ep);
+            const int first = lo + ((lane - (lo - sp)) & 31);   // the position of this lane inside the window, if any
+            if (first <= hi && sm_picked[first - span_lo]) elig &= ~(1u << ((first - sp) >> 5));
+          } else {
+            if (lane == 0) set_label(pick, lab);
+            if (type == 1 && done >= 4) break;
+            mark_neighbors(pick);
+          }
+        }
+      }
+    }
+    if (lane == 0) { sh_counts[0] = n_sharp; sh_counts[1] = n_lsharp; sh_counts[2] = n_flat; }
   }
   __syncthreads();
-  const int n = sh_n;
-  int n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  for (int t = n + threadIdx.x; t < n2; t += SORT_THREADS) keys[t] = ~0ull;
-  __syncthreads();
-  if (n > 1) bitonic_sort_u64(keys, n2, n2);
-  for (int t = threadIdx.x; t < n; t += SORT_THREADS) {
-    const unsigned long long k = keys[t];
-    const int list = (int)(k >> 53);
-    const unsigned tb = (unsigned)(k & 0x1fffffull);
-    st.scan_list[base + a + t] = (list & 1) ? tb : (0x1fffffu - tb);
-  }
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int l = 0; l < 12; ++l) { offs[l] = run; run += sh_cnt[l]; }
-    offs[12] = run;
-    if (slot_in_sorted_range && sh_slot_min != ~0ull) {
-      st.slot4[s * 2 + 0] = (unsigned)(sh_slot_min >> 32);
-      st.slot4[s * 2 + 1] = (unsigned)(sh_slot_min & 0xffffffffull);
-    }
-  }
-}
-
-// ---- 2. greedy picks ----------------------------------------------------------------------------
-// One WARP per (ring, sequence); the six sextants of a ring must run in order because a pick
-// suppresses up to 5 neighbours on either side, across sextant boundaries.  Each step tests 32
-// consecutive candidates of the pre-sorted list at once; the only mutable state is
-// cloudNeighborPicked, kept as bytes in shared memory for the ring's span (other indices go to
-// global memory).
-#define PICK_WARPS 4
-
-__global__ void __launch_bounds__(PICK_WARPS * 32) k_feature_pick(DevState st) {
-  extern __shared__ unsigned char sh_picked_all[];  // [PICK_WARPS][H + 32] picked bytes, then [PICK_WARPS][H + 32] u16 column indices, then u16 lists
-  __shared__ int sh_stale[PICK_WARPS];
-  const DevParams& p = st.p;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int ring = blockIdx.x * PICK_WARPS + wid, s = blockIdx.y;
-  if (ring >= p.V) return;
-  const size_t base = (size_t)s * p.N;
-  const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
-  const int a = start - 4, b = end + 6;  // this ring's points are [a, b)
-  const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
-  const int L = max(0, span_hi - span_lo);
-  unsigned char* sm_picked = sh_picked_all + (size_t)wid * (p.H + 32);
-  // segmentedCloudColInd of the span (columns < H <= 65535): the neighbour suppression of every pick reads up to
-  // twelve of them, and a pick is a chain of dependent steps, so they must not come from global memory
-  unsigned short* sm_col = reinterpret_cast<unsigned short*>(sh_picked_all + (size_t)PICK_WARPS * (p.H + 32)) + (size_t)wid * (p.H + 32);
-  for (int t = lane; t < L; t += 32) {
-    sm_picked[t] = (unsigned char)(st.picked[base + span_lo + t] != 0);
-    sm_col[t] = (unsigned short)st.seg_col[base + span_lo + t];
-  }
-  const size_t rs = (size_t)s * p.V + ring;
-  // the twelve candidate lists of the ring (contiguous, offsets relative to a) as 16-bit positions inside the ring,
-  // and their thirteen offsets in lanes 0..12: nothing inside the pick loops below comes from global memory
-  unsigned short* sm_list = reinterpret_cast<unsigned short*>(sh_picked_all + (size_t)PICK_WARPS * (p.H + 32) * 3) + (size_t)wid * (p.H + 32);
-  const int off_lane = lane < 13 ? st.sext_off[rs * 16 + lane] : 0;
-  bool stale_here = false;
-  {
-    const int l0 = __shfl_sync(0xffffffffu, off_lane, 0), l1 = __shfl_sync(0xffffffffu, off_lane, 12);
-    const unsigned* src = st.scan_list + base + a;
-    for (int t = l0 + lane; t < l1; t += 32) {
-      int d = (int)src[t] - a;
-      // the stale cloudSmoothness entry at position 4 (k_feature_sort) may point anywhere in the cloud: escape code
-      if (d < 0 || d >= 0xffff) { sh_stale[wid] = (int)src[t]; d = 0xffff; }
-      if (d < 4 || (int)src[t] > end) stale_here = true;  // not one of this ring's own candidates [start, end]
-      sm_list[t] = (unsigned short)d;
-    }
-  }
-  __syncwarp();
-  int* o_sharp_i = st.st_sharp_ind + rs * 12;
-  int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
-  int* o_flat_i = st.st_flat_ind + rs * 24;
-  int n_sharp = 0, n_lsharp = 0, n_flat = 0;
-  const int colsz = p.N;  // segInfo.segmentedCloudColInd.size()
-  auto in_span = [&](int g) { return g >= span_lo && g < span_hi; };
-  auto get_picked = [&](int g) -> int { return in_span(g) ? (int)sm_picked[g - span_lo] : st.picked[base + g]; };
-  auto set_picked = [&](int g) { if (in_span(g)) sm_picked[g - span_lo] = 1; else st.picked[base + g] = 1; };
-  auto get_col = [&](int g) -> int { return in_span(g) ? (int)sm_col[g - span_lo] : (int)st.seg_col[base + g]; };
-  // featureAssociation.cpp:306-326 / 344-366: lanes 1..5 handle ind+1..ind+5, lanes 6..10 handle ind-1..ind-5
-  auto mark_neighbors = [&](int ind) {
-    int g = -1;          // index this lane may mark
-    bool bad = false;    // column gap > 10 right before it (stops the loop)
-    bool skip = true;    // `continue` cases: out of range
-    if (lane >= 1 && lane <= 5) {
-      g = ind + lane;
-      if (g < colsz) { skip = false; bad = abs(get_col(g) - get_col(g - 1)) > 10; }
-    } else if (lane >= 6 && lane <= 10) {
-      g = ind - (lane - 5);
-      if (g >= 0) { skip = false; bad = abs(get_col(g) - get_col(g + 1)) > 10; }
-    }
-    const unsigned bm = __ballot_sync(0xffffffffu, bad);
-    const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
-    const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
-    if (lane == 0) set_picked(ind);
-    if (!skip && lane >= 1 && lane <= 5 && lane < stop_f) set_picked(g);
-    if (!skip && lane >= 6 && lane <= 10 && lane < stop_b) set_picked(g);
-    __syncwarp();
-  };
-  // Fast accessors: every candidate of a ring lies in [start, end], so the pick and its +-5 neighbours are inside the
-  // span held in shared memory and inside [0, colsz): no range checks, no global fall-back.  Only the stale
-  // cloudSmoothness entry of position 4 (ring 0) can point elsewhere; a ring that holds such an entry uses the general
-  // accessors above.
-  auto get_picked_fast = [&](int g) -> int { return (int)sm_picked[g - span_lo]; };
-  auto mark_neighbors_fast = [&](int ind) {
-    const int off = lane <= 5 ? lane : 5 - lane;  // lane 0: the pick; 1..5: ind+1..ind+5; 6..10: ind-1..ind-5
-    const int l = ind - span_lo + off;
-    bool bad = false;
-    // l < 0 only for ind - k < 0 at the very start of the cloud: the reference `continue`s there (:317)
-    if (lane >= 1 && lane <= 10 && l >= 0) bad = abs((int)sm_col[l] - (int)sm_col[l + (lane <= 5 ? -1 : 1)]) > 10;
-    const unsigned bm = __ballot_sync(0xffffffffu, bad);
-    const unsigned fwd = bm & 0x3eu, bwd = bm & 0x7c0u;
-    const int stop_f = fwd ? __ffs(fwd) - 1 : 32, stop_b = bwd ? __ffs(bwd) - 1 : 32;
-    if (l >= 0 && (lane == 0 || (lane <= 5 && lane < stop_f) || (lane >= 6 && lane <= 10 && lane < stop_b))) sm_picked[l] = 1;
-    __syncwarp();
-  };
-  const bool has_stale = __ballot_sync(0xffffffffu, stale_here) != 0u;
-#define PICK_SEXTANTS(GET_PICKED, MARK_NEIGHBORS) \
-  for (int j = 0; j < 6; ++j) { \
-    { \
-      const int lo = __shfl_sync(0xffffffffu, off_lane, 2 * j); \
-      const unsigned short* list = sm_list + lo; \
-      const int len = __shfl_sync(0xffffffffu, off_lane, 2 * j + 1) - lo; \
-      int largest = 0; \
-      for (int wbase = 0; wbase < len && largest < 20; wbase += 32) { \
-        const int t = wbase + lane; \
-        const bool have = t < len; \
-        const int ind = have ? (list[t] == 0xffff ? sh_stale[wid] : a + (int)list[t]) : 0; \
-        int next = 0; \
-        while (largest < 20) { \
-          const bool cand = have && lane >= next && GET_PICKED(ind) == 0; \
-          const unsigned m = __ballot_sync(0xffffffffu, cand); \
-          if (m == 0) break; \
-          const int w = __ffs(m) - 1; \
-          const int pick = __shfl_sync(0xffffffffu, ind, w); \
-          largest++; \
-          if (lane == 0) { \
-            if (largest <= 2) { \
-              st.cloud_label[base + pick] = 2; \
-              o_sharp_i[n_sharp] = pick; \
-            } else { \
-              st.cloud_label[base + pick] = 1; \
-            } \
-            o_lsharp_i[n_lsharp] = pick; \
-          } \
-          if (largest <= 2) n_sharp++; \
-          n_lsharp++; \
-          MARK_NEIGHBORS(pick); \
-          next = w + 1; \
-        } \
-      } \
-    } \
-    { \
-      const int lo = __shfl_sync(0xffffffffu, off_lane, 2 * j + 1); \
-      const unsigned short* list = sm_list + lo; \
-      const int len = __shfl_sync(0xffffffffu, off_lane, 2 * j + 2) - lo; \
-      int smallest = 0; \
-      for (int wbase = 0; wbase < len && smallest < 4; wbase += 32) { \
-        const int t = wbase + lane; \
-        const bool have = t < len; \
-        const int ind = have ? (list[t] == 0xffff ? sh_stale[wid] : a + (int)list[t]) : 0; \
-        int next = 0; \
-        while (true) { \
-          const bool cand = have && lane >= next && GET_PICKED(ind) == 0; \
-          const unsigned m = __ballot_sync(0xffffffffu, cand); \
-          if (m == 0) break; \
-          const int w = __ffs(m) - 1; \
-          const int pick = __shfl_sync(0xffffffffu, ind, w); \
-          smallest++; \
-          if (lane == 0) { \
-            st.cloud_label[base + pick] = -1; \
-            o_flat_i[n_flat] = pick; \
-          } \
-          n_flat++; \
-          if (smallest >= 4) break; \
-          MARK_NEIGHBORS(pick); \
-          next = w + 1; \
-        } \
-      } \
-    } \
-  }
-  if (has_stale) {
-    PICK_SEXTANTS(get_picked, mark_neighbors)
-  } else {
-    PICK_SEXTANTS(get_picked_fast, mark_neighbors_fast)
-  }
-#undef PICK_SEXTANTS
-  __syncwarp();
-  // persist cloudNeighborPicked for this ring's own range (entries are only ever set to 1 here)
-  for (int t = lane; t < L; t += 32) {
+  // persist cloudNeighborPicked (entries are only ever set to 1 here) and cloudLabel for this ring's own range
+  for (int t = threadIdx.x; t < L; t += FR_THREADS) {
     const int g = span_lo + t;
     if (g >= a - 1 && g < b && sm_picked[t]) st.picked[base + g] = 1;
+    if (g >= start && g <= end) st.cloud_label[base + g] = (int)sm_label[t];
   }
-  if (lane == 0) {
-    int* o_counts = st.ring_counts + rs * 8;
-    o_counts[0] = n_sharp;
-    o_counts[1] = n_lsharp;
-    o_counts[2] = n_flat;
-  }
-}
-
-// ---- 3. less-flat collection + per-ring VoxelGrid ----------------------------------------------
-#define LF_THREADS 256
-
-__global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
-  extern __shared__ unsigned long long lf_keys[];  // [pow2(H)], then u16 lfpos[H] (positions relative to the ring's first), then int vox[H]
-  __shared__ int warp_tot[33];
-  __shared__ int sh_sp[6], sh_ep[6];
-  __shared__ int sh_imn[3], sh_imx[3];
-  const DevParams& p = st.p;
-  const int ring = blockIdx.x, s = blockIdx.y;
-  const size_t base = (size_t)s * p.N;
-  int hp2 = 1;
-  while (hp2 < p.H) hp2 <<= 1;
-  unsigned long long* keys = lf_keys;
-  unsigned short* sm_lfpos = (unsigned short*)(lf_keys + hp2);
-  const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
-  const size_t rs = (size_t)s * p.V + ring;
+  // ---- 3. less-flat collection (featureAssociation.cpp:370-374): by POSITION k over the active sextants ----
   float4* o_lflat = st.st_less_flat + rs * p.H;
-  int* o_counts = st.ring_counts + rs * 8;
-  if (threadIdx.x < 6) {
-    const int j = threadIdx.x;
-    sh_sp[j] = (start * (6 - j) + end * j) / 6;
-    sh_ep[j] = (start * (5 - j) + end * (j + 1)) / 6 - 1;
-  }
-  __syncthreads();
-  // less-flat collection (featureAssociation.cpp:370-374): by POSITION k over the active sextants
   int n_raw = 0;
   const int k_lo = sh_sp[0];
   {
     const int k_hi = sh_ep[5];
     int run = 0;
-    for (int k0 = k_lo; k0 <= k_hi; k0 += LF_THREADS) {
+    for (int k0 = k_lo; k0 <= k_hi; k0 += FR_THREADS) {
       const int k = k0 + threadIdx.x;
       int f = 0;
       if (k <= k_hi && k >= 0 && k < p.N) {
         bool active = false;
 #pragma unroll
         for (int j = 0; j < 6; ++j) active = active || (sh_sp[j] < sh_ep[j] && k >= sh_sp[j] && k <= sh_ep[j]);
-        if (active && st.cloud_label[base + k] <= 0) f = 1;
+        const int lab = (k >= span_lo && k < span_hi) ? (int)sm_label[k - span_lo] : st.cloud_label[base + k];
+        if (active && lab <= 0) f = 1;
       }
       int total;
       const int ex = block_exclusive_scan(f, warp_tot, &total);
@@ -488,7 +580,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
     if (threadIdx.x < 3) { sh_imn[threadIdx.x] = f2ord(FLT_MAX); sh_imx[threadIdx.x] = f2ord(-FLT_MAX); }
     __syncthreads();
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) {
+    for (int t = threadIdx.x; t < n_raw; t += FR_THREADS) {
       const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[t]];
       mn[0] = fminf(mn[0], q.x); mx[0] = fmaxf(mx[0], q.x);
       mn[1] = fminf(mn[1], q.y); mx[1] = fmaxf(mx[1], q.y);
@@ -500,7 +592,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
         mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
         mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
       }
-      if ((threadIdx.x & 31) == 0) {
+      if (lane == 0) {
         atomicMin(&sh_imn[d], f2ord(mn[d]));
         atomicMax(&sh_imx[d], f2ord(mx[d]));
       }
@@ -517,20 +609,16 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
     const long long dz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
     if (dx * dy * dz > 2147483647LL) {
       // PCL refuses to filter (index overflow) and returns the input unchanged
-      for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) o_lflat[t] = st.seg_cloud[base + k_lo + sm_lfpos[t]];
+      for (int t = threadIdx.x; t < n_raw; t += FR_THREADS) o_lflat[t] = st.seg_cloud[base + k_lo + sm_lfpos[t]];
       n_ds = n_raw;
     } else {
       const int minb0 = (int)floorf(bmn[0] * inv), minb1 = (int)floorf(bmn[1] * inv), minb2 = (int)floorf(bmn[2] * inv);
       const int div0 = (int)floorf(bmx[0] * inv) - minb0 + 1, div1 = (int)floorf(bmx[1] * inv) - minb1 + 1;
-      // Consecutive points of a ring mostly share a voxel, so the sort runs over RUNS of equal voxel
-      // index (key = voxel index major, first input position minor) instead of over points; runs of the
-      // same voxel end up adjacent and in input order, so each voxel's float sums keep the input order.
       int pos_bits = 0;
       while ((1 << pos_bits) < n_raw) ++pos_bits;
-      int* sm_vox = (int*)(sm_lfpos + ((p.H + 1) & ~1));  // [H] voxel index of every collected point
       int* sm_runend = sm_vox;  // [H] end position (exclusive) of the run starting at position t; written only after the
                                 // last read of sm_vox (barrier after the run keys), so the two share their space
-      for (int t = threadIdx.x; t < n_raw; t += LF_THREADS) {
+      for (int t = threadIdx.x; t < n_raw; t += FR_THREADS) {
         const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[t]];
         const int i0 = (int)floorf(q.x * inv) - minb0;
         const int i1 = (int)floorf(q.y * inv) - minb1;
@@ -542,7 +630,7 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
       int n_runs = 0;
       {
         int run = 0;
-        for (int t0 = 0; t0 < n_raw; t0 += LF_THREADS) {
+        for (int t0 = 0; t0 < n_raw; t0 += FR_THREADS) {
           const int t = t0 + threadIdx.x;
           int head = 0;
           if (t < n_raw) head = (t == 0) || (sm_vox[t] != sm_vox[t - 1]);
@@ -555,20 +643,42 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
       }
       __syncthreads();
       // run ends: the next run head in input order (keys are still in input order here)
-      for (int r = threadIdx.x; r < n_runs; r += LF_THREADS) {
+      for (int r = threadIdx.x; r < n_runs; r += FR_THREADS) {
         const unsigned pos_mask0 = (1u << pos_bits) - 1u;
         const int startp = (int)((unsigned)keys[r] & pos_mask0);
         const int endp = (r + 1 < n_runs) ? (int)((unsigned)keys[r + 1] & pos_mask0) : n_raw;
         sm_runend[startp] = endp;
       }
-      int n2 = 1;
-      while (n2 < n_runs) n2 <<= 1;
-      for (int t = n_runs + threadIdx.x; t < n2; t += LF_THREADS) keys[t] = ~0ull;
       __syncthreads();
-      if (n_runs > 1) bitonic_sort_t<unsigned long long>(keys, n2);
+      // sort the runs by (voxel, first position): a few hundred keys -- rank by counting, no synchronised passes
+      if (n_runs <= 96) {
+        unsigned long long* sorted = keys + cap2 / 2;
+        for (int r = threadIdx.x; r < n_runs; r += FR_THREADS) {
+          const unsigned long long key = keys[r];
+          int rank = 0;
+          int u = 0;
+          for (; u + 4 <= n_runs; u += 4) {
+            rank += keys[u] < key ? 1 : 0;
+            rank += keys[u + 1] < key ? 1 : 0;
+            rank += keys[u + 2] < key ? 1 : 0;
+            rank += keys[u + 3] < key ? 1 : 0;
+          }
+          for (; u < n_runs; ++u) rank += keys[u] < key ? 1 : 0;
+          sorted[rank] = key;
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < n_runs; r += FR_THREADS) keys[r] = sorted[r];
+        __syncthreads();
+      } else {
+        int r2 = 1;
+        while (r2 < n_runs) r2 <<= 1;
+        for (int t = n_runs + threadIdx.x; t < r2; t += FR_THREADS) keys[t] = ~0ull;
+        __syncthreads();
+        bitonic_sort_t<unsigned long long>(keys, r2);
+      }
       const unsigned pos_mask = (1u << pos_bits) - 1u;
       int run = 0;
-      for (int t0 = 0; t0 < n_runs; t0 += LF_THREADS) {
+      for (int t0 = 0; t0 < n_runs; t0 += FR_THREADS) {
         const int t = t0 + threadIdx.x;
         int head = 0;
         if (t < n_runs) head = (t == 0) || ((unsigned)(keys[t] >> pos_bits) != (unsigned)(keys[t - 1] >> pos_bits));
@@ -595,6 +705,10 @@ __global__ void __launch_bounds__(LF_THREADS) k_feature_lessflat(DevState st) {
     }
   }
   if (threadIdx.x == 0) {
+    int* o_counts = st.ring_counts + rs * 8;
+    o_counts[0] = sh_counts[0];
+    o_counts[1] = sh_counts[1];
+    o_counts[2] = sh_counts[2];
     o_counts[3] = n_ds;
     o_counts[4] = n_raw;
   }
@@ -653,35 +767,19 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
   }
   const dim3 grid_rings(p.V, p.B);
   {
+    // 37 KB at H = 2048: six blocks per SM
     const int cap2 = next_pow2(p.H);
-    const size_t smem = (size_t)cap2 * 8;
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaFuncSetAttribute(k_feature_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured = smem;
+    const size_t smem = (size_t)cap2 * 8 + (size_t)p.H * 4 + (size_t)(p.H + 32) * (2 * 2 + 2);
+    // the opt-in shared-memory size is a per-device attribute of the kernel
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+      cudaFuncSetAttribute(k_feature_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_feature_ring, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      configured[dev] = smem;
     }
-    LL_LAUNCH(ctx, "k_feature_sort", k_feature_sort<<<grid_rings, SORT_THREADS, smem, ctx.stream>>>(st, cap2));
-  }
-  {
-    const size_t smem = (size_t)PICK_WARPS * (p.H + 32) * 5;  // picked bytes + u16 columns + u16 candidate lists
-    static size_t pick_configured = 0;
-    if (smem > 48 * 1024 && smem > pick_configured) {
-      cudaFuncSetAttribute(k_feature_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      pick_configured = smem;
-    }
-    LL_LAUNCH(ctx, "k_feature_pick",
-              k_feature_pick<<<dim3((p.V + PICK_WARPS - 1) / PICK_WARPS, p.B), PICK_WARPS * 32, smem, ctx.stream>>>(st));
-  }
-  {
-    // 28 KB at H = 2048: seven blocks per SM, so the 1024 blocks of 16 sequences x 64 rings are resident in one wave
-    const size_t smem = (size_t)next_pow2(p.H) * 8 + (size_t)((p.H + 1) & ~1) * 2 + (size_t)p.H * 4;
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaFuncSetAttribute(k_feature_lessflat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(k_feature_lessflat, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      configured = smem;
-    }
-    LL_LAUNCH(ctx, "k_feature_lessflat", k_feature_lessflat<<<grid_rings, LF_THREADS, smem, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_feature_ring", k_feature_ring<<<grid_rings, FR_THREADS, smem, ctx.stream>>>(st, cap2));
   }
   LL_LAUNCH(ctx, "k_feature_compact", k_feature_compact<<<grid_rings, 256, 0, ctx.stream>>>(st));
 }
