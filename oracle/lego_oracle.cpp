@@ -21,7 +21,10 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../include/ll_smallmat.h"
@@ -1611,6 +1614,125 @@ int lo_knn(const float* cloud, int n, const float* query, int nq, int k, int* id
     P4 p; p.x = query[4 * q]; p.y = query[4 * q + 1]; p.z = query[4 * q + 2]; p.i = 0;
     t.nearestKSearch(p, k, idx + (size_t)q * k, d2 + (size_t)q * k);
   }
+  return 0;
+}
+
+/* ---- the reference's own threading (main.cpp:37-47, channel.h): ImageProjection on the caller's thread,
+ * FeatureAssociation and MapOptimization on a thread each, joined by one-slot channels whose send blocks until the slot
+ * is free (bag mode, main.cpp:37-38).  Three oracle objects play the three stage objects; what crosses a channel is a
+ * copy of exactly the members ProjectionOut / AssociationOut carry (utility.h:64-80). ---- */
+}  /* extern "C" */
+namespace {
+
+struct ProjectionPayload {
+  std::vector<P4> segmented_cloud, outlier_cloud;
+  std::vector<int> start_ring, end_ring;
+  float start_ori, end_ori, ori_diff;
+  std::vector<uint8_t> seg_ground_flag;
+  std::vector<uint32_t> seg_col_ind;
+  std::vector<float> seg_range;
+  int frame;
+};
+struct AssociationPayload {
+  std::vector<P4> corner_last, surf_last, outlier_last;
+  float laser_odometry[6];
+  int frame;
+};
+
+template <typename T>
+class SlotChannel { /* channel.h:11-56 with blocking send */
+ public:
+  void send(T&& item) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return empty_; });
+    item_ = std::move(item);
+    empty_ = false;
+    cv_.notify_all();
+  }
+  void receive(T& item) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_.wait(lk, [&] { return !empty_; });
+    item = std::move(item_);
+    empty_ = true;
+    cv_.notify_all();
+  }
+ private:
+  T item_;
+  bool empty_ = true;
+  std::mutex m_;
+  std::condition_variable cv_;
+};
+
+}  // namespace
+
+extern "C" {
+
+/* Runs frames [0, n_frames) of one sequence through three stage threads.  h_ip / h_fa / h_mo: the three stage objects
+ * (h_mo may already hold key frames and poses).  scans[f]: xyzi of frame f, counts[f] points.  stage_ms[f*3 + k]:
+ * milliseconds stage k (0 IP, 1 FA, 2 MO; MO = 0 on frames that are not handed over) spent on frame f; *wall_s: seconds from
+ * the first frame >= first_timed_frame entering ImageProjection until the last stage is idle. */
+int lo_run_pipeline(lo_handle* h_ip, lo_handle* h_fa, lo_handle* h_mo, const float* const* scans, const int* counts, int n_frames,
+                    int first_timed_frame, double* stage_ms, double* wall_s) {
+  SlotChannel<ProjectionPayload> ch1;
+  SlotChannel<AssociationPayload> ch2;
+  for (int i = 0; i < n_frames * 3; ++i) stage_ms[i] = 0.0;
+  std::thread fa([&] {
+    for (;;) {
+      ProjectionPayload in;
+      ch1.receive(in);
+      if (in.frame < 0) break;
+      const double t0 = now_s();
+      h_fa->segmented_cloud = std::move(in.segmented_cloud); h_fa->outlier_cloud = std::move(in.outlier_cloud);
+      h_fa->start_ring = std::move(in.start_ring); h_fa->end_ring = std::move(in.end_ring);
+      h_fa->start_ori = in.start_ori; h_fa->end_ori = in.end_ori; h_fa->ori_diff = in.ori_diff;
+      h_fa->seg_ground_flag = std::move(in.seg_ground_flag); h_fa->seg_col_ind = std::move(in.seg_col_ind);
+      h_fa->seg_range = std::move(in.seg_range);
+      const int handed = h_fa->runFeatureAssociationOnce();
+      AssociationPayload out;
+      if (handed == 1) { /* featureAssociation.cpp:1434-1447: deep copies */
+        out.corner_last = h_fa->cornerLast; out.surf_last = h_fa->surfLast; out.outlier_last = h_fa->outlierLast;
+        for (int i = 0; i < 6; ++i) out.laser_odometry[i] = h_fa->transformSum[i];
+        out.frame = in.frame;
+      }
+      stage_ms[in.frame * 3 + 1] = 1e3 * (now_s() - t0);
+      if (handed == 1) ch2.send(std::move(out));
+    }
+    AssociationPayload stop;
+    stop.frame = -1;
+    ch2.send(std::move(stop));
+  });
+  std::thread mo([&] {
+    for (;;) {
+      AssociationPayload in;
+      ch2.receive(in);
+      if (in.frame < 0) break;
+      const double t0 = now_s();
+      h_mo->cornerLast = std::move(in.corner_last); h_mo->surfLast = std::move(in.surf_last); h_mo->outlierLast = std::move(in.outlier_last);
+      for (int i = 0; i < 6; ++i) h_mo->transformSum[i] = in.laser_odometry[i];  /* OdometryToTransform, mapOptmization.cpp:1539 */
+      h_mo->mappingCycle();
+      stage_ms[in.frame * 3 + 2] = 1e3 * (now_s() - t0);
+    }
+  });
+  double t_start = 0.0;
+  for (int f = 0; f < n_frames; ++f) {
+    if (f == first_timed_frame) t_start = now_s();
+    const double t0 = now_s();
+    h_ip->cloudHandler(scans[f], counts[f]);
+    ProjectionPayload out; /* imageProjection.cpp:538-547: the filled clouds travel, the stage gets fresh ones */
+    out.segmented_cloud = h_ip->segmented_cloud; out.outlier_cloud = h_ip->outlier_cloud;
+    out.start_ring = h_ip->start_ring; out.end_ring = h_ip->end_ring;
+    out.start_ori = h_ip->start_ori; out.end_ori = h_ip->end_ori; out.ori_diff = h_ip->ori_diff;
+    out.seg_ground_flag = h_ip->seg_ground_flag; out.seg_col_ind = h_ip->seg_col_ind; out.seg_range = h_ip->seg_range;
+    out.frame = f;
+    stage_ms[f * 3 + 0] = 1e3 * (now_s() - t0);
+    ch1.send(std::move(out));
+  }
+  ProjectionPayload stop;
+  stop.frame = -1;
+  ch1.send(std::move(stop));
+  fa.join();
+  mo.join();
+  *wall_s = now_s() - t_start;
   return 0;
 }
 

@@ -68,6 +68,12 @@ int lo_voxel_grid(const float* xyzi, int n, float leaf, float* out_xyzi);
 /* k-NN on its own (for kd-tree pin tests): idx[nq*k], d2[nq*k]. */
 int lo_knn(const float* cloud_xyzi, int n, const float* query_xyzi, int nq, int k, int* idx, float* d2);
 
+/* The reference's own threading (main.cpp:37-47): ImageProjection on the caller's thread, FeatureAssociation and
+ * MapOptimization on a thread each, one-slot blocking channels in between.  Three stage objects of one sequence; see
+ * lego_oracle.cpp for the arguments. */
+int lo_run_pipeline(lo_handle* h_ip, lo_handle* h_fa, lo_handle* h_mo, const float* const* scans, const int* counts, int n_frames,
+                    int first_timed_frame, double* stage_ms, double* wall_s);
+
 /* Wall-clock seconds spent inside each stage since the last lo_reset_timers:
  * [0] image projection, [1] feature extraction (adjust..extract), [2] scan-to-scan LM + glue,
  * [3] scan-to-map incl. tree builds, [4] downsampleCurrentScan. */

@@ -79,6 +79,7 @@ def load(prefer_ref=True):
         lib.lo_map_download_keyframe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.lo_get_timer_map_assembly.argtypes = [C.c_void_p]
         lib.lo_get_timer_map_assembly.restype = C.c_double
+        lib.lo_run_pipeline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.lo_decode_pointcloud2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _libs[key] = lib
     return _libs[key]
@@ -214,6 +215,20 @@ class Oracle:
 
     def reset_timers(self):
         self.lib.lo_reset_timers(self.h)
+
+
+def run_pipeline(o_ip, o_fa, o_mo, scans, first_timed_frame=0):
+    """The reference's three stage threads + blocking one-slot channels (main.cpp:37-47) over one sequence.
+    scans: list of float32 [n, 4]; returns (stage_ms float64 [n_frames, 3], wall seconds from first_timed_frame on)."""
+    o_mo._select()
+    scans = [np.ascontiguousarray(a, np.float32) for a in scans]
+    n = len(scans)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in scans])
+    counts = np.array([len(a) for a in scans], np.int32)
+    stage_ms = np.zeros((n, 3), np.float64)
+    wall = C.c_double(0)
+    o_ip.lib.lo_run_pipeline(o_ip.h, o_fa.h, o_mo.h, ptrs, counts.ctypes.data, n, first_timed_frame, stage_ms.ctypes.data, C.byref(wall))
+    return stage_ms, wall.value
 
 
 def decode_pointcloud2(data, n_points, point_step, off_x, off_y, off_z, off_intensity, is_dense, prefer_ref=True):

@@ -108,6 +108,20 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_strong_scaling_split_covers_every_sequence_once():
+    """--total-seqs: SURVEY 8e's 64 / 32 / 16 / 8 sequences per GPU at 1 / 2 / 4 / 8 GPUs."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for world in (1, 2, 4, 8, 3):
+        shares = [bench.shard_total(r, world, 64) for r in range(world)]
+        assert sorted(sum(shares, [])) == list(range(64))
+        assert max(map(len, shares)) - min(map(len, shares)) <= 1
+        if 64 % world == 0:
+            assert all(len(x) == 64 // world for x in shares)
+    v, worst = bench.aggregate_throughput(8, 64 / 8, 20, 2.0)
+    assert abs(v - 64 * 20 / 2e-3) < 1e-6
+
+
 def test_sharding_over_two_gloo_ranks():
     """Independent sequences are split over ranks without overlap; the job throughput is all scans over the
     slowest rank's time (the contract's max-over-ranks)."""

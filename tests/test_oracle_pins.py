@@ -251,3 +251,24 @@ def test_float_accumulation_of_the_normal_equations_stays_inside_the_tolerance(b
                     worst_t = max(worst_t, float(np.abs(a[3:] - b[3:]).max()))
         assert worst_rot <= 1e-5 and worst_t <= 1e-4, (cfgname, worst_rot, worst_t)
         assert cycles >= 3
+
+
+def test_three_stage_thread_pipeline_equals_inline_run(built):
+    """lo_run_pipeline (the reference's threading: main.cpp:37-47, three stage threads + blocking one-slot channels, the
+    payloads of utility.h:64-80 copied between three stage objects) gives the poses and key frames of the inline run."""
+    from lego_loam_bor_b200 import config_params, synth
+    from oracle.oracle_py import Oracle, run_pipeline
+    p = config_params("T")
+    cfg = synth.make_config(p)
+    scans = [synth.scan(cfg, 3, f) for f in range(27)]
+    ref = Oracle(p, libm=True)
+    for a in scans:
+        ref.image_projection(a)
+        if ref.feature_association() == 1:
+            ref.mapping_cycle()
+    o_ip, o_fa, o_mo = Oracle(p, libm=True), Oracle(p, libm=True), Oracle(p, libm=True)
+    ms, wall = run_pipeline(o_ip, o_fa, o_mo, scans, 1)
+    assert ms.shape == (27, 3) and wall > 0 and (ms[:, 2] > 0).sum() == 5 and np.all(ms[:, :2] > 0)
+    assert np.array_equal(ref.download("TRANSFORM_SUM"), o_fa.download("TRANSFORM_SUM"))
+    for name in ("TRANSFORM_AFT_MAPPED", "KEYFRAME_STATE", "KEY_POSES_6D", "MAP_SURF"):
+        assert np.array_equal(ref.download(name), o_mo.download(name)), name
