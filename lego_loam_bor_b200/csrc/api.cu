@@ -15,6 +15,11 @@ struct ll_handle {
   LegoLoamParams prm;
   DevState st;
   LaunchCtx ctx;
+  // MapOptimization runs on a stream of its own, like the reference's MapOptimization thread (mapOptmization.cpp:122):
+  // a mapping cycle overlaps the next scans of FeatureAssociation; events order the two where they share data
+  LaunchCtx ctx_map;
+  cudaEvent_t ev_a2b = nullptr, ev_ds_done = nullptr, ev_b_tail = nullptr;
+  cudaEvent_t pose_ev_b[2] = {nullptr, nullptr};
   int device = 0;
   bool own_stream = false;
   std::vector<void*> allocs;
@@ -67,6 +72,24 @@ namespace {
       return LL_ERR_CUDA;                                                            \
     }                                                                                \
   } while (0)
+
+// the mapping stream sees everything enqueued on the frame stream so far
+int map_waits_frames(ll_handle* h) {
+  CK(cudaEventRecord(h->ev_a2b, h->ctx.stream));
+  CK(cudaStreamWaitEvent(h->ctx_map.stream, h->ev_a2b, 0));
+  return LL_OK;
+}
+// the frame stream waits for everything enqueued on the mapping stream so far
+int frames_wait_map(ll_handle* h) {
+  CK(cudaEventRecord(h->ev_b_tail, h->ctx_map.stream));
+  CK(cudaStreamWaitEvent(h->ctx.stream, h->ev_b_tail, 0));
+  return LL_OK;
+}
+int sync_all(ll_handle* h) {
+  CK(cudaStreamSynchronize(h->ctx.stream));
+  CK(cudaStreamSynchronize(h->ctx_map.stream));
+  return LL_OK;
+}
 
 template <typename T>
 cudaError_t dev_alloc(ll_handle* h, T** p, size_t n, bool zero = true) {
@@ -149,11 +172,12 @@ int reset_keyframes(ll_handle* h) {
 }
 
 int check_stream(ll_handle* h, const char* where) {
-  if (h->ctx.first_error != cudaSuccess) {
-    h->err = std::string(where) + ": launch of " + (h->ctx.first_error_kernel ? h->ctx.first_error_kernel : "?") +
-             " failed: " + cudaGetErrorString(h->ctx.first_error);
-    return LL_ERR_CUDA;
-  }
+  for (const LaunchCtx* c : {&h->ctx, &h->ctx_map})
+    if (c->first_error != cudaSuccess) {
+      h->err = std::string(where) + ": launch of " + (c->first_error_kernel ? c->first_error_kernel : "?") +
+               " failed: " + cudaGetErrorString(c->first_error);
+      return LL_ERR_CUDA;
+    }
   return LL_OK;
 }
 
@@ -190,6 +214,10 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
     if (cudaStreamCreateWithFlags(&h->ctx.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LL_ERR_CUDA; }
     h->own_stream = true;
   }
+  if (cudaStreamCreateWithFlags(&h->ctx_map.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return LL_ERR_CUDA; }
+  if (cudaEventCreateWithFlags(&h->ev_a2b, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_ds_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_b_tail, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->pose_ev_b[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->pose_ev_b[1], cudaEventDisableTiming) != cudaSuccess) { delete h; return LL_ERR_CUDA; }
   memset(&h->st, 0, sizeof(DevState));
   DevState& st = h->st;
   DevParams& p = st.p;
@@ -285,7 +313,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.vox_tmp_counts, (size_t)B * 2));
   for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&h->ev[i]));
   for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->pose_ev[i], cudaEventDisableTiming));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   *out = h;
   return LL_OK;
 }
@@ -309,16 +337,25 @@ int ll_destroy(ll_handle* h) {
     delete[] h->ctx.ev_stop;
     delete[] h->ctx.ev_name;
   }
+  if (h->ctx_map.stream) { cudaStreamSynchronize(h->ctx_map.stream); cudaStreamDestroy(h->ctx_map.stream); }
+  for (cudaEvent_t e : {h->ev_a2b, h->ev_ds_done, h->ev_b_tail, h->pose_ev_b[0], h->pose_ev_b[1]}) if (e) cudaEventDestroy(e);
+  if (h->ctx_map.ev_start) {
+    for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { cudaEventDestroy(h->ctx_map.ev_start[i]); cudaEventDestroy(h->ctx_map.ev_stop[i]); }
+    delete[] h->ctx_map.ev_start;
+    delete[] h->ctx_map.ev_stop;
+    delete[] h->ctx_map.ev_name;
+  }
   if (h->own_stream) cudaStreamDestroy(h->ctx.stream);
   delete h;
   return LL_OK;
 }
 
 const char* ll_last_error(const ll_handle* h) { return h ? h->err.c_str() : "null handle"; }
-int64_t ll_kernel_launches(const ll_handle* h) { return h ? h->ctx.launches : 0; }
+int64_t ll_kernel_launches(const ll_handle* h) { return h ? h->ctx.launches + h->ctx_map.launches : 0; }
 
 int ll_reset_feature_association(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   const DevParams& p = st.p;
   const size_t BN = (size_t)p.B * p.N;
@@ -514,7 +551,7 @@ static int ensure_map_capacity(ll_handle* h, int nc, int ns) {
   // (re)allocate with headroom; maps of other sequences are preserved
   const int ncap = nc > st.cap_map_corner ? (int)(nc * 1.25) + 1024 : st.cap_map_corner;
   const int scap = ns > st.cap_map_surf ? (int)(ns * 1.25) + 1024 : st.cap_map_surf;
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   float4 *mc = nullptr, *ms = nullptr;
   CK(dev_alloc(h, &mc, (size_t)B * ncap));
   CK(dev_alloc(h, &ms, (size_t)B * scap));
@@ -529,6 +566,7 @@ static int ensure_map_capacity(ll_handle* h, int nc, int ns) {
 
 int ll_map_set_local(ll_handle* h, int seq, const float* corner, int nc, const float* surf, int ns) {
   if (!h || seq < 0 || seq >= h->st.p.B || nc < 0 || ns < 0) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   const int rc = ensure_map_capacity(h, nc, ns);
   if (rc) return rc;
   DevState& st = h->st;
@@ -536,20 +574,21 @@ int ll_map_set_local(ll_handle* h, int seq, const float* corner, int nc, const f
   if (ns) CK(cudaMemcpyAsync(st.map_surf + (size_t)seq * st.cap_map_surf, surf, (size_t)ns * 16, cudaMemcpyHostToDevice, h->ctx.stream));
   const int cnt[2] = {nc, ns};
   CK(cudaMemcpyAsync(st.map_counts + seq * 2, cnt, 8, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   h->map_set = true;
   return LL_OK;
 }
 
 int ll_map_set_scan(ll_handle* h, int seq, const float* corner, int nc, const float* surf, int ns) {
   if (!h || seq < 0 || seq >= h->st.p.B || nc < 0 || ns < 0) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   if (nc > st.p.cap_less_sharp || ns > st.p.N) { h->err = "ll_map_set_scan: cloud larger than capacity"; return LL_ERR_CAPACITY; }
   if (nc) CK(cudaMemcpyAsync(st.scan_corner_ds + (size_t)seq * st.p.cap_less_sharp, corner, (size_t)nc * 16, cudaMemcpyHostToDevice, h->ctx.stream));
   if (ns) CK(cudaMemcpyAsync(st.scan_surf_ds + (size_t)seq * st.p.N, surf, (size_t)ns * 16, cudaMemcpyHostToDevice, h->ctx.stream));
   const int cnt[2] = {nc, ns};
   CK(cudaMemcpyAsync(st.scan_ds_counts + seq * 2, cnt, 8, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
@@ -559,41 +598,50 @@ int ll_map_downsample_current_scan(ll_handle* h) {
   // pose that belongs to this scan is kept with them (AssociationOut::laser_odometry, mapOptmization.cpp:1539), so that
   // FeatureAssociation may integrate further frames before the mapping cycle runs
   CK(cudaMemcpyAsync(h->st.map_odom, h->st.transform_sum, (size_t)h->st.p.B * 24, cudaMemcpyDeviceToDevice, h->ctx.stream));
-  launch_downsample_current_scan(h->ctx, h->st);
+  // from here on the cycle runs on the mapping stream, behind everything enqueued for the scan so far; the next
+  // publishCloudsLast (frame stream) waits until the last-frame clouds have been read
+  { const int rc = map_waits_frames(h); if (rc) return rc; }
+  launch_downsample_current_scan(h->ctx_map, h->st);
+  CK(cudaEventRecord(h->ev_ds_done, h->ctx_map.stream));
+  h->ctx.wait_before_publish = h->ev_ds_done;
   return check_stream(h, "ll_map_downsample_current_scan");
 }
 
 int ll_map_set_initial_guess(ll_handle* h, const float* t) {
   if (!h || !t) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
 int ll_map_set_initial_guess_async(ll_handle* h, const float* t) {
   if (!h || !t) return LL_ERR_INVALID_ARG;
-  CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
+  CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx_map.stream));
   return LL_OK;
 }
 
 int ll_map_set_poses(ll_handle* h, const float* aft, const float* bef) {
   if (!h || !aft || !bef) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   CK(cudaMemcpyAsync(h->st.transform_aft_mapped, aft, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
   CK(cudaMemcpyAsync(h->st.transform_bef_mapped, bef, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
 int ll_map_set_odometry(ll_handle* h, const float* transform_sum) {
   if (!h || !transform_sum) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   CK(cudaMemcpyAsync(h->st.map_odom, transform_sum, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
 int ll_map_predict_pose(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
-  launch_map_predict_pose(h->ctx, h->st);
+  { const int rc = map_waits_frames(h); if (rc) return rc; }
+  launch_map_predict_pose(h->ctx_map, h->st);
   return check_stream(h, "ll_map_predict_pose");
 }
 
@@ -601,12 +649,14 @@ int ll_scan_to_map(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (!h->map_set) { h->err = "ll_scan_to_map: no local map set"; return LL_ERR_STATE; }
   if (h->st.cap_map_corner == 0 || h->st.cap_map_surf == 0) return LL_OK;  // empty maps: the guard of :1316 fails for every sequence
-  launch_scan_to_map(h->ctx, h->st);
+  { const int rc = map_waits_frames(h); if (rc) return rc; }
+  launch_scan_to_map(h->ctx_map, h->st);
   return check_stream(h, "ll_scan_to_map");
 }
 
 int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, int max_map_corner, int max_map_surf) {
   if (!h || max_keyframes < 1 || max_keyframes > 32768 || pool_points < 1 || max_map_corner < 1 || max_map_surf < 1) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   if (h->prm.enable_loop_closure) { h->err = "ll_map_enable_keyframes: the loop-closure branch of extractSurroundingKeyFrames is not built"; return LL_ERR_STATE; }
   DevState& st = h->st;
   KeyframeStore& kf = st.kf;
@@ -668,7 +718,7 @@ int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, in
   }
   kf.enabled = 1;
   { const int rc = reset_keyframes(h); if (rc) return rc; }
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   h->map_set = true;
   return LL_OK;
 }
@@ -676,14 +726,16 @@ int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, in
 int ll_map_extract_surrounding_keyframes(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (!h->st.kf.enabled) { h->err = "ll_map_extract_surrounding_keyframes: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
-  launch_extract_surrounding_keyframes(h->ctx, h->st);
+  { const int rc = map_waits_frames(h); if (rc) return rc; }
+  launch_extract_surrounding_keyframes(h->ctx_map, h->st);
   return check_stream(h, "ll_map_extract_surrounding_keyframes");
 }
 
 int ll_map_save_keyframe(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (!h->st.kf.enabled) { h->err = "ll_map_save_keyframe: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
-  launch_save_keyframe(h->ctx, h->st);
+  { const int rc = map_waits_frames(h); if (rc) return rc; }
+  launch_save_keyframe(h->ctx_map, h->st);
   return check_stream(h, "ll_map_save_keyframe");
 }
 
@@ -715,8 +767,8 @@ int ll_mapping_cycle(ll_handle* h) {
   rc = ll_map_save_keyframe(h);
   if (rc < 0) return rc;
   if (!h->kf_err_pending) {
-    CK(cudaMemcpyAsync(h->h_kf_err, h->st.kf.err, sizeof(int32_t) * h->st.p.B, cudaMemcpyDeviceToHost, h->ctx.stream));
-    CK(cudaEventRecord(h->kf_err_ev, h->ctx.stream));
+    CK(cudaMemcpyAsync(h->h_kf_err, h->st.kf.err, sizeof(int32_t) * h->st.p.B, cudaMemcpyDeviceToHost, h->ctx_map.stream));
+    CK(cudaEventRecord(h->kf_err_ev, h->ctx_map.stream));
     h->kf_err_pending = true;
   }
   return LL_OK;
@@ -724,14 +776,15 @@ int ll_mapping_cycle(ll_handle* h) {
 
 int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, void* dst, size_t dst_bytes, size_t* n_elems) {
   if (!h || seq < 0 || seq >= h->st.p.B || which < 0 || which > 2) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   KeyframeStore& kf = h->st.kf;
   if (!kf.enabled) { h->err = "ll_map_download_keyframe: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
   int count = 0, off[4];
   CK(cudaMemcpyAsync(&count, kf.kf_count + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   if (keyframe < 0 || keyframe >= count) return LL_ERR_INVALID_ARG;
   CK(cudaMemcpyAsync(off, kf.kf_off + ((size_t)seq * kf.kf_cap + keyframe) * 4, 16, cudaMemcpyDeviceToHost, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   const size_t n = (size_t)(off[which + 1] - off[which]);
   if (n_elems) *n_elems = n;
   if (!dst) return LL_OK;
@@ -742,7 +795,7 @@ int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, voi
   std::vector<int> perm(n);
   CK(cudaMemcpyAsync(pts.data(), kf.pool_pts + (size_t)seq * kf.pool_cap + off[which], n * 16, cudaMemcpyDeviceToHost, h->ctx.stream));
   CK(cudaMemcpyAsync(perm.data(), kf.pool_perm + (size_t)seq * kf.pool_cap + off[which], n * 4, cudaMemcpyDeviceToHost, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   float* out = (float*)dst;
   for (size_t u = 0; u < n; ++u) {
     if (perm[u] < 0 || (size_t)perm[u] >= n) { h->err = "ll_map_download_keyframe: corrupt permutation"; return LL_ERR_STATE; }
@@ -769,7 +822,7 @@ int ll_process_scans(ll_handle* h) {
       rc = ll_scan_to_map(h);
       if (rc < 0) return rc;
     }
-    if (h->timing) cudaEventRecord(h->ev[5], h->ctx.stream);
+    if (h->timing) { frames_wait_map(h); cudaEventRecord(h->ev[5], h->ctx.stream); }  // (timing serialises the two streams)
     h->ev_valid = true;
     return 1;
   }
@@ -780,17 +833,18 @@ int ll_process_scans(ll_handle* h) {
 
 int ll_synchronize(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
 int ll_get_poses(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   if (!h) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   const size_t bytes = (size_t)h->st.p.B * 24;
   if (tsum) CK(cudaMemcpyAsync(tsum, h->st.transform_sum, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   if (tcur) CK(cudaMemcpyAsync(tcur, h->st.transform_cur, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
@@ -838,12 +892,13 @@ void ll_odometry_to_transform(const double* o, float* t) {
 
 int ll_get_odometry(ll_handle* h, double* laser_odometry, double* odom_aft_mapped) {
   if (!h) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   const int B = h->st.p.B;
   std::vector<float> ts((size_t)B * 6), ta((size_t)B * 6), tb((size_t)B * 6);
   CK(cudaMemcpyAsync(ts.data(), h->st.transform_sum, (size_t)B * 24, cudaMemcpyDeviceToHost, h->ctx.stream));
   CK(cudaMemcpyAsync(ta.data(), h->st.transform_aft_mapped, (size_t)B * 24, cudaMemcpyDeviceToHost, h->ctx.stream));
   CK(cudaMemcpyAsync(tb.data(), h->st.transform_bef_mapped, (size_t)B * 24, cudaMemcpyDeviceToHost, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   for (int s = 0; s < B; ++s) {
     if (laser_odometry) ll_transform_to_odometry(&ts[(size_t)s * 6], laser_odometry + (size_t)s * 7);
     if (odom_aft_mapped) {
@@ -861,8 +916,11 @@ int ll_get_poses_async(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   const size_t bytes = (size_t)h->st.p.B * 24;
   if (tsum) CK(cudaMemcpyAsync(tsum, h->st.transform_sum, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
   if (tcur) CK(cudaMemcpyAsync(tcur, h->st.transform_cur, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
-  if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
+  // transformTobeMapped belongs to MapOptimization: read behind the mapping cycles enqueued so far (it is the pose of the
+  // last cycle that has been handed over, like a subscriber of /aft_mapped_to_init sees it)
+  if (tmap) CK(cudaMemcpyAsync(tmap, h->st.transform_tobe_mapped, bytes, cudaMemcpyDeviceToHost, h->ctx_map.stream));
   CK(cudaEventRecord(h->pose_ev[(h->pose_head + h->pose_pending) & 1], h->ctx.stream));
+  CK(cudaEventRecord(h->pose_ev_b[(h->pose_head + h->pose_pending) & 1], h->ctx_map.stream));
   h->pose_pending += 1;
   return LL_OK;
 }
@@ -871,6 +929,7 @@ int ll_wait_poses(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   if (h->pose_pending == 0) { h->err = "ll_wait_poses: no ll_get_poses_async pending"; return LL_ERR_STATE; }
   CK(cudaEventSynchronize(h->pose_ev[h->pose_head]));  // the oldest one
+  CK(cudaEventSynchronize(h->pose_ev_b[h->pose_head]));
   h->pose_head ^= 1;
   h->pose_pending -= 1;
   return LL_OK;
@@ -878,50 +937,58 @@ int ll_wait_poses(ll_handle* h) {
 
 int ll_time_kernel(ll_handle* h, const char* kernel_name) {
   if (!h) return LL_ERR_INVALID_ARG;
-  LaunchCtx& c = h->ctx;
-  CK(cudaStreamSynchronize(c.stream));
-  if (!c.ev_start) {
-    c.ev_start = new cudaEvent_t[LaunchCtx::kMaxTimed];
-    c.ev_stop = new cudaEvent_t[LaunchCtx::kMaxTimed];
-    c.ev_name = new const char*[LaunchCtx::kMaxTimed];
-    for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { CK(cudaEventCreate(&c.ev_start[i])); CK(cudaEventCreate(&c.ev_stop[i])); }
+  { const int rc = sync_all(h); if (rc) return rc; }
+  for (LaunchCtx* cp : {&h->ctx, &h->ctx_map}) {
+    LaunchCtx& c = *cp;
+    if (!c.ev_start) {
+      c.ev_start = new cudaEvent_t[LaunchCtx::kMaxTimed];
+      c.ev_stop = new cudaEvent_t[LaunchCtx::kMaxTimed];
+      c.ev_name = new const char*[LaunchCtx::kMaxTimed];
+      for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { CK(cudaEventCreate(&c.ev_start[i])); CK(cudaEventCreate(&c.ev_stop[i])); }
+    }
+    c.timed_used = 0;
+    memset(c.timed_name, 0, sizeof(c.timed_name));
+    if (kernel_name) strncpy(c.timed_name, kernel_name, sizeof(c.timed_name) - 1);
   }
-  c.timed_used = 0;
-  memset(c.timed_name, 0, sizeof(c.timed_name));
-  if (kernel_name) strncpy(c.timed_name, kernel_name, sizeof(c.timed_name) - 1);
   return LL_OK;
 }
 
 int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches) {
   if (!h || !total_ms || !launches) return LL_ERR_INVALID_ARG;
-  LaunchCtx& c = h->ctx;
-  CK(cudaStreamSynchronize(c.stream));
+  { const int rc = sync_all(h); if (rc) return rc; }
   double tot = 0.0;
-  for (int i = 0; i < c.timed_used; ++i) {
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, c.ev_start[i], c.ev_stop[i]));
-    tot += ms;
+  int n = 0;
+  for (LaunchCtx* cp : {&h->ctx, &h->ctx_map}) {
+    LaunchCtx& c = *cp;
+    for (int i = 0; i < c.timed_used; ++i) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, c.ev_start[i], c.ev_stop[i]));
+      tot += ms;
+    }
+    n += c.timed_used;
   }
   *total_ms = tot;
-  *launches = c.timed_used;
+  *launches = n;
   return LL_OK;
 }
 
 int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap) {
   if (!h || !buf || cap < 2) return LL_ERR_INVALID_ARG;
-  LaunchCtx& c = h->ctx;
-  CK(cudaStreamSynchronize(c.stream));
+  { const int rc = sync_all(h); if (rc) return rc; }
   std::vector<std::string> names;
   std::vector<double> ms;
   std::vector<int> cnt;
-  for (int i = 0; i < c.timed_used; ++i) {
-    float t = 0.f;
-    CK(cudaEventElapsedTime(&t, c.ev_start[i], c.ev_stop[i]));
-    size_t k = 0;
-    for (; k < names.size(); ++k) if (names[k] == c.ev_name[i]) break;
-    if (k == names.size()) { names.push_back(c.ev_name[i]); ms.push_back(0.0); cnt.push_back(0); }
-    ms[k] += t;
-    cnt[k] += 1;
+  for (LaunchCtx* cp : {&h->ctx, &h->ctx_map}) {
+    LaunchCtx& c = *cp;
+    for (int i = 0; i < c.timed_used; ++i) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, c.ev_start[i], c.ev_stop[i]));
+      size_t k = 0;
+      for (; k < names.size(); ++k) if (names[k] == c.ev_name[i]) break;
+      if (k == names.size()) { names.push_back(c.ev_name[i]); ms.push_back(0.0); cnt.push_back(0); }
+      ms[k] += t;
+      cnt[k] += 1;
+    }
   }
   std::string out;
   char line[160];
@@ -937,7 +1004,7 @@ int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap) {
 int ll_enable_index_trace(ll_handle* h, int enable) {
   if (!h) return LL_ERR_INVALID_ARG;
   DevState& st = h->st;
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   if (enable) {
     if (!h->trace_knn) {
       CK(dev_alloc(h, &h->trace_knn, (size_t)st.p.B * 10 * st.map_knn_cap * 5, false));
@@ -964,7 +1031,7 @@ int ll_enable_stage_timing(ll_handle* h, int enable) {
 int ll_get_stage_times_ms(ll_handle* h, float* ms5) {
   if (!h || !ms5) return LL_ERR_INVALID_ARG;
   if (!h->timing || !h->ev_valid) { h->err = "ll_get_stage_times_ms: timing not enabled or no frame processed"; return LL_ERR_STATE; }
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   for (int i = 0; i < 5; ++i) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
@@ -975,12 +1042,13 @@ int ll_get_stage_times_ms(ll_handle* h, float* ms5) {
 
 static int fetch_count(ll_handle* h, const int* dev, int* out) {
   CK(cudaMemcpyAsync(out, dev, sizeof(int), cudaMemcpyDeviceToHost, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
 int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, size_t* n_elems) {
   if (!h || seq < 0 || seq >= h->st.p.B) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   const DevParams& p = st.p;
   const size_t N = p.N;
@@ -1053,7 +1121,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       if (!st.map_knn_trace) { h->err = "ll_download: call ll_enable_index_trace first"; return LL_ERR_STATE; }
       int qn[2];
       CK(cudaMemcpyAsync(qn, st.scan_ds_counts + seq * 2, 8, cudaMemcpyDeviceToHost, h->ctx.stream));
-      CK(cudaStreamSynchronize(h->ctx.stream));
+      { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
       const size_t Q = (size_t)qn[0] + (size_t)qn[1];
       if (n_elems) *n_elems = 10 * Q;
       if (!dst) return LL_OK;
@@ -1061,7 +1129,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       for (int it = 0; it < 10 && Q; ++it)
         CK(cudaMemcpyAsync((char*)dst + (size_t)it * Q * 20, st.map_knn_trace + (((size_t)seq * 10 + it) * st.map_knn_cap) * 5, Q * 20,
                            cudaMemcpyDeviceToHost, h->ctx.stream));
-      CK(cudaStreamSynchronize(h->ctx.stream));
+      { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
       return LL_OK;
     }
     case LL_BUF_KEYFRAME_STATE: {
@@ -1071,7 +1139,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       CK(cudaMemcpyAsync(&v[1], st.kf.sur_n + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
       CK(cudaMemcpyAsync(&v[2], st.kf.sur_last_erased + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
       CK(cudaMemcpyAsync(&v[3], st.kf.err + seq, 4, cudaMemcpyDeviceToHost, h->ctx.stream));
-      CK(cudaStreamSynchronize(h->ctx.stream));
+      { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
       if (n_elems) *n_elems = 4;
       if (!dst) return LL_OK;
       if (dst_bytes < 16) return LL_ERR_CAPACITY;
@@ -1087,7 +1155,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
       // gathered from the per-ring counters (stride 8)
       std::vector<int> rc((size_t)p.V * 8);
       CK(cudaMemcpyAsync(rc.data(), st.ring_counts + (size_t)seq * p.V * 8, rc.size() * 4, cudaMemcpyDeviceToHost, h->ctx.stream));
-      CK(cudaStreamSynchronize(h->ctx.stream));
+      { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
       if (n_elems) *n_elems = p.V;
       if (!dst) return LL_OK;
       if (dst_bytes < (size_t)p.V * 4) return LL_ERR_CAPACITY;
@@ -1103,13 +1171,14 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
   if (dst_bytes < n * elem) return LL_ERR_CAPACITY;
   if (n) {
     CK(cudaMemcpyAsync(dst, src, n * elem, cudaMemcpyDeviceToHost, h->ctx.stream));
-    CK(cudaStreamSynchronize(h->ctx.stream));
+    { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   }
   return LL_OK;
 }
 
 int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems) {
   if (!h || seq < 0 || seq >= h->st.p.B || !src) return LL_ERR_INVALID_ARG;
+  { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   float* dst = nullptr;
   switch (buffer) {
@@ -1122,7 +1191,7 @@ int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems
   }
   if (n_elems != 6) return LL_ERR_INVALID_ARG;
   CK(cudaMemcpyAsync(dst, src, 24, cudaMemcpyHostToDevice, h->ctx.stream));
-  CK(cudaStreamSynchronize(h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 

@@ -24,6 +24,9 @@ struct LaunchCtx {
   const char** ev_name = nullptr;  // kernel name of every recorded launch
   int timed_used = 0;
   bool timing_now = false;
+  // set by the hand-over to MapOptimization (api.cu): the next k_publish_clouds_last overwrites the last-frame clouds that
+  // downsampleCurrentScan is still reading on the mapping stream and has to wait for this event first
+  cudaEvent_t wait_before_publish = nullptr;
   inline bool is_timed(const char* name) const {
     if (!timed_name[0] || !ev_start) return false;
     if (timed_name[0] == '*' && timed_name[1] == 0) return true;  // "*": every kernel

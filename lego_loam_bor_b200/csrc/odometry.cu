@@ -965,6 +965,10 @@ void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
     LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp + SEARCH_GROUPS * 4 - 1) / (SEARCH_GROUPS * 4), p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
     LL_LAUNCH(ctx, "k_odom_stage_corner", k_odom_stage<STAGE_CORNER><<<p.B, LM_THREADS, stage_smem(p, false), ctx.stream>>>(st));
   }
+  if (ctx.wait_before_publish) {
+    cudaStreamWaitEvent(ctx.stream, ctx.wait_before_publish, 0);
+    ctx.wait_before_publish = nullptr;
+  }
   LL_LAUNCH(ctx, "k_publish_clouds_last", k_publish_clouds_last<<<dim3((p.N + 255) / 256, p.B), 256, 0, ctx.stream>>>(st, first_frame ? 1 : 0));
   launch_grid_build2(ctx, p.B, st.grid_corner_last, st.corner_last, p.cap_less_sharp, st.last_counts, 2, 0,
                      st.grid_surf_last, st.surf_last, p.N, st.last_counts, 2, 1, st.odom_flags + 2, 4, /*pack_ring=*/true);
