@@ -180,6 +180,7 @@ def algorithmic_bytes(kernel, st):
         "k_voxel_grid": 16 * (lf + ls + out) * 2, "k_voxel_grid_total": 16 * qs * 2,
         "k_map_knn": (qs + qc) * (16 + 176) + (ms + mc) * 16,
         "k_map_iter": (qs + qc) * (16 + 4 + 5 * 16), "k_map_solve": 0,
+        "k_map_knn_reuse": (qs + qc) * (16 + 176 + 4), "k_map_iter_cached": (qs + qc) * (16 + 4 + 32),
         "k_kf_select": 0, "k_kf_decide": 0, "k_kf_accumulate": kfp * (16 + 8 + 2 * 28),
         "k_kf_extract": (ms + mc) * (8 + 20 + 16), "k_kf_store": kfp * (16 + 28),
         "k_kfx_sort_new": 0, "k_kfx_merge": (ms + mc) * 24, "k_kfx_alive": (ms + mc) * 8, "k_kfx_output": (ms + mc) * (4 + 20 + 16),
@@ -624,6 +625,7 @@ def main():
             f += 1
             for si, ss in enumerate(sub_streams):
                 step_ev[si][i].record(ss)
+        gpu.join_mapping()   # the mapping cycles run on streams of their own: the region ends when they have finished too
         join()
         ev1.record(stream)
     torch.cuda.synchronize(dev)
@@ -725,6 +727,7 @@ def main():
                 h2d += int(counts[f0 + j].sum()) * (12 if kind == "xyz" else 16) + B * 4
                 step_host(j)
             drain()
+            gpu.join_mapping()
             join()
             e1.record(stream)
         torch.cuda.synchronize(dev)

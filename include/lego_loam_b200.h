@@ -300,6 +300,11 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
  * LL_BUF_TRANSFORM_AFT_MAPPED. */
 int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems);
 int ll_synchronize(ll_handle* h);
+/* MapOptimization's work is enqueued on a stream of its own (the reference runs it on a thread of its own,
+ * mapOptmization.cpp:122) and overlaps the following scans.  ll_join_mapping makes the handle's frame stream wait, on the
+ * device, for every mapping cycle enqueued so far -- no host synchronisation; an event recorded on the frame stream
+ * afterwards marks the completion of both.  ll_synchronize waits on the host for both streams. */
+int ll_join_mapping(ll_handle* h);
 
 /* Index-level parity aid: when enabled, ll_scan_to_map records LL_BUF_MAP_KNN_IDX and ll_feature_association records
  * LL_BUF_ODOM_SEARCH_IDX (extra kernels / stores; off by default). */

@@ -37,7 +37,7 @@ EXPORTS = [
     "ll_set_scans_host", "ll_set_scans_device", "ll_image_projection", "ll_feature_association",
     "ll_map_set_local", "ll_map_set_scan", "ll_map_downsample_current_scan", "ll_map_set_initial_guess",
     "ll_map_set_initial_guess_async", "ll_map_set_poses", "ll_map_set_odometry", "ll_map_predict_pose",
-    "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_get_poses_async", "ll_wait_poses", "ll_download", "ll_upload", "ll_synchronize",
+    "ll_scan_to_map", "ll_process_scans", "ll_get_poses", "ll_get_poses_async", "ll_wait_poses", "ll_download", "ll_upload", "ll_synchronize", "ll_join_mapping",
     "ll_enable_stage_timing", "ll_enable_index_trace", "ll_get_stage_times_ms", "ll_time_kernel", "ll_get_kernel_time",
     "ll_get_kernel_time_table",
     "ll_map_enable_keyframes", "ll_map_extract_surrounding_keyframes", "ll_map_save_keyframe", "ll_mapping_cycle",
@@ -157,7 +157,7 @@ def load_library(path=None):
     lib.ll_map_set_poses.argtypes = [vp, vp, vp]
     lib.ll_map_set_odometry.argtypes = [vp, vp]
     for name in ("ll_image_projection", "ll_feature_association", "ll_map_downsample_current_scan",
-                 "ll_scan_to_map", "ll_process_scans", "ll_synchronize", "ll_map_predict_pose"):
+                 "ll_scan_to_map", "ll_process_scans", "ll_synchronize", "ll_map_predict_pose", "ll_join_mapping"):
         getattr(lib, name).argtypes = [vp]
     lib.ll_map_set_local.argtypes = [vp, ip, vp, ip, vp, ip]
     lib.ll_map_set_scan.argtypes = [vp, ip, vp, ip, vp, ip]
@@ -362,6 +362,9 @@ class LegoLoam:
     def synchronize(self):
         self._ck(self.lib.ll_synchronize(self.h), "ll_synchronize")
 
+    def join_mapping(self):
+        self._ck(self.lib.ll_join_mapping(self.h), "ll_join_mapping")
+
     def poses(self):
         ts = np.zeros((self.batch, 6), np.float32)
         tc = np.zeros((self.batch, 6), np.float32)
@@ -520,6 +523,10 @@ class LegoLoamStreams:
     def synchronize(self):
         for p in self.parts:
             p.synchronize()
+
+    def join_mapping(self):
+        for p in self.parts:
+            p.join_mapping()
 
     def odometry(self):
         """(laser_odometry f64[batch, 7], odom_aft_mapped f64[batch, 13]): the nav_msgs/Odometry fields of the path."""

@@ -831,6 +831,11 @@ int ll_process_scans(ll_handle* h) {
   return 0;
 }
 
+int ll_join_mapping(ll_handle* h) {
+  if (!h) return LL_ERR_INVALID_ARG;
+  return frames_wait_map(h);
+}
+
 int ll_synchronize(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
