@@ -62,6 +62,9 @@ def parse_args(argv=None):
     ap.add_argument("--e2e-input", default="pc2", choices=["pc2", "xyz", "xyzi"])
     ap.add_argument("--e2e-alt-steps", type=int, default=10)
     ap.add_argument("--streams", type=int, default=4, help="split the batch over this many handles / CUDA streams")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed `value` region, for `ncu --profile-from-start off` launch lists "
+                         "(a number printed by a run under ncu is never a bench value)")
     a = ap.parse_args(argv)
     if a.no_map:
         a.map = "none"
@@ -615,6 +618,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] for _ in sub_streams]
     launches1 = gpu.kernel_launches()
+    if args.ncu_range:
+        torch.cuda.profiler.start()
     t_begin = time.time()
     mapping_steps = 0
     with torch.cuda.stream(stream):
@@ -630,6 +635,8 @@ def main():
         ev1.record(stream)
     torch.cuda.synchronize(dev)
     t_end = time.time()
+    if args.ncu_range:
+        torch.cuda.profiler.stop()
     if world > 1:
         dist.barrier()
     dev_ms = ev0.elapsed_time(ev1)

@@ -41,6 +41,8 @@ gpu.time_kernel("*")
 for f in range(F):
     if f == 12 and "--steady" in sys.argv:
         gpu.time_kernel("*")   # restart the table: only steady-state cycles (one appended key frame each) are counted
+    if f == 12 and "--ncu-range" in sys.argv:
+        torch.cuda.synchronize(); torch.cuda.profiler.start()   # ncu --profile-from-start off: only the steady-state frames
     pts, counts = frames[f]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gpu.set_scans_device(pts.data_ptr(), counts, N)
@@ -55,6 +57,8 @@ for f in range(F):
                               "iters_rows": [int(x) for x in gpu.download("MAP_ITERS")]})
     else:
         res.setdefault("plain_ms", []).append(e0.elapsed_time(e1))
+if "--ncu-range" in sys.argv:
+    torch.cuda.synchronize(); torch.cuda.profiler.stop()
 tab = gpu.kernel_time_table()
 res["kernels_ms_total"] = {k: [round(v[0], 3), v[1]] for k, v in sorted(tab.items(), key=lambda kv: -kv[1][0])}
 if check:
