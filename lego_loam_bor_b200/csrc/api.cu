@@ -289,7 +289,9 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.stage_clocks, (size_t)B * 16)); CK(dev_alloc(h, &st.odom_cl, (size_t)B * p.cap_flat));
   CK(dev_alloc(h, &st.odom_gb, (size_t)B * p.cap_sharp)); CK(dev_alloc(h, &st.odom_s0, (size_t)B * p.cap_flat));
   CK(dev_alloc(h, &st.outlier_last, (size_t)B * st.cap_outlier));
-  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp / 2, true); if (rc) return rc; }
+  // (a roomy table for the small corner cloud: an EMPTY cell that hashes onto an occupied bucket costs the search a useless
+  // bucket visit, and a feature with no neighbour within 5 m looks at all 1331 cells around it)
+  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp * 4, true); if (rc) return rc; }
   { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f, N / 3, true); if (rc) return rc; }
   CK(dev_alloc(h, &st.transform_cur, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_sum, (size_t)B * 6));
   CK(dev_alloc(h, &st.odom_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.odom_flags, (size_t)B * 4));
