@@ -30,7 +30,7 @@ struct ll_handle {
   bool handed_to_mapping = false;
   // pinned staging ring for the per-sequence point counts (a slot is reused only after its copy ran)
   int32_t* h_n_in = nullptr;
-  cudaEvent_t slot_ev[16];
+  cudaEvent_t slot_ev[16] = {};
   bool slot_used[16] = {false};
   int slot = 0;
   // ll_set_scans_host double-buffers the input on its own copy stream, so the H2D copy of scan f+1
@@ -39,7 +39,7 @@ struct ll_handle {
   int* n_in_buf[2] = {nullptr, nullptr};
   int* n_in_default = nullptr;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copied[2], consumed[2];
+  cudaEvent_t copied[2] = {}, consumed[2] = {};
   bool consumed_valid[2] = {false, false};
   uint8_t* raw_buf[2] = {nullptr, nullptr};  // ll_set_scans_pointcloud2_host: raw message bytes, [B][raw_stride]
   size_t raw_stride = 0;
@@ -49,7 +49,7 @@ struct ll_handle {
   int wr = 0;        // buffer the next ll_set_scans_host writes
   int pending = -1;  // buffer waiting to be consumed by ll_image_projection
   bool timing = false;
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[6] = {};
   cudaEvent_t pose_ev[2] = {nullptr, nullptr};  // ll_get_poses_async / ll_wait_poses: up to two read-backs in flight
   int pose_head = 0, pose_pending = 0;
   float stage_ms[5];
@@ -107,6 +107,21 @@ int next_pow2(int v) {
   int n = 1;
   while (n < v) n <<= 1;
   return n;
+}
+
+// release one device allocation of the handle early (a superseded map / grid)
+template <typename T>
+void dev_free(ll_handle* h, T*& p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->allocs.size(); ++i)
+    if (h->allocs[i] == (void*)p) { h->allocs.erase(h->allocs.begin() + i); break; }
+  cudaFree((void*)p);
+  p = nullptr;
+}
+
+void free_grid(ll_handle* h, HashGrid* g) {
+  dev_free(h, g->cell_start); dev_free(h, g->cursor); dev_free(h, g->cnt); dev_free(h, g->occ);
+  dev_free(h, g->tile_tot); dev_free(h, g->sorted); dev_free(h, g->count); dev_free(h, g->sig);
 }
 
 int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell, int expected_points = 0, bool ring_sig = false) {
@@ -206,6 +221,9 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LL_ERR_NO_DEVICE;
   if (cudaSetDevice(device) != cudaSuccess) return LL_ERR_NO_DEVICE;
   ll_handle* h = new ll_handle();
+  // (every failure below releases what has been allocated so far)
+#undef CK
+#define CK(call) do { const cudaError_t e__ = (call); if (e__ != cudaSuccess) { ll_destroy(h); return LL_ERR_CUDA; } } while (0)
   h->prm = *prm;
   h->device = device;
   if (cuda_stream) {
@@ -291,8 +309,8 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.outlier_last, (size_t)B * st.cap_outlier));
   // (a roomy table for the small corner cloud: an EMPTY cell that hashes onto an occupied bucket costs the search a useless
   // bucket visit, and a feature with no neighbour within 5 m looks at all 1331 cells around it)
-  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp * 4, true); if (rc) return rc; }
-  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f, N / 3, true); if (rc) return rc; }
+  { const int rc = alloc_grid(h, &st.grid_corner_last, B, p.cap_less_sharp, 1.0f, p.cap_less_sharp * 4, true); if (rc) { ll_destroy(h); return rc; } }
+  { const int rc = alloc_grid(h, &st.grid_surf_last, B, N, 1.0f, N / 3, true); if (rc) { ll_destroy(h); return rc; } }
   CK(dev_alloc(h, &st.transform_cur, (size_t)B * 6)); CK(dev_alloc(h, &st.transform_sum, (size_t)B * 6));
   CK(dev_alloc(h, &st.odom_iters, (size_t)B * 2)); CK(dev_alloc(h, &st.odom_flags, (size_t)B * 4));
   CK(dev_alloc(h, &st.odom_matP, (size_t)B * 9));
@@ -318,20 +336,30 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   *out = h;
   return LL_OK;
+#undef CK
+#define CK(call)                                                                     \
+  do {                                                                               \
+    const cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                        \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+      return LL_ERR_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
 }
 
 int ll_destroy(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->ctx.stream);
+  if (h->ctx.stream) cudaStreamSynchronize(h->ctx.stream);
   for (void* q : h->allocs) cudaFree(q);
   if (h->h_n_in) cudaFreeHost(h->h_n_in);
   if (h->h_kf_err) cudaFreeHost(h->h_kf_err);
   if (h->kf_err_ev) cudaEventDestroy(h->kf_err_ev);
-  for (int i = 0; i < 16; ++i) cudaEventDestroy(h->slot_ev[i]);
-  for (int b = 0; b < 2; ++b) { cudaEventDestroy(h->copied[b]); cudaEventDestroy(h->consumed[b]); }
+  for (int i = 0; i < 16; ++i) if (h->slot_ev[i]) cudaEventDestroy(h->slot_ev[i]);
+  for (int b = 0; b < 2; ++b) { if (h->copied[b]) cudaEventDestroy(h->copied[b]); if (h->consumed[b]) cudaEventDestroy(h->consumed[b]); }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-  for (int i = 0; i < 6; ++i) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 2; ++i) if (h->pose_ev[i]) cudaEventDestroy(h->pose_ev[i]);
   if (h->ctx.ev_start) {
     for (int i = 0; i < LaunchCtx::kMaxTimed; ++i) { cudaEventDestroy(h->ctx.ev_start[i]); cudaEventDestroy(h->ctx.ev_stop[i]); }
@@ -357,6 +385,7 @@ int64_t ll_kernel_launches(const ll_handle* h) { return h ? h->ctx.launches + h-
 
 int ll_reset_feature_association(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   const DevParams& p = st.p;
@@ -384,6 +413,7 @@ int ll_reset_feature_association(ll_handle* h) {
 
 int ll_reset(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc = ll_reset_feature_association(h); if (rc) return rc; }
   DevState& st = h->st;
   const DevParams& p = st.p;
@@ -398,6 +428,7 @@ int ll_reset(ll_handle* h) {
 
 int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, int stride_points) {
   if (!h || !xyzi || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   DevState& st = h->st;
   const int B = st.p.B;
   if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_host: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
@@ -420,6 +451,7 @@ int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, 
 
 int ll_set_scans_xyz_host(ll_handle* h, const float* xyz, const int32_t* n_points, int stride_points) {
   if (!h || !xyz || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   DevState& st = h->st;
   const int B = st.p.B;
   if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_xyz_host: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
@@ -443,6 +475,7 @@ int ll_set_scans_xyz_host(ll_handle* h, const float* xyz, const int32_t* n_point
 int ll_set_scans_pointcloud2_host(ll_handle* h, const uint8_t* data, const int32_t* n_points, size_t stride_bytes, int point_step,
                                   int off_x, int off_y, int off_z, int off_intensity, int is_dense) {
   if (!h || !data || !n_points || point_step < 12) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   const int offs[4] = {off_x, off_y, off_z, off_intensity};
   for (int k = 0; k < 4; ++k) {
     if (k == 3 && offs[k] < 0) continue;  // no intensity field in the message
@@ -487,6 +520,7 @@ int ll_set_scans_pointcloud2_host(ll_handle* h, const uint8_t* data, const int32
 
 int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_points, int stride_points) {
   if (!h || !xyzi_dev || !n_points || stride_points < 1) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   DevState& st = h->st;
   if (stride_points > st.p.max_pts) { h->err = "ll_set_scans_device: stride_points exceeds max_points"; return LL_ERR_CAPACITY; }
   { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_device", h->n_in_default, h->ctx.stream); if (rc) return rc; }
@@ -500,6 +534,7 @@ int ll_set_scans_device(ll_handle* h, const float* xyzi_dev, const int32_t* n_po
 
 int ll_image_projection(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   const int pb = h->pending;
   if (pb >= 0) {
     // scans staged by ll_set_scans_host: the kernels wait for that copy only
@@ -526,6 +561,7 @@ int ll_image_projection(ll_handle* h) {
 
 int ll_feature_association(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   const bool first = (h->frames == 0);
   launch_feature_extraction(h->ctx, h->st);
   if (h->timing) cudaEventRecord(h->ev[3], h->ctx.stream);
@@ -559,6 +595,9 @@ static int ensure_map_capacity(ll_handle* h, int nc, int ns) {
   CK(dev_alloc(h, &ms, (size_t)B * scap));
   if (st.map_corner) CK(cudaMemcpy2DAsync(mc, (size_t)ncap * 16, st.map_corner, (size_t)st.cap_map_corner * 16, (size_t)st.cap_map_corner * 16, B, cudaMemcpyDeviceToDevice, h->ctx.stream));
   if (st.map_surf) CK(cudaMemcpy2DAsync(ms, (size_t)scap * 16, st.map_surf, (size_t)st.cap_map_surf * 16, (size_t)st.cap_map_surf * 16, B, cudaMemcpyDeviceToDevice, h->ctx.stream));
+  { const int rc_s = sync_all(h); if (rc_s) return rc_s; }   // the copies are done: the superseded maps and grids can go
+  dev_free(h, st.map_corner); dev_free(h, st.map_surf);
+  free_grid(h, &st.grid_map_corner); free_grid(h, &st.grid_map_surf);
   st.map_corner = mc; st.map_surf = ms;
   st.cap_map_corner = ncap; st.cap_map_surf = scap;
   { const int rc = alloc_grid(h, &st.grid_map_corner, B, ncap, 1.0f); if (rc) return rc; }
@@ -568,6 +607,7 @@ static int ensure_map_capacity(ll_handle* h, int nc, int ns) {
 
 int ll_map_set_local(ll_handle* h, int seq, const float* corner, int nc, const float* surf, int ns) {
   if (!h || seq < 0 || seq >= h->st.p.B || nc < 0 || ns < 0) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   const int rc = ensure_map_capacity(h, nc, ns);
   if (rc) return rc;
@@ -583,6 +623,7 @@ int ll_map_set_local(ll_handle* h, int seq, const float* corner, int nc, const f
 
 int ll_map_set_scan(ll_handle* h, int seq, const float* corner, int nc, const float* surf, int ns) {
   if (!h || seq < 0 || seq >= h->st.p.B || nc < 0 || ns < 0) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   if (nc > st.p.cap_less_sharp || ns > st.p.N) { h->err = "ll_map_set_scan: cloud larger than capacity"; return LL_ERR_CAPACITY; }
@@ -596,6 +637,7 @@ int ll_map_set_scan(ll_handle* h, int seq, const float* corner, int nc, const fl
 
 int ll_map_downsample_current_scan(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   // the hand-over to MapOptimization: the scan's clouds are down-sampled into buffers of their own and the odometry
   // pose that belongs to this scan is kept with them (AssociationOut::laser_odometry, mapOptmization.cpp:1539), so that
   // FeatureAssociation may integrate further frames before the mapping cycle runs
@@ -611,6 +653,7 @@ int ll_map_downsample_current_scan(ll_handle* h) {
 
 int ll_map_set_initial_guess(ll_handle* h, const float* t) {
   if (!h || !t) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
@@ -619,12 +662,14 @@ int ll_map_set_initial_guess(ll_handle* h, const float* t) {
 
 int ll_map_set_initial_guess_async(ll_handle* h, const float* t) {
   if (!h || !t) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   CK(cudaMemcpyAsync(h->st.transform_tobe_mapped, t, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx_map.stream));
   return LL_OK;
 }
 
 int ll_map_set_poses(ll_handle* h, const float* aft, const float* bef) {
   if (!h || !aft || !bef) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   CK(cudaMemcpyAsync(h->st.transform_aft_mapped, aft, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
   CK(cudaMemcpyAsync(h->st.transform_bef_mapped, bef, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
@@ -634,6 +679,7 @@ int ll_map_set_poses(ll_handle* h, const float* aft, const float* bef) {
 
 int ll_map_set_odometry(ll_handle* h, const float* transform_sum) {
   if (!h || !transform_sum) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   CK(cudaMemcpyAsync(h->st.map_odom, transform_sum, (size_t)h->st.p.B * 24, cudaMemcpyHostToDevice, h->ctx.stream));
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
@@ -642,6 +688,7 @@ int ll_map_set_odometry(ll_handle* h, const float* transform_sum) {
 
 int ll_map_predict_pose(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc = map_waits_frames(h); if (rc) return rc; }
   launch_map_predict_pose(h->ctx_map, h->st);
   return check_stream(h, "ll_map_predict_pose");
@@ -649,6 +696,7 @@ int ll_map_predict_pose(ll_handle* h) {
 
 int ll_scan_to_map(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (!h->map_set) { h->err = "ll_scan_to_map: no local map set"; return LL_ERR_STATE; }
   if (h->st.cap_map_corner == 0 || h->st.cap_map_surf == 0) return LL_OK;  // empty maps: the guard of :1316 fails for every sequence
   { const int rc = map_waits_frames(h); if (rc) return rc; }
@@ -658,6 +706,7 @@ int ll_scan_to_map(ll_handle* h) {
 
 int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, int max_map_corner, int max_map_surf) {
   if (!h || max_keyframes < 1 || max_keyframes > 32768 || pool_points < 1 || max_map_corner < 1 || max_map_surf < 1) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   if (h->prm.enable_loop_closure) { h->err = "ll_map_enable_keyframes: the loop-closure branch of extractSurroundingKeyFrames is not built"; return LL_ERR_STATE; }
   DevState& st = h->st;
@@ -727,6 +776,7 @@ int ll_map_enable_keyframes(ll_handle* h, int max_keyframes, int pool_points, in
 
 int ll_map_extract_surrounding_keyframes(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (!h->st.kf.enabled) { h->err = "ll_map_extract_surrounding_keyframes: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
   { const int rc = map_waits_frames(h); if (rc) return rc; }
   launch_extract_surrounding_keyframes(h->ctx_map, h->st);
@@ -735,6 +785,7 @@ int ll_map_extract_surrounding_keyframes(ll_handle* h) {
 
 int ll_map_save_keyframe(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (!h->st.kf.enabled) { h->err = "ll_map_save_keyframe: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
   { const int rc = map_waits_frames(h); if (rc) return rc; }
   launch_save_keyframe(h->ctx_map, h->st);
@@ -743,6 +794,7 @@ int ll_map_save_keyframe(ll_handle* h) {
 
 int ll_mapping_cycle(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (!h->st.kf.enabled) { h->err = "ll_mapping_cycle: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
   // capacity errors of the previous cycle (a sequence that outgrew the key-frame slots, the point pool, a voxel table or
   // the local-map capacity) are reported here, one cycle late, so that no call ever waits for the device
@@ -778,6 +830,7 @@ int ll_mapping_cycle(ll_handle* h) {
 
 int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, void* dst, size_t dst_bytes, size_t* n_elems) {
   if (!h || seq < 0 || seq >= h->st.p.B || which < 0 || which > 2) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   KeyframeStore& kf = h->st.kf;
   if (!kf.enabled) { h->err = "ll_map_download_keyframe: call ll_map_enable_keyframes first"; return LL_ERR_STATE; }
@@ -808,6 +861,7 @@ int ll_map_download_keyframe(ll_handle* h, int seq, int keyframe, int which, voi
 
 int ll_process_scans(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   int rc = ll_image_projection(h);
   if (rc < 0) return rc;
   rc = ll_feature_association(h);
@@ -835,17 +889,20 @@ int ll_process_scans(ll_handle* h) {
 
 int ll_join_mapping(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   return frames_wait_map(h);
 }
 
 int ll_synchronize(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   return LL_OK;
 }
 
 int ll_get_poses(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   const size_t bytes = (size_t)h->st.p.B * 24;
   if (tsum) CK(cudaMemcpyAsync(tsum, h->st.transform_sum, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
@@ -899,6 +956,7 @@ void ll_odometry_to_transform(const double* o, float* t) {
 
 int ll_get_odometry(ll_handle* h, double* laser_odometry, double* odom_aft_mapped) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   const int B = h->st.p.B;
   std::vector<float> ts((size_t)B * 6), ta((size_t)B * 6), tb((size_t)B * 6);
@@ -919,6 +977,7 @@ int ll_get_odometry(ll_handle* h, double* laser_odometry, double* odom_aft_mappe
 
 int ll_get_poses_async(ll_handle* h, float* tsum, float* tcur, float* tmap) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (h->pose_pending >= 2) { h->err = "ll_get_poses_async: two read-backs already in flight, call ll_wait_poses"; return LL_ERR_STATE; }
   const size_t bytes = (size_t)h->st.p.B * 24;
   if (tsum) CK(cudaMemcpyAsync(tsum, h->st.transform_sum, bytes, cudaMemcpyDeviceToHost, h->ctx.stream));
@@ -934,6 +993,7 @@ int ll_get_poses_async(ll_handle* h, float* tsum, float* tcur, float* tmap) {
 
 int ll_wait_poses(ll_handle* h) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (h->pose_pending == 0) { h->err = "ll_wait_poses: no ll_get_poses_async pending"; return LL_ERR_STATE; }
   CK(cudaEventSynchronize(h->pose_ev[h->pose_head]));  // the oldest one
   CK(cudaEventSynchronize(h->pose_ev_b[h->pose_head]));
@@ -944,6 +1004,7 @@ int ll_wait_poses(ll_handle* h) {
 
 int ll_time_kernel(ll_handle* h, const char* kernel_name) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc = sync_all(h); if (rc) return rc; }
   for (LaunchCtx* cp : {&h->ctx, &h->ctx_map}) {
     LaunchCtx& c = *cp;
@@ -962,6 +1023,7 @@ int ll_time_kernel(ll_handle* h, const char* kernel_name) {
 
 int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches) {
   if (!h || !total_ms || !launches) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc = sync_all(h); if (rc) return rc; }
   double tot = 0.0;
   int n = 0;
@@ -981,6 +1043,7 @@ int ll_get_kernel_time(ll_handle* h, double* total_ms, int* launches) {
 
 int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap) {
   if (!h || !buf || cap < 2) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc = sync_all(h); if (rc) return rc; }
   std::vector<std::string> names;
   std::vector<double> ms;
@@ -1010,6 +1073,7 @@ int ll_get_kernel_time_table(ll_handle* h, char* buf, size_t cap) {
 
 int ll_enable_index_trace(ll_handle* h, int enable) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   DevState& st = h->st;
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   if (enable) {
@@ -1030,6 +1094,7 @@ int ll_enable_index_trace(ll_handle* h, int enable) {
 
 int ll_enable_stage_timing(ll_handle* h, int enable) {
   if (!h) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   h->timing = enable != 0;
   h->ev_valid = false;
   return LL_OK;
@@ -1037,6 +1102,7 @@ int ll_enable_stage_timing(ll_handle* h, int enable) {
 
 int ll_get_stage_times_ms(ll_handle* h, float* ms5) {
   if (!h || !ms5) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   if (!h->timing || !h->ev_valid) { h->err = "ll_get_stage_times_ms: timing not enabled or no frame processed"; return LL_ERR_STATE; }
   { const int rc_s = sync_all(h); if (rc_s) return rc_s; }
   for (int i = 0; i < 5; ++i) {
@@ -1055,6 +1121,7 @@ static int fetch_count(ll_handle* h, const int* dev, int* out) {
 
 int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, size_t* n_elems) {
   if (!h || seq < 0 || seq >= h->st.p.B) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   const DevParams& p = st.p;
@@ -1185,6 +1252,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
 
 int ll_upload(ll_handle* h, int seq, int buffer, const void* src, size_t n_elems) {
   if (!h || seq < 0 || seq >= h->st.p.B || !src) return LL_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   { const int rc_s0 = sync_all(h); if (rc_s0) return rc_s0; }  // both streams idle before host-driven reads / writes of device state
   DevState& st = h->st;
   float* dst = nullptr;

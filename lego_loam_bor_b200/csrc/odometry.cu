@@ -953,11 +953,14 @@ void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
   const DevParams& p = st.p;
   if (!first_frame) {
     if (st.odom_trace) cudaMemsetAsync(st.odom_trace, 0xff, (size_t)p.B * 2 * 5 * p.cap_flat * 3 * sizeof(int), ctx.stream);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in shared-memory size is a per-device attribute of the kernel
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
       cudaFuncSetAttribute(k_odom_stage<STAGE_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaFuncSetAttribute(k_odom_stage<STAGE_CORNER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done = true;
+      attr_done[dev] = true;
     }
     // surf stage then corner stage (featureAssociation.cpp:1216-1234), then integrateTransformation
     LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<dim3((p.cap_flat + SEARCH_GROUPS - 1) / SEARCH_GROUPS, p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));

@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(VG_THREADS) k_voxel_grid(VoxArgs args) {
   const long long dz = (long long)((bmx[2] - bmn[2]) * inv) + 1;
   if (dx * dy * dz > 2147483647LL) {
     // PCL: "leaf size is too small for the input dataset" -> output = input
-    for (int i = threadIdx.x; i < n; i += VG_THREADS) out[i] = vox_point(job, s, i, na);
-    if (threadIdx.x == 0) job.nout[s * job.nout_stride] = n;
+    const int nc = min(n, job.stride_out);  // never past the output cloud's capacity
+    for (int i = threadIdx.x; i < nc; i += VG_THREADS) out[i] = vox_point(job, s, i, na);
+    if (threadIdx.x == 0) job.nout[s * job.nout_stride] = nc;
     return;
   }
   const int minb0 = (int)floorf(bmn[0] * inv), minb1 = (int)floorf(bmn[1] * inv), minb2 = (int)floorf(bmn[2] * inv);

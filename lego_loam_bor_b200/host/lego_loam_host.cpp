@@ -86,6 +86,7 @@ void ImageProjection::cloudHandler(const float* xyzi, int n_points, double stamp
 void ImageProjection::cloudHandler(const ll_pointcloud2_view& msg) {
   // pcl::fromROSMsg needs x, y, z FLOAT32 fields; big-endian messages are not produced by any supported driver
   if (msg.is_bigendian || msg.off_x < 0 || msg.off_y < 0 || msg.off_z < 0 || msg.point_step < 12 ||
+      (uint64_t)msg.width * (uint64_t)msg.height > 0x7fffffffull ||
       (uint64_t)msg.width * msg.height * msg.point_step > msg.data_len)
     throw std::runtime_error("ImageProjection::cloudHandler: unsupported or inconsistent sensor_msgs/PointCloud2");
   handle((double)msg.stamp_sec + 1e-9 * (double)msg.stamp_nsec, [&]() {
