@@ -731,7 +731,9 @@ def main():
             e0.record(stream)
             fork(e0)
             for j in range(e2e_warm, e2e_warm + steps):
-                h2d += int(counts[f0 + j].sum()) * (12 if kind == "xyz" else 16) + B * 4
+                # what the library copies: per handle one strided copy whose rows carry the longest scan of that sub-batch
+                cj = counts[f0 + j].reshape(len(parts), -1)
+                h2d += int((cj.max(axis=1) * cj.shape[1]).sum()) * (12 if kind == "xyz" else 16) + B * 4
                 step_host(j)
             drain()
             gpu.join_mapping()

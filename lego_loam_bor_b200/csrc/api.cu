@@ -436,11 +436,14 @@ int ll_set_scans_host(ll_handle* h, const float* xyzi, const int32_t* n_points, 
   // the buffer may still be read by the projection kernels of two scans ago
   if (h->consumed_valid[b]) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[b], 0));
   { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_host", h->n_in_buf[b], h->copy_stream); if (rc) return rc; }
-  // one copy per sequence of just the valid points (no batched-memcpy API is used)
-  for (int s = 0; s < B; ++s) {
-    if (n_points[s] == 0) continue;
-    CK(cudaMemcpyAsync(h->in_buf[b] + (size_t)s * st.p.max_pts, xyzi + (size_t)s * stride_points * 4,
-                       (size_t)n_points[s] * 16, cudaMemcpyHostToDevice, h->copy_stream));
+  // ONE strided copy for the whole batch: every row carries the longest scan's bytes (scans of a batch are of similar
+  // length, so little padding crosses PCIe, and the DMA engine gets one descriptor instead of one per sequence)
+  {
+    int max_n = 0;
+    for (int s = 0; s < B; ++s) max_n = n_points[s] > max_n ? n_points[s] : max_n;
+    if (max_n > 0)
+      CK(cudaMemcpy2DAsync(h->in_buf[b], (size_t)st.p.max_pts * 16, xyzi, (size_t)stride_points * 16, (size_t)max_n * 16, B,
+                           cudaMemcpyHostToDevice, h->copy_stream));
   }
   CK(cudaEventRecord(h->copied[b], h->copy_stream));
   h->buf_xyz3[b] = false;
@@ -460,10 +463,12 @@ int ll_set_scans_xyz_host(ll_handle* h, const float* xyz, const int32_t* n_point
   { const int rc = stage_counts(h, n_points, stride_points, "ll_set_scans_xyz_host", h->n_in_buf[b], h->copy_stream); if (rc) return rc; }
   // the same input buffer, packed: sequence s starts at float 3 * s * max_pts
   float* dst = reinterpret_cast<float*>(h->in_buf[b]);
-  for (int s = 0; s < B; ++s) {
-    if (n_points[s] == 0) continue;
-    CK(cudaMemcpyAsync(dst + (size_t)s * st.p.max_pts * 3, xyz + (size_t)s * stride_points * 3,
-                       (size_t)n_points[s] * 12, cudaMemcpyHostToDevice, h->copy_stream));
+  {
+    int max_n = 0;
+    for (int s = 0; s < B; ++s) max_n = n_points[s] > max_n ? n_points[s] : max_n;
+    if (max_n > 0)
+      CK(cudaMemcpy2DAsync(dst, (size_t)st.p.max_pts * 12, xyz, (size_t)stride_points * 12, (size_t)max_n * 12, B,
+                           cudaMemcpyHostToDevice, h->copy_stream));
   }
   CK(cudaEventRecord(h->copied[b], h->copy_stream));
   h->buf_xyz3[b] = true;
@@ -500,10 +505,12 @@ int ll_set_scans_pointcloud2_host(ll_handle* h, const uint8_t* data, const int32
   const int b = h->wr;
   if (h->consumed_valid[b]) CK(cudaStreamWaitEvent(h->copy_stream, h->consumed[b], 0));
   { const int rc = stage_counts(h, n_points, st.p.max_pts, "ll_set_scans_pointcloud2_host", h->n_raw_buf[b], h->copy_stream); if (rc) return rc; }
-  for (int s = 0; s < B; ++s) {
-    if (n_points[s] == 0) continue;
-    CK(cudaMemcpyAsync(h->raw_buf[b] + (size_t)s * h->raw_stride, data + (size_t)s * stride_bytes, (size_t)n_points[s] * point_step,
-                       cudaMemcpyHostToDevice, h->copy_stream));
+  {
+    int max_n = 0;
+    for (int s = 0; s < B; ++s) max_n = n_points[s] > max_n ? n_points[s] : max_n;
+    if (max_n > 0)
+      CK(cudaMemcpy2DAsync(h->raw_buf[b], h->raw_stride, data, stride_bytes, (size_t)max_n * point_step, B, cudaMemcpyHostToDevice,
+                           h->copy_stream));
   }
   Pc2Args a;
   a.raw = h->raw_buf[b]; a.raw_stride = h->raw_stride; a.n_raw = h->n_raw_buf[b];
