@@ -171,7 +171,7 @@ def algorithmic_bytes(kernel, st):
         "k_gather_ground": 29 * N + 16 * g * N,
         "k_ccl_rows": 12 * N, "k_ccl_merge": 8 * N, "k_ccl_flatten": 8 * N,
         "k_ccl_tile": 4 * N + 4 * N, "k_ccl_border": 8 * N / 8,
-        "k_seg_count": 5 * N, "k_seg_emit": 5 * N + 45 * S + 4 * S, "k_label_final": 8 * N,
+        "k_seg_count": 5 * N + N, "k_seg_emit": N + 45 * S + 4 * S, "k_label_final": 8 * N,
         "k_feature_prep": 61 * S + 4 * S,
         "k_feature_sort": 21 * S, "k_feature_pick": 8 * S, "k_feature_lessflat": 24 * S + 16 * lf,
         "k_feature_ring": 21 * S + 8 * S + 24 * S + 16 * lf,
@@ -179,7 +179,7 @@ def algorithmic_bytes(kernel, st):
         "k_odom_search_surf": ff * 96 + lf * 16, "k_odom_search_corner": fs * 80 + ls * 16,
         "k_odom_stage_surf": ff * 69, "k_odom_stage_corner": fs * 85,
         "k_publish_clouds_last": 32 * (lf + ls + out),
-        "k_grid_count": 16 * (lf + ls), "k_grid_tile_sums": 0, "k_grid_scan": 0, "k_grid_fill": 32 * (lf + ls),
+        "k_grid_count": 16 * (lf + ls), "k_grid_scan": 0, "k_grid_fill": 32 * (lf + ls),
         "k_voxel_grid": 16 * (lf + ls + out) * 2, "k_voxel_grid_total": 16 * qs * 2,
         "k_map_knn": (qs + qc) * (16 + 176) + (ms + mc) * 16,
         "k_map_iter": (qs + qc) * (16 + 4 + 5 * 16), "k_map_solve": 0,

@@ -30,6 +30,7 @@ BUFFERS = {
     "SCAN_OUTLIER_DS": (39, np.float32, 4), "STAGE_CLOCKS": (40, np.int64, 1),
     "KEYFRAME_STATE": (41, np.int32, 1), "KEY_POSES_6D": (42, np.float32, 6), "SURROUNDING_KEY_IDS": (43, np.int32, 1),
     "INPUT_CLOUD": (44, np.float32, 4), "MAP_KNN_IDX": (45, np.int32, 5), "ODOM_SEARCH_IDX": (46, np.int32, 3),
+    "RING_CLOCKS": (47, np.int64, 10),
 }
 
 EXPORTS = [

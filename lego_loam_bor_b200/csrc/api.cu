@@ -28,6 +28,7 @@ struct ll_handle {
   int64_t odom_cycles = 0;   // _cycle_count of featureAssociation.cpp:1429-1433
   bool map_set = false;
   bool handed_to_mapping = false;
+  bool labels_pending = false;  // _label_mat of the last frame still lacks the numbers of its non-root cells (k_label_final runs on demand)
   // pinned staging ring for the per-sequence point counts (a slot is reused only after its copy ran)
   int32_t* h_n_in = nullptr;
   cudaEvent_t slot_ev[16] = {};
@@ -120,7 +121,7 @@ void dev_free(ll_handle* h, T*& p) {
 }
 
 void free_grid(ll_handle* h, HashGrid* g) {
-  dev_free(h, g->cell_start); dev_free(h, g->cursor); dev_free(h, g->cnt); dev_free(h, g->occ);
+  dev_free(h, g->cell_start); dev_free(h, g->cnt); dev_free(h, g->occ);
   dev_free(h, g->tile_tot); dev_free(h, g->sorted); dev_free(h, g->count); dev_free(h, g->sig);
 }
 
@@ -133,8 +134,7 @@ int alloc_grid(ll_handle* h, HashGrid* g, int B, int cap, float cell, int expect
   const int want = expected_points > 0 ? expected_points : cap;
   g->tbl = next_pow2(want < 4096 ? 4096 : want);
   g->ntiles = g->tbl / 4096;
-  CK(dev_alloc(h, &g->cell_start, (size_t)B * (g->tbl + 1)));
-  CK(dev_alloc(h, &g->cursor, (size_t)B * g->tbl));
+  CK(dev_alloc(h, &g->cell_start, (size_t)B * grid_cs_stride(*g)));
   CK(dev_alloc(h, &g->cnt, (size_t)B * g->tbl));
   CK(dev_alloc(h, &g->occ, (size_t)B * (g->tbl / 32)));
   CK(dev_alloc(h, &g->tile_tot, (size_t)B * g->ntiles));
@@ -283,7 +283,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(dev_alloc(h, &st.tile_counts, (size_t)B * V * 4));
   CK(dev_alloc(h, &st.orientation, (size_t)B * 4)); CK(dev_alloc(h, &st.half_idx, B));
   CK(dev_alloc(h, &st.seg_cloud, BN)); CK(dev_alloc(h, &st.seg_range, BN));
-  CK(dev_alloc(h, &st.seg_col, BN)); CK(dev_alloc(h, &st.seg_ground, BN)); CK(dev_alloc(h, &st.seg_ori, BN));
+  CK(dev_alloc(h, &st.seg_col, BN)); CK(dev_alloc(h, &st.seg_ground, BN)); CK(dev_alloc(h, &st.seg_ori, BN)); CK(dev_alloc(h, &st.seg_class, BN));
   CK(dev_alloc(h, &st.start_ring, (size_t)B * V)); CK(dev_alloc(h, &st.end_ring, (size_t)B * V));
   CK(dev_alloc(h, &st.seg_count, B));
   CK(dev_alloc(h, &st.outlier_cloud, (size_t)B * st.cap_outlier)); CK(dev_alloc(h, &st.outlier_count, B));
@@ -304,7 +304,7 @@ int ll_create(const LegoLoamParams* prm, int batch, int max_points, int device, 
   CK(cudaMemsetAsync(st.win_first, 0x7f, (size_t)2 * B * 2 * (LL_MAX_RINGS + 8) * 4, h->ctx.stream));
   CK(cudaMemsetAsync(st.win_last, 0xff, (size_t)2 * B * 2 * (LL_MAX_RINGS + 8) * 4, h->ctx.stream));
   CK(dev_alloc(h, &st.odom_ga, (size_t)B * p.cap_flat)); CK(dev_alloc(h, &st.odom_ok, (size_t)B * p.cap_flat));
-  CK(dev_alloc(h, &st.stage_clocks, (size_t)B * 16)); CK(dev_alloc(h, &st.odom_cl, (size_t)B * p.cap_flat));
+  CK(dev_alloc(h, &st.stage_clocks, (size_t)B * 16)); CK(dev_alloc(h, &st.ring_clocks, (size_t)B * V * 10)); CK(dev_alloc(h, &st.odom_cl, (size_t)B * p.cap_flat));
   CK(dev_alloc(h, &st.odom_gb, (size_t)B * p.cap_sharp)); CK(dev_alloc(h, &st.odom_s0, (size_t)B * p.cap_flat));
   CK(dev_alloc(h, &st.outlier_last, (size_t)B * st.cap_outlier));
   // (a roomy table for the small corner cloud: an EMPTY cell that hashes onto an occupied bucket costs the search a useless
@@ -397,10 +397,10 @@ int ll_reset_feature_association(ll_handle* h) {
   CK(cudaMemsetAsync(st.transform_cur, 0, (size_t)p.B * 24, sm)); CK(cudaMemsetAsync(st.transform_sum, 0, (size_t)p.B * 24, sm));
   CK(cudaMemsetAsync(st.last_counts, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_flags, 0, (size_t)p.B * 16, sm));
   CK(cudaMemsetAsync(st.odom_iters, 0, (size_t)p.B * 8, sm)); CK(cudaMemsetAsync(st.odom_matP, 0, (size_t)p.B * 36, sm));
-  CK(cudaMemsetAsync(st.grid_corner_last.cell_start, 0, (size_t)p.B * (st.grid_corner_last.tbl + 1) * 4, sm));
+  CK(cudaMemsetAsync(st.grid_corner_last.cell_start, 0, (size_t)p.B * grid_cs_stride(st.grid_corner_last) * 4, sm));
   CK(cudaMemsetAsync(st.grid_corner_last.occ, 0, (size_t)p.B * (st.grid_corner_last.tbl / 32) * 4, sm));
   CK(cudaMemsetAsync(st.grid_surf_last.occ, 0, (size_t)p.B * (st.grid_surf_last.tbl / 32) * 4, sm));
-  CK(cudaMemsetAsync(st.grid_surf_last.cell_start, 0, (size_t)p.B * (st.grid_surf_last.tbl + 1) * 4, sm));
+  CK(cudaMemsetAsync(st.grid_surf_last.cell_start, 0, (size_t)p.B * grid_cs_stride(st.grid_surf_last) * 4, sm));
   CK(cudaMemsetAsync(st.win_first, 0x7f, (size_t)2 * p.B * 2 * (LL_MAX_RINGS + 8) * 4, sm));
   CK(cudaMemsetAsync(st.win_last, 0xff, (size_t)2 * p.B * 2 * (LL_MAX_RINGS + 8) * 4, sm));
   CK(cudaMemsetAsync(st.grid_corner_last.sig, 0, (size_t)p.B * st.grid_corner_last.tbl * 4, sm));
@@ -562,6 +562,7 @@ int ll_image_projection(ll_handle* h) {
   }
   if (h->timing) cudaEventRecord(h->ev[1], h->ctx.stream);
   launch_segmentation(h->ctx, h->st);
+  h->labels_pending = true;
   if (h->timing) cudaEventRecord(h->ev[2], h->ctx.stream);
   return check_stream(h, "ll_image_projection");
 }
@@ -1143,7 +1144,15 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_RANGE_MAT: FIXED(st.range_mat, 4, N); break;
     case LL_BUF_FULL_CLOUD: FIXED(st.full_cloud, 16, N); break;
     case LL_BUF_GROUND_MAT: FIXED(st.ground_mat, 1, N); break;
-    case LL_BUF_LABEL_MAT: FIXED(st.label_mat, 4, N); break;
+    case LL_BUF_LABEL_MAT:
+      // labelMat is private to ImageProjection and cloudSegmentation only tests it for > 0 / == 999999 (imageProjection.cpp:
+      // 363-383), which the device decides from the union-find forest; the NUMBERS of the non-root cells are filled in here
+      if (h->labels_pending) {
+        launch_label_final(h->ctx, st);
+        h->labels_pending = false;
+        { const int rc_l = sync_all(h); if (rc_l) return rc_l; }
+      }
+      FIXED(st.label_mat, 4, N); break;
     case LL_BUF_SEG_CLOUD: COUNTED(st.seg_cloud, 16, N, st.seg_count + seq); break;
     case LL_BUF_SEG_GROUND_FLAG: COUNTED(st.seg_ground, 1, N, st.seg_count + seq); break;
     case LL_BUF_SEG_COL_IND: COUNTED(st.seg_col, 4, N, st.seg_count + seq); break;
@@ -1176,6 +1185,7 @@ int ll_download(ll_handle* h, int seq, int buffer, void* dst, size_t dst_bytes, 
     case LL_BUF_TRANSFORM_TOBE_MAPPED: src = st.transform_tobe_mapped + seq * 6; elem = 4; n = 6; break;
     case LL_BUF_MAP_ITERS: src = st.map_iters + seq * 2; elem = 4; n = 2; break;
     case LL_BUF_STAGE_CLOCKS: src = st.stage_clocks + (size_t)seq * 16; elem = 8; n = 16; break;
+    case LL_BUF_RING_CLOCKS: src = st.ring_clocks + (size_t)seq * p.V * 10; elem = 80; n = (size_t)p.V; break;
     case LL_BUF_MAP_TRACE: src = st.map_trace + (size_t)seq * 340; elem = 8; n = 340; break;
     case LL_BUF_SCAN_SURF_DS: COUNTED(st.vox_tmp_surf, 16, N, st.vox_tmp_counts + seq * 2 + 0); break;
     case LL_BUF_SCAN_OUTLIER_DS: COUNTED(st.vox_tmp_out, 16, (size_t)st.cap_outlier, st.vox_tmp_counts + seq * 2 + 1); break;

@@ -169,6 +169,85 @@ __device__ __forceinline__ int f2ord(float f) {
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 #define FR_THREADS 256
+#define FR_WARPS (FR_THREADS / 32)
+#define FR_RADIX_MIN 512    // voxel runs of a ring: above this many, a stable radix sort instead of the bitonic network
+#define FR_RADIX_MAX 2048   // 8 warps x 8 trips of 32
+
+struct RingSortSmem {
+  unsigned short whist[FR_WARPS][256];
+  unsigned base[256];
+};
+
+// Stable LSD radix sort of n <= FR_RADIX_MAX (key, value) pairs in shared memory by the low `bits` bits of the key, 8 bits a
+// pass, ping-pong between (k0, v0) and (k1, v1); returns the buffer (0 / 1) that holds the result.  Every warp owns a
+// contiguous chunk of the input and ranks it 32 keys at a time (match_any: peers of equal digit, in lane order), carrying
+// its own digit counters from trip to trip, so a pass needs no barrier per trip: count, one scan over (digit, warp), scatter.
+// Called by all FR_THREADS threads; ends with a barrier.
+__device__ __noinline__ int ring_radix_sort(unsigned* k0, unsigned short* v0, unsigned* k1, unsigned short* v1, int n, int bits,
+                                               RingSortSmem& sm, int* warp_tot) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int chunk = (((n + FR_WARPS - 1) / FR_WARPS) + 31) & ~31;   // keys per warp: a multiple of 32, <= 256
+  const int c0 = wid * chunk;
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    const unsigned* kin = cur ? k1 : k0;
+    const unsigned short* vin = cur ? v1 : v0;
+    unsigned* kout = cur ? k0 : k1;
+    unsigned short* vout = cur ? v0 : v1;
+    for (int d = threadIdx.x; d < FR_WARPS * 256; d += FR_THREADS) (&sm.whist[0][0])[d] = 0;
+    __syncthreads();
+    unsigned rpack[4] = {0u, 0u, 0u, 0u};   // rank of this lane's key of trip t inside the warp's chunk and digit, 16 bits each
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t * 32 < chunk) {   // warp-uniform
+        const int i = c0 + t * 32 + lane;
+        const bool act = i < n;
+        const unsigned amask = __ballot_sync(0xffffffffu, act);
+        unsigned dg = 0u, peers = 0u, prev = 0u, r = 0u;
+        if (act) {
+          dg = (kin[i] >> shift) & 255u;
+          peers = __match_any_sync(amask, dg);
+          r = __popc(peers & ((1u << lane) - 1u));
+          prev = sm.whist[wid][dg];
+        }
+        __syncwarp();
+        if (act && r == 0u) sm.whist[wid][dg] = (unsigned short)(prev + __popc(peers));
+        __syncwarp();
+        rpack[t >> 1] |= (prev + r) << (16 * (t & 1));
+      }
+    }
+    __syncthreads();
+    {
+      // per digit: exclusive scan over the warps, then over the digits
+      unsigned run = 0u;
+#pragma unroll
+      for (int w = 0; w < FR_WARPS; ++w) {
+        const unsigned c = sm.whist[w][threadIdx.x];
+        sm.whist[w][threadIdx.x] = (unsigned short)run;
+        run += c;
+      }
+      int total;
+      sm.base[threadIdx.x] = (unsigned)block_exclusive_scan((int)run, warp_tot, &total);   // FR_THREADS == 256 digits
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t * 32 < chunk) {
+        const int i = c0 + t * 32 + lane;
+        if (i < n) {
+          const unsigned k = kin[i];
+          const unsigned dg = (k >> shift) & 255u;
+          const unsigned pos = sm.base[dg] + sm.whist[wid][dg] + ((rpack[t >> 1] >> (16 * (t & 1))) & 0xffffu);
+          kout[pos] = k;
+          vout[pos] = vin[i];
+        }
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
 
 // ---- per-ring feature extraction: candidate sort, greedy picks, less-flat collection + VoxelGrid, in ONE block ---------
 // One block per (ring, sequence); everything between the loads of the ring's span and its results lives in shared
@@ -192,9 +271,10 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 // 3. Less-flat collection by POSITION (:370-374) and the per-ring 0.2 m pcl::VoxelGrid (:101,377-381): consecutive points
 //    of a ring mostly share a voxel, so the sort runs over RUNS of equal voxel index; runs of the same voxel end up
 //    adjacent and in input order, so each voxel's float sums keep the input order.
-__global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int cap2) {
-  extern __shared__ unsigned long long fr_keys[];  // [cap2] u64, then int vox[H], u16 col / lfpos [H+32] each, u8 picked, i8 label [H+32] each
+__global__ void __launch_bounds__(FR_THREADS, 5) k_feature_ring(DevState st, int cap2) {
+  extern __shared__ unsigned long long fr_keys[];  // [cap2] u64, then int vox[H], u16 lfpos / col [H+32] each, u8 picked, i8 label [H+32] each
   __shared__ int warp_tot[33];
+  __shared__ RingSortSmem sh_sort;
   __shared__ int sh_sp[6], sh_ep[6];
   __shared__ int sh_imn[3], sh_imx[3];
   __shared__ int sh_stale, sh_has_stale;
@@ -203,17 +283,40 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
   __shared__ int sh_ne[6], sh_nf[6], sh_spill_r[6], sh_spill_l[6];
   __shared__ unsigned long long sh_slot_min;
   const DevParams& p = st.p;
-  const int ring = blockIdx.x, s = blockIdx.y;
+  const int s = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // Longest ring first: a block lasts about as long as its ring has points (10 .. 130 us), and the launch lasts as long as
+  // its last block.  Blocks are dispatched in grid order (x = sequence fastest), so the block with blockIdx.y = r takes the
+  // ring with the r-th largest span of its sequence: the long rings of all sequences start at once, the short ones fill in.
+  __shared__ int sh_span[LL_MAX_RINGS];
+  __shared__ int sh_ring;
+  for (int r = threadIdx.x; r < p.V; r += FR_THREADS) sh_span[r] = st.end_ring[s * p.V + r] - st.start_ring[s * p.V + r];
+  __syncthreads();
+  for (int r = threadIdx.x; r < p.V; r += FR_THREADS) {
+    const int mine = sh_span[r];
+    int rank = 0;
+    for (int q = 0; q < p.V; ++q) rank += (sh_span[q] > mine || (sh_span[q] == mine && q < r)) ? 1 : 0;
+    if (rank == (int)blockIdx.y) sh_ring = r;
+  }
+  __syncthreads();
+  const int ring = sh_ring;
   const size_t base = (size_t)s * p.N;
   const size_t rs = (size_t)s * p.V + ring;
   const int HP = p.H + 32;
   unsigned long long* keys = fr_keys;
   int* sm_vox = reinterpret_cast<int*>(fr_keys + cap2);
-  unsigned short* sm_col = reinterpret_cast<unsigned short*>(sm_vox + p.H);
-  unsigned short* sm_lfpos = sm_col + HP;
-  unsigned char* sm_picked = reinterpret_cast<unsigned char*>(sm_lfpos + HP);
+  // (col, picked and label are dead once the less-flat positions are collected: 4 (H + 32) contiguous bytes, the second
+  // key buffer of the radix sort of the voxel runs)
+  unsigned short* sm_lfpos = reinterpret_cast<unsigned short*>(sm_vox + p.H);
+  unsigned short* sm_col = sm_lfpos + HP;
+  unsigned char* sm_picked = reinterpret_cast<unsigned char*>(sm_col + HP);
   signed char* sm_label = reinterpret_cast<signed char*>(sm_picked + HP);
+  // LL_BUF_RING_CLOCKS (profiling aid, thread 0): SM cycles per phase of this block (every slot is passed at most once)
+  long long* ring_clk = st.ring_clocks + rs * 10;
+  if (threadIdx.x < 10) ring_clk[threadIdx.x] = 0;
+  const long long rc_begin = clock64();
+  long long rc_mark = rc_begin;
+#define RING_CLOCK(slot) do { if (threadIdx.x == 0) { const long long t__ = clock64(); ring_clk[slot] = t__ - rc_mark; rc_mark = t__; } } while (0)
   const int start = st.start_ring[s * p.V + ring], end = st.end_ring[s * p.V + ring];
   const int a = start - 4, b = end + 6;  // this ring's points are [a - 1, b)
   const int span_lo = max(0, a - 8), span_hi = min(p.N, b + 8);
@@ -276,6 +379,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
     st.slot4[s * 2 + 0] = (unsigned)(sh_slot_min >> 32);
     st.slot4[s * 2 + 1] = (unsigned)(sh_slot_min & 0xffffffffull);
   }
+  RING_CLOCK(1);
   // ---- 2. greedy picks ----
   // The six sextants of a ring run in order in the reference because a pick suppresses up to 5 neighbours on either side,
   // across a sextant boundary.  Only the first five positions of a sextant can be reached from the previous one, so the
@@ -358,22 +462,36 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
     };
     if (wid < 6) run_sextant(wid, 0u);
     __syncthreads();
-    if (wid == 0) {
-      // boundaries in order; a sextant whose speculative run picked a position its predecessor marks is run again
-      for (int j = 1; j < 6; ++j) {
-        const unsigned r = (unsigned)sh_spill_r[j - 1];
-        if (r == 0u) continue;
-        bool hit = false;
-        const int np = sh_ne[j] + sh_nf[j];
-        if (lane < 24) {
-          const bool mine = lane < 20 ? lane < sh_ne[j] : (lane - 20) < sh_nf[j];
-          if (mine) {
-            const int q = k_first + (int)sh_pick[j][lane] - sh_sp[j];
-            hit = q < 5 && ((r >> q) & 1u);
+    RING_CLOCK(2);
+    // Boundaries.  Sextant j ran with the marks `used` of its predecessor in place (none, at first); the predecessor's
+    // run says `r`.  The run stands if r == used, or if r only ADDS marks at positions sextant j never picked (a candidate
+    // that was never picked never influenced a decision); otherwise sextant j is reset and run again with r in place.
+    // All sextants decide on the same snapshot of the spill masks and re-run in parallel, a warp each; sextants 0 .. k are
+    // final after round k (sextant 0 has no predecessor), so this ends after at most five rounds -- usually one.
+    {
+      unsigned used = 0u;   // warp j: the marks its last run started with
+      for (int round = 0; round < 6; ++round) {
+        bool rerun = false;
+        unsigned r = 0u;
+        if (wid >= 1 && wid < 6) {
+          const int j = wid;
+          r = (unsigned)sh_spill_r[j - 1];
+          if (r != used) {
+            bool hit = (used & ~r) != 0u;   // a mark this run assumed has gone: a position it avoided may be free again
+            if (lane < 24) {
+              const bool mine = lane < 20 ? lane < sh_ne[j] : (lane - 20) < sh_nf[j];
+              if (mine) {
+                const int q = k_first + (int)sh_pick[j][lane] - sh_sp[j];
+                hit = hit || (q < 5 && (((r & ~used) >> q) & 1u));
+              }
+            }
+            rerun = __any_sync(0xffffffffu, hit);
+            if (!rerun) used = r;   // the added marks change nothing for this run; they reach sm_picked with the spills below
           }
         }
-        (void)np;
-        if (__any_sync(0xffffffffu, hit)) {
+        if (!__syncthreads_or(rerun ? 1 : 0)) break;   // (also orders the reads of the spill masks before the re-runs write them)
+        if (rerun) {
+          const int j = wid;
           // reset sextant j to the state before any pick (picked flags from global memory, labels 0: its candidates lie
           // in [5, S-5), where calculateSmoothness has just reset cloudLabel) and run it with the marks in place
           for (int t = sh_sp[j] + lane; t <= sh_ep[j]; t += 32) sm_picked[t - span_lo] = (unsigned char)(st.picked[base + t] != 0);
@@ -384,8 +502,9 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
           // marks sextant j itself put into its predecessor's range are dropped with the run; the new run records its own
           __syncwarp();
           run_sextant(j, r);
-          __syncwarp();
+          used = r;
         }
+        __syncthreads();
       }
     }
     __syncthreads();
@@ -542,6 +661,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
     if (lane == 0) { sh_counts[0] = n_sharp; sh_counts[1] = n_lsharp; sh_counts[2] = n_flat; }
   }
   __syncthreads();
+  RING_CLOCK(3);
   // persist cloudNeighborPicked (entries are only ever set to 1 here) and cloudLabel for this ring's own range
   for (int t = threadIdx.x; t < L; t += FR_THREADS) {
     const int g = span_lo + t;
@@ -573,8 +693,10 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
     n_raw = run;
   }
   __syncthreads();
+  RING_CLOCK(4);
   // pcl::VoxelGrid, leaf 0.2 (featureAssociation.cpp:101,377-381; algorithm: SURVEY.md section 8 f1)
   int n_ds = 0;
+  int n_runs_dbg = 0;
   if (n_raw > 0) {
     const float inv = 1.0f / 0.2f;
     if (threadIdx.x < 3) { sh_imn[threadIdx.x] = f2ord(FLT_MAX); sh_imx[threadIdx.x] = f2ord(-FLT_MAX); }
@@ -626,6 +748,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
         sm_vox[t] = i0 + i1 * div0 + i2 * div0 * div1;
       }
       __syncthreads();
+      RING_CLOCK(5);
       // run heads -> compact run keys
       int n_runs = 0;
       {
@@ -650,8 +773,37 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
         sm_runend[startp] = endp;
       }
       __syncthreads();
-      // sort the runs by (voxel, first position): a few hundred keys -- rank by counting, no synchronised passes
-      if (n_runs <= 96) {
+      RING_CLOCK(6);
+      n_runs_dbg = n_runs;
+      // sort the runs by (voxel, first position)
+      const unsigned pos_mask = (1u << pos_bits) - 1u;
+      // sorted runs: (voxel, first position) of run t; the radix path keeps them as two arrays
+      const unsigned* rk = nullptr;
+      const unsigned short* rv = nullptr;
+      unsigned short* sm_slot = sm_col;  // output slot of every voxel, see below (sm_col is dead by now)
+      if (n_runs > FR_RADIX_MIN && n_runs <= FR_RADIX_MAX && p.H <= FR_RADIX_MAX) {
+        // Many runs (a ring of far, sparse points: nearly every point a voxel of its own): stable LSD radix sort by voxel
+        // -- the runs are in order of first position already.  Key buffers 0 / 1: the two halves of the u64 key area; value
+        // buffers 0 / 1: the dead col / picked / label area.  The u64 keys are split in place, 256 at a time in ascending
+        // order: the 32-bit keys of a chunk land in bytes whose u64 keys have been read already.
+        unsigned* k0 = reinterpret_cast<unsigned*>(keys);
+        unsigned* k1 = k0 + p.H;
+        unsigned short* v0 = sm_col;
+        unsigned short* v1 = v0 + p.H;
+        for (int r0 = 0; r0 < n_runs; r0 += FR_THREADS) {
+          const int r = r0 + threadIdx.x;
+          const unsigned long long mine = r < n_runs ? keys[r] : 0ull;
+          __syncthreads();
+          if (r < n_runs) { k0[r] = (unsigned)(mine >> pos_bits); v0[r] = (unsigned short)((unsigned)mine & pos_mask); }
+        }
+        int vbits = 1;
+        while (vbits < 31 && ((dx * dy * dz - 1) >> vbits) > 0) ++vbits;
+        const int res = ring_radix_sort(k0, v0, k1, v1, n_runs, vbits, sh_sort, warp_tot);  // starts and ends with a barrier
+        rk = res ? k1 : k0;
+        rv = res ? v1 : v0;
+        sm_slot = res ? v0 : v1;
+      } else if (n_runs <= 96) {
+        // a few dozen keys: rank by counting, no synchronised passes
         unsigned long long* sorted = keys + cap2 / 2;
         for (int r = threadIdx.x; r < n_runs; r += FR_THREADS) {
           const unsigned long long key = keys[r];
@@ -676,35 +828,45 @@ __global__ void __launch_bounds__(FR_THREADS) k_feature_ring(DevState st, int ca
         __syncthreads();
         bitonic_sort_t<unsigned long long>(keys, r2);
       }
-      const unsigned pos_mask = (1u << pos_bits) - 1u;
+      RING_CLOCK(7);
+      auto vox_of = [&](int t) -> unsigned { return rk ? rk[t] : (unsigned)(keys[t] >> pos_bits); };
+      auto pos_of = [&](int t) -> int { return rk ? (int)rv[t] : (int)((unsigned)keys[t] & pos_mask); };
+      // output slot of every voxel (= of the first run of every group of equal voxel)
       int run = 0;
       for (int t0 = 0; t0 < n_runs; t0 += FR_THREADS) {
         const int t = t0 + threadIdx.x;
         int head = 0;
-        if (t < n_runs) head = (t == 0) || ((unsigned)(keys[t] >> pos_bits) != (unsigned)(keys[t - 1] >> pos_bits));
+        if (t < n_runs) head = (t == 0) || (vox_of(t) != vox_of(t - 1));
         int total;
         const int ex = block_exclusive_scan(head, warp_tot, &total);
-        if (head) {
-          const unsigned vox = (unsigned)(keys[t] >> pos_bits);
-          float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
-          int cnt = 0;
-          for (int u = t; u < n_runs && (unsigned)(keys[u] >> pos_bits) == vox; ++u) {
-            const int ps = (int)((unsigned)keys[u] & pos_mask), pe = sm_runend[ps];
-            for (int v = ps; v < pe; ++v) {
-              const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[v]];
-              cx += q.x; cy += q.y; cz += q.z; ci += q.w;
-              ++cnt;
-            }
-          }
-          const float fc = (float)cnt;
-          o_lflat[run + ex] = make_float4(cx / fc, cy / fc, cz / fc, ci / fc);
-        }
+        if (t < n_runs) sm_slot[t] = head ? (unsigned short)(run + ex) : (unsigned short)0xffff;
         run += total;
+      }
+      // centroids: no barrier in this loop, so the point loads of different voxels overlap across the warps
+      for (int t = threadIdx.x; t < n_runs; t += FR_THREADS) {
+        const unsigned slot = sm_slot[t];
+        if (slot == 0xffffu) continue;
+        const unsigned vox = vox_of(t);
+        float cx = 0.f, cy = 0.f, cz = 0.f, ci = 0.f;
+        int cnt = 0;
+        for (int u = t; u < n_runs && vox_of(u) == vox; ++u) {
+          const int ps = pos_of(u), pe = sm_runend[ps];
+          for (int v = ps; v < pe; ++v) {
+            const float4 q = st.seg_cloud[base + k_lo + sm_lfpos[v]];
+            cx += q.x; cy += q.y; cz += q.z; ci += q.w;
+            ++cnt;
+          }
+        }
+        const float fc = (float)cnt;
+        o_lflat[slot] = make_float4(cx / fc, cy / fc, cz / fc, ci / fc);
       }
       n_ds = run;
     }
   }
+  RING_CLOCK(8);
   if (threadIdx.x == 0) {
+    ring_clk[0] = clock64() - rc_begin;
+    ring_clk[9] = (long long)L | ((long long)n_raw << 16) | ((long long)n_runs_dbg << 32);
     int* o_counts = st.ring_counts + rs * 8;
     o_counts[0] = sh_counts[0];
     o_counts[1] = sh_counts[1];
@@ -767,7 +929,7 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
   }
   const dim3 grid_rings(p.V, p.B);
   {
-    // 37 KB at H = 2048: six blocks per SM
+    // 37 KB at H = 2048: six blocks per SM; grid (sequence, rank of the ring by length)
     const int cap2 = next_pow2(p.H);
     const size_t smem = (size_t)cap2 * 8 + (size_t)p.H * 4 + (size_t)(p.H + 32) * (2 * 2 + 2);
     // the opt-in shared-memory size is a per-device attribute of the kernel
@@ -779,7 +941,7 @@ void launch_feature_extraction(LaunchCtx& ctx, DevState& st) {
       cudaFuncSetAttribute(k_feature_ring, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       configured[dev] = smem;
     }
-    LL_LAUNCH(ctx, "k_feature_ring", k_feature_ring<<<grid_rings, FR_THREADS, smem, ctx.stream>>>(st, cap2));
+    LL_LAUNCH(ctx, "k_feature_ring", k_feature_ring<<<dim3(p.B, p.V), FR_THREADS, smem, ctx.stream>>>(st, cap2));
   }
   LL_LAUNCH(ctx, "k_feature_compact", k_feature_compact<<<grid_rings, 256, 0, ctx.stream>>>(st));
 }

@@ -31,7 +31,7 @@ __device__ __forceinline__ float nn_dist2(float qx, float qy, float qz, const fl
 __device__ __forceinline__ void warp_nn1(const HashGrid& g, int s, float qx, float qy, float qz, float max_d2,
                                          float* out_d2, int* out_idx) {
   const int lane = threadIdx.x & 31;
-  const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+  const int* cs = g.cell_start + (size_t)s * grid_cs_stride(g);
   const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
   const float4* pts = g.sorted + (size_t)s * g.cap;
   const int cx = grid_cell(qx, g.inv_cell), cy = grid_cell(qy, g.inv_cell), cz = grid_cell(qz, g.inv_cell);
@@ -73,7 +73,7 @@ __device__ __forceinline__ void warp_nn1(const HashGrid& g, int s, float qx, flo
 // exact).  Results ascending by (d2, idx); returns the number found (<= 5).
 __device__ __forceinline__ int thread_knn5(const HashGrid& g, int s, float qx, float qy, float qz, float max_d2,
                                            float* d2o, int* idxo) {
-  const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+  const int* cs = g.cell_start + (size_t)s * grid_cs_stride(g);
   const float4* pts = g.sorted + (size_t)s * g.cap;
   const int cx = grid_cell(qx, g.inv_cell), cy = grid_cell(qy, g.inv_cell), cz = grid_cell(qz, g.inv_cell);
   int n = 0;

@@ -23,12 +23,11 @@
 
 // hash grid over a point cloud (replaces nanoflann::KdTreeFLANN, nanoflann_pcl.h:54-152)
 struct HashGrid {
-  int* cell_start;   // [B][tbl+1] exclusive prefix of bucket counts
-  int* cursor;       // [B][tbl]   fill cursors
-  int* cnt;          // [B][tbl]   bucket counters (zero at rest)
+  int* cell_start;   // [B][tbl+4] exclusive prefix of bucket counts (tbl + 1 entries; rows padded to 16 bytes: grid_cs_stride)
+  int* cnt;          // [B][tbl]   bucket counters (zero at rest: the fill counts them back down)
   unsigned* occ;     // [B][tbl/32] bit h set <=> bucket h is not empty (tested before touching cell_start)
   unsigned* sig;     // [B][tbl] or null: bit ((ring id + 1) & 31) set for every ring id present in the bucket
-  int* tile_tot;     // [B][ntiles] per-tile counter sums of the scan
+  int* tile_tot;     // [B][ntiles] per-tile counter sums (accumulated by the count kernel, zero at rest)
   int ntiles;        // tbl / 4096
   float4* sorted;    // [B][cap]   points bucket by bucket; .w carries the original index (int bits)
   int* count;        // [B]        points indexed
@@ -37,6 +36,7 @@ struct HashGrid {
   int tbl;           // buckets per sequence (power of two)
   int cap;           // point capacity per sequence
 };
+__host__ __device__ __forceinline__ size_t grid_cs_stride(const HashGrid& g) { return (size_t)g.tbl + 4; }
 
 // Sparse voxel accumulator of one local map (keyframes.cu): open-addressing table keyed by the absolute voxel
 // coordinates, split into `parts` independent sub-tables (a voxel belongs to exactly one, chosen by a hash of its key).
@@ -141,6 +141,7 @@ struct DevState {
   float* seg_range;            // [B][N]
   uint32_t* seg_col;           // [B][N]
   uint8_t* seg_ground;         // [B][N]
+  uint8_t* seg_class;          // [B][N] per CELL: classify_cell flags of this frame (k_seg_count -> k_seg_emit)
   float* seg_ori;              // [B][N] -atan2(y, x) of every segmented point (adjustDistortion's raw orientation)
   int* start_ring;             // [B][V]
   int* end_ring;               // [B][V]
@@ -180,6 +181,7 @@ struct DevState {
   uint8_t* odom_ok;     // [B][24V]
   int* odom_cl;         // [B][24V] closest point (index into the last-frame cloud) or -1
   long long* stage_clocks;  // [B][16] see LL_BUF_STAGE_CLOCKS
+  long long* ring_clocks;   // [B][V][10] see LL_BUF_RING_CLOCKS
   float4* outlier_last; // [B][cap_outlier]
   HashGrid grid_corner_last, grid_surf_last;  // index the clouds the "kd-trees" were last built on
   float* transform_cur;  // [B][6]

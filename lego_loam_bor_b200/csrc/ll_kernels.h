@@ -65,6 +65,7 @@ struct LaunchCtx {
 void launch_projection(LaunchCtx& ctx, DevState& st);
 // segmentation.cu: cloudSegmentation / labelComponents
 void launch_segmentation(LaunchCtx& ctx, DevState& st);
+void launch_label_final(LaunchCtx& ctx, DevState& st);  // numeric labels of the non-root cells, on demand (LL_BUF_LABEL_MAT)
 // features.cu: adjustDistortion, calculateSmoothness, markOccludedPoints, extractFeatures
 void launch_feature_extraction(LaunchCtx& ctx, DevState& st);
 // odometry.cu: first-frame initialisation / updateTransformation + integrateTransformation + publishCloudsLast

@@ -221,7 +221,7 @@ __device__ __forceinline__ void knn_search_warp(const DevState& st, int s, int q
   const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
   const float4 sel = point_associate_to_map(mp, ori);
   const HashGrid& g = corner ? st.grid_map_corner : st.grid_map_surf;
-  const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+  const int* cs = g.cell_start + (size_t)s * grid_cs_stride(g);
   const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
   const float4* pts = g.sorted + (size_t)s * g.cap;
   const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int ite
       const float4 ori = corner ? st.scan_corner_ds[(size_t)s * p.cap_less_sharp + q] : st.scan_surf_ds[(size_t)s * p.N + (q - nc)];
       const float4 sel = point_associate_to_map(mp, ori);
       const HashGrid& g = corner ? st.grid_map_corner : st.grid_map_surf;
-      const int* cs = g.cell_start + (size_t)s * (g.tbl + 1);
+      const int* cs = g.cell_start + (size_t)s * grid_cs_stride(g);
       const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
       const float4* pts = g.sorted + (size_t)s * g.cap;
       const int cx = grid_cell(sel.x, g.inv_cell), cy = grid_cell(sel.y, g.inv_cell), cz = grid_cell(sel.z, g.inv_cell);

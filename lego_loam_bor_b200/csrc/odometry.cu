@@ -292,7 +292,7 @@ __device__ __forceinline__ CorrS group_search(const DevState& st, const WinTable
   const DevParams& p = st.p;
   const bool surf = (STAGE == STAGE_SURF);
   const HashGrid& g = surf ? st.grid_surf_last : st.grid_corner_last;
-  const int* cs_tab = g.cell_start + (size_t)s * (g.tbl + 1);
+  const int* cs_tab = g.cell_start + (size_t)s * grid_cs_stride(g);
   const unsigned* occ = g.occ + (size_t)s * (g.tbl / 32);
   const unsigned* sig = g.sig + (size_t)s * g.tbl;
   const float4* pts = g.sorted + (size_t)s * g.cap;

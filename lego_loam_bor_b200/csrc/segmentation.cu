@@ -17,7 +17,7 @@
 //   k_ccl_flatten   one thread per cell: final root, component size / row mask (warp-aggregated atomics)
 //   k_seg_count     one block per (sequence, row): feasible roots, kept cells, outlier cells
 //   k_seg_emit      one block per (sequence, row): ordered compaction into segmented cloud + cloud_info
-//   k_label_final   one thread per cell: numeric labels of non-root cells / 999999 (imageProjection.cpp:489-495)
+//   k_label_final   one thread per cell: numeric labels of non-root cells / 999999 (imageProjection.cpp:489-495); on demand
 #include "ll_device.cuh"
 #include "ll_kernels.h"
 
@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) k_seg_count(DevState st) {
   int c_root = 0, c_keep = 0, c_out = 0;
   for (int col = threadIdx.x; col < p.H; col += blockDim.x) {
     const int f = classify_cell(st, base, row, col);
+    st.seg_class[base + (size_t)row * p.H + col] = (uint8_t)f;  // k_seg_emit orders the cells by these flags
     c_root += f & 1;
     c_keep += (f >> 1) & 1;
     c_out += (f >> 2) & 1;
@@ -286,8 +287,8 @@ __device__ __forceinline__ void block_exclusive_scan_trips(const int (&v)[SEG_TR
 }
 
 // One block per (sequence, row).  The row is handled SEG_TRIPS x 256 columns at a time: the classification of all those
-// cells (a chain of dependent loads each: parent -> component size -> row mask), then the points of the kept cells and
-// their orientation, are in flight together, and one multi-scan orders them; the kernel is a single wave of blocks, so its
+// cells (left by k_seg_count, one byte per cell), then the points of the kept cells and their orientation, are in flight
+// together, and one multi-scan orders them; the kernel is a single wave of blocks, so its
 // duration is the latency of one block.
 __global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
   __shared__ int sh_pre[3];
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
 #pragma unroll
     for (int t = 0; t < SEG_TRIPS; ++t) {
       const int col = c0 + t * 256 + threadIdx.x;
-      f[t] = col < p.H ? classify_cell(st, base, row, col) : 0;
+      f[t] = col < p.H ? (int)st.seg_class[base + (size_t)row * p.H + col] : 0;
       // one packed scan for the three flags (each partial sum <= 256 < 2^10)
       packed[t] = (f[t] & 1) | (((f[t] >> 1) & 1) << 10) | (((f[t] >> 2) & 1) << 20);
     }
@@ -407,5 +408,13 @@ void launch_segmentation(LaunchCtx& ctx, DevState& st) {
   LL_LAUNCH(ctx, "k_ccl_flatten", k_ccl_flatten<<<grid_cells, 256, 0, ctx.stream>>>(st));
   LL_LAUNCH(ctx, "k_seg_count", k_seg_count<<<grid_rows, 256, 0, ctx.stream>>>(st));
   LL_LAUNCH(ctx, "k_seg_emit", k_seg_emit<<<grid_rows, 256, 0, ctx.stream>>>(st));
+}
+
+// Not part of the per-scan path: the reference never publishes labelMat, and everything cloudSegmentation reads from it is
+// decided above from the forest (feasible or not); the numbers of the non-root cells are written when a caller asks for the
+// matrix (ll_download(LL_BUF_LABEL_MAT)), before the next scan re-initialises the forest.
+void launch_label_final(LaunchCtx& ctx, DevState& st) {
+  const DevParams& p = st.p;
+  const dim3 grid_cells((p.N + 255) / 256, p.B);
   LL_LAUNCH(ctx, "k_label_final", k_label_final<<<grid_cells, 256, 0, ctx.stream>>>(st));
 }
