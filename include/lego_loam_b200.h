@@ -129,7 +129,7 @@ typedef enum ll_buffer {
   LL_BUF_RING_CLOCKS = 47,     /* i64[V][10] profiling aid: SM cycles the feature extraction of every ring of the last frame spent per
                                   phase ({0 total, 1 load + keys, 2 speculative picks, 3 boundary check + re-runs, 4 persist + less-flat
                                   collection, 5 bounding box + voxel keys, 6 run heads, 7 run sort, 8 centroids, 9 span | n_raw << 16 |
-                                  runs << 32}) */
+                                  runs << 32 | re-run rounds << 48}) */
   /* MapOptimization key frames and local map (mapOptimization.h:96-135; needs ll_map_enable_keyframes) */
   LL_BUF_KEYFRAME_STATE = 41,      /* i32[4] key frames stored (cloudKeyPoses3D->size()), surroundingExistingKeyPosesID.size(),
                                       1 if the last extractSurroundingKeyFrames erased a key frame, capacity error bits (0 = none:

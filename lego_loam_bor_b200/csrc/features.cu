@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_feature_ring(DevState st, int
   // exactly what the sequential scan does (a candidate that was never picked never influenced a decision); otherwise
   // sextant j is reset and run again with those marks in place.  Ring 0 (the stale cloudSmoothness entry may point
   // anywhere) and rings with sextants shorter than 6 points take the sequential path below.
+  int n_rounds_dbg = 0;
   bool speculative = sh_has_stale == 0;
 #pragma unroll
   for (int j = 0; j < 6; ++j) speculative = speculative && (sh_sp[j] >= sh_ep[j] ? false : (sh_ep[j] - sh_sp[j] + 1 >= 6));
@@ -460,7 +461,24 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_feature_ring(DevState st, int
       }
       if (lane == 0) { sh_ne[j] = n_edge; sh_nf[j] = n_flat; sh_spill_r[j] = spill_r; sh_spill_l[j] = spill_l; }
     };
-    if (wid < 6) run_sextant(wid, 0u);
+    // One pick of the predecessor is known in advance: the reference's sort leaves out position ep but both scans include
+    // it, so an edge candidate at ep is met FIRST by the descending scan (key 0xffffffff) and, unless it is occluded, picked
+    // whatever else happens -- nothing of its own sextant has been picked yet and the marks of the sextant before reach
+    // only five positions, less than a speculative sextant is long.  Its marks on the first positions of this sextant are
+    // applied before the speculative run; without them about every fourth boundary of a ring of noisy far points (nearly
+    // every point an edge candidate) forced a re-run.
+    unsigned pre = 0u;
+    if (wid >= 1 && wid < 6) {
+      const int e = sh_ep[wid - 1];
+      const int le = e - span_lo;
+      const bool elig_e = ctype[e - k_first] == 0 && ckey[e - k_first] == 0xffffffffu && sm_picked[le] == 0;
+      bool bad = false;
+      if (lane >= 1 && lane <= 5) bad = abs((int)sm_col[le + lane] - (int)sm_col[le + lane - 1]) > 10;   // featureAssociation.cpp:306-316
+      const unsigned bm = __ballot_sync(0xffffffffu, bad) & 0x3eu;
+      const int stop = bm ? __ffs(bm) - 1 : 6;   // ep + stop is the first position the marking loop does not reach
+      if (elig_e) pre = (1u << (stop - 1)) - 1u;
+    }
+    if (wid < 6) run_sextant(wid, pre);
     __syncthreads();
     RING_CLOCK(2);
     // Boundaries.  Sextant j ran with the marks `used` of its predecessor in place (none, at first); the predecessor's
@@ -469,8 +487,9 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_feature_ring(DevState st, int
     // All sextants decide on the same snapshot of the spill masks and re-run in parallel, a warp each; sextants 0 .. k are
     // final after round k (sextant 0 has no predecessor), so this ends after at most five rounds -- usually one.
     {
-      unsigned used = 0u;   // warp j: the marks its last run started with
+      unsigned used = pre;   // warp j: the marks its last run started with
       for (int round = 0; round < 6; ++round) {
+        n_rounds_dbg = round;
         bool rerun = false;
         unsigned r = 0u;
         if (wid >= 1 && wid < 6) {
@@ -515,20 +534,23 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_feature_ring(DevState st, int
       if (i < 5) { if ((sh_spill_r[j] >> i) & 1) { const int g = ep + 1 + i; if (g >= span_lo && g < span_hi) sm_picked[g - span_lo] = 1; } }
       else { if ((sh_spill_l[j] >> (i - 5)) & 1) { const int g = sp - 1 - (i - 5); if (g >= span_lo && g < span_hi) sm_picked[g - span_lo] = 1; } }
     }
-    if (threadIdx.x == 0) {
-      int* o_sharp_i = st.st_sharp_ind + rs * 12;
-      int* o_lsharp_i = st.st_less_sharp_ind + rs * 120;
-      int* o_flat_i = st.st_flat_ind + rs * 24;
-      int n_sharp = 0, n_lsharp = 0, n_flat = 0;
-      for (int j = 0; j < 6; ++j) {
-        for (int t = 0; t < sh_ne[j]; ++t) {
+    // outputs in scan order: sextant by sextant, edge picks (the first two of a sextant are also the sharp ones), flat picks
+    if (threadIdx.x < 6 * 24) {
+      const int j = threadIdx.x / 24, t = threadIdx.x % 24;
+      int o_sharp = 0, o_lsharp = 0, o_flat = 0;
+      for (int q = 0; q < j; ++q) { o_sharp += min(sh_ne[q], 2); o_lsharp += sh_ne[q]; o_flat += sh_nf[q]; }
+      if (t < 20) {
+        if (t < sh_ne[j]) {
           const int pick = k_first + (int)sh_pick[j][t];
-          if (t < 2) o_sharp_i[n_sharp++] = pick;
-          o_lsharp_i[n_lsharp++] = pick;
+          if (t < 2) st.st_sharp_ind[rs * 12 + o_sharp + t] = pick;
+          st.st_less_sharp_ind[rs * 120 + o_lsharp + t] = pick;
         }
-        for (int t = 0; t < sh_nf[j]; ++t) o_flat_i[n_flat++] = k_first + (int)sh_pick[j][20 + t];
+      } else if (t - 20 < sh_nf[j]) {
+        st.st_flat_ind[rs * 24 + o_flat + (t - 20)] = k_first + (int)sh_pick[j][t];
       }
-      sh_counts[0] = n_sharp; sh_counts[1] = n_lsharp; sh_counts[2] = n_flat;
+      if (j == 5 && t == 0) {
+        sh_counts[0] = o_sharp + min(sh_ne[5], 2); sh_counts[1] = o_lsharp + sh_ne[5]; sh_counts[2] = o_flat + sh_nf[5];
+      }
     }
   } else
   if (wid == 0) {
@@ -866,7 +888,7 @@ __global__ void __launch_bounds__(FR_THREADS, 5) k_feature_ring(DevState st, int
   RING_CLOCK(8);
   if (threadIdx.x == 0) {
     ring_clk[0] = clock64() - rc_begin;
-    ring_clk[9] = (long long)L | ((long long)n_raw << 16) | ((long long)n_runs_dbg << 32);
+    ring_clk[9] = (long long)L | ((long long)n_raw << 16) | ((long long)n_runs_dbg << 32) | ((long long)n_rounds_dbg << 48);
     int* o_counts = st.ring_counts + rs * 8;
     o_counts[0] = sh_counts[0];
     o_counts[1] = sh_counts[1];

@@ -120,7 +120,9 @@ __device__ __forceinline__ bool odom_guard(const DevState& st, int s) {
   return !(st.last_counts[s * 2 + 0] < 10 || st.last_counts[s * 2 + 1] < 100);
 }
 
+#ifndef LM_THREADS
 #define LM_THREADS 768
+#endif
 #define LM_WARPS (LM_THREADS / 32)
 #define WIN_R (LL_MAX_RINGS + 8)
 

@@ -24,9 +24,10 @@ r = np.concatenate(rows).astype(np.float64)          # [frames * B * V][10]
 names = ["total", "load+keys", "spec picks", "boundary/reruns", "persist+collect", "bbox+voxkeys", "run heads", "run sort", "centroids"]
 ghz = 1.965
 info = r[:, 9].astype(np.int64)
-span, nraw, nruns = info & 0xffff, (info >> 16) & 0xffff, (info >> 32) & 0xffff
+span, nraw, nruns, rounds = info & 0xffff, (info >> 16) & 0xffff, (info >> 32) & 0xffff, (info >> 48) & 0xff
 order = np.argsort(-r[:, 0])
 print("rings %d   span mean %.0f max %d   n_raw mean %.0f max %d   runs mean %.0f max %d" % (len(r), span.mean(), span.max(), nraw.mean(), nraw.max(), nruns.mean(), nruns.max()))
 for k, n in enumerate(names):
     print("  %-16s mean %8.1f us   p95 %8.1f us   max %8.1f us   in the 16 slowest rings %8.1f us" % (n, r[:, k].mean() / ghz / 1e3, np.percentile(r[:, k], 95) / ghz / 1e3, r[:, k].max() / ghz / 1e3, r[order[:16], k].mean() / ghz / 1e3))
+print("re-run rounds histogram", np.bincount(rounds).tolist())
 print("slowest rings: (span, n_raw, runs, total us)", [(int(span[i]), int(nraw[i]), int(nruns[i]), round(r[i, 0] / ghz / 1e3, 1)) for i in order[:8]])
