@@ -314,7 +314,10 @@ __device__ __forceinline__ void knn_search_warp(const DevState& st, int s, int q
   }
 }
 
-__global__ void __launch_bounds__(KNN_THREADS, 5) k_map_knn(DevState st, int iter) {
+#ifndef KNN_MIN_BLOCKS
+#define KNN_MIN_BLOCKS 5   // 6 (80 registers) and 8 (64, spills) measured alike
+#endif
+__global__ void __launch_bounds__(KNN_THREADS, KNN_MIN_BLOCKS) k_map_knn(DevState st, int iter) {
   __shared__ int sh_need[KNN_THREADS];
   __shared__ int sh_coop[KNN_THREADS / 32][96];
   __shared__ int sh_n;

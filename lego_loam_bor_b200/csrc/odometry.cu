@@ -121,7 +121,9 @@ __device__ __forceinline__ bool odom_guard(const DevState& st, int s) {
 }
 
 #ifndef LM_THREADS
+#ifndef LM_THREADS
 #define LM_THREADS 768
+#endif
 #endif
 #define LM_WARPS (LM_THREADS / 32)
 #define WIN_R (LL_MAX_RINGS + 8)
@@ -186,6 +188,9 @@ __device__ __forceinline__ void build_window_tables(WinTables& w, const DevState
 #define LM_GROUPS (LM_THREADS / SG)
 #define SEARCH_THREADS 256
 #define SEARCH_GROUPS (SEARCH_THREADS / SG)
+#ifndef SEARCH_QPW_CORNER
+#define SEARCH_QPW_CORNER 4   // corner feature points per warp of k_odom_search (1 / 2 / 4 measured alike)
+#endif
 
 // Warp-wide reduction of Best (all 32 lanes; SG == 32): hardware integer min-reductions on the distance bits
 // (non-negative floats order like unsigned ints) and on the tie-break key, payload from the winning lane.
@@ -691,7 +696,7 @@ __device__ __forceinline__ bool corr_geometry(const CorrS& c, const float4* __re
 template <int STAGE>
 __global__ void __launch_bounds__(SEARCH_THREADS) k_odom_search(DevState st) {
   // feature points per warp: the long SURF searches want as many warps in flight as possible
-  constexpr int SEARCH_QPW = STAGE == STAGE_SURF ? 1 : 4;
+  constexpr int SEARCH_QPW = STAGE == STAGE_SURF ? 1 : SEARCH_QPW_CORNER;
   __shared__ WinTables win;
   const DevParams& p = st.p;
   const bool surf = (STAGE == STAGE_SURF);
@@ -967,7 +972,7 @@ void launch_odometry(LaunchCtx& ctx, DevState& st, bool first_frame) {
     // surf stage then corner stage (featureAssociation.cpp:1216-1234), then integrateTransformation
     LL_LAUNCH(ctx, "k_odom_search_surf", k_odom_search<STAGE_SURF><<<dim3((p.cap_flat + SEARCH_GROUPS - 1) / SEARCH_GROUPS, p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
     LL_LAUNCH(ctx, "k_odom_stage_surf", k_odom_stage<STAGE_SURF><<<p.B, LM_THREADS, stage_smem(p, true), ctx.stream>>>(st));
-    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp + SEARCH_GROUPS * 4 - 1) / (SEARCH_GROUPS * 4), p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
+    LL_LAUNCH(ctx, "k_odom_search_corner", k_odom_search<STAGE_CORNER><<<dim3((p.cap_sharp + SEARCH_GROUPS * SEARCH_QPW_CORNER - 1) / (SEARCH_GROUPS * SEARCH_QPW_CORNER), p.B), SEARCH_THREADS, 0, ctx.stream>>>(st));
     LL_LAUNCH(ctx, "k_odom_stage_corner", k_odom_stage<STAGE_CORNER><<<p.B, LM_THREADS, stage_smem(p, false), ctx.stream>>>(st));
   }
   if (ctx.wait_before_publish) {
