@@ -159,6 +159,9 @@ def survey_bytes(st):
     return {"P": P, "G": G, "S": Sg, "F": F, "total": P + G + Sg + F}
 
 
+KNN_REC_BYTES = (8 + 1) * 16   # LL_KNN_K + 1 float4 per query (ll_device.cuh)
+
+
 def algorithmic_bytes(kernel, st):
     """Per-kernel, per-sequence bytes (each kernel's own compulsory reads + writes)."""
     N, S, n_in, g = st["N"], st["S"], st["n_in"], st["g"]
@@ -181,9 +184,9 @@ def algorithmic_bytes(kernel, st):
         "k_publish_clouds_last": 32 * (lf + ls + out),
         "k_grid_count": 16 * (lf + ls), "k_grid_scan": 0, "k_grid_fill": 32 * (lf + ls),
         "k_voxel_grid": 16 * (lf + ls + out) * 2, "k_voxel_grid_total": 16 * qs * 2,
-        "k_map_knn": (qs + qc) * (16 + 176) + (ms + mc) * 16,
+        "k_map_knn": (qs + qc) * (16 + KNN_REC_BYTES) + (ms + mc) * 16,
         "k_map_iter": (qs + qc) * (16 + 4 + 5 * 16), "k_map_solve": 0,
-        "k_map_knn_reuse": (qs + qc) * (16 + 176 + 4), "k_map_iter_cached": (qs + qc) * (16 + 4 + 32),
+        "k_map_knn_reuse": (qs + qc) * (16 + KNN_REC_BYTES + 4), "k_map_iter_cached": (qs + qc) * (16 + 4 + 32),
         "k_kf_select": 0, "k_kf_decide": 0, "k_kf_accumulate": kfp * (16 + 8 + 2 * 28),
         "k_kf_extract": (ms + mc) * (8 + 20 + 16), "k_kf_store": kfp * (16 + 28),
         "k_kfx_sort_new": 0, "k_kfx_merge": (ms + mc) * 24, "k_kfx_alive": (ms + mc) * 8, "k_kfx_output": (ms + mc) * (4 + 20 + 16),

@@ -17,7 +17,7 @@
 #define LL_MAX_RINGS 128
 // scan-to-map k-NN: map points recorded per query by a full search (mapping.cu, k_map_knn); <= 16 (4-bit positions)
 #ifndef LL_KNN_K
-#define LL_KNN_K 10
+#define LL_KNN_K 8
 #endif
 #define LL_INVALID_LABEL 999999
 
