@@ -84,7 +84,9 @@ typedef enum ll_buffer {
   LL_BUF_RANGE_MAT = 0,   /* f32[N]  _range_mat, row-major, FLT_MAX = no return */
   LL_BUF_FULL_CLOUD = 1,  /* pt[N]   _full_cloud (NaN xyz where empty) */
   LL_BUF_GROUND_MAT = 2,  /* i8[N]   _ground_mat */
-  LL_BUF_LABEL_MAT = 3,   /* i32[N]  _label_mat */
+  LL_BUF_LABEL_MAT = 3,   /* i32[N]  _label_mat (private to ImageProjection, imageProjection.h; the per-scan path decides everything
+                             cloudSegmentation reads from it -- > 0 / == 999999 -- from the component forest and numbers the roots;
+                             the numbers of the other cells are filled in when this buffer is first read after a scan) */
   /* ProjectionOut (utility.h:64-70) and cloud_info (cloud_info.msg:1-13) */
   LL_BUF_SEG_CLOUD = 4,        /* pt[S]  segmented_cloud (after ll_feature_association: axis-swapped + time-tagged) */
   LL_BUF_SEG_GROUND_FLAG = 5,  /* u8[S]  segmentedCloudGroundFlag */

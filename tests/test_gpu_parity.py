@@ -167,3 +167,31 @@ def test_last_writer_wins(built):
     o.image_projection(both)
     for name in ("RANGE_MAT", "FULL_CLOUD", "LABEL_MAT"):
         assert same_bits(gpu.download(name), o.download(name)), name
+
+
+def test_label_mat_on_demand_and_ring_clocks():
+    """_label_mat's numbers of the non-root cells are written when LL_BUF_LABEL_MAT is read, not per scan: reading it only after
+    the feature stage of a LATER scan (nothing read in between), twice in a row, and for every sequence of the batch must give
+    the oracle's matrix of that scan.  LL_BUF_RING_CLOCKS: one row of ten counters per ring, total >= the sum of the phases."""
+    from lego_loam_bor_b200.capi import LegoLoam
+    from oracle.oracle_py import Oracle
+    seqs = [0, 1]
+    p, cfg, scans = make_scans("T", seqs, range(3))
+    gpu = LegoLoam(p, batch=len(seqs))
+    oracles = [Oracle(p) for _ in seqs]
+    for f in range(3):
+        gpu.set_scans_host([scans[(s, f)] for s in seqs])
+        gpu.image_projection()
+        gpu.feature_association()
+        for k, s in enumerate(seqs):
+            oracles[k].image_projection(scans[(s, f)])
+            oracles[k].feature_association()
+        if f == 0:
+            continue   # nothing is read after the first scan: its pending labels must not leak into the next one
+        for rep in range(2):
+            for k in range(len(seqs)):
+                a, b = gpu.download("LABEL_MAT", k), oracles[k].download("LABEL_MAT")
+                assert same_bits(a, b), f"frame {f} seq {k} read {rep}: " + describe_mismatch("LABEL_MAT", a, b)
+    clk = gpu.download("RING_CLOCKS", 0)
+    assert clk.shape == (p.num_vertical_scans, 10)
+    assert np.all(clk[:, 0] > 0) and np.all(clk[:, 0] >= clk[:, 1:9].sum(axis=1))
