@@ -127,7 +127,8 @@ typedef enum ll_buffer {
   LL_BUF_SCAN_SURF_DS = 38,    /* pt[..] laserCloudSurfLastDS (before the outlier cloud is appended) */
   LL_BUF_SCAN_OUTLIER_DS = 39, /* pt[..] laserCloudOutlierLastDS */
   LL_BUF_STAGE_CLOCKS = 40,    /* i64[16] profiling aid: nanoseconds the two scan-to-scan LM stages of the last frame spent per phase
-                                  (stage*8 + {0 total, 1 prologue, 2 re-search, 3 rows + reduction, 4 solve, 5 re-searched points}) */
+                                  (stage*8 + {0 total, 1 prologue, 2 re-search, 3 rows + reduction, 4 solve, 5 re-searched points}); the per-phase
+                                  entries only after ll_enable_stage_timing(h, 1) */
   LL_BUF_RING_CLOCKS = 47,     /* i64[V][10] profiling aid: SM cycles the feature extraction of every ring of the last frame spent per
                                   phase ({0 total, 1 load + keys, 2 speculative picks, 3 boundary check + re-runs, 4 persist + less-flat
                                   collection, 5 bounding box + voxel keys, 6 run heads, 7 run sort, 8 centroids, 9 span | n_raw << 16 |

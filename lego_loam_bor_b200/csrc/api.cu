@@ -1104,6 +1104,7 @@ int ll_enable_stage_timing(ll_handle* h, int enable) {
   if (!h) return LL_ERR_INVALID_ARG;
   cudaSetDevice(h->device);  // the handle's device, whatever the caller's current one is
   h->timing = enable != 0;
+  h->st.stage_clocks_on = enable != 0 ? 1 : 0;
   h->ev_valid = false;
   return LL_OK;
 }

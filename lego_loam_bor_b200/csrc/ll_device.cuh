@@ -181,6 +181,7 @@ struct DevState {
   uint8_t* odom_ok;     // [B][24V]
   int* odom_cl;         // [B][24V] closest point (index into the last-frame cloud) or -1
   long long* stage_clocks;  // [B][16] see LL_BUF_STAGE_CLOCKS
+  int stage_clocks_on;      // per-phase clocks of the LM stage kernels (ll_enable_stage_timing); the total is always written
   long long* ring_clocks;   // [B][V][10] see LL_BUF_RING_CLOCKS
   float4* outlier_last; // [B][cap_outlier]
   HashGrid grid_corner_last, grid_surf_last;  // index the clouds the "kd-trees" were last built on

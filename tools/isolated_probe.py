@@ -13,6 +13,7 @@ p = config_params("C"); cfg = synth.make_arena(p, n_keyframes=10)
 dev = torch.device("cuda", 0)
 gen = synth.ArenaDeviceGenerator(cfg, list(range(B)), dev)
 gpu = LegoLoam(p, batch=B)
+gpu.enable_stage_timing(True)
 gpu.enable_index_trace(True)
 cap = 24 * p.num_vertical_scans
 rows = []

@@ -11,6 +11,7 @@ p = config_params("C"); cfg = synth.make_arena(p, n_keyframes=10)
 dev = torch.device("cuda", 0)
 gen = synth.ArenaDeviceGenerator(cfg, list(range(B)), dev)
 gpu = LegoLoam(p, batch=B)
+gpu.enable_stage_timing(True)
 rows = []
 for f in range(F):
     pts, counts = gen.scans(synth.DRIVE, f)
