@@ -787,7 +787,7 @@ def main():
         alg = algorithmic_bytes(dominant, st) * sub   # one launch covers one sub-batch
         traffic = None
         try:  # dram bytes per launch from the committed ncu --set full captures (profiles/*traffic.json)
-            for name in ("r2_traffic.json", "r1_traffic.json"):
+            for name in ("r2_final_traffic.json", "r2_traffic.json", "r1_traffic.json"):
                 pth = os.path.join(ROOT, "profiles", name)
                 if os.path.exists(pth):
                     tr = json.load(open(pth))
