@@ -272,16 +272,26 @@ __device__ __forceinline__ void block_exclusive_scan_trips(const int (&v)[SEG_TR
     for (int t = 0; t < SEG_TRIPS; ++t) sh[wid][t] = inc[t];
   }
   __syncthreads();
+  // the nw x SEG_TRIPS warp totals are one value per lane of warp 0: exclusive prefix over the warps of every trip with
+  // shuffles of stride SEG_TRIPS (a loop over the warps in every thread was a sixth of this kernel's instructions)
+  static_assert(8 * SEG_TRIPS <= 32, "one warp total per lane");
+  if (wid == 0) {
+    const int w = lane / SEG_TRIPS, t = lane % SEG_TRIPS;
+    const int x0 = w < nw ? sh[w][t] : 0;
+    int incl = x0;
+#pragma unroll
+    for (int o = SEG_TRIPS; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    if (w < nw) sh[w][t] = incl - x0;
+    if (w == nw - 1) sh[8][t] = incl;   // total of the trip
+  }
+  __syncthreads();
 #pragma unroll
   for (int t = 0; t < SEG_TRIPS; ++t) {
-    int pre = 0, tot = 0;
-    for (int w = 0; w < nw; ++w) {
-      const int x = sh[w][t];
-      if (w < wid) pre += x;
-      tot += x;
-    }
-    ex[t] = pre + inc[t] - v[t];
-    total[t] = tot;
+    ex[t] = sh[wid][t] + inc[t] - v[t];
+    total[t] = sh[8][t];
   }
   __syncthreads();
 }
@@ -292,7 +302,7 @@ __device__ __forceinline__ void block_exclusive_scan_trips(const int (&v)[SEG_TR
 // duration is the latency of one block.
 __global__ void __launch_bounds__(256) k_seg_emit(DevState st) {
   __shared__ int sh_pre[3];
-  __shared__ int sh_scan[8][SEG_TRIPS];
+  __shared__ int sh_scan[9][SEG_TRIPS];   // warp totals -> exclusive prefixes; row 8: the totals
   const DevParams& p = st.p;
   const int row = blockIdx.x, s = blockIdx.y;
   const size_t base = (size_t)s * p.N;
