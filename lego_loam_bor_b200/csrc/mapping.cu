@@ -744,11 +744,22 @@ void launch_scan_to_map(LaunchCtx& ctx, DevState& st) {
                      st.grid_map_surf, st.map_surf, st.cap_map_surf, st.map_counts, 2, 1, nullptr, 0);
   LL_LAUNCH(ctx, "k_map_begin", k_map_begin<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
   if (st.map_knn_trace) cudaMemsetAsync(st.map_knn_trace, 0xff, (size_t)p.B * 10 * st.map_knn_cap * 5 * sizeof(int), ctx.stream);
+#ifdef MAP_ITER_NAMES   // measurement build (LEGO_LOAM_B200_NVCC_EXTRA=-DMAP_ITER_NAMES): one timing name per LM iteration
+  static const char* const knn_names[10] = {"k_map_knn", "k_map_knn_r1", "k_map_knn_r2", "k_map_knn_r3", "k_map_knn_r4", "k_map_knn_r5", "k_map_knn_r6", "k_map_knn_r7", "k_map_knn_r8", "k_map_knn_r9"};
+  static const char* const iter_names[10] = {"k_map_iter", "k_map_iter_c1", "k_map_iter_c2", "k_map_iter_c3", "k_map_iter_c4", "k_map_iter_c5", "k_map_iter_c6", "k_map_iter_c7", "k_map_iter_c8", "k_map_iter_c9"};
+#endif
   for (int iter = 0; iter < 10; ++iter) {
     // (two names so that per-kernel timing tells the full search of iteration 0 from the reuse / re-search launches)
-    LL_LAUNCH(ctx, iter == 0 ? "k_map_knn" : "k_map_knn_reuse", k_map_knn<<<dim3(KNN_BLOCKS, p.B), KNN_THREADS, 0, ctx.stream>>>(st, iter));
+#ifdef MAP_ITER_NAMES
+    const char* kn = knn_names[iter];
+    const char* in = iter_names[iter];
+#else
+    const char* kn = iter == 0 ? "k_map_knn" : "k_map_knn_reuse";
+    const char* in = iter == 0 ? "k_map_iter" : "k_map_iter_cached";
+#endif
+    LL_LAUNCH(ctx, kn, k_map_knn<<<dim3(KNN_BLOCKS, p.B), KNN_THREADS, 0, ctx.stream>>>(st, iter));
     if (st.map_knn_trace) LL_LAUNCH(ctx, "k_map_knn_trace", k_map_knn_trace<<<dim3(32, p.B), 256, 0, ctx.stream>>>(st, iter));
-    LL_LAUNCH(ctx, iter == 0 ? "k_map_iter" : "k_map_iter_cached", k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st, iter));
+    LL_LAUNCH(ctx, in, k_map_iter<<<dim3(MAP_BLOCKS, p.B), MAP_THREADS, 0, ctx.stream>>>(st, iter));
   }
   LL_LAUNCH(ctx, "k_map_update", k_map_update<<<(p.B + 63) / 64, 64, 0, ctx.stream>>>(st));
 }
